@@ -1,0 +1,175 @@
+/*
+ * umv.h -- C ABI of the B200-native UniMedVL inference engine (libumv.so).
+ *
+ * The reference (uni-medical/UniMedVL) has no FFI, plugin registry or native code: its boundary for
+ * the unified understanding+generation forward path is the Python method surface of
+ * codes/modeling/unimedvl/bagel.py:Bagel and its sub-models.  Each entry point
+ * below names the reference interface it stands in for; unimedvl_b200/bagel.py re-creates the
+ * Python surface on top of these calls (ctypes binding: unimedvl_b200/_lib.py, maintainers' stub
+ * in INTEGRATION.md).
+ *
+ * Conventions: every function returns 0 (UMV_OK) or a negative umv_status; umv_last_error() gives
+ * the message of the calling thread's last failure.  Bulk tensors are DEVICE pointers (bf16 unless
+ * stated), small index/shape metadata are HOST pointers.  `stream` is a cudaStream_t passed as
+ * void* (NULL = legacy default stream).  One engine per GPU per process; a handle is not
+ * thread-safe (the reference is single-threaded, codes/interactive_vqa_inferencer.py:19-20).
+ * There is no CPU fallback: without a CUDA device every compute call fails with UMV_ERR_CUDA.
+ */
+#ifndef UMV_H_
+#define UMV_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define UMV_ABI_VERSION 1
+
+typedef enum umv_status {
+    UMV_OK = 0,
+    UMV_ERR_INVALID = -1,        /* bad argument            -> Python ValueError        */
+    UMV_ERR_UNSUPPORTED = -2,    /* not implemented variant -> Python NotImplementedError */
+    UMV_ERR_CUDA = -3,           /* CUDA runtime / launch failure -> RuntimeError        */
+    UMV_ERR_NOMEM = -4,          /* KV page pool or workspace exhausted -> MemoryError  */
+    UMV_ERR_STATE = -5           /* call order violated (e.g. weights not finalized) -> AssertionError */
+} umv_status;
+
+typedef enum umv_dtype { UMV_BF16 = 0, UMV_F32 = 1, UMV_I64 = 2, UMV_I32 = 3, UMV_U8 = 4 } umv_dtype;
+
+/* Model geometry.  Reference: Qwen2Config (qwen2_navit.py:46-204), SiglipVisionConfig
+ * (siglip_navit.py:21-99), BagelConfig (bagel.py:30-88); values come from the checkpoint's
+ * llm_config.json / vit_config.json (interactive_vqa_inferencer.py:206-213). */
+typedef struct umv_dims {
+    int32_t hidden, heads, kv_heads, inter, layers, vocab;
+    float rope_theta, rms_eps;
+    int32_t vit_hidden, vit_heads, vit_inter, vit_layers, vit_patch_dim, vit_positions;
+    float vit_eps;
+    int32_t vit_pos_table;        /* vit_max_num_patch_per_side^2 (bagel.py:143)   */
+    int32_t latent_dim;           /* latent_patch_size^2 * z_channels (bagel.py:113) */
+    int32_t latent_pos_table;     /* max_latent_size^2 (bagel.py:120)              */
+    int32_t max_tokens;           /* workspace rows: largest packed query length of one call */
+    int32_t max_seqs;             /* largest number of samples in one call         */
+    int32_t kv_pages;             /* KV page pool size (pages of UMV_PAGE_TOKENS tokens) */
+    int32_t enable_vit, enable_gen;   /* allocate ViT / generation-expert weights  */
+} umv_dims;
+
+#define UMV_PAGE_TOKENS 64
+
+typedef struct umv_engine umv_engine;
+
+const char* umv_last_error(void);
+int umv_abi_version(void);
+
+/* ---- lifetime / weights ------------------------------------------------------------------
+ * Stands in for Bagel.__init__ + load_checkpoint_and_dispatch(dtype=bf16)
+ * (interactive_vqa_inferencer.py:225-229,153-156).  Tensor names are the reference state_dict
+ * keys (SURVEY.md section 8b "Weight interface"); the engine re-lays them out (fused QKV, gate/up
+ * interleaved in 64-row blocks). */
+int umv_create(const umv_dims* dims, umv_engine** out);
+int umv_destroy(umv_engine* e);
+int umv_load_tensor(umv_engine* e, const char* name, const void* data, int dtype, int ndim,
+                    const int64_t* shape, int data_on_device);
+int umv_export_tensor(umv_engine* e, const char* name, void* host_dst, size_t bytes);
+int umv_fill_synthetic(umv_engine* e, uint64_t seed);   /* random-init weights generated on the device */
+int umv_finalize(umv_engine* e);
+int umv_weight_bytes(umv_engine* e, int64_t* bytes);
+
+/* ---- KV sequences: NaiveCache (qwen2_navit.py:207-221) as ref-counted pages -----------------
+ * One sequence per sample.  fork == copy.deepcopy(gen_context) (inferencer.py:261,587,600,607)
+ * without copying pages (copy-on-write of the partial tail page).  export gives the reference's
+ * packed layout [len, kv_heads, head_dim] for parity tests. */
+int umv_seq_new(umv_engine* e, int32_t* seq);
+int umv_seq_fork(umv_engine* e, int32_t src, int32_t* dst);
+int umv_seq_free(umv_engine* e, int32_t seq);
+int umv_seq_len(umv_engine* e, int32_t seq, int32_t* len);
+int umv_seq_truncate(umv_engine* e, int32_t seq, int32_t len);
+int umv_seq_export(umv_engine* e, int32_t seq, int32_t layer, void* k_dev, void* v_dev, void* stream);
+int umv_pages_free(umv_engine* e, int32_t* n);
+
+/* ---- ViT + connector: SiglipVisionModel.forward (siglip_navit.py:389-402) + MLPconnector +
+ * vit_pos_embed, i.e. bagel.py:581-594.  pixels: f32 [n_tokens, vit_patch_dim] (patchify order
+ * h,w,p,q,c); pos_ids: i64 [n_tokens] device; seqlens: host i32 [n_images]; out: bf16
+ * [n_tokens, hidden]. */
+int umv_vit_embed(umv_engine* e, const float* pixels, const int64_t* pos_ids, const int32_t* seqlens,
+                  int32_t n_images, void* out, void* stream);
+
+/* ---- embedding rows: language_model.model.embed_tokens (bagel.py:438,577,1264) ------------- */
+int umv_embed_tokens(umv_engine* e, const int64_t* ids, int32_t n, void* out, void* stream);
+
+/* ---- packed LLM forward: Qwen2ForCausalLM.forward_inference (qwen2_navit.py:1243-1274).
+ * x: bf16 [M, hidden] packed query sequence (samples contiguous, in seq order); q_lens / seqs:
+ * host i32 [n_seqs]; positions: host i32 [M] (packed_query_position_ids); row_is_gen: host u8 [M]
+ * or NULL (mode "und"); non-NULL selects mode "gen" with rows==1 routed to the *_moe_gen weights
+ * (packed_vae_token_indexes) and rows==0 to the understanding weights (packed_text_indexes).
+ * update_kv: update_past_key_values.  out: bf16 [M, hidden] final-normed hidden states (may be
+ * NULL when only the cache update is wanted). */
+int umv_llm_forward(umv_engine* e, const void* x, int32_t n_seqs, const int32_t* seqs, const int32_t* q_lens,
+                    const int32_t* positions, const uint8_t* row_is_gen, int32_t is_causal, int32_t update_kv,
+                    void* out, void* stream);
+
+/* lm_head (bagel.py:1295): hidden bf16 [m, hidden] -> logits bf16 [m, vocab]. */
+int umv_lm_head(umv_engine* e, const void* hidden, int32_t m, void* logits, void* stream);
+
+/* ---- greedy / sampled decode loop: Bagel.generate_text (bagel.py:1236-1317) ----------------
+ * Runs `n_steps` forward passes entirely on the device (no per-step host sync).  tokens_out: i64
+ * [n_steps, n_seqs] device, row 0 = start tokens (the reference's layout).  forced_tokens (i64
+ * [n_steps, n_seqs] device, optional) teacher-forces the inputs; logits_out (bf16
+ * [n_steps, n_seqs, vocab] device, optional) receives every step's logits.  temperature <= 0 ->
+ * argmax (ties -> lowest index, torch.argmax); > 0 -> softmax(logits/T) sampling with the engine's
+ * own counter-based RNG (seed).  KV lengths advance by n_steps. */
+int umv_generate_text(umv_engine* e, int32_t n_seqs, const int32_t* seqs, const int64_t* start_tokens,
+                      const int32_t* positions, int32_t n_steps, float temperature, uint64_t seed,
+                      const int64_t* forced_tokens, int64_t* tokens_out, void* logits_out, void* stream);
+
+/* ---- rectified-flow step: Bagel._forward_flow (bagel.py:989-1211) -------------------------
+ * One velocity evaluation incl. up to three LLM forwards (main / cfg_text / cfg_img contexts) and
+ * the CFG mix + renorm.  x_t: f32 [n_lat, latent_dim] device; v_out: f32 [n_lat, latent_dim].
+ * Markers (packed_text_ids) are given per sequence: 2 ids each.  lat_lens: latent tokens per image.
+ * renorm_type: 0 global (per image), 1 channel, 2 text_channel.  *_seqs may be NULL
+ * when the corresponding scale <= 1.  v_is_f32_out tells the caller whether the reference would
+ * have produced an fp32 (1) or bf16-valued (0) velocity. */
+typedef struct umv_flow_args {
+    int32_t n_seqs;
+    const int32_t* seqs;            /* main context                                  */
+    const int32_t* cfg_text_seqs;   /* or NULL                                        */
+    const int32_t* cfg_img_seqs;    /* or NULL                                        */
+    const int32_t* lat_lens;        /* host [n_seqs] h*w per image                    */
+    const int32_t* positions;       /* host [n_seqs] rope position of each image (main) */
+    const int32_t* cfg_text_positions;
+    const int32_t* cfg_img_positions;
+    const int64_t* marker_ids;      /* host [2] start_of_image, end_of_image          */
+    const int64_t* lat_pos_ids;     /* device i64 [n_lat] packed_vae_position_ids     */
+    float timestep;
+    float cfg_text_scale, cfg_img_scale, cfg_renorm_min;
+    int32_t renorm_type;
+} umv_flow_args;
+int umv_flow_velocity(umv_engine* e, const umv_flow_args* a, const float* x_t, float* v_out, void* stream);
+/* x_t <- x_t - bf16(v * dt) (bagel.py:983; v*dt rounds to bf16 when v is bf16-valued). */
+int umv_flow_euler(umv_engine* e, float* x_t, const float* v, int64_t n, float dt, int32_t v_is_bf16, void* stream);
+
+/* ---- op-level entry points (parity tests; each is the kernel the model path uses) ---------- */
+/* y[M,N] = x[M,K] @ w[N,K]^T (+bias) with epilogue `epi`: 0 bf16, 1 gelu_tanh, 2 swiglu (w rows
+ * interleaved 64 gate | 64 up, y is [M, N/2]), 3 +residual (y = bf16(bf16(acc+bias) + res)).
+ * impl: 0 auto, 1 tcgen05 token-major (prefill), 2 tcgen05 weight-major (decode, M<=32, split-K),
+ * 3 simple reference kernel. */
+int umv_op_linear(const void* x, const void* w, const void* bias, const void* residual, void* y, int32_t M,
+                  int32_t N, int32_t K, int32_t epi, int32_t impl, void* stream);
+int umv_op_rmsnorm(const void* x, const void* w, void* y, int32_t M, int32_t D, float eps, void* stream);
+int umv_op_layernorm(const void* x, const void* w, const void* b, void* y, int32_t M, int32_t D, float eps,
+                     void* stream);
+/* varlen attention over packed q [Tq,H,dh], k/v [Tk,Hkv,dh] (flash_attn_varlen_func call sites
+ * qwen2_navit.py:605-614, siglip_navit.py:232-241); q_lens/k_lens host i32 [n]. */
+int umv_op_attention(const void* q, const void* k, const void* v, void* out, int32_t n, const int32_t* q_lens,
+                     const int32_t* k_lens, int32_t heads, int32_t kv_heads, int32_t head_dim, int32_t causal,
+                     void* stream);
+int umv_op_argmax(const void* logits, int32_t rows, int32_t vocab, int64_t* out, void* stream);
+
+/* Kernel launches issued by this library since load (bench.py "gpu_launches"). */
+int64_t umv_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* UMV_H_ */

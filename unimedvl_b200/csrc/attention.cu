@@ -1,0 +1,332 @@
+// Variable-length GQA attention for the packed LLM (head_dim 128, paged KV) and the ViT
+// (head_dim 72, packed K/V): flash-style single pass, warp-level mma.sync m16n8k16 bf16 tiles,
+// cp.async double-buffered 64-key blocks staged in (swizzled) shared memory, fp32 online softmax with
+// warp-shuffle row reductions, probabilities rounded to bf16 before the PV product.
+//
+// Rows of a CTA tile are (token, head-in-group) pairs of ONE kv head, so a K/V block is read once
+// for all `group` query heads that share it; the same kernel therefore serves prefill (many tokens)
+// and decode (1 token x group heads) -- decode adds split-KV over key blocks plus a combine pass.
+//
+// Replaces flash_attn_varlen_func (flash-attn 2.x, external to the reference) at
+// qwen2_navit.py:605-614 (causal = bottom-right aligned, or full) and siglip_navit.py:232-241, and the
+// per-step full KV re-materialisation of qwen2_navit.py:589-600 (the cache is read in place).
+#include "../../include/umv.h"
+#include "common.cuh"
+#include "gemm.cuh"
+#include "kernels.cuh"
+#include "ptx.cuh"
+
+namespace umv {
+
+constexpr int kAttnThreads = 128;
+constexpr int kTileRows = 64;   // query rows per CTA (4 warps x 16)
+constexpr int kTileKeys = 64;   // keys per block == KV page size
+
+template <int HD>
+struct AttnCfg {
+    static constexpr int kChunks = HD / 8;                          // 16-byte chunks of real data per row
+    static constexpr int kKSteps = (HD + 15) / 16;                  // QK^T k-steps (HD padded to 16)
+    static constexpr int kDTiles = HD / 8;                          // PV n-tiles
+    static constexpr bool kSwizzle = (HD == 128);
+    static constexpr int kRowBytes = kSwizzle ? 256 : (kKSteps * 32 + 16);   // 72 -> 176 B (conflict-free ldmatrix)
+    static constexpr int kTileBytes = kTileRows * kRowBytes;
+    static constexpr int kSmemBytes = 5 * kTileBytes;               // Q + 2 x (K, V)
+};
+
+template <int HD>
+__device__ __forceinline__ uint32_t tile_off(int row, int chunk) {
+    if (AttnCfg<HD>::kSwizzle) return row * 256 + (((chunk ^ (row & 7)) & 15) << 4);
+    return row * AttnCfg<HD>::kRowBytes + (chunk << 4);
+}
+
+template <int HD>
+__global__ void __launch_bounds__(kAttnThreads) attn_fwd_kernel(AttnArgs a, float scale_log2) {
+    using Cfg = AttnCfg<HD>;
+    extern __shared__ __align__(128) uint8_t smem[];
+    uint8_t* sQ = smem;
+    uint8_t* sK = smem + Cfg::kTileBytes;
+    uint8_t* sV = smem + 3 * Cfg::kTileBytes;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int b = blockIdx.y / a.Hkv, kvh = blockIdx.y % a.Hkv;
+    const int split = blockIdx.z;
+    const int G = a.H / a.Hkv;
+    const int qlen = a.q_len[b], kvlen = a.kv_len[b];
+    const int r0 = blockIdx.x * kTileRows;
+    const int nrows = qlen * G;
+    if (r0 >= nrows) return;
+    const int qs = a.q_start[b];
+    const int ks0 = a.paged ? 0 : a.k_start[b];
+
+    // visible key range of this tile
+    const int last_tok = min(qlen - 1, (r0 + kTileRows - 1) / G);
+    const int vis_keys = a.causal ? min(kvlen, kvlen - qlen + last_tok + 1) : kvlen;
+    const int blocks_total = (vis_keys + kTileKeys - 1) / kTileKeys;
+    const int bps = (blocks_total + a.splits - 1) / a.splits;
+    const int kb_begin = split * bps, kb_end = min(blocks_total, kb_begin + bps);
+
+    if (!Cfg::kSwizzle) {
+        // zero the padding chunk (columns HD..HD+7) that the last QK^T k-step reads
+        for (int i = tid; i < 5 * kTileRows; i += kAttnThreads)
+            *reinterpret_cast<U4*>(smem + (i / kTileRows) * Cfg::kTileBytes + tile_off<HD>(i % kTileRows, Cfg::kChunks)) = U4{0, 0, 0, 0};
+    }
+
+    // ---- stage Q
+    for (int i = tid; i < kTileRows * Cfg::kChunks; i += kAttnThreads) {
+        const int r = i / Cfg::kChunks, ch = i % Cfg::kChunks;
+        const int R = r0 + r;
+        const bool ok = R < nrows;
+        const int tok = ok ? R / G : 0, head = kvh * G + (ok ? R % G : 0);
+        cp_async16(sQ + tile_off<HD>(r, ch), a.q + (size_t)(qs + tok) * a.ldq + head * HD + ch * 8, ok);
+    }
+    auto load_kv = [&](int kb, int stage) {
+        const bf16* kbase;
+        const bf16* vbase;
+        size_t kstride, vstride;
+        if (a.paged) {
+            const int page = a.page_table[(size_t)b * a.max_pages + kb];
+            kbase = a.pool.base + a.pool.tile_offset(page, a.layer, 0, kvh);
+            vbase = a.pool.base + a.pool.tile_offset(page, a.layer, 1, kvh);
+            kstride = vstride = HD;
+        } else {
+            kbase = a.k + (size_t)(ks0 + kb * kTileKeys) * a.ldk + kvh * HD;
+            vbase = a.v + (size_t)(ks0 + kb * kTileKeys) * a.ldv + kvh * HD;
+            kstride = a.ldk;
+            vstride = a.ldv;
+        }
+        uint8_t* dk = sK + stage * Cfg::kTileBytes;
+        uint8_t* dv = sV + stage * Cfg::kTileBytes;
+        for (int i = tid; i < kTileKeys * Cfg::kChunks; i += kAttnThreads) {
+            const int r = i / Cfg::kChunks, ch = i % Cfg::kChunks;
+            const bool ok = kb * kTileKeys + r < kvlen;
+            cp_async16(dk + tile_off<HD>(r, ch), kbase + (size_t)(ok ? r : 0) * kstride + ch * 8, ok);
+            cp_async16(dv + tile_off<HD>(r, ch), vbase + (size_t)(ok ? r : 0) * vstride + ch * 8, ok);
+        }
+    };
+    if (kb_begin < kb_end) load_kv(kb_begin, 0);
+    cp_async_commit();
+
+    const int g = lane >> 2, t = lane & 3;
+    const int Ra = r0 + warp * 16 + g, Rb = Ra + 8;
+    const int tok_a = min(Ra, nrows - 1) / G, tok_b = min(Rb, nrows - 1) / G;
+    const int lim_a = a.causal ? (kvlen - qlen + tok_a) : (kvlen - 1);   // last visible key index per row
+    const int lim_b = a.causal ? (kvlen - qlen + tok_b) : (kvlen - 1);
+
+    uint32_t qf[Cfg::kKSteps][4];
+    float o[Cfg::kDTiles][4];
+#pragma unroll
+    for (int i = 0; i < Cfg::kDTiles; ++i) o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f;
+    float m_a = -INFINITY, m_b = -INFINITY, l_a = 0.f, l_b = 0.f;
+
+    for (int kb = kb_begin; kb < kb_end; ++kb) {
+        const int stage = (kb - kb_begin) & 1;
+        if (kb + 1 < kb_end) {
+            load_kv(kb + 1, stage ^ 1);
+            cp_async_commit();
+            cp_async_wait<1>();
+        } else {
+            cp_async_wait<0>();
+        }
+        __syncthreads();
+        if (kb == kb_begin) {
+#pragma unroll
+            for (int ks = 0; ks < Cfg::kKSteps; ++ks)
+                ldmatrix_x4(qf[ks][0], qf[ks][1], qf[ks][2], qf[ks][3],
+                            smem_u32(sQ + tile_off<HD>(warp * 16 + (lane & 15), ks * 2 + (lane >> 4))));
+        }
+        const uint8_t* cK = sK + stage * Cfg::kTileBytes;
+        const uint8_t* cV = sV + stage * Cfg::kTileBytes;
+
+        // ---- S = Q K^T  (16 rows x 64 keys per warp)
+        float s[8][4];
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
+#pragma unroll
+        for (int ks = 0; ks < Cfg::kKSteps; ++ks) {
+#pragma unroll
+            for (int np = 0; np < 4; ++np) {
+                uint32_t b0, b1, b2, b3;
+                ldmatrix_x4(b0, b1, b2, b3,
+                            smem_u32(cK + tile_off<HD>(np * 16 + (lane & 7) + ((lane >> 4) << 3), ks * 2 + ((lane >> 3) & 1))));
+                mma_bf16_16816(s[2 * np], qf[ks], b0, b1);
+                mma_bf16_16816(s[2 * np + 1], qf[ks], b2, b3);
+            }
+        }
+        // ---- mask, online softmax
+        float mx_a = -INFINITY, mx_b = -INFINITY;
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) {
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int key = kb * kTileKeys + nt * 8 + 2 * t + e;
+                s[nt][e] = key <= lim_a ? s[nt][e] * scale_log2 : -INFINITY;
+                s[nt][2 + e] = key <= lim_b ? s[nt][2 + e] * scale_log2 : -INFINITY;
+                mx_a = fmaxf(mx_a, s[nt][e]);
+                mx_b = fmaxf(mx_b, s[nt][2 + e]);
+            }
+        }
+        mx_a = fmaxf(mx_a, __shfl_xor_sync(0xffffffffu, mx_a, 1));
+        mx_a = fmaxf(mx_a, __shfl_xor_sync(0xffffffffu, mx_a, 2));
+        mx_b = fmaxf(mx_b, __shfl_xor_sync(0xffffffffu, mx_b, 1));
+        mx_b = fmaxf(mx_b, __shfl_xor_sync(0xffffffffu, mx_b, 2));
+        const float mn_a = fmaxf(m_a, mx_a), mn_b = fmaxf(m_b, mx_b);
+        const float ms_a = mn_a == -INFINITY ? 0.f : mn_a, ms_b = mn_b == -INFINITY ? 0.f : mn_b;
+        const float al_a = exp2f(m_a - ms_a), al_b = exp2f(m_b - ms_b);
+        m_a = mn_a;
+        m_b = mn_b;
+        float rs_a = 0.f, rs_b = 0.f;
+        uint32_t pf[4][4];
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) {
+            const float p0 = exp2f(s[nt][0] - ms_a), p1 = exp2f(s[nt][1] - ms_a);
+            const float p2 = exp2f(s[nt][2] - ms_b), p3 = exp2f(s[nt][3] - ms_b);
+            rs_a += p0 + p1;
+            rs_b += p2 + p3;
+            // accumulator layout of two adjacent n-tiles == A-fragment layout of one 16-key k-step
+            pf[nt >> 1][(nt & 1) * 2 + 0] = pack2(p0, p1);
+            pf[nt >> 1][(nt & 1) * 2 + 1] = pack2(p2, p3);
+        }
+        l_a = l_a * al_a + rs_a;
+        l_b = l_b * al_b + rs_b;
+#pragma unroll
+        for (int dt = 0; dt < Cfg::kDTiles; ++dt) {
+            o[dt][0] *= al_a; o[dt][1] *= al_a;
+            o[dt][2] *= al_b; o[dt][3] *= al_b;
+        }
+        // ---- O += P V
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) {
+#pragma unroll
+            for (int dp = 0; dp + 1 < Cfg::kDTiles; dp += 2) {
+                uint32_t b0, b1, b2, b3;
+                asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+                             : "=r"(b0), "=r"(b1), "=r"(b2), "=r"(b3)
+                             : "r"(smem_u32(cV + tile_off<HD>(kk * 16 + (lane & 7) + (((lane >> 3) & 1) << 3), dp + (lane >> 4)))));
+                mma_bf16_16816(o[dp], pf[kk], b0, b1);
+                mma_bf16_16816(o[dp + 1], pf[kk], b2, b3);
+            }
+            if (Cfg::kDTiles & 1) {
+                uint32_t b0, b1;
+                ldmatrix_x2_trans(b0, b1, smem_u32(cV + tile_off<HD>(kk * 16 + (lane & 15), Cfg::kDTiles - 1)));
+                mma_bf16_16816(o[Cfg::kDTiles - 1], pf[kk], b0, b1);
+            }
+        }
+        __syncthreads();
+    }
+    cp_async_wait<0>();
+
+    l_a += __shfl_xor_sync(0xffffffffu, l_a, 1);
+    l_a += __shfl_xor_sync(0xffffffffu, l_a, 2);
+    l_b += __shfl_xor_sync(0xffffffffu, l_b, 1);
+    l_b += __shfl_xor_sync(0xffffffffu, l_b, 2);
+    const float il_a = l_a > 0.f ? 1.f / l_a : 0.f, il_b = l_b > 0.f ? 1.f / l_b : 0.f;
+
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+        const int R = half ? Rb : Ra;
+        if (R >= nrows) continue;
+        const int tok = R / G, head = kvh * G + R % G;
+        const float il = half ? il_b : il_a;
+        if (a.splits == 1) {
+            bf16* dst = a.out + (size_t)(qs + tok) * a.ldo + head * HD;
+#pragma unroll
+            for (int dt = 0; dt < Cfg::kDTiles; ++dt)
+                *reinterpret_cast<uint32_t*>(dst + dt * 8 + 2 * t) = pack2(o[dt][half * 2] * il, o[dt][half * 2 + 1] * il);
+        } else {
+            const size_t ridx = (size_t)(qs + tok) * a.H + head;
+            float* dst = a.ws + ((size_t)split * a.total_q * a.H + ridx) * HD;
+#pragma unroll
+            for (int dt = 0; dt < Cfg::kDTiles; ++dt)
+                *reinterpret_cast<float2*>(dst + dt * 8 + 2 * t) = make_float2(o[dt][half * 2] * il, o[dt][half * 2 + 1] * il);
+            if (t == 0) {
+                const float m = half ? m_b : m_a, l = half ? l_b : l_a;
+                a.ws[(size_t)a.splits * a.total_q * a.H * HD + (size_t)split * a.total_q * a.H + ridx] =
+                    l > 0.f ? m + log2f(l) : -INFINITY;
+            }
+        }
+    }
+}
+
+// Split-KV combine: out = sum_s w_s O_s / sum_s w_s, w_s = 2^(lse_s - max lse).   one warp per (token, head)
+template <int HD>
+__global__ void attn_combine_kernel(AttnArgs a) {
+    const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    const int rows = a.total_q * a.H;
+    if (gw >= rows) return;
+    const float* lse = a.ws + (size_t)a.splits * rows * HD;
+    float mx = -INFINITY;
+    for (int s = 0; s < a.splits; ++s) mx = fmaxf(mx, lse[(size_t)s * rows + gw]);
+    float acc[(HD + 31) / 32];
+#pragma unroll
+    for (int i = 0; i < (HD + 31) / 32; ++i) acc[i] = 0.f;
+    float wsum = 0.f;
+    for (int s = 0; s < a.splits; ++s) {
+        const float l = lse[(size_t)s * rows + gw];
+        const float w = (l == -INFINITY) ? 0.f : exp2f(l - mx);
+        wsum += w;
+        const float* src = a.ws + ((size_t)s * rows + gw) * HD;
+#pragma unroll
+        for (int i = 0; i < (HD + 31) / 32; ++i) {
+            const int d = lane + i * 32;
+            if (d < HD) acc[i] += w * src[d];
+        }
+    }
+    const float inv = wsum > 0.f ? 1.f / wsum : 0.f;
+    const int tok = gw / a.H, head = gw % a.H;
+    bf16* dst = a.out + (size_t)tok * a.ldo + head * HD;
+#pragma unroll
+    for (int i = 0; i < (HD + 31) / 32; ++i) {
+        const int d = lane + i * 32;
+        if (d < HD) dst[d] = f2b(acc[i] * inv);
+    }
+}
+
+int attention_init() {
+    cudaFuncSetAttribute(attn_fwd_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnCfg<128>::kSmemBytes);
+    cudaFuncSetAttribute(attn_fwd_kernel<72>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnCfg<72>::kSmemBytes);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        set_error("attention_init: %s", cudaGetErrorString(e));
+        return UMV_ERR_CUDA;
+    }
+    return UMV_OK;
+}
+
+template <int HD>
+static int launch_attn(const AttnArgs& a, cudaStream_t s) {
+    const int G = a.H / a.Hkv;
+    const int row_tiles = (a.max_q_len * G + kTileRows - 1) / kTileRows;
+    const float scale_log2 = (1.0f / sqrtf((float)HD)) * 1.4426950408889634f;
+    dim3 grid(row_tiles, a.n * a.Hkv, a.splits);
+    attn_fwd_kernel<HD><<<grid, kAttnThreads, AttnCfg<HD>::kSmemBytes, s>>>(a, scale_log2);
+    ++g_launches;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        set_error("attn_fwd_kernel<%d> launch failed: %s", HD, cudaGetErrorString(e));
+        return UMV_ERR_CUDA;
+    }
+    if (a.splits > 1) {
+        const int rows = a.total_q * a.H;
+        attn_combine_kernel<HD><<<(rows * 32 + 127) / 128, 128, 0, s>>>(a);
+        ++g_launches;
+        e = cudaGetLastError();
+        if (e != cudaSuccess) {
+            set_error("attn_combine_kernel launch failed: %s", cudaGetErrorString(e));
+            return UMV_ERR_CUDA;
+        }
+    }
+    return UMV_OK;
+}
+
+int attention_forward(const AttnArgs& a, cudaStream_t s) {
+    if (a.n <= 0 || a.max_q_len <= 0) return UMV_OK;
+    UMV_REQUIRE(a.H % a.Hkv == 0, UMV_ERR_INVALID, "attention: heads %d not a multiple of kv heads %d", a.H, a.Hkv);
+    UMV_REQUIRE(a.splits == 1 || a.ws != nullptr, UMV_ERR_INVALID, "attention: split-KV needs a workspace");
+    UMV_REQUIRE(a.ldq % 8 == 0 && a.ldo % 2 == 0, UMV_ERR_INVALID, "attention: q/out row strides must keep 16-byte rows");
+    if (a.dh == 128) return launch_attn<128>(a, s);
+    if (a.dh == 72) return launch_attn<72>(a, s);
+    set_error("attention: head_dim %d is not built (128 and 72 are)", a.dh);
+    return UMV_ERR_UNSUPPORTED;
+}
+
+}  // namespace umv

@@ -1,0 +1,940 @@
+// Engine: weights in the engine layout, ref-counted KV pages, packed LLM / ViT forward orchestration,
+// device-resident greedy decode loop (CUDA-graph replay) and the C ABI of include/umv.h.
+//
+// Reference drivers restated here: Bagel.forward_cache_update_{text,vit} (bagel.py:412-458,523-615),
+// Qwen2Model.forward_inference (qwen2_navit.py:1115-1176), Qwen2MoTDecoderLayer.forward_inference
+// (:843-902), SiglipVisionTransformer.forward (siglip_navit.py:345-371), Bagel.generate_text
+// (bagel.py:1236-1317), NaiveCache + deepcopy forks (qwen2_navit.py:207-221, inferencer.py:261,587-607).
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "engine.cuh"
+#include "gemm.cuh"
+#include "kernels.cuh"
+
+namespace umv {
+
+static thread_local char g_err[1024] = "";
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+const char* get_error() { return g_err; }
+
+template <typename T>
+static int dev_alloc(umv_engine* e, T** out, size_t n) {
+    void* p = nullptr;
+    cudaError_t err = cudaMalloc(&p, std::max<size_t>(n, 1) * sizeof(T));
+    if (err != cudaSuccess) {
+        set_error("cudaMalloc(%zu bytes) failed: %s", n * sizeof(T), cudaGetErrorString(err));
+        return UMV_ERR_NOMEM;
+    }
+    e->allocs.push_back(p);
+    *out = static_cast<T*>(p);
+    return UMV_OK;
+}
+#define UMV_TRY(expr)            \
+    do {                         \
+        int _rc = (expr);        \
+        if (_rc != UMV_OK) return _rc; \
+    } while (0)
+
+static void reg(umv_engine* e, const std::string& name, bf16* dst, int64_t rows, int64_t cols, int64_t dst_ld, int ndim,
+                int kind = SLOT_PLAIN, float bound = 0.02f * 1.7320508f, float mean = 0.f) {
+    Slot s;
+    s.dst = dst; s.rows = rows; s.cols = cols; s.dst_ld = dst_ld; s.ndim = ndim; s.kind = kind;
+    s.synth_bound = bound; s.synth_mean = mean;
+    e->slots[name] = s;
+}
+
+// Allocates one linear layer [rows, cols] (+ optional bias) and registers its reference names.
+static int alloc_linear(umv_engine* e, const std::string& name, int64_t rows, int64_t cols, bool bias, bf16** w, bf16** b,
+                        int64_t ld = 0) {
+    if (ld == 0) ld = cols;
+    UMV_TRY(dev_alloc(e, w, (size_t)rows * ld));
+    if (ld != cols) cudaMemset(*w, 0, (size_t)rows * ld * sizeof(bf16));
+    reg(e, name + ".weight", *w, rows, cols, ld, 2, SLOT_PLAIN, std::sqrt(3.0f / (float)cols));
+    if (bias) {
+        UMV_TRY(dev_alloc(e, b, (size_t)rows));
+        reg(e, name + ".bias", *b, 1, rows, rows, 1);
+    }
+    return UMV_OK;
+}
+static int alloc_vec(umv_engine* e, const std::string& name, int64_t n, bf16** p, float mean, float bound) {
+    UMV_TRY(dev_alloc(e, p, (size_t)n));
+    reg(e, name, *p, 1, n, n, 1, SLOT_PLAIN, bound, mean);
+    return UMV_OK;
+}
+
+static int build_weights(umv_engine* e) {
+    const umv_dims& d = e->d;
+    const int D = d.hidden, I = d.inter, dh = e->dh, H = d.heads, Hkv = d.kv_heads, QN = e->qkvn;
+    const std::string LM = "language_model.";
+    UMV_TRY(dev_alloc(e, &e->embed, (size_t)d.vocab * D));
+    reg(e, LM + "model.embed_tokens.weight", e->embed, d.vocab, D, D, 2);
+    UMV_TRY(dev_alloc(e, &e->lm_head, (size_t)d.vocab * D));
+    reg(e, LM + "lm_head.weight", e->lm_head, d.vocab, D, D, 2);
+    const int nexp = d.enable_gen ? 2 : 1;
+    const char* sfx[2] = {"", "_moe_gen"};
+    for (int x = 0; x < nexp; ++x) UMV_TRY(alloc_vec(e, LM + "model.norm" + sfx[x] + ".weight", D, &e->final_norm[x], 1.f, 0.1f));
+    e->layers.resize(d.layers);
+    for (int li = 0; li < d.layers; ++li) {
+        LayerW& L = e->layers[li];
+        memset(&L, 0, sizeof(L));
+        const std::string P = LM + "model.layers." + std::to_string(li) + ".";
+        for (int x = 0; x < nexp; ++x) {
+            const std::string s = sfx[x];
+            UMV_TRY(dev_alloc(e, &L.wqkv[x], (size_t)QN * D));
+            UMV_TRY(dev_alloc(e, &L.bqkv[x], (size_t)QN));
+            reg(e, P + "self_attn.q_proj" + s + ".weight", L.wqkv[x], H * dh, D, D, 2);
+            reg(e, P + "self_attn.k_proj" + s + ".weight", L.wqkv[x] + (size_t)H * dh * D, Hkv * dh, D, D, 2);
+            reg(e, P + "self_attn.v_proj" + s + ".weight", L.wqkv[x] + (size_t)(H + Hkv) * dh * D, Hkv * dh, D, D, 2);
+            reg(e, P + "self_attn.q_proj" + s + ".bias", L.bqkv[x], 1, H * dh, H * dh, 1);
+            reg(e, P + "self_attn.k_proj" + s + ".bias", L.bqkv[x] + H * dh, 1, Hkv * dh, Hkv * dh, 1);
+            reg(e, P + "self_attn.v_proj" + s + ".bias", L.bqkv[x] + (H + Hkv) * dh, 1, Hkv * dh, Hkv * dh, 1);
+            bf16* nob = nullptr;
+            UMV_TRY(alloc_linear(e, P + "self_attn.o_proj" + s, D, H * dh, false, &L.wo[x], &nob));
+            UMV_TRY(dev_alloc(e, &L.wgu[x], (size_t)2 * I * D));
+            reg(e, P + "mlp" + s + ".gate_proj.weight", L.wgu[x], I, D, D, 2, SLOT_GATE);
+            reg(e, P + "mlp" + s + ".up_proj.weight", L.wgu[x] + (size_t)64 * D, I, D, D, 2, SLOT_UP);
+            UMV_TRY(alloc_linear(e, P + "mlp" + s + ".down_proj", D, I, false, &L.wdown[x], &nob));
+            UMV_TRY(alloc_vec(e, P + "input_layernorm" + s + ".weight", D, &L.ln1[x], 1.f, 0.1f));
+            UMV_TRY(alloc_vec(e, P + "post_attention_layernorm" + s + ".weight", D, &L.ln2[x], 1.f, 0.1f));
+            UMV_TRY(alloc_vec(e, P + "self_attn.q_norm" + s + ".weight", dh, &L.qn[x], 1.f, 0.1f));
+            UMV_TRY(alloc_vec(e, P + "self_attn.k_norm" + s + ".weight", dh, &L.kn[x], 1.f, 0.1f));
+        }
+    }
+    if (d.enable_vit) {
+        const int Dv = d.vit_hidden, Iv = d.vit_inter;
+        const std::string V = "vit_model.vision_model.";
+        UMV_TRY(alloc_linear(e, V + "embeddings.patch_embedding", Dv, d.vit_patch_dim, true, &e->vit_patch_w, &e->vit_patch_b,
+                             e->vit_kpad));
+        UMV_TRY(dev_alloc(e, &e->vit_pos, (size_t)d.vit_positions * Dv));
+        reg(e, V + "embeddings.position_embedding.weight", e->vit_pos, d.vit_positions, Dv, Dv, 2);
+        e->vit.resize(d.vit_layers);
+        for (int li = 0; li < d.vit_layers; ++li) {
+            VitLayerW& L = e->vit[li];
+            const std::string P = V + "encoder.layers." + std::to_string(li) + ".";
+            UMV_TRY(dev_alloc(e, &L.wqkv, (size_t)3 * Dv * Dv));
+            UMV_TRY(dev_alloc(e, &L.bqkv, (size_t)3 * Dv));
+            const char* nm[3] = {"q_proj", "k_proj", "v_proj"};
+            for (int j = 0; j < 3; ++j) {
+                reg(e, P + "self_attn." + nm[j] + ".weight", L.wqkv + (size_t)j * Dv * Dv, Dv, Dv, Dv, 2, SLOT_PLAIN,
+                    std::sqrt(3.0f / Dv));
+                reg(e, P + "self_attn." + nm[j] + ".bias", L.bqkv + j * Dv, 1, Dv, Dv, 1);
+            }
+            UMV_TRY(alloc_linear(e, P + "self_attn.out_proj", Dv, Dv, true, &L.wo, &L.bo));
+            UMV_TRY(alloc_linear(e, P + "mlp.fc1", Iv, Dv, true, &L.w1, &L.b1));
+            UMV_TRY(alloc_linear(e, P + "mlp.fc2", Dv, Iv, true, &L.w2, &L.b2));
+            UMV_TRY(alloc_vec(e, P + "layer_norm1.weight", Dv, &L.ln1w, 1.f, 0.1f));
+            UMV_TRY(alloc_vec(e, P + "layer_norm1.bias", Dv, &L.ln1b, 0.f, 0.05f));
+            UMV_TRY(alloc_vec(e, P + "layer_norm2.weight", Dv, &L.ln2w, 1.f, 0.1f));
+            UMV_TRY(alloc_vec(e, P + "layer_norm2.bias", Dv, &L.ln2b, 0.f, 0.05f));
+        }
+        UMV_TRY(alloc_vec(e, V + "post_layernorm.weight", Dv, &e->vit_post_w, 1.f, 0.1f));
+        UMV_TRY(alloc_vec(e, V + "post_layernorm.bias", Dv, &e->vit_post_b, 0.f, 0.05f));
+        UMV_TRY(alloc_linear(e, "connector.fc1", D, Dv, true, &e->conn_w1, &e->conn_b1));
+        UMV_TRY(alloc_linear(e, "connector.fc2", D, D, true, &e->conn_w2, &e->conn_b2));
+        UMV_TRY(dev_alloc(e, &e->vit_pos_embed, (size_t)d.vit_pos_table * D));
+        reg(e, "vit_pos_embed.pos_embed", e->vit_pos_embed, d.vit_pos_table, D, D, 2, SLOT_PLAIN, 1.0f);
+    }
+    if (d.enable_gen) {
+        UMV_TRY(alloc_linear(e, "time_embedder.mlp.0", D, 256, true, &e->t_w0, &e->t_b0));
+        UMV_TRY(alloc_linear(e, "time_embedder.mlp.2", D, D, true, &e->t_w2, &e->t_b2));
+        UMV_TRY(alloc_linear(e, "vae2llm", D, d.latent_dim, true, &e->vae2llm_w, &e->vae2llm_b));
+        UMV_TRY(alloc_linear(e, "llm2vae", d.latent_dim, D, true, &e->llm2vae_w, &e->llm2vae_b));
+        UMV_TRY(dev_alloc(e, &e->latent_pos, (size_t)d.latent_pos_table * D));
+        reg(e, "latent_pos_embed.pos_embed", e->latent_pos, d.latent_pos_table, D, D, 2, SLOT_PLAIN, 1.0f);
+    }
+    return UMV_OK;
+}
+
+static int build_runtime(umv_engine* e) {
+    const umv_dims& d = e->d;
+    const int D = d.hidden, Dv = d.enable_vit ? d.vit_hidden : 0, Iv = d.enable_vit ? d.vit_inter : 0;
+    const int Mmax = d.max_tokens;
+    e->w_h = std::max(D, Dv);
+    e->w_qkv = std::max(e->qkvn, 3 * Dv);
+    e->w_act = std::max(std::max(d.inter, Iv), D);
+    UMV_TRY(dev_alloc(e, &e->h, (size_t)Mmax * e->w_h));
+    UMV_TRY(dev_alloc(e, &e->xn, (size_t)Mmax * e->w_h));
+    UMV_TRY(dev_alloc(e, &e->qkv, (size_t)Mmax * e->w_qkv));
+    UMV_TRY(dev_alloc(e, &e->attn, (size_t)Mmax * e->w_h));
+    UMV_TRY(dev_alloc(e, &e->act, (size_t)Mmax * e->w_act));
+    UMV_TRY(dev_alloc(e, &e->logits, (size_t)64 * d.vocab));
+    const int Tmax = std::min(Mmax, 8 * d.max_seqs);
+    UMV_TRY(dev_alloc(e, &e->xt, (size_t)Tmax * std::max(D, d.inter)));
+    UMV_TRY(dev_alloc(e, &e->ht, (size_t)Tmax * D));
+    UMV_TRY(dev_alloc(e, &e->yt, (size_t)Tmax * std::max(e->qkvn, D)));
+    UMV_TRY(dev_alloc(e, &e->actt, (size_t)Tmax * d.inter));
+    e->ws_elems = (size_t)16 * 64 * std::max(e->qkvn, D);
+    UMV_TRY(dev_alloc(e, &e->ws, e->ws_elems));
+    e->attn_ws_elems = (size_t)16 * 64 * d.heads * (e->dh + 1);
+    UMV_TRY(dev_alloc(e, &e->attn_ws, e->attn_ws_elems));
+    // RoPE inverse frequencies: ROPE_INIT_FUNCTIONS['default'] -> 1 / theta^(2i/dh), fp32 (never bf16)
+    std::vector<float> inv(e->dh / 2);
+    for (int i = 0; i < e->dh / 2; ++i) {
+        const float ex = (float)(2 * i) / (float)e->dh;          // arange(0,dh,2).float() / dh
+        inv[i] = 1.0f / powf(d.rope_theta, ex);                  // fp32 pow, as torch does on the host
+    }
+    UMV_TRY(dev_alloc(e, &e->inv_freq, inv.size()));
+    cudaMemcpy(e->inv_freq, inv.data(), inv.size() * sizeof(float), cudaMemcpyHostToDevice);
+    // KV pool
+    e->pool.layers = d.layers;
+    e->pool.kv_heads = d.kv_heads;
+    e->pool.head_dim = e->dh;
+    const size_t page_elems = (size_t)d.layers * 2 * d.kv_heads * kPageTokens * e->dh;
+    UMV_TRY(dev_alloc(e, &e->pool.base, page_elems * d.kv_pages));
+    e->page_ref.assign(d.kv_pages, 0);
+    e->free_pages.clear();
+    for (int p = d.kv_pages - 1; p >= 0; --p) e->free_pages.push_back(p);
+    // metadata staging
+    e->meta_bytes = (size_t)64 * 1024 + (size_t)20 * Mmax + (size_t)4 * d.max_seqs * 3 * (std::min(d.kv_pages, 8192) + 8);
+    for (int i = 0; i < umv_engine::kMetaRing; ++i) {
+        if (cudaMallocHost(reinterpret_cast<void**>(&e->meta_host[i]), e->meta_bytes) != cudaSuccess) {
+            set_error("cudaMallocHost(%zu) failed", e->meta_bytes);
+            return UMV_ERR_NOMEM;
+        }
+        UMV_TRY(dev_alloc(e, &e->meta_dev[i], e->meta_bytes));
+        cudaEventCreateWithFlags(&e->meta_ev[i], cudaEventDisableTiming);
+    }
+    // decode state
+    UMV_TRY(dev_alloc(e, &e->dec_tokens, 64));
+    UMV_TRY(dev_alloc(e, &e->dec_pos, 64));
+    UMV_TRY(dev_alloc(e, &e->dec_kvlen, 64));
+    UMV_TRY(dev_alloc(e, &e->dec_kvpos, 64));
+    UMV_TRY(dev_alloc(e, &e->dec_rowseq, 64));
+    UMV_TRY(dev_alloc(e, &e->dec_qstart, 65));
+    UMV_TRY(dev_alloc(e, &e->dec_qlen, 64));
+    UMV_TRY(dev_alloc(e, &e->dec_step, 1));
+    e->dec_pages_cap = 64 * std::min(d.kv_pages, 4096);
+    UMV_TRY(dev_alloc(e, &e->dec_pages, (size_t)e->dec_pages_cap));
+    return UMV_OK;
+}
+
+// ------------------------------------------------------------------------------ KV sequences
+static int page_alloc(umv_engine* e, int* page) {
+    if (e->free_pages.empty()) {
+        set_error("KV page pool exhausted (%d pages of %d tokens)", e->d.kv_pages, kPageTokens);
+        return UMV_ERR_NOMEM;
+    }
+    *page = e->free_pages.back();
+    e->free_pages.pop_back();
+    e->page_ref[*page] = 1;
+    return UMV_OK;
+}
+static void page_release(umv_engine* e, int page) {
+    if (--e->page_ref[page] == 0) e->free_pages.push_back(page);
+}
+static Seq* get_seq(umv_engine* e, int id) {
+    if (id < 0 || id >= (int)e->seqs.size() || !e->seqs[id].alive) {
+        set_error("invalid sequence id %d", id);
+        return nullptr;
+    }
+    return &e->seqs[id];
+}
+// Make slots [len, new_len) of `s` writable: private partial tail page (copy-on-write) + enough pages.
+static int seq_reserve(umv_engine* e, Seq* s, int new_len, cudaStream_t st) {
+    if (new_len <= s->len) return UMV_OK;
+    if (s->len % kPageTokens != 0) {
+        const int tail = s->len / kPageTokens;
+        if (e->page_ref[s->pages[tail]] > 1) {
+            int np;
+            UMV_TRY(page_alloc(e, &np));
+            UMV_TRY(copy_page(e->pool, s->pages[tail], np, st));
+            page_release(e, s->pages[tail]);
+            s->pages[tail] = np;
+        }
+    }
+    const int need = (new_len + kPageTokens - 1) / kPageTokens;
+    // pages past the committed length may be scratch left by a no-update forward; keep them only if private
+    const int committed = (s->len + kPageTokens - 1) / kPageTokens;
+    for (int p = committed; p < (int)s->pages.size(); ++p) {
+        if (e->page_ref[s->pages[p]] > 1) {
+            int np;
+            UMV_TRY(page_alloc(e, &np));
+            page_release(e, s->pages[p]);
+            s->pages[p] = np;
+        }
+    }
+    while ((int)s->pages.size() < need) {
+        int np;
+        UMV_TRY(page_alloc(e, &np));
+        s->pages.push_back(np);
+    }
+    return UMV_OK;
+}
+
+// ------------------------------------------------------------------------------ call metadata
+struct MetaBuilder {
+    umv_engine* e;
+    uint8_t* host;
+    uint8_t* dev;
+    size_t off = 0;
+    int slot;
+    template <typename T>
+    T* put(const T* src, size_t n, T** dev_ptr) {
+        off = (off + 15) & ~size_t(15);
+        T* h = reinterpret_cast<T*>(host + off);
+        if (src) memcpy(h, src, n * sizeof(T));
+        *dev_ptr = reinterpret_cast<T*>(dev + off);
+        off += n * sizeof(T);
+        return h;
+    }
+};
+static int meta_begin(umv_engine* e, MetaBuilder* mb, size_t need) {
+    if (need + 4096 > e->meta_bytes) {
+        set_error("call metadata (%zu bytes) exceeds the staging buffer (%zu); raise max_tokens / max_seqs", need, e->meta_bytes);
+        return UMV_ERR_NOMEM;
+    }
+    mb->e = e;
+    mb->slot = e->meta_next;
+    e->meta_next = (e->meta_next + 1) % umv_engine::kMetaRing;
+    cudaEventSynchronize(e->meta_ev[mb->slot]);     // previous use of this staging slot has been consumed
+    mb->host = e->meta_host[mb->slot];
+    mb->dev = e->meta_dev[mb->slot];
+    mb->off = 0;
+    return UMV_OK;
+}
+static int meta_commit(umv_engine* e, MetaBuilder* mb, cudaStream_t st) {
+    UMV_CUDA_OK(cudaMemcpyAsync(mb->dev, mb->host, mb->off, cudaMemcpyHostToDevice, st));
+    UMV_CUDA_OK(cudaEventRecord(e->meta_ev[mb->slot], st));
+    return UMV_OK;
+}
+
+// ------------------------------------------------------------------------------ LLM layers
+struct LlmRun {
+    int M = 0, n_seqs = 0, max_q_len = 0, max_kv_len = 0;
+    bool causal = true, gen = false, weight_major = false;
+    CallMeta m;
+};
+
+static int lin(umv_engine* e, const bf16* x, int ldx, const bf16* w, const bf16* bias, const bf16* res, bf16* y, int ldy, int M,
+               int N, int K, int epi, cudaStream_t st, int impl = GEMM_AUTO, float* ws = nullptr, int splits = 1) {
+    LinearCall c;
+    c.x = x; c.ldx = ldx; c.w = w; c.bias = bias; c.residual = res; c.y = y; c.ldy = ldy;
+    c.M = M; c.N = N; c.K = K; c.epi = epi; c.ws = ws; c.splits = splits;
+    c.impl = e->gemm_impl ? e->gemm_impl : impl;
+    if (c.impl == GEMM_SIMPLE && epi == EPI_PARTIAL) c.impl = GEMM_WEIGHT_MAJOR;
+    return linear_forward(c, st);
+}
+
+static int llm_layers(umv_engine* e, const LlmRun& r, bf16* out, cudaStream_t st) {
+    const umv_dims& d = e->d;
+    const int D = d.hidden, I = d.inter, H = d.heads, Hkv = d.kv_heads, dh = e->dh, QN = e->qkvn, M = r.M;
+    const int E = r.gen ? 1 : 0;
+    const bool partial = r.weight_major && !r.gen && e->use_splitk && e->gemm_impl != GEMM_SIMPLE;
+    const int T = r.gen ? r.m.n_text : 0;
+    int pending_splits = 0;     // >0: e->ws holds split-K partials of the last residual-branch linear
+
+    auto norm = [&](const bf16* w0, const bf16* w1, bf16* y) {
+        AddNormArgs a;
+        a.h = e->h; a.M = M; a.D = D; a.eps = d.rms_eps; a.w0 = w0; a.w1 = w1 ? w1 : w0;
+        a.row_sel = r.gen ? r.m.row_sel : nullptr;
+        a.y = y;
+        if (pending_splits > 0) { a.partial = e->ws; a.splits = pending_splits; }
+        pending_splits = 0;
+        return add_rmsnorm(a, st);
+    };
+
+    int attn_splits = 1;
+    if (r.weight_major && r.max_q_len == 1) {
+        const int blocks = (r.max_kv_len + kPageTokens - 1) / kPageTokens;
+        attn_splits = std::max(1, std::min(std::min(16, blocks), (2 * e->sm_count + r.n_seqs * Hkv - 1) / (r.n_seqs * Hkv)));
+    }
+
+    for (int li = 0; li < d.layers; ++li) {
+        const LayerW& L = e->layers[li];
+        UMV_TRY(norm(L.ln1[0], L.ln1[1], e->xn));
+        // ---- q/k/v projections
+        RopeAppendArgs ra;
+        if (partial) {
+            const int s = pick_splits(QN, D, e->sm_count);
+            UMV_TRY(lin(e, e->xn, D, L.wqkv[0], nullptr, nullptr, nullptr, 0, M, QN, D, EPI_PARTIAL, st, GEMM_WEIGHT_MAJOR, e->ws, s));
+            ra.partial = e->ws; ra.splits = s; ra.bias = L.bqkv[0];
+        } else {
+            UMV_TRY(lin(e, e->xn, D, L.wqkv[E], L.bqkv[E], nullptr, e->qkv, QN, M, QN, D, EPI_BF16, st));
+            if (T > 0) {
+                UMV_TRY(copy_rows(e->xn, D, r.m.text_rows, e->xt, D, T, D, 0, st));
+                UMV_TRY(lin(e, e->xt, D, L.wqkv[0], L.bqkv[0], nullptr, e->yt, QN, T, QN, D, EPI_BF16, st));
+                UMV_TRY(copy_rows(e->yt, QN, r.m.text_rows, e->qkv, QN, T, QN, 1, st));
+            }
+            ra.qkv = e->qkv;
+        }
+        ra.q_out = e->qkv; ra.ldq = QN;
+        ra.positions = r.m.positions; ra.row_seq = r.m.row_seq; ra.row_kvpos = r.m.row_kvpos;
+        ra.page_table = r.m.page_table; ra.max_pages = r.m.max_pages; ra.inv_freq = e->inv_freq;
+        ra.qn0 = L.qn[0]; ra.kn0 = L.kn[0]; ra.qn1 = L.qn[E]; ra.kn1 = L.kn[E];
+        ra.row_sel = r.gen ? r.m.row_sel : nullptr; ra.gen_mode = r.gen ? 1 : 0;
+        ra.pool = e->pool; ra.layer = li; ra.M = M; ra.H = H; ra.Hkv = Hkv; ra.dh = dh; ra.eps = d.rms_eps;
+        UMV_TRY(rope_append(ra, st));
+        // ---- attention over the paged cache (past + the rows just appended)
+        AttnArgs aa;
+        aa.q = e->qkv; aa.ldq = QN; aa.out = e->attn; aa.ldo = D;
+        aa.paged = 1; aa.pool = e->pool; aa.layer = li; aa.page_table = r.m.page_table; aa.max_pages = r.m.max_pages;
+        aa.q_start = r.m.q_start; aa.q_len = r.m.q_len; aa.kv_len = r.m.kv_len;
+        aa.n = r.n_seqs; aa.H = H; aa.Hkv = Hkv; aa.dh = dh; aa.causal = r.causal ? 1 : 0;
+        aa.max_q_len = r.max_q_len; aa.max_kv_len = r.max_kv_len; aa.splits = attn_splits; aa.ws = e->attn_ws; aa.total_q = M;
+        UMV_TRY(attention_forward(aa, st));
+        // ---- output projection + residual
+        if (partial) {
+            const int s = pick_splits(D, D, e->sm_count);
+            UMV_TRY(lin(e, e->attn, D, L.wo[0], nullptr, nullptr, nullptr, 0, M, D, D, EPI_PARTIAL, st, GEMM_WEIGHT_MAJOR, e->ws, s));
+            pending_splits = s;
+        } else {
+            if (T > 0) {
+                UMV_TRY(copy_rows(e->attn, D, r.m.text_rows, e->xt, D, T, D, 0, st));
+                UMV_TRY(copy_rows(e->h, D, r.m.text_rows, e->ht, D, T, D, 0, st));
+                UMV_TRY(lin(e, e->xt, D, L.wo[0], nullptr, e->ht, e->yt, D, T, D, D, EPI_RESID, st));
+            }
+            UMV_TRY(lin(e, e->attn, D, L.wo[E], nullptr, e->h, e->h, D, M, D, D, EPI_RESID, st));
+            if (T > 0) UMV_TRY(copy_rows(e->yt, D, r.m.text_rows, e->h, D, T, D, 1, st));
+        }
+        UMV_TRY(norm(L.ln2[0], L.ln2[1], e->xn));
+        // ---- SwiGLU MLP + residual
+        if (T > 0) {
+            UMV_TRY(copy_rows(e->xn, D, r.m.text_rows, e->xt, D, T, D, 0, st));
+            UMV_TRY(lin(e, e->xt, D, L.wgu[0], nullptr, nullptr, e->actt, I, T, 2 * I, D, EPI_SWIGLU, st));
+            UMV_TRY(copy_rows(e->h, D, r.m.text_rows, e->ht, D, T, D, 0, st));
+            UMV_TRY(lin(e, e->actt, I, L.wdown[0], nullptr, e->ht, e->yt, D, T, D, I, EPI_RESID, st));
+        }
+        UMV_TRY(lin(e, e->xn, D, L.wgu[E], nullptr, nullptr, e->act, I, M, 2 * I, D, EPI_SWIGLU, st));
+        if (partial) {
+            const int s = pick_splits(D, I, e->sm_count);
+            UMV_TRY(lin(e, e->act, I, L.wdown[0], nullptr, nullptr, nullptr, 0, M, D, I, EPI_PARTIAL, st, GEMM_WEIGHT_MAJOR, e->ws, s));
+            pending_splits = s;
+        } else {
+            UMV_TRY(lin(e, e->act, I, L.wdown[E], nullptr, e->h, e->h, D, M, D, I, EPI_RESID, st));
+            if (T > 0) UMV_TRY(copy_rows(e->yt, D, r.m.text_rows, e->h, D, T, D, 1, st));
+        }
+    }
+    // final norm (norm / norm_moe_gen, qwen2_navit.py:1162-1169); also folds the last down-proj partials
+    return norm(e->final_norm[0], e->final_norm[1], out ? out : e->xn);
+}
+
+}  // namespace umv
+
+using namespace umv;
+
+// =============================================================================================
+//                                           C ABI
+// =============================================================================================
+extern "C" {
+
+const char* umv_last_error(void) { return get_error(); }
+int umv_abi_version(void) { return UMV_ABI_VERSION; }
+int64_t umv_launch_count(void) { return g_launches; }
+
+int umv_create(const umv_dims* dims, umv_engine** out) {
+    UMV_REQUIRE(dims && out, UMV_ERR_INVALID, "umv_create: null argument");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        set_error("umv_create: no CUDA device (this engine has no CPU fallback)");
+        return UMV_ERR_CUDA;
+    }
+    const umv_dims& d = *dims;
+    UMV_REQUIRE(d.hidden > 0 && d.heads > 0 && d.kv_heads > 0 && d.hidden % d.heads == 0 && d.heads % d.kv_heads == 0,
+                UMV_ERR_INVALID, "umv_create: bad head geometry");
+    UMV_REQUIRE(d.hidden / d.heads == 128, UMV_ERR_UNSUPPORTED, "umv_create: LLM head_dim %d (128 is built)", d.hidden / d.heads);
+    UMV_REQUIRE(d.inter % 64 == 0 && d.hidden % 8 == 0 && d.vocab % 8 == 0, UMV_ERR_UNSUPPORTED,
+                "umv_create: inter %% 64, hidden %% 8 and vocab %% 8 must be 0");
+    UMV_REQUIRE(!d.enable_vit || (d.vit_hidden % d.vit_heads == 0 && d.vit_hidden / d.vit_heads == 72 && d.vit_inter % 8 == 0),
+                UMV_ERR_UNSUPPORTED, "umv_create: ViT head_dim must be 72 and vit_inter %% 8 == 0");
+    UMV_REQUIRE(d.max_tokens > 0 && d.max_seqs > 0 && d.max_seqs <= 64 && d.kv_pages > 0, UMV_ERR_INVALID,
+                "umv_create: max_tokens/max_seqs(<=64)/kv_pages must be positive");
+    umv_engine* e = new umv_engine();
+    e->d = d;
+    e->dh = d.hidden / d.heads;
+    e->qkvn = (d.heads + 2 * d.kv_heads) * e->dh;
+    e->vit_kpad = (d.vit_patch_dim + 7) / 8 * 8;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&e->sm_count, cudaDevAttrMultiProcessorCount, dev);
+    if (const char* v = getenv("UMV_SPLITK")) e->use_splitk = atoi(v) != 0;
+    if (const char* v = getenv("UMV_GRAPH")) e->use_graph = atoi(v) != 0;
+    if (const char* v = getenv("UMV_GEMM_IMPL")) e->gemm_impl = atoi(v);
+    int rc = gemm_init();
+    if (rc == UMV_OK) rc = attention_init();
+    if (rc == UMV_OK) rc = build_weights(e);
+    if (rc == UMV_OK) rc = build_runtime(e);
+    if (rc != UMV_OK) {
+        umv_destroy(e);
+        return rc;
+    }
+    *out = e;
+    return UMV_OK;
+}
+
+int umv_destroy(umv_engine* e) {
+    if (!e) return UMV_OK;
+    cudaDeviceSynchronize();
+    for (void* p : e->allocs) cudaFree(p);
+    for (int i = 0; i < umv_engine::kMetaRing; ++i) {
+        if (e->meta_host[i]) cudaFreeHost(e->meta_host[i]);
+        if (e->meta_ev[i]) cudaEventDestroy(e->meta_ev[i]);
+    }
+    delete e;
+    return UMV_OK;
+}
+
+static int slot_copy(umv_engine* e, Slot& s, void* host, bool to_device) {
+    // geometry of the engine-side region, expressed as a 2-D pitched copy
+    size_t width, height, dpitch, spitch = 0;
+    bf16* dst = s.dst;
+    if (s.kind == SLOT_PLAIN) {
+        width = (size_t)s.cols * 2; height = (size_t)s.rows; dpitch = (size_t)s.dst_ld * 2; spitch = width;
+    } else {   // gate/up: 64-row blocks of the source land every 128 rows
+        width = (size_t)64 * s.cols * 2; height = (size_t)s.rows / 64; dpitch = (size_t)128 * s.dst_ld * 2; spitch = width;
+    }
+    cudaError_t err = to_device ? cudaMemcpy2D(dst, dpitch, host, spitch, width, height, cudaMemcpyDefault)
+                                : cudaMemcpy2D(host, spitch, dst, dpitch, width, height, cudaMemcpyDeviceToHost);
+    if (err != cudaSuccess) {
+        set_error("weight copy failed: %s", cudaGetErrorString(err));
+        return UMV_ERR_CUDA;
+    }
+    return UMV_OK;
+}
+
+int umv_load_tensor(umv_engine* e, const char* name, const void* data, int dtype, int ndim, const int64_t* shape,
+                    int data_on_device) {
+    UMV_REQUIRE(e && name && data && shape, UMV_ERR_INVALID, "umv_load_tensor: null argument");
+    auto it = e->slots.find(name);
+    UMV_REQUIRE(it != e->slots.end(), UMV_ERR_INVALID, "umv_load_tensor: unknown tensor '%s'", name);
+    Slot& s = it->second;
+    const int64_t rows = ndim == 2 ? shape[0] : 1, cols = ndim == 2 ? shape[1] : shape[0];
+    UMV_REQUIRE(ndim == s.ndim && rows == s.rows && cols == s.cols, UMV_ERR_INVALID,
+                "umv_load_tensor: '%s' expects shape [%lld,%lld] (ndim %d), got ndim %d [%lld,%lld]", name, (long long)s.rows,
+                (long long)s.cols, s.ndim, ndim, (long long)rows, (long long)cols);
+    UMV_REQUIRE(dtype == UMV_BF16 || (dtype == UMV_F32 && !data_on_device), UMV_ERR_UNSUPPORTED,
+                "umv_load_tensor: dtype must be bf16 (or host fp32)");
+    UMV_REQUIRE(s.kind == SLOT_PLAIN || s.rows % 64 == 0, UMV_ERR_UNSUPPORTED, "gate/up rows must be a multiple of 64");
+    int rc;
+    if (dtype == UMV_F32) {
+        const size_t n = (size_t)rows * cols;
+        std::vector<bf16> tmp(n);
+        const float* f = static_cast<const float*>(data);
+        for (size_t i = 0; i < n; ++i) tmp[i] = __float2bfloat16_rn(f[i]);
+        rc = slot_copy(e, s, tmp.data(), true);
+    } else {
+        rc = slot_copy(e, s, const_cast<void*>(data), true);
+    }
+    if (rc == UMV_OK) s.loaded = true;
+    return rc;
+}
+
+int umv_export_tensor(umv_engine* e, const char* name, void* host_dst, size_t bytes) {
+    UMV_REQUIRE(e && name && host_dst, UMV_ERR_INVALID, "umv_export_tensor: null argument");
+    auto it = e->slots.find(name);
+    UMV_REQUIRE(it != e->slots.end(), UMV_ERR_INVALID, "umv_export_tensor: unknown tensor '%s'", name);
+    Slot& s = it->second;
+    UMV_REQUIRE(bytes == (size_t)s.rows * s.cols * 2, UMV_ERR_INVALID, "umv_export_tensor: '%s' needs %zu bytes", name,
+                (size_t)s.rows * s.cols * 2);
+    return slot_copy(e, s, host_dst, false);
+}
+
+int umv_fill_synthetic(umv_engine* e, uint64_t seed) {
+    UMV_REQUIRE(e, UMV_ERR_INVALID, "null engine");
+    uint64_t k = 0;
+    for (auto& kv : e->slots) {
+        Slot& s = kv.second;
+        const uint64_t sd = seed * 0x9E3779B97F4A7C15ull + (++k) * 0xD1B54A32D192ED03ull;
+        if (s.kind == SLOT_PLAIN) {
+            for (int64_t r = 0; r < s.rows && s.dst_ld != s.cols; ++r)
+                UMV_TRY(fill_uniform_bf16(s.dst + r * s.dst_ld, (size_t)s.cols, sd + r, s.synth_bound, s.synth_mean, 0));
+            if (s.dst_ld == s.cols) UMV_TRY(fill_uniform_bf16(s.dst, (size_t)s.rows * s.cols, sd, s.synth_bound, s.synth_mean, 0));
+        } else {
+            for (int64_t blk = 0; blk < s.rows / 64; ++blk)
+                UMV_TRY(fill_uniform_bf16(s.dst + blk * 128 * s.dst_ld, (size_t)64 * s.cols, sd + blk, s.synth_bound, s.synth_mean, 0));
+        }
+        s.loaded = true;
+    }
+    UMV_CUDA_OK(cudaDeviceSynchronize());
+    return UMV_OK;
+}
+
+int umv_finalize(umv_engine* e) {
+    UMV_REQUIRE(e, UMV_ERR_INVALID, "null engine");
+    for (auto& kv : e->slots)
+        UMV_REQUIRE(kv.second.loaded, UMV_ERR_STATE, "umv_finalize: tensor '%s' was never loaded", kv.first.c_str());
+    UMV_CUDA_OK(cudaDeviceSynchronize());
+    e->finalized = true;
+    return UMV_OK;
+}
+
+int umv_weight_bytes(umv_engine* e, int64_t* bytes) {
+    UMV_REQUIRE(e && bytes, UMV_ERR_INVALID, "null argument");
+    int64_t n = 0;
+    for (auto& kv : e->slots) n += kv.second.rows * kv.second.cols * 2;
+    *bytes = n;
+    return UMV_OK;
+}
+
+// ------------------------------------------------------------------------------ sequences
+int umv_seq_new(umv_engine* e, int32_t* seq) {
+    UMV_REQUIRE(e && seq, UMV_ERR_INVALID, "null argument");
+    for (size_t i = 0; i < e->seqs.size(); ++i)
+        if (!e->seqs[i].alive) {
+            e->seqs[i] = Seq();
+            e->seqs[i].alive = true;
+            *seq = (int)i;
+            return UMV_OK;
+        }
+    e->seqs.emplace_back();
+    e->seqs.back().alive = true;
+    *seq = (int)e->seqs.size() - 1;
+    return UMV_OK;
+}
+int umv_seq_fork(umv_engine* e, int32_t src, int32_t* dst) {
+    UMV_REQUIRE(e && dst, UMV_ERR_INVALID, "null argument");
+    Seq* s = get_seq(e, src);
+    if (!s) return UMV_ERR_INVALID;
+    const int committed = (s->len + kPageTokens - 1) / kPageTokens;
+    std::vector<int> pages(s->pages.begin(), s->pages.begin() + committed);
+    const int len = s->len;
+    UMV_TRY(umv_seq_new(e, dst));      // may reallocate e->seqs
+    Seq& n = e->seqs[*dst];
+    n.pages = pages;
+    n.len = len;
+    for (int p : n.pages) ++e->page_ref[p];
+    return UMV_OK;
+}
+int umv_seq_free(umv_engine* e, int32_t seq) {
+    UMV_REQUIRE(e, UMV_ERR_INVALID, "null engine");
+    Seq* s = get_seq(e, seq);
+    if (!s) return UMV_ERR_INVALID;
+    for (int p : s->pages) page_release(e, p);
+    *s = Seq();
+    return UMV_OK;
+}
+int umv_seq_len(umv_engine* e, int32_t seq, int32_t* len) {
+    UMV_REQUIRE(e && len, UMV_ERR_INVALID, "null argument");
+    Seq* s = get_seq(e, seq);
+    if (!s) return UMV_ERR_INVALID;
+    *len = s->len;
+    return UMV_OK;
+}
+int umv_seq_truncate(umv_engine* e, int32_t seq, int32_t len) {
+    UMV_REQUIRE(e, UMV_ERR_INVALID, "null engine");
+    Seq* s = get_seq(e, seq);
+    if (!s) return UMV_ERR_INVALID;
+    UMV_REQUIRE(len >= 0 && len <= s->len, UMV_ERR_INVALID, "umv_seq_truncate: %d not in [0,%d]", len, s->len);
+    s->len = len;
+    const int keep = (len + kPageTokens - 1) / kPageTokens;
+    while ((int)s->pages.size() > keep) {
+        page_release(e, s->pages.back());
+        s->pages.pop_back();
+    }
+    return UMV_OK;
+}
+int umv_pages_free(umv_engine* e, int32_t* n) {
+    UMV_REQUIRE(e && n, UMV_ERR_INVALID, "null argument");
+    *n = (int)e->free_pages.size();
+    return UMV_OK;
+}
+int umv_seq_export(umv_engine* e, int32_t seq, int32_t layer, void* k_dev, void* v_dev, void* stream) {
+    UMV_REQUIRE(e && k_dev && v_dev, UMV_ERR_INVALID, "null argument");
+    Seq* s = get_seq(e, seq);
+    if (!s) return UMV_ERR_INVALID;
+    UMV_REQUIRE(layer >= 0 && layer < e->d.layers, UMV_ERR_INVALID, "bad layer %d", layer);
+    if (s->len == 0) return UMV_OK;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    MetaBuilder mb;
+    UMV_TRY(meta_begin(e, &mb, s->pages.size() * 4));
+    int* dpages;
+    mb.put<int>(s->pages.data(), s->pages.size(), &dpages);
+    UMV_TRY(meta_commit(e, &mb, st));
+    return export_kv(e->pool, layer, dpages, s->len, static_cast<bf16*>(k_dev), static_cast<bf16*>(v_dev), st);
+}
+
+// ------------------------------------------------------------------------------ forward passes
+int umv_embed_tokens(umv_engine* e, const int64_t* ids, int32_t n, void* out, void* stream) {
+    UMV_REQUIRE(e && e->finalized, UMV_ERR_STATE, "engine not finalized");
+    return embed_rows(e->embed, ids, n, e->d.hidden, e->d.vocab, static_cast<bf16*>(out), static_cast<cudaStream_t>(stream));
+}
+
+int umv_llm_forward(umv_engine* e, const void* x, int32_t n_seqs, const int32_t* seqs, const int32_t* q_lens,
+                    const int32_t* positions, const uint8_t* row_is_gen, int32_t is_causal, int32_t update_kv, void* out,
+                    void* stream) {
+    UMV_REQUIRE(e && e->finalized, UMV_ERR_STATE, "engine not finalized");
+    UMV_REQUIRE(x && seqs && q_lens && positions && n_seqs > 0, UMV_ERR_INVALID, "umv_llm_forward: null/empty argument");
+    UMV_REQUIRE(n_seqs <= 3 * e->d.max_seqs, UMV_ERR_INVALID, "umv_llm_forward: %d sequences > 3*max_seqs", n_seqs);
+    UMV_REQUIRE(!row_is_gen || e->d.enable_gen, UMV_ERR_STATE, "generation expert weights were not enabled");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int D = e->d.hidden;
+    LlmRun r;
+    r.n_seqs = n_seqs;
+    r.causal = is_causal != 0;
+    r.gen = row_is_gen != nullptr;
+    int M = 0;
+    for (int b = 0; b < n_seqs; ++b) {
+        UMV_REQUIRE(q_lens[b] > 0, UMV_ERR_INVALID, "umv_llm_forward: empty query for sample %d", b);
+        M += q_lens[b];
+    }
+    UMV_REQUIRE(M <= e->d.max_tokens, UMV_ERR_NOMEM, "umv_llm_forward: %d tokens > max_tokens %d", M, e->d.max_tokens);
+    r.M = M;
+    // reserve pages, gather geometry
+    int max_pages = 0;
+    std::vector<Seq*> sq(n_seqs);
+    for (int b = 0; b < n_seqs; ++b) {
+        sq[b] = get_seq(e, seqs[b]);
+        if (!sq[b]) return UMV_ERR_INVALID;
+        for (int c = 0; c < b; ++c) UMV_REQUIRE(seqs[c] != seqs[b], UMV_ERR_INVALID, "sequence %d appears twice in one call", seqs[b]);
+        UMV_TRY(seq_reserve(e, sq[b], sq[b]->len + q_lens[b], st));
+        max_pages = std::max(max_pages, (int)sq[b]->pages.size());
+        r.max_q_len = std::max(r.max_q_len, q_lens[b]);
+        r.max_kv_len = std::max(r.max_kv_len, sq[b]->len + q_lens[b]);
+    }
+    MetaBuilder mb;
+    UMV_TRY(meta_begin(e, &mb, (size_t)(n_seqs * 16 + 64) + (size_t)M * 20 + (size_t)n_seqs * max_pages * 4));
+    CallMeta& m = r.m;
+    m.max_pages = max_pages;
+    int* hq = mb.put<int>(nullptr, n_seqs + 1, &m.q_start);
+    int* hql = mb.put<int>(nullptr, n_seqs, &m.q_len);
+    int* hkl = mb.put<int>(nullptr, n_seqs, &m.kv_len);
+    mb.put<int>(positions, M, &m.positions);
+    int* hrs = mb.put<int>(nullptr, M, &m.row_seq);
+    int* hrp = mb.put<int>(nullptr, M, &m.row_kvpos);
+    int* hpt = mb.put<int>(nullptr, (size_t)n_seqs * max_pages, &m.page_table);
+    int row = 0;
+    hq[0] = 0;
+    for (int b = 0; b < n_seqs; ++b) {
+        hql[b] = q_lens[b];
+        hkl[b] = sq[b]->len + q_lens[b];
+        for (int j = 0; j < q_lens[b]; ++j, ++row) {
+            hrs[row] = b;
+            hrp[row] = sq[b]->len + j;
+        }
+        hq[b + 1] = row;
+        for (int p = 0; p < max_pages; ++p) hpt[(size_t)b * max_pages + p] = p < (int)sq[b]->pages.size() ? sq[b]->pages[p] : 0;
+    }
+    if (r.gen) {
+        std::vector<int> text;
+        for (int i = 0; i < M; ++i)
+            if (!row_is_gen[i]) text.push_back(i);
+        UMV_REQUIRE((int)text.size() <= std::min(e->d.max_tokens, 8 * e->d.max_seqs), UMV_ERR_NOMEM,
+                    "umv_llm_forward: %zu understanding-expert rows in a gen-mode call exceed the staging size", text.size());
+        mb.put<uint8_t>(row_is_gen, M, &m.row_sel);
+        mb.put<int>(text.data(), text.size(), &m.text_rows);
+        m.n_text = (int)text.size();
+    }
+    UMV_TRY(meta_commit(e, &mb, st));
+    UMV_CUDA_OK(cudaMemcpy2DAsync(e->h, (size_t)D * 2, x, (size_t)D * 2, (size_t)D * 2, M, cudaMemcpyDeviceToDevice, st));
+    r.weight_major = M <= 64;
+    UMV_TRY(llm_layers(e, r, static_cast<bf16*>(out), st));
+    if (update_kv)
+        for (int b = 0; b < n_seqs; ++b) sq[b]->len += q_lens[b];
+    return UMV_OK;
+}
+
+int umv_lm_head(umv_engine* e, const void* hidden, int32_t m, void* logits, void* stream) {
+    UMV_REQUIRE(e && e->finalized, UMV_ERR_STATE, "engine not finalized");
+    return lin(e, static_cast<const bf16*>(hidden), e->d.hidden, e->lm_head, nullptr, nullptr, static_cast<bf16*>(logits),
+               e->d.vocab, m, e->d.vocab, e->d.hidden, EPI_BF16, static_cast<cudaStream_t>(stream));
+}
+
+int umv_vit_embed(umv_engine* e, const float* pixels, const int64_t* pos_ids, const int32_t* seqlens, int32_t n_images,
+                  void* out, void* stream) {
+    UMV_REQUIRE(e && e->finalized, UMV_ERR_STATE, "engine not finalized");
+    UMV_REQUIRE(e->d.enable_vit, UMV_ERR_STATE, "ViT weights were not enabled");
+    UMV_REQUIRE(pixels && pos_ids && seqlens && out && n_images > 0, UMV_ERR_INVALID, "umv_vit_embed: null/empty argument");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const umv_dims& d = e->d;
+    const int Dv = d.vit_hidden, Iv = d.vit_inter, D = d.hidden, Kp = e->vit_kpad;
+    int M = 0, max_len = 0;
+    for (int i = 0; i < n_images; ++i) {
+        UMV_REQUIRE(seqlens[i] > 0, UMV_ERR_INVALID, "umv_vit_embed: empty image %d", i);
+        M += seqlens[i];
+        max_len = std::max(max_len, seqlens[i]);
+    }
+    UMV_REQUIRE(M <= d.max_tokens, UMV_ERR_NOMEM, "umv_vit_embed: %d patches > max_tokens %d", M, d.max_tokens);
+    MetaBuilder mb;
+    UMV_TRY(meta_begin(e, &mb, (size_t)n_images * 16 + 64));
+    int *dq, *dl;
+    int* hq = mb.put<int>(nullptr, n_images + 1, &dq);
+    mb.put<int>(seqlens, n_images, &dl);
+    hq[0] = 0;
+    for (int i = 0; i < n_images; ++i) hq[i + 1] = hq[i] + seqlens[i];
+    UMV_TRY(meta_commit(e, &mb, st));
+
+    bf16* hv = e->h;        // residual stream [M, Dv]
+    bf16* xb = e->act;      // bf16 pixels [M, Kp]
+    UMV_TRY(f32_to_bf16_padded(pixels, xb, M, d.vit_patch_dim, Kp, st));
+    UMV_TRY(lin(e, xb, Kp, e->vit_patch_w, e->vit_patch_b, nullptr, hv, Dv, M, Dv, Kp, EPI_BF16, st));
+    UMV_TRY(gather_add_rows(hv, e->vit_pos, pos_ids, M, Dv, st));
+    for (int li = 0; li < d.vit_layers; ++li) {
+        const VitLayerW& L = e->vit[li];
+        UMV_TRY(layernorm_bf16(hv, L.ln1w, L.ln1b, e->xn, M, Dv, d.vit_eps, st));
+        UMV_TRY(lin(e, e->xn, Dv, L.wqkv, L.bqkv, nullptr, e->qkv, 3 * Dv, M, 3 * Dv, Dv, EPI_BF16, st));
+        AttnArgs aa;
+        aa.q = e->qkv; aa.ldq = 3 * Dv; aa.k = e->qkv + Dv; aa.v = e->qkv + 2 * Dv; aa.ldk = aa.ldv = 3 * Dv;
+        aa.out = e->attn; aa.ldo = Dv;
+        aa.q_start = dq; aa.k_start = dq; aa.q_len = dl; aa.kv_len = dl;
+        aa.n = n_images; aa.H = d.vit_heads; aa.Hkv = d.vit_heads; aa.dh = Dv / d.vit_heads; aa.causal = 0;
+        aa.max_q_len = max_len; aa.max_kv_len = max_len; aa.total_q = M;
+        UMV_TRY(attention_forward(aa, st));
+        UMV_TRY(lin(e, e->attn, Dv, L.wo, L.bo, hv, hv, Dv, M, Dv, Dv, EPI_RESID, st));
+        UMV_TRY(layernorm_bf16(hv, L.ln2w, L.ln2b, e->xn, M, Dv, d.vit_eps, st));
+        UMV_TRY(lin(e, e->xn, Dv, L.w1, L.b1, nullptr, e->act, Iv, M, Iv, Dv, EPI_GELU, st));
+        UMV_TRY(lin(e, e->act, Iv, L.w2, L.b2, hv, hv, Dv, M, Dv, Iv, EPI_RESID, st));
+    }
+    UMV_TRY(layernorm_bf16(hv, e->vit_post_w, e->vit_post_b, e->xn, M, Dv, d.vit_eps, st));
+    // connector (modeling_utils.py:119-123) + vit_pos_embed (bagel.py:590-594)
+    UMV_TRY(lin(e, e->xn, Dv, e->conn_w1, e->conn_b1, nullptr, e->act, D, M, D, Dv, EPI_GELU, st));
+    UMV_TRY(lin(e, e->act, D, e->conn_w2, e->conn_b2, nullptr, static_cast<bf16*>(out), D, M, D, D, EPI_BF16, st));
+    return gather_add_rows(static_cast<bf16*>(out), e->vit_pos_embed, pos_ids, M, D, st);
+}
+
+int umv_generate_text(umv_engine* e, int32_t n_seqs, const int32_t* seqs, const int64_t* start_tokens,
+                      const int32_t* positions, int32_t n_steps, float temperature, uint64_t seed,
+                      const int64_t* forced_tokens, int64_t* tokens_out, void* logits_out, void* stream) {
+    UMV_REQUIRE(e && e->finalized, UMV_ERR_STATE, "engine not finalized");
+    UMV_REQUIRE(seqs && start_tokens && positions && tokens_out && n_seqs > 0 && n_steps > 0, UMV_ERR_INVALID,
+                "umv_generate_text: null/empty argument");
+    UMV_REQUIRE(n_seqs <= e->d.max_seqs && n_seqs <= 64, UMV_ERR_INVALID, "umv_generate_text: %d sequences > max_seqs", n_seqs);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const umv_dims& d = e->d;
+    const int B = n_seqs, D = d.hidden, V = d.vocab;
+    std::vector<Seq*> sq(B);
+    int max_pages = 0;
+    LlmRun r;
+    r.M = B; r.n_seqs = B; r.max_q_len = 1; r.causal = true; r.gen = false; r.weight_major = true;
+    for (int b = 0; b < B; ++b) {
+        sq[b] = get_seq(e, seqs[b]);
+        if (!sq[b]) return UMV_ERR_INVALID;
+        for (int c = 0; c < b; ++c) UMV_REQUIRE(seqs[c] != seqs[b], UMV_ERR_INVALID, "sequence %d appears twice", seqs[b]);
+        UMV_TRY(seq_reserve(e, sq[b], sq[b]->len + n_steps, st));
+        max_pages = std::max(max_pages, (int)sq[b]->pages.size());
+        r.max_kv_len = std::max(r.max_kv_len, sq[b]->len + n_steps);
+    }
+    UMV_REQUIRE(B * max_pages <= e->dec_pages_cap, UMV_ERR_NOMEM, "decode page table too large");
+    // upload the loop state
+    std::vector<int> hpos(B), hkl(B), hkp(B), hrs(B), hqs(B + 1), hql(B), hpt((size_t)B * max_pages, 0);
+    for (int b = 0; b < B; ++b) {
+        hpos[b] = positions[b]; hkl[b] = sq[b]->len + 1; hkp[b] = sq[b]->len; hrs[b] = b; hqs[b] = b; hql[b] = 1;
+        for (size_t p = 0; p < sq[b]->pages.size(); ++p) hpt[(size_t)b * max_pages + p] = sq[b]->pages[p];
+    }
+    hqs[B] = B;
+    const int zero = 0;
+    UMV_CUDA_OK(cudaMemcpyAsync(e->dec_tokens, start_tokens, B * sizeof(int64_t), cudaMemcpyHostToDevice, st));
+    UMV_CUDA_OK(cudaMemcpyAsync(e->dec_pos, hpos.data(), B * 4, cudaMemcpyHostToDevice, st));
+    UMV_CUDA_OK(cudaMemcpyAsync(e->dec_kvlen, hkl.data(), B * 4, cudaMemcpyHostToDevice, st));
+    UMV_CUDA_OK(cudaMemcpyAsync(e->dec_kvpos, hkp.data(), B * 4, cudaMemcpyHostToDevice, st));
+    UMV_CUDA_OK(cudaMemcpyAsync(e->dec_rowseq, hrs.data(), B * 4, cudaMemcpyHostToDevice, st));
+    UMV_CUDA_OK(cudaMemcpyAsync(e->dec_qstart, hqs.data(), (B + 1) * 4, cudaMemcpyHostToDevice, st));
+    UMV_CUDA_OK(cudaMemcpyAsync(e->dec_qlen, hql.data(), B * 4, cudaMemcpyHostToDevice, st));
+    UMV_CUDA_OK(cudaMemcpyAsync(e->dec_pages, hpt.data(), hpt.size() * 4, cudaMemcpyHostToDevice, st));
+    UMV_CUDA_OK(cudaMemcpyAsync(e->dec_step, &zero, 4, cudaMemcpyHostToDevice, st));
+    UMV_CUDA_OK(cudaStreamSynchronize(st));     // host vectors above go out of scope; also a clean capture start
+    r.m.q_start = e->dec_qstart; r.m.q_len = e->dec_qlen; r.m.kv_len = e->dec_kvlen; r.m.positions = e->dec_pos;
+    r.m.row_seq = e->dec_rowseq; r.m.row_kvpos = e->dec_kvpos; r.m.page_table = e->dec_pages; r.m.max_pages = max_pages;
+    DecodeState ds{e->dec_tokens, e->dec_pos, e->dec_kvlen, e->dec_kvpos, e->dec_step};
+
+    auto step = [&](cudaStream_t s, bf16* logits) -> int {
+        UMV_TRY(decode_begin_step(e->embed, D, V, ds, forced_tokens, tokens_out, B, e->h, s));
+        UMV_TRY(llm_layers(e, r, e->xn, s));
+        UMV_TRY(lin(e, e->xn, D, e->lm_head, nullptr, nullptr, logits, V, B, V, D, EPI_BF16, s));
+        if (temperature > 0.f) UMV_TRY(sample_rows(logits, B, V, temperature, seed, e->dec_step, e->dec_tokens, s));
+        else UMV_TRY(argmax_rows(logits, B, V, e->dec_tokens, s));
+        return decode_end_step(ds, B, s);
+    };
+
+    const bool graph_ok = e->use_graph && logits_out == nullptr && st != nullptr && n_steps > 1;
+    if (graph_ok) {
+        cudaGraph_t graph = nullptr;
+        cudaGraphExec_t exec = nullptr;
+        UMV_CUDA_OK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+        int rc = step(st, e->logits);
+        cudaError_t ce = cudaStreamEndCapture(st, &graph);
+        if (rc != UMV_OK) { if (graph) cudaGraphDestroy(graph); return rc; }
+        UMV_CUDA_OK(ce);
+        UMV_CUDA_OK(cudaGraphInstantiate(&exec, graph, 0));
+        for (int i = 0; i < n_steps; ++i) {
+            cudaError_t le = cudaGraphLaunch(exec, st);
+            if (le != cudaSuccess) {
+                set_error("cudaGraphLaunch failed at step %d: %s", i, cudaGetErrorString(le));
+                cudaGraphExecDestroy(exec); cudaGraphDestroy(graph);
+                return UMV_ERR_CUDA;
+            }
+        }
+        cudaGraphExecDestroy(exec);
+        cudaGraphDestroy(graph);
+    } else {
+        for (int i = 0; i < n_steps; ++i) {
+            bf16* lg = logits_out ? static_cast<bf16*>(logits_out) + (size_t)i * B * V : e->logits;
+            UMV_TRY(step(st, lg));
+        }
+    }
+    for (int b = 0; b < B; ++b) sq[b]->len += n_steps;
+    return UMV_OK;
+}
+
+// ------------------------------------------------------------------------------ flow (next milestone)
+int umv_flow_velocity(umv_engine*, const umv_flow_args*, const float*, float*, void*) {
+    set_error("umv_flow_velocity: not built yet");
+    return UMV_ERR_UNSUPPORTED;
+}
+int umv_flow_euler(umv_engine*, float*, const float*, int64_t, float, int32_t, void*) {
+    set_error("umv_flow_euler: not built yet");
+    return UMV_ERR_UNSUPPORTED;
+}
+
+// ------------------------------------------------------------------------------ op-level entry points
+int umv_op_linear(const void* x, const void* w, const void* bias, const void* residual, void* y, int32_t M, int32_t N,
+                  int32_t K, int32_t epi, int32_t impl, void* stream) {
+    UMV_REQUIRE(x && w && y, UMV_ERR_INVALID, "umv_op_linear: null argument");
+    UMV_REQUIRE(epi >= 0 && epi <= 3, UMV_ERR_INVALID, "umv_op_linear: epi %d", epi);
+    LinearCall c;
+    c.x = static_cast<const bf16*>(x); c.ldx = K; c.w = static_cast<const bf16*>(w);
+    c.bias = static_cast<const bf16*>(bias); c.residual = static_cast<const bf16*>(residual);
+    c.y = static_cast<bf16*>(y); c.ldy = epi == EPI_SWIGLU ? N / 2 : N; c.M = M; c.N = N; c.K = K; c.epi = epi; c.impl = impl;
+    return linear_forward(c, static_cast<cudaStream_t>(stream));
+}
+int umv_op_rmsnorm(const void* x, const void* w, void* y, int32_t M, int32_t D, float eps, void* stream) {
+    AddNormArgs a;
+    a.h = const_cast<bf16*>(static_cast<const bf16*>(x)); a.w0 = a.w1 = static_cast<const bf16*>(w);
+    a.y = static_cast<bf16*>(y); a.M = M; a.D = D; a.eps = eps;
+    return add_rmsnorm(a, static_cast<cudaStream_t>(stream));
+}
+int umv_op_layernorm(const void* x, const void* w, const void* b, void* y, int32_t M, int32_t D, float eps, void* stream) {
+    return layernorm_bf16(static_cast<const bf16*>(x), static_cast<const bf16*>(w), static_cast<const bf16*>(b),
+                          static_cast<bf16*>(y), M, D, eps, static_cast<cudaStream_t>(stream));
+}
+int umv_op_attention(const void* q, const void* k, const void* v, void* out, int32_t n, const int32_t* q_lens,
+                     const int32_t* k_lens, int32_t heads, int32_t kv_heads, int32_t head_dim, int32_t causal, void* stream) {
+    UMV_REQUIRE(q && k && v && out && q_lens && k_lens && n > 0, UMV_ERR_INVALID, "umv_op_attention: null/empty argument");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    std::vector<int> meta(4 * n + 2);
+    int* qs = meta.data(); int* ks = qs + n + 1; int* ql = ks + n + 1; int* kl = ql + n;
+    qs[0] = ks[0] = 0;
+    int mq = 0, mk = 0;
+    for (int i = 0; i < n; ++i) {
+        qs[i + 1] = qs[i] + q_lens[i]; ks[i + 1] = ks[i] + k_lens[i]; ql[i] = q_lens[i]; kl[i] = k_lens[i];
+        mq = std::max(mq, q_lens[i]); mk = std::max(mk, k_lens[i]);
+    }
+    int* dmeta = nullptr;
+    UMV_CUDA_OK(cudaMalloc(&dmeta, meta.size() * 4));
+    cudaMemcpyAsync(dmeta, meta.data(), meta.size() * 4, cudaMemcpyHostToDevice, st);
+    AttnArgs a;
+    a.q = static_cast<const bf16*>(q); a.ldq = heads * head_dim; a.out = static_cast<bf16*>(out); a.ldo = heads * head_dim;
+    a.k = static_cast<const bf16*>(k); a.v = static_cast<const bf16*>(v); a.ldk = a.ldv = kv_heads * head_dim;
+    a.q_start = dmeta; a.k_start = dmeta + n + 1; a.q_len = dmeta + 2 * n + 2; a.kv_len = dmeta + 3 * n + 2;
+    a.n = n; a.H = heads; a.Hkv = kv_heads; a.dh = head_dim; a.causal = causal; a.max_q_len = mq; a.max_kv_len = mk;
+    a.total_q = qs[n];
+    int rc = attention_init();
+    if (rc == UMV_OK) rc = attention_forward(a, st);
+    cudaStreamSynchronize(st);
+    cudaFree(dmeta);
+    return rc;
+}
+int umv_op_argmax(const void* logits, int32_t rows, int32_t vocab, int64_t* out, void* stream) {
+    return argmax_rows(static_cast<const bf16*>(logits), rows, vocab, out, static_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

@@ -1,0 +1,106 @@
+// Engine state: weights in the engine layout, KV page pool + sequences, workspaces.
+#pragma once
+#include <cstdint>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/umv.h"
+#include "common.cuh"
+#include "kernels.cuh"
+
+namespace umv {
+
+enum SlotKind : int { SLOT_PLAIN = 0, SLOT_GATE = 1, SLOT_UP = 2 };
+
+// One reference state-dict tensor -> where it lives in the engine layout.
+struct Slot {
+    bf16* dst = nullptr;     // first destination element
+    int64_t rows = 1, cols = 1;   // reference shape (1-D tensors: rows = 1)
+    int64_t dst_ld = 0;      // destination row stride in elements
+    int kind = SLOT_PLAIN;
+    int ndim = 2;
+    bool loaded = false;
+    float synth_bound = 0.02f * 1.7320508f, synth_mean = 0.f;
+};
+
+struct LayerW {                    // index 0: understanding expert, 1: generation expert (*_moe_gen)
+    bf16 *wqkv[2], *bqkv[2], *wo[2], *wgu[2], *wdown[2], *ln1[2], *ln2[2], *qn[2], *kn[2];
+};
+struct VitLayerW {
+    bf16 *ln1w, *ln1b, *wqkv, *bqkv, *wo, *bo, *ln2w, *ln2b, *w1, *b1, *w2, *b2;
+};
+
+struct Seq {
+    std::vector<int> pages;
+    int len = 0;
+    bool alive = false;
+};
+
+// Device-side metadata of one packed forward call (one H2D copy).
+struct CallMeta {
+    int* q_start = nullptr;     // [n+1]
+    int* k_start = nullptr;     // [n+1] (un-paged attention)
+    int* q_len = nullptr;       // [n]
+    int* kv_len = nullptr;      // [n]
+    int* positions = nullptr;   // [M]
+    int* row_seq = nullptr;     // [M]
+    int* row_kvpos = nullptr;   // [M]
+    int* page_table = nullptr;  // [n][max_pages]
+    int* text_rows = nullptr;   // [T] rows routed to the understanding expert (gen mode)
+    uint8_t* row_sel = nullptr; // [M]
+    int max_pages = 0, n_text = 0;
+};
+
+}  // namespace umv
+
+struct umv_engine {
+    umv_dims d{};
+    int dh = 0, qkvn = 0, vit_kpad = 0, sm_count = 148;
+    bool finalized = false;
+    bool use_splitk = true, use_graph = true;
+    int gemm_impl = 0;
+
+    std::vector<void*> allocs;
+    std::map<std::string, umv::Slot> slots;
+
+    // LLM
+    umv::bf16 *embed = nullptr, *lm_head = nullptr, *final_norm[2] = {nullptr, nullptr};
+    std::vector<umv::LayerW> layers;
+    float* inv_freq = nullptr;
+    // ViT + connector
+    umv::bf16 *vit_patch_w = nullptr, *vit_patch_b = nullptr, *vit_pos = nullptr, *vit_post_w = nullptr, *vit_post_b = nullptr;
+    std::vector<umv::VitLayerW> vit;
+    umv::bf16 *conn_w1 = nullptr, *conn_b1 = nullptr, *conn_w2 = nullptr, *conn_b2 = nullptr, *vit_pos_embed = nullptr;
+    // generation glue
+    umv::bf16 *t_w0 = nullptr, *t_b0 = nullptr, *t_w2 = nullptr, *t_b2 = nullptr, *vae2llm_w = nullptr, *vae2llm_b = nullptr,
+              *llm2vae_w = nullptr, *llm2vae_b = nullptr, *latent_pos = nullptr;
+
+    // KV
+    umv::KVPool pool;
+    std::vector<int> page_ref, free_pages;
+    std::vector<umv::Seq> seqs;
+
+    // workspaces
+    umv::bf16 *h = nullptr, *xn = nullptr, *qkv = nullptr, *attn = nullptr, *act = nullptr, *logits = nullptr;
+    umv::bf16 *xt = nullptr, *ht = nullptr, *yt = nullptr, *actt = nullptr;   // text-row (understanding expert) staging, gen mode
+    float* ws = nullptr;          // split-K partials
+    size_t ws_elems = 0;
+    float* attn_ws = nullptr;     // split-KV partials
+    size_t attn_ws_elems = 0;
+    int w_h = 0, w_qkv = 0, w_act = 0;   // workspace row widths
+
+    // call metadata staging
+    static constexpr int kMetaRing = 4;
+    uint8_t* meta_host[kMetaRing] = {};
+    uint8_t* meta_dev[kMetaRing] = {};
+    cudaEvent_t meta_ev[kMetaRing] = {};
+    size_t meta_bytes = 0;
+    int meta_next = 0;
+
+    // decode state
+    int64_t* dec_tokens = nullptr;
+    int *dec_pos = nullptr, *dec_kvlen = nullptr, *dec_kvpos = nullptr, *dec_step = nullptr, *dec_rowseq = nullptr,
+        *dec_qstart = nullptr, *dec_qlen = nullptr, *dec_pages = nullptr;
+    int dec_pages_cap = 0;
+};

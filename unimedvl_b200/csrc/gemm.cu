@@ -1,0 +1,515 @@
+// Linear layers (y = x W^T + b with fused epilogues) for sm_100a.
+//
+// One persistent, warp-specialised kernel: TMA (cp.async.bulk.tensor, 128-byte swizzle) stages
+// 128 x 64 / BN x 64 bf16 operand tiles through a multi-stage mbarrier ring, a single elected thread
+// issues tcgen05.mma (M=128, N=BN, K=16, kind::f16, fp32 accumulators in TMEM, double buffered) and
+// four epilogue warps drain TMEM with tcgen05.ld and apply the reference's rounding points.
+//
+//   token-major  (prefill, M large): A = activations [M,K], B = weights [N,K]; TMEM lane = token,
+//                column = output feature.  Tensor-core bound.
+//   weight-major (decode,  M <= 64): A = weights [N,K] streamed once from HBM (evict-first),
+//                B = activations; TMEM lane = output feature, column = token.  HBM bound; optional
+//                split-K writes fp32 partials that the consumer kernel reduces in a fixed order.
+//
+// Replaces the reference's F.linear -> cuBLAS call sites:
+// qwen2_navit.py:541-543,555-562,617-620; modeling_qwen2.py:234-235; bagel.py:1295;
+// siglip_navit.py:190,216-218,243,256-258; modeling_utils.py:108,120-122.
+#include <cuda.h>
+#include <cstdarg>
+#include <cstring>
+#include <mutex>
+
+#include "../../include/umv.h"
+#include "common.cuh"
+#include "gemm.cuh"
+#include "ptx.cuh"
+
+namespace umv {
+
+long long g_launches = 0;
+
+constexpr int BM = 128;   // UMMA M (TMEM lanes)
+constexpr int BK = 64;    // 64 bf16 = one 128-byte swizzle row
+constexpr int kATile = BM * BK * 2;
+
+struct GemmParams {
+    int a_rows, b_rows, K;
+    int a_tiles, b_tiles, splits, kb_total, kb_per_split;
+    int tokens, features;
+    bf16* y;
+    int ldy;
+    const bf16* bias;
+    const bf16* residual;
+    float* ws;
+    int epi;
+};
+
+template <int BN, bool SWAP>
+struct TcCfg {
+    static constexpr int kBTile = BN * BK * 2;
+    static constexpr int kStageBytes = kATile + kBTile;
+    static constexpr int kStagesRaw = (196 * 1024) / kStageBytes;
+    static constexpr int kStages = kStagesRaw > 10 ? 10 : kStagesRaw;
+    static constexpr int kTmemCols = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
+    static constexpr int kBarBytes = 256;
+    static constexpr int kExchBytes = SWAP ? 64 * BN * 4 : 0;   // swiglu gate/up exchange (weight-major only)
+    static constexpr int kSmemBytes = 1024 + kStages * kStageBytes + kBarBytes + kExchBytes;
+};
+
+__device__ __forceinline__ float epi_value(int epi, float acc, float bias) {
+    float v = rbf(acc + bias);
+    if (epi == EPI_GELU) v = rbf(gelu_tanh_f(v));
+    return v;
+}
+
+// MODE 0: bf16 / gelu / +residual (runtime p.epi), 1: fp32 split-K partials, 2: swiglu
+template <int BN, int MODE, bool SWAP>
+__global__ void __launch_bounds__(192, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
+    using Cfg = TcCfg<BN, SWAP>;
+    constexpr int kStages = Cfg::kStages;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    uint8_t* sA = smem;
+    uint8_t* sB = smem + kStages * kATile;
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + kStages * Cfg::kStageBytes);
+    uint64_t* empty = full + kStages;
+    uint64_t* tfull = empty + kStages;
+    uint64_t* tempty = tfull + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+    float* sExch = reinterpret_cast<float*>(smem + kStages * Cfg::kStageBytes + Cfg::kBarBytes);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmA);
+        tma_prefetch_desc(&tmB);
+    }
+    if (warp == 1) {
+        if (lane == 0) {
+            for (int i = 0; i < kStages; ++i) {
+                mbar_init(&full[i], 1);
+                mbar_init(&empty[i], 1);
+            }
+            for (int i = 0; i < 2; ++i) {
+                mbar_init(&tfull[i], 1);
+                mbar_init(&tempty[i], 4);
+            }
+            fence_mbar_init();
+        }
+        __syncwarp();
+        tmem_alloc<Cfg::kTmemCols>(tmem_slot);
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const int num_tiles = p.a_tiles * p.b_tiles * p.splits;
+
+    if (warp == 0) {
+        // ------------------------------------------------------------ TMA producer
+        if (elect_one()) {
+            const uint64_t hintA = SWAP ? kEvictFirst : kEvictNormal;
+            const uint64_t hintB = SWAP ? kEvictLast : kEvictNormal;
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                const int split = tile % p.splits;
+                const int t2 = tile / p.splits;
+                const int a_tile = t2 % p.a_tiles, b_tile = t2 / p.a_tiles;
+                const int kb0 = split * p.kb_per_split;
+                const int kb1 = min(p.kb_total, kb0 + p.kb_per_split);
+                for (int kb = kb0; kb < kb1; ++kb) {
+                    mbar_wait(&empty[stage], phase ^ 1u);
+                    mbar_expect_tx(&full[stage], Cfg::kStageBytes);
+                    tma_load_2d(sA + stage * kATile, &tmA, &full[stage], kb * BK, a_tile * BM, hintA);
+                    tma_load_2d(sB + stage * Cfg::kBTile, &tmB, &full[stage], kb * BK, b_tile * BN, hintB);
+                    if (++stage == kStages) { stage = 0; phase ^= 1u; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ------------------------------------------------------------ MMA issuer
+        if (elect_one()) {
+            constexpr uint32_t idesc = umma_idesc_bf16(BN);
+            int stage = 0, acc = 0;
+            uint32_t phase = 0, acc_phase = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                const int split = tile % p.splits;
+                const int kb0 = split * p.kb_per_split;
+                const int kb1 = min(p.kb_total, kb0 + p.kb_per_split);
+                mbar_wait(&tempty[acc], acc_phase ^ 1u);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + acc * BN;
+                for (int kb = kb0; kb < kb1; ++kb) {
+                    mbar_wait(&full[stage], phase);
+                    tc_fence_after();
+                    const uint32_t a_addr = smem_u32(sA + stage * kATile);
+                    const uint32_t b_addr = smem_u32(sB + stage * Cfg::kBTile);
+#pragma unroll
+                    for (int k = 0; k < BK / 16; ++k) {
+                        umma_bf16(d_tmem, umma_desc_sw128(a_addr + k * 32), umma_desc_sw128(b_addr + k * 32), idesc,
+                                  (kb > kb0 || k > 0) ? 1u : 0u);
+                    }
+                    umma_commit(&empty[stage]);
+                    if (++stage == kStages) { stage = 0; phase ^= 1u; }
+                }
+                umma_commit(&tfull[acc]);
+                if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+            }
+        }
+    } else {
+        // ------------------------------------------------------------ epilogue (4 warps)
+        const int quarter = warp & 3;                  // TMEM lane quarter this warp may read
+        const int lrow = quarter * 32 + lane;          // lane within the 128-row tile
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            const int split = tile % p.splits;
+            const int t2 = tile / p.splits;
+            const int a_tile = t2 % p.a_tiles, b_tile = t2 / p.a_tiles;
+            mbar_wait(&tfull[acc], acc_phase);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN;
+
+            if constexpr (!SWAP && MODE == 0) {
+                const int row = a_tile * BM + lrow;            // token
+                const bool row_ok = row < p.tokens;
+#pragma unroll 1
+                for (int c0 = 0; c0 < BN; c0 += 16) {
+                    uint32_t r[16];
+                    tmem_ld16(taddr + c0, r);
+                    tmem_ld_wait();
+                    const int n0 = b_tile * BN + c0;
+                    if (row_ok && n0 < p.features) {
+#pragma unroll
+                        for (int h = 0; h < 2; ++h) {
+                            const int n = n0 + h * 8;
+                            if (n < p.features) {
+                                U4 bv = {0, 0, 0, 0}, rv = {0, 0, 0, 0};
+                                if (p.bias) bv = ldg16(p.bias + n);
+                                if (p.epi == EPI_RESID) rv = ldg16(p.residual + (size_t)row * p.ldy + n);
+                                const uint32_t* bw = &bv.x;
+                                const uint32_t* rw = &rv.x;
+                                uint32_t o[4];
+#pragma unroll
+                                for (int j = 0; j < 4; ++j) {
+                                    const float2 b2 = unpack2(bw[j]);
+                                    float v0 = epi_value(p.epi, __uint_as_float(r[h * 8 + 2 * j]), b2.x);
+                                    float v1 = epi_value(p.epi, __uint_as_float(r[h * 8 + 2 * j + 1]), b2.y);
+                                    if (p.epi == EPI_RESID) {
+                                        const float2 r2 = unpack2(rw[j]);
+                                        v0 += r2.x;
+                                        v1 += r2.y;
+                                    }
+                                    o[j] = pack2(v0, v1);
+                                }
+                                stg16(p.y + (size_t)row * p.ldy + n, U4{o[0], o[1], o[2], o[3]});
+                            }
+                        }
+                    }
+                }
+            } else if constexpr (!SWAP && MODE == 2) {
+                // weight rows interleaved [64 gate | 64 up] -> tile columns [blk*128 + c] / [blk*128 + 64 + c]
+                const int row = a_tile * BM + lrow;
+                const bool row_ok = row < p.tokens;
+#pragma unroll 1
+                for (int blk = 0; blk < BN / 128; ++blk) {
+#pragma unroll 1
+                    for (int c0 = 0; c0 < 64; c0 += 16) {
+                        uint32_t g[16], u[16];
+                        tmem_ld16(taddr + blk * 128 + c0, g);
+                        tmem_ld16(taddr + blk * 128 + 64 + c0, u);
+                        tmem_ld_wait();
+                        const int j0 = (b_tile * BN) / 2 + blk * 64 + c0;       // activation column
+                        if (row_ok && j0 < p.features / 2) {
+                            uint32_t o[8];
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) {
+                                float a0 = rbf(silu_f(rbf(__uint_as_float(g[2 * j])))) * rbf(__uint_as_float(u[2 * j]));
+                                float a1 = rbf(silu_f(rbf(__uint_as_float(g[2 * j + 1])))) * rbf(__uint_as_float(u[2 * j + 1]));
+                                o[j] = pack2(a0, a1);
+                            }
+                            bf16* dst = p.y + (size_t)row * p.ldy + j0;
+                            stg16(dst, U4{o[0], o[1], o[2], o[3]});
+                            stg16(dst + 8, U4{o[4], o[5], o[6], o[7]});
+                        }
+                    }
+                }
+            } else if constexpr (SWAP && MODE != 2) {
+                const int f = a_tile * BM + lrow;              // output feature
+                const bool f_ok = f < p.features;
+                float bias = 0.f;
+                if (MODE == 0 && p.bias && f_ok) bias = b2f(p.bias[f]);
+#pragma unroll 1
+                for (int c0 = 0; c0 < BN; c0 += 16) {
+                    uint32_t r[16];
+                    tmem_ld16(taddr + c0, r);
+                    tmem_ld_wait();
+                    if (f_ok) {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) {
+                            const int t = b_tile * BN + c0 + j;
+                            if (t < p.tokens) {
+                                const float a = __uint_as_float(r[j]);
+                                if constexpr (MODE == 1) {
+                                    p.ws[((size_t)split * p.tokens + t) * p.features + f] = a;
+                                } else {
+                                    float v = epi_value(p.epi, a, bias);
+                                    if (p.epi == EPI_RESID) v += b2f(p.residual[(size_t)t * p.ldy + f]);
+                                    p.y[(size_t)t * p.ldy + f] = f2b(v);
+                                }
+                            }
+                        }
+                    }
+                }
+            } else {
+                // SWAP + swiglu: lanes 0..63 hold gate rows, 64..127 the matching up rows.
+                const bool is_up = lrow >= 64;
+                const int jl = lrow & 63;
+                const int jglob = a_tile * 64 + jl;
+#pragma unroll 1
+                for (int c0 = 0; c0 < BN; c0 += 16) {
+                    uint32_t r[16];
+                    tmem_ld16(taddr + c0, r);
+                    tmem_ld_wait();
+                    if (is_up) {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) sExch[(c0 + j) * 64 + jl] = rbf(__uint_as_float(r[j]));
+                    }
+                    asm volatile("bar.sync 1, 128;" ::: "memory");
+                    if (!is_up && jglob < p.features / 2) {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) {
+                            const int t = b_tile * BN + c0 + j;
+                            if (t < p.tokens) {
+                                const float gv = rbf(silu_f(rbf(__uint_as_float(r[j]))));
+                                p.y[(size_t)t * p.ldy + jglob] = f2b(gv * sExch[(c0 + j) * 64 + jl]);
+                            }
+                        }
+                    }
+                    asm volatile("bar.sync 1, 128;" ::: "memory");
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty[acc]);
+            if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc<Cfg::kTmemCols>(tmem_base);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Plain CUDA-core kernel: same contract, used for shapes TMA cannot address (row stride not a
+// multiple of 16 bytes) and as the in-library cross-check of the tcgen05 path (impl = 3).
+__global__ void gemm_simple_kernel(const bf16* __restrict__ x, int ldx, const bf16* __restrict__ w,
+                                   const bf16* __restrict__ bias, const bf16* __restrict__ residual,
+                                   bf16* __restrict__ y, int ldy, int M, int N, int K, int epi) {
+    const int n_out = (epi == EPI_SWIGLU) ? N / 2 : N;
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    const int m = blockIdx.y * blockDim.y + threadIdx.y;
+    if (m >= M || n >= n_out) return;
+    const bf16* xr = x + (size_t)m * ldx;
+    if (epi == EPI_SWIGLU) {
+        const bf16* wg = w + (size_t)((n / 64) * 128 + (n % 64)) * K;
+        const bf16* wu = wg + (size_t)64 * K;
+        float g = 0.f, u = 0.f;
+        for (int k = 0; k < K; ++k) {
+            const float xv = b2f(xr[k]);
+            g = fmaf(xv, b2f(wg[k]), g);
+            u = fmaf(xv, b2f(wu[k]), u);
+        }
+        y[(size_t)m * ldy + n] = f2b(rbf(silu_f(rbf(g))) * rbf(u));
+        return;
+    }
+    const bf16* wr = w + (size_t)n * K;
+    float acc = 0.f;
+    for (int k = 0; k < K; ++k) acc = fmaf(b2f(xr[k]), b2f(wr[k]), acc);
+    float v = epi_value(epi, acc, bias ? b2f(bias[n]) : 0.f);
+    if (epi == EPI_RESID) v += b2f(residual[(size_t)m * ldy + n]);
+    y[(size_t)m * ldy + n] = f2b(v);
+}
+
+// ---------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn g_encode = nullptr;
+static int g_sm_count = 148;
+static std::once_flag g_init_once;
+static int g_init_status = 0;
+
+template <int BN, int MODE, bool SWAP>
+static void set_smem_attr() {
+    cudaFuncSetAttribute(gemm_tc_kernel<BN, MODE, SWAP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         TcCfg<BN, SWAP>::kSmemBytes);
+}
+
+int gemm_init() {
+    std::call_once(g_init_once, [] {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+        if (e != cudaSuccess || fn == nullptr || qres != cudaDriverEntryPointSuccess) {
+            set_error("cuTensorMapEncodeTiled unavailable (%s): a CUDA 12 driver and an sm_100a GPU are required",
+                      cudaGetErrorString(e));
+            g_init_status = UMV_ERR_CUDA;
+            return;
+        }
+        g_encode = reinterpret_cast<EncodeTiledFn>(fn);
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev);
+        set_smem_attr<256, 0, false>(); set_smem_attr<128, 0, false>(); set_smem_attr<64, 0, false>();
+        set_smem_attr<256, 2, false>(); set_smem_attr<128, 2, false>();
+        set_smem_attr<16, 0, true>(); set_smem_attr<32, 0, true>(); set_smem_attr<64, 0, true>();
+        set_smem_attr<16, 1, true>(); set_smem_attr<32, 1, true>(); set_smem_attr<64, 1, true>();
+        set_smem_attr<16, 2, true>(); set_smem_attr<32, 2, true>(); set_smem_attr<64, 2, true>();
+        cudaError_t le = cudaGetLastError();
+        if (le != cudaSuccess) {
+            set_error("cudaFuncSetAttribute(max dynamic smem) failed: %s", cudaGetErrorString(le));
+            g_init_status = UMV_ERR_CUDA;
+        }
+    });
+    return g_init_status;
+}
+
+static int make_tmap(CUtensorMap* m, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows) {
+    cuuint64_t dims[2] = {cols, rows};
+    cuuint64_t strides[1] = {ld * 2};
+    cuuint32_t box[2] = {BK, box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled failed (%d) ptr=%p rows=%llu cols=%llu ld=%llu box=%u", (int)r, ptr,
+                  (unsigned long long)rows, (unsigned long long)cols, (unsigned long long)ld, box_rows);
+        return UMV_ERR_CUDA;
+    }
+    return UMV_OK;
+}
+
+int pick_splits(int N, int K, int sm_count) {
+    const int a_tiles = (N + BM - 1) / BM;
+    const int kb_total = (K + BK - 1) / BK;
+    if (a_tiles >= sm_count) return 1;
+    int s = (sm_count + a_tiles / 2) / a_tiles;          // ~one wave of CTAs
+    const int max_by_k = kb_total / 8 > 0 ? kb_total / 8 : 1;   // keep >= 8 k-blocks (128 KB of weights) per split
+    if (s > max_by_k) s = max_by_k;
+    if (s > 16) s = 16;
+    if (s < 1) s = 1;
+    const int per = (kb_total + s - 1) / s;
+    return (kb_total + per - 1) / per;        // effective count: no empty split
+}
+
+template <int BN, int MODE, bool SWAP>
+static int launch_tc(const LinearCall& c, cudaStream_t stream) {
+    GemmParams p{};
+    const bf16* A = SWAP ? c.w : c.x;
+    const bf16* B = SWAP ? c.x : c.w;
+    p.a_rows = SWAP ? c.N : c.M;
+    p.b_rows = SWAP ? c.M : c.N;
+    const int lda = SWAP ? c.K : c.ldx, ldb = SWAP ? c.ldx : c.K;
+    p.K = c.K;
+    p.a_tiles = (p.a_rows + BM - 1) / BM;
+    p.b_tiles = (p.b_rows + BN - 1) / BN;
+    p.kb_total = (c.K + BK - 1) / BK;
+    int splits = (MODE == 1) ? (c.splits < 1 ? 1 : c.splits) : 1;
+    p.kb_per_split = (p.kb_total + splits - 1) / splits;
+    p.splits = (p.kb_total + p.kb_per_split - 1) / p.kb_per_split;
+    if (MODE == 1 && p.splits != splits) {
+        set_error("linear: split count %d leaves empty splits for K=%d (use %d)", splits, c.K, p.splits);
+        return UMV_ERR_INVALID;
+    }
+    p.tokens = c.M;
+    p.features = c.N;
+    p.y = c.y;
+    p.ldy = c.ldy;
+    p.bias = c.bias;
+    p.residual = c.residual;
+    p.ws = c.ws;
+    p.epi = c.epi;
+    CUtensorMap tmA, tmB;
+    int rc = make_tmap(&tmA, A, p.a_rows, c.K, lda, BM);
+    if (rc) return rc;
+    rc = make_tmap(&tmB, B, p.b_rows, c.K, ldb, BN);
+    if (rc) return rc;
+    const int tiles = p.a_tiles * p.b_tiles * p.splits;
+    const int grid = tiles < g_sm_count ? tiles : g_sm_count;
+    gemm_tc_kernel<BN, MODE, SWAP><<<grid, 192, TcCfg<BN, SWAP>::kSmemBytes, stream>>>(tmA, tmB, p);
+    ++g_launches;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        set_error("gemm_tc_kernel<%d,%d,%d> launch failed: %s", BN, MODE, (int)SWAP, cudaGetErrorString(e));
+        return UMV_ERR_CUDA;
+    }
+    return UMV_OK;
+}
+
+int linear_forward(const LinearCall& c, cudaStream_t stream) {
+    if (c.M <= 0 || c.N <= 0 || c.K <= 0) return UMV_OK;
+    int impl = c.impl;
+    const bool tma_ok = (c.K % 8 == 0) && (c.ldx % 8 == 0) && ((reinterpret_cast<uintptr_t>(c.x) & 15) == 0) &&
+                        ((reinterpret_cast<uintptr_t>(c.w) & 15) == 0);
+    if (impl == GEMM_AUTO) {
+        if (!tma_ok) impl = GEMM_SIMPLE;
+        else if (c.M <= 64) impl = GEMM_WEIGHT_MAJOR;
+        else impl = GEMM_TOKEN_MAJOR;
+    }
+    if (c.epi == EPI_SWIGLU && (c.N % 128 != 0)) {
+        set_error("linear: swiglu epilogue needs N %% 128 == 0 (got %d)", c.N);
+        return UMV_ERR_INVALID;
+    }
+    if (impl == GEMM_TOKEN_MAJOR && (c.N % 8 != 0 || c.ldy % 8 != 0)) impl = GEMM_SIMPLE;
+    if (impl == GEMM_WEIGHT_MAJOR && c.M > 64) impl = GEMM_TOKEN_MAJOR;
+    if (impl != GEMM_SIMPLE) {
+        if (!tma_ok) {
+            set_error("linear: tcgen05 path needs 16-byte aligned rows (K=%d ldx=%d)", c.K, c.ldx);
+            return UMV_ERR_INVALID;
+        }
+        int rc = gemm_init();
+        if (rc) return rc;
+    }
+    if (c.epi == EPI_PARTIAL && impl != GEMM_WEIGHT_MAJOR) {
+        set_error("linear: split-K partial epilogue exists only on the weight-major path");
+        return UMV_ERR_INVALID;
+    }
+    if (impl == GEMM_SIMPLE) {
+        dim3 block(32, 8);
+        const int n_out = c.epi == EPI_SWIGLU ? c.N / 2 : c.N;
+        dim3 grid((n_out + 31) / 32, (c.M + 7) / 8);
+        gemm_simple_kernel<<<grid, block, 0, stream>>>(c.x, c.ldx, c.w, c.bias, c.residual, c.y, c.ldy, c.M, c.N, c.K,
+                                                       c.epi);
+        ++g_launches;
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) {
+            set_error("gemm_simple_kernel launch failed: %s", cudaGetErrorString(e));
+            return UMV_ERR_CUDA;
+        }
+        return UMV_OK;
+    }
+    if (impl == GEMM_TOKEN_MAJOR) {
+        if (c.epi == EPI_SWIGLU) {
+            return (c.N % 256 == 0) ? launch_tc<256, 2, false>(c, stream) : launch_tc<128, 2, false>(c, stream);
+        }
+        if (c.N > 128) return launch_tc<256, 0, false>(c, stream);
+        if (c.N > 64) return launch_tc<128, 0, false>(c, stream);
+        return launch_tc<64, 0, false>(c, stream);
+    }
+    // weight-major
+    const int bn = c.M <= 16 ? 16 : (c.M <= 32 ? 32 : 64);
+    const int mode = c.epi == EPI_PARTIAL ? 1 : (c.epi == EPI_SWIGLU ? 2 : 0);
+#define UMV_WM(BN_)                                                             \
+    (mode == 0 ? launch_tc<BN_, 0, true>(c, stream)                             \
+               : mode == 1 ? launch_tc<BN_, 1, true>(c, stream) : launch_tc<BN_, 2, true>(c, stream))
+    if (bn == 16) return UMV_WM(16);
+    if (bn == 32) return UMV_WM(32);
+    return UMV_WM(64);
+#undef UMV_WM
+}
+
+}  // namespace umv

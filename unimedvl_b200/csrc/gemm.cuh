@@ -1,0 +1,43 @@
+// Host-side interface of the linear-layer kernels (gemm.cu).
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+#include "common.cuh"
+
+namespace umv {
+
+enum Epilogue : int {
+    EPI_BF16 = 0,      // y = bf16(acc + bias)
+    EPI_GELU = 1,      // y = bf16(gelu_tanh(bf16(acc + bias)))
+    EPI_SWIGLU = 2,    // weight rows interleaved [64 gate | 64 up]; y[:, j] = bf16(bf16(silu(g)) * u), g,u = bf16(acc)
+    EPI_RESID = 3,     // y = bf16(bf16(acc + bias) + residual)
+    EPI_PARTIAL = 4,   // fp32 split-K partials ws[split][token][feature] (weight-major only)
+};
+
+enum GemmImpl : int { GEMM_AUTO = 0, GEMM_TOKEN_MAJOR = 1, GEMM_WEIGHT_MAJOR = 2, GEMM_SIMPLE = 3 };
+
+struct LinearCall {
+    const bf16* x = nullptr;        // [M, K] activations, row stride ldx elements
+    int ldx = 0;
+    const bf16* w = nullptr;        // [N, K] weights (nn.Linear layout), contiguous rows
+    const bf16* bias = nullptr;     // [N] or null
+    const bf16* residual = nullptr; // [M, N] (EPI_RESID), row stride ldy
+    bf16* y = nullptr;              // [M, N] (or [M, N/2] for EPI_SWIGLU), row stride ldy
+    int ldy = 0;
+    float* ws = nullptr;            // split-K workspace (EPI_PARTIAL)
+    int splits = 1;
+    int M = 0, N = 0, K = 0;
+    int epi = EPI_BF16;
+    int impl = GEMM_AUTO;
+};
+
+// Returns 0 or a umv_status.  For EPI_PARTIAL the caller sums ws[0..splits) in a fixed order.
+int linear_forward(const LinearCall& c, cudaStream_t stream);
+// Heuristic split count for a weight-major (decode) GEMM: fills the 148 SMs without starving a split.
+int pick_splits(int N, int K, int sm_count);
+// Must be called once before the first tcgen05 launch (resolves cuTensorMapEncodeTiled, sets smem attrs).
+int gemm_init();
+
+extern long long g_launches;   // kernel launch counter (umv_launch_count)
+
+}  // namespace umv

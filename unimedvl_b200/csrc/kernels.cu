@@ -1,0 +1,527 @@
+// HBM-bound glue of the LLM / ViT forward: residual+RMSNorm, LayerNorm, q/k-norm + RoPE + paged KV
+// append, embedding gathers, argmax/sampling and the device-resident decode-loop state.
+// Each kernel restates the reference's bf16 rounding points; they
+// replace the ~6-20 eager elementwise kernels per op of the reference.
+#include "../../include/umv.h"
+#include "common.cuh"
+#include "gemm.cuh"
+#include "kernels.cuh"
+
+namespace umv {
+
+#define UMV_LAUNCH_CHECK(name)                                                        \
+    do {                                                                              \
+        ++g_launches;                                                                 \
+        cudaError_t _e = cudaGetLastError();                                          \
+        if (_e != cudaSuccess) {                                                      \
+            set_error("%s launch failed: %s", name, cudaGetErrorString(_e));          \
+            return UMV_ERR_CUDA;                                                      \
+        }                                                                             \
+    } while (0)
+
+// ------------------------------------------------------------------------------------------
+// h (+= delta) ; y = w * bf16(h * rsqrt(mean(h^2) + eps))          one CTA per row
+constexpr int kNormThreads = 256;
+constexpr int kNormMaxChunks = 8;   // 8 chunks * 8 elems * 256 threads = D <= 16384
+
+__global__ void __launch_bounds__(kNormThreads) add_rmsnorm_kernel(AddNormArgs a) {
+    __shared__ float red[32];
+    const int row = blockIdx.x;
+    const int nchunk = a.D / 8;
+    bf16* hrow = a.h + (size_t)row * a.D;
+    float v[kNormMaxChunks][8];
+    float ss = 0.f;
+#pragma unroll
+    for (int c = 0; c < kNormMaxChunks; ++c) {
+        const int ch = threadIdx.x + c * kNormThreads;
+        if (ch < nchunk) {
+            const U4 hv = ldg16(hrow + ch * 8);
+            const uint32_t* hw = &hv.x;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float2 f = unpack2(hw[j]);
+                v[c][2 * j] = f.x;
+                v[c][2 * j + 1] = f.y;
+            }
+            if (a.delta || a.partial) {
+                float d[8];
+                if (a.delta) {
+                    const U4 dv = ldg16(a.delta + (size_t)row * a.D + ch * 8);
+                    const uint32_t* dw = &dv.x;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const float2 f = unpack2(dw[j]);
+                        d[2 * j] = f.x;
+                        d[2 * j + 1] = f.y;
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) d[j] = 0.f;
+                    for (int s = 0; s < a.splits; ++s) {   // fixed order -> deterministic
+                        const float4* pp = reinterpret_cast<const float4*>(a.partial + ((size_t)s * a.M + row) * a.D + ch * 8);
+                        const float4 p0 = pp[0], p1 = pp[1];
+                        d[0] += p0.x; d[1] += p0.y; d[2] += p0.z; d[3] += p0.w;
+                        d[4] += p1.x; d[5] += p1.y; d[6] += p1.z; d[7] += p1.w;
+                    }
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) d[j] = rbf(d[j]);      // the Linear's own bf16 output (R3)
+                }
+                uint32_t o[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    v[c][2 * j] = rbf(v[c][2 * j] + d[2 * j]);         // residual add in bf16 (R7)
+                    v[c][2 * j + 1] = rbf(v[c][2 * j + 1] + d[2 * j + 1]);
+                    o[j] = pack2(v[c][2 * j], v[c][2 * j + 1]);
+                }
+                stg16(hrow + ch * 8, U4{o[0], o[1], o[2], o[3]});
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) ss += v[c][j] * v[c][j];
+        }
+    }
+    if (a.y == nullptr) return;
+    ss = block_sum(ss, red);
+    const float inv = 1.0f / sqrtf(ss / (float)a.D + a.eps);
+    const bf16* w = (a.row_sel && a.row_sel[row]) ? a.w1 : a.w0;
+    bf16* yrow = a.y + (size_t)row * a.D;
+#pragma unroll
+    for (int c = 0; c < kNormMaxChunks; ++c) {
+        const int ch = threadIdx.x + c * kNormThreads;
+        if (ch < nchunk) {
+            const U4 wv = ldg16(w + ch * 8);
+            const uint32_t* ww = &wv.x;
+            uint32_t o[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float2 wf = unpack2(ww[j]);
+                o[j] = pack2(wf.x * rbf(v[c][2 * j] * inv), wf.y * rbf(v[c][2 * j + 1] * inv));   // R2
+            }
+            stg16(yrow + ch * 8, U4{o[0], o[1], o[2], o[3]});
+        }
+    }
+}
+
+int add_rmsnorm(const AddNormArgs& a, cudaStream_t s) {
+    if (a.M <= 0) return UMV_OK;
+    UMV_REQUIRE(a.D % 8 == 0 && a.D <= 8 * kNormThreads * kNormMaxChunks, UMV_ERR_UNSUPPORTED,
+                "add_rmsnorm: D=%d must be a multiple of 8 and <= %d", a.D, 8 * kNormThreads * kNormMaxChunks);
+    add_rmsnorm_kernel<<<a.M, kNormThreads, 0, s>>>(a);
+    UMV_LAUNCH_CHECK("add_rmsnorm_kernel");
+    return UMV_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// LayerNorm, fp32 statistics (two pass over registers), bf16 out.        one CTA per row
+__global__ void __launch_bounds__(kNormThreads) layernorm_kernel(const bf16* __restrict__ x, const bf16* __restrict__ w,
+                                                                  const bf16* __restrict__ b, bf16* __restrict__ y, int D,
+                                                                  float eps) {
+    __shared__ float red[32];
+    const int row = blockIdx.x;
+    const int nchunk = D / 8;
+    float v[kNormMaxChunks][8];
+    float sum = 0.f;
+#pragma unroll
+    for (int c = 0; c < kNormMaxChunks; ++c) {
+        const int ch = threadIdx.x + c * kNormThreads;
+        if (ch < nchunk) {
+            const U4 hv = ldg16(x + (size_t)row * D + ch * 8);
+            const uint32_t* hw = &hv.x;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float2 f = unpack2(hw[j]);
+                v[c][2 * j] = f.x;
+                v[c][2 * j + 1] = f.y;
+                sum += f.x + f.y;
+            }
+        }
+    }
+    const float mean = block_sum(sum, red) / (float)D;
+    float sq = 0.f;
+#pragma unroll
+    for (int c = 0; c < kNormMaxChunks; ++c) {
+        const int ch = threadIdx.x + c * kNormThreads;
+        if (ch < nchunk) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float dlt = v[c][j] - mean;
+                sq += dlt * dlt;
+            }
+        }
+    }
+    const float var = block_sum(sq, red) / (float)D;
+    const float inv = 1.0f / sqrtf(var + eps);
+#pragma unroll
+    for (int c = 0; c < kNormMaxChunks; ++c) {
+        const int ch = threadIdx.x + c * kNormThreads;
+        if (ch < nchunk) {
+            const U4 wv = ldg16(w + ch * 8), bv = ldg16(b + ch * 8);
+            const uint32_t* ww = &wv.x;
+            const uint32_t* bw = &bv.x;
+            uint32_t o[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float2 wf = unpack2(ww[j]), bf = unpack2(bw[j]);
+                o[j] = pack2((v[c][2 * j] - mean) * inv * wf.x + bf.x, (v[c][2 * j + 1] - mean) * inv * wf.y + bf.y);
+            }
+            stg16(y + (size_t)row * D + ch * 8, U4{o[0], o[1], o[2], o[3]});
+        }
+    }
+}
+
+int layernorm_bf16(const bf16* x, const bf16* w, const bf16* b, bf16* y, int M, int D, float eps, cudaStream_t s) {
+    if (M <= 0) return UMV_OK;
+    UMV_REQUIRE(D % 8 == 0 && D <= 8 * kNormThreads * kNormMaxChunks, UMV_ERR_UNSUPPORTED, "layernorm: bad D=%d", D);
+    layernorm_kernel<<<M, kNormThreads, 0, s>>>(x, w, b, y, D, eps);
+    UMV_LAUNCH_CHECK("layernorm_kernel");
+    return UMV_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// One warp per (row, head-slot): slots [0,H) = q heads, [H,H+Hkv) = k heads, [H+Hkv,H+2Hkv) = v heads.
+// head_dim 128: lane l owns elements 4l..4l+3; the rotate_half partner (i +- 64) lives in lane l^16.
+__global__ void __launch_bounds__(256) rope_append_kernel(RopeAppendArgs a) {
+    const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    const int slots = a.H + 2 * a.Hkv;
+    if (gw >= a.M * slots) return;
+    const int row = gw / slots, slot = gw % slots;
+    const int ncols = slots * a.dh;
+    const int col = slot * a.dh + lane * 4;
+
+    float x[4];
+    if (a.partial) {
+        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+        for (int s = 0; s < a.splits; ++s) {
+            const float4 p = *reinterpret_cast<const float4*>(a.partial + ((size_t)s * a.M + row) * ncols + col);
+            acc[0] += p.x; acc[1] += p.y; acc[2] += p.z; acc[3] += p.w;
+        }
+        const uint2 bv = *reinterpret_cast<const uint2*>(a.bias + col);
+        const float2 b0 = unpack2(bv.x), b1 = unpack2(bv.y);
+        x[0] = rbf(acc[0] + b0.x); x[1] = rbf(acc[1] + b0.y); x[2] = rbf(acc[2] + b1.x); x[3] = rbf(acc[3] + b1.y);
+    } else {
+        const uint2 qv = *reinterpret_cast<const uint2*>(a.qkv + (size_t)row * ncols + col);
+        const float2 f0 = unpack2(qv.x), f1 = unpack2(qv.y);
+        x[0] = f0.x; x[1] = f0.y; x[2] = f1.x; x[3] = f1.y;
+    }
+
+    const bool is_q = slot < a.H;
+    const bool is_v = slot >= a.H + a.Hkv;
+    float o[4];
+    if (is_v) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) o[j] = x[j];
+    } else {
+        const bool gen_row = a.row_sel && a.row_sel[row];
+        const bf16* nw = is_q ? (gen_row ? a.qn1 : a.qn0) : (gen_row ? a.kn1 : a.kn0);
+        float ss = x[0] * x[0] + x[1] * x[1] + x[2] * x[2] + x[3] * x[3];
+        ss = warp_sum(ss);
+        const float inv = 1.0f / sqrtf(ss / (float)a.dh + a.eps);
+        const uint2 wv = *reinterpret_cast<const uint2*>(nw + lane * 4);
+        const float2 w0 = unpack2(wv.x), w1 = unpack2(wv.y);
+        const float w[4] = {w0.x, w0.y, w1.x, w1.y};
+        float n[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            if (a.gen_mode) n[j] = __fmul_rn(w[j], __fmul_rn(x[j], inv));          // fp32 throughout
+            else n[j] = rbf(w[j] * rbf(x[j] * inv));                               // R4: two bf16 roundings
+        }
+        const float pos = (float)a.positions[row];
+        const int half = a.dh / 2;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int i = lane * 4 + j;
+            const float ang = __fmul_rn(pos, a.inv_freq[i % half]);
+            const float c = rbf(cosf(ang)), sn = rbf(sinf(ang));                    // cos/sin cast to bf16 (R5)
+            const float partner = __shfl_xor_sync(0xffffffffu, n[j], 16);
+            const float rot = (i < half) ? -partner : partner;
+            if (a.gen_mode) o[j] = rbf(__fadd_rn(__fmul_rn(n[j], c), __fmul_rn(rot, sn)));
+            else o[j] = rbf(rbf(n[j] * c) + rbf(rot * sn));                         // R5: three roundings
+        }
+    }
+    const uint2 packed = make_uint2(pack2(o[0], o[1]), pack2(o[2], o[3]));
+    if (is_q) {
+        *reinterpret_cast<uint2*>(a.q_out + (size_t)row * a.ldq + col) = packed;
+    } else {
+        const int kv = is_v ? 1 : 0;
+        const int head = slot - a.H - (is_v ? a.Hkv : 0);
+        const int pos_kv = a.row_kvpos[row];
+        const int page = a.page_table[(size_t)a.row_seq[row] * a.max_pages + pos_kv / kPageTokens];
+        bf16* dst = a.pool.base + a.pool.tile_offset(page, a.layer, kv, head) + (size_t)(pos_kv % kPageTokens) * a.dh + lane * 4;
+        *reinterpret_cast<uint2*>(dst) = packed;
+    }
+}
+
+int rope_append(const RopeAppendArgs& a, cudaStream_t s) {
+    if (a.M <= 0) return UMV_OK;
+    UMV_REQUIRE(a.dh == 128, UMV_ERR_UNSUPPORTED, "rope_append: head_dim %d (only 128 is built)", a.dh);
+    const long long warps = (long long)a.M * (a.H + 2 * a.Hkv);
+    const int blocks = (int)((warps * 32 + 255) / 256);
+    rope_append_kernel<<<blocks, 256, 0, s>>>(a);
+    UMV_LAUNCH_CHECK("rope_append_kernel");
+    return UMV_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+__global__ void embed_rows_kernel(const bf16* __restrict__ table, const int64_t* __restrict__ ids, int D, int64_t vocab,
+                                  bf16* __restrict__ out) {
+    const int row = blockIdx.x;
+    int64_t id = ids[row];
+    if (id < 0 || id >= vocab) id = 0;      // host validates ids; never read out of bounds
+    const U4* src = reinterpret_cast<const U4*>(table + (size_t)id * D);
+    U4* dst = reinterpret_cast<U4*>(out + (size_t)row * D);
+    for (int c = threadIdx.x; c < D / 8; c += blockDim.x) dst[c] = src[c];
+}
+int embed_rows(const bf16* table, const int64_t* ids, int n, int D, int64_t vocab, bf16* out, cudaStream_t s) {
+    if (n <= 0) return UMV_OK;
+    embed_rows_kernel<<<n, 128, 0, s>>>(table, ids, D, vocab, out);
+    UMV_LAUNCH_CHECK("embed_rows_kernel");
+    return UMV_OK;
+}
+
+__global__ void gather_add_rows_kernel(bf16* __restrict__ x, const bf16* __restrict__ table, const int64_t* __restrict__ ids,
+                                       int D) {
+    const int row = blockIdx.x;
+    const bf16* t = table + (size_t)ids[row] * D;
+    bf16* xr = x + (size_t)row * D;
+    for (int c = threadIdx.x; c < D / 8; c += blockDim.x) {
+        const U4 a = ldg16(xr + c * 8), b = ldg16(t + c * 8);
+        const uint32_t* aw = &a.x;
+        const uint32_t* bw = &b.x;
+        uint32_t o[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float2 fa = unpack2(aw[j]), fb = unpack2(bw[j]);
+            o[j] = pack2(fa.x + fb.x, fa.y + fb.y);
+        }
+        stg16(xr + c * 8, U4{o[0], o[1], o[2], o[3]});
+    }
+}
+int gather_add_rows(bf16* x, const bf16* table, const int64_t* ids, int M, int D, cudaStream_t s) {
+    if (M <= 0) return UMV_OK;
+    gather_add_rows_kernel<<<M, 128, 0, s>>>(x, table, ids, D);
+    UMV_LAUNCH_CHECK("gather_add_rows_kernel");
+    return UMV_OK;
+}
+
+__global__ void f32_to_bf16_padded_kernel(const float* __restrict__ x, bf16* __restrict__ y, int K, int Kpad) {
+    const int row = blockIdx.x;
+    for (int c = threadIdx.x; c < Kpad; c += blockDim.x)
+        y[(size_t)row * Kpad + c] = c < K ? f2b(x[(size_t)row * K + c]) : f2b(0.f);
+}
+int f32_to_bf16_padded(const float* x, bf16* y, int M, int K, int Kpad, cudaStream_t s) {
+    if (M <= 0) return UMV_OK;
+    f32_to_bf16_padded_kernel<<<M, 128, 0, s>>>(x, y, K, Kpad);
+    UMV_LAUNCH_CHECK("f32_to_bf16_padded_kernel");
+    return UMV_OK;
+}
+
+// rows[]: scatter==0: dst[i] = src[rows[i]] ; scatter==1: dst[rows[i]] = src[i]
+__global__ void copy_rows_kernel(const bf16* __restrict__ src, int lds, const int* __restrict__ rows, bf16* __restrict__ dst,
+                                 int ldd, int D, int scatter) {
+    const int i = blockIdx.x;
+    const int r = rows[i];
+    const bf16* s = src + (size_t)(scatter ? i : r) * lds;
+    bf16* d = dst + (size_t)(scatter ? r : i) * ldd;
+    for (int c = threadIdx.x; c < D / 8; c += blockDim.x) stg16(d + c * 8, ldg16(s + c * 8));
+}
+int copy_rows(const bf16* src, int lds, const int* rows, bf16* dst, int ldd, int n, int D, int scatter, cudaStream_t s) {
+    if (n <= 0) return UMV_OK;
+    copy_rows_kernel<<<n, 128, 0, s>>>(src, lds, rows, dst, ldd, D, scatter);
+    UMV_LAUNCH_CHECK("copy_rows_kernel");
+    return UMV_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// torch.argmax over bf16 logits: maximum value, ties -> lowest index (R8).  One CTA per row.
+__global__ void __launch_bounds__(1024) argmax_kernel(const bf16* __restrict__ logits, int vocab, int64_t* __restrict__ out) {
+    __shared__ float sval[32];
+    __shared__ int sidx[32];
+    const bf16* row = logits + (size_t)blockIdx.x * vocab;
+    float best = -INFINITY;
+    int bi = 0x7fffffff;
+    const int nchunk = vocab / 8;
+    for (int c = threadIdx.x; c < nchunk; c += blockDim.x) {
+        const U4 v = ldg16_stream(row + c * 8);
+        const uint32_t* w = &v.x;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float2 f = unpack2(w[j]);
+            const int i0 = c * 8 + 2 * j;
+            if (f.x > best || (f.x == best && i0 < bi)) { best = f.x; bi = i0; }
+            if (f.y > best || (f.y == best && i0 + 1 < bi)) { best = f.y; bi = i0 + 1; }
+        }
+    }
+    for (int i = nchunk * 8 + threadIdx.x; i < vocab; i += blockDim.x) {
+        const float f = b2f(row[i]);
+        if (f > best || (f == best && i < bi)) { best = f; bi = i; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+    }
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    if (lane == 0) { sval[wid] = best; sidx[wid] = bi; }
+    __syncthreads();
+    if (wid == 0) {
+        const int nw = blockDim.x >> 5;
+        best = lane < nw ? sval[lane] : -INFINITY;
+        bi = lane < nw ? sidx[lane] : 0x7fffffff;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+            if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+        }
+        if (lane == 0) out[blockIdx.x] = (bi == 0x7fffffff) ? 0 : bi;   // all-NaN row -> 0
+    }
+}
+int argmax_rows(const bf16* logits, int rows, int vocab, int64_t* out, cudaStream_t s) {
+    if (rows <= 0) return UMV_OK;
+    UMV_REQUIRE((reinterpret_cast<uintptr_t>(logits) & 15) == 0 && vocab % 8 == 0, UMV_ERR_INVALID,
+                "argmax: logits must be 16-byte aligned with vocab %% 8 == 0 (vocab=%d)", vocab);
+    argmax_kernel<<<rows, 1024, 0, s>>>(logits, vocab, out);
+    UMV_LAUNCH_CHECK("argmax_kernel");
+    return UMV_OK;
+}
+
+// softmax(logits / T) sampling (bagel.py:1298-1299) with a counter-based hash RNG: u ~ U[0,1) from
+// (seed, step, row); inverse-CDF over the fp32 probabilities.  One CTA per row.
+__device__ __forceinline__ uint64_t splitmix64(uint64_t x) {
+    x += 0x9E3779B97F4A7C15ull;
+    x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+    x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+    return x ^ (x >> 31);
+}
+__global__ void __launch_bounds__(1024) sample_kernel(const bf16* __restrict__ logits, int vocab, float inv_t, uint64_t seed,
+                                                       const int* __restrict__ step, int64_t* __restrict__ out) {
+    __shared__ float red[32];
+    __shared__ float s_prefix[1024];
+    const bf16* row = logits + (size_t)blockIdx.x * vocab;
+    float mx = -INFINITY;
+    for (int i = threadIdx.x; i < vocab; i += blockDim.x) mx = fmaxf(mx, rbf(b2f(row[i]) * inv_t));
+    mx = warp_max(mx);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = mx;
+    __syncthreads();
+    mx = red[0];
+    for (int w = 1; w < (blockDim.x >> 5); ++w) mx = fmaxf(mx, red[w]);
+    __syncthreads();
+    // each thread owns a contiguous span so the CDF is in index order
+    const int span = (vocab + blockDim.x - 1) / blockDim.x;
+    const int i0 = threadIdx.x * span, i1 = min(vocab, i0 + span);
+    float local = 0.f;
+    for (int i = i0; i < i1; ++i) local += expf(rbf(b2f(row[i]) * inv_t) - mx);
+    s_prefix[threadIdx.x] = local;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float run = 0.f;
+        for (int t = 0; t < blockDim.x; ++t) { const float v = s_prefix[t]; s_prefix[t] = run; run += v; }
+        red[0] = run;
+    }
+    __syncthreads();
+    const float total = red[0];
+    const uint64_t h = splitmix64(seed ^ splitmix64(((uint64_t)(step ? *step : 0) << 32) | blockIdx.x));
+    const float target = (float)((h >> 40) * (1.0 / 16777216.0)) * total;
+    const float before = s_prefix[threadIdx.x];
+    if (target >= before && (target < before + local || threadIdx.x == blockDim.x - 1) && i0 < i1) {
+        float run = before;
+        int pick = i1 - 1;
+        for (int i = i0; i < i1; ++i) {
+            run += expf(rbf(b2f(row[i]) * inv_t) - mx);
+            if (target < run) { pick = i; break; }
+        }
+        out[blockIdx.x] = pick;
+    }
+}
+int sample_rows(const bf16* logits, int rows, int vocab, float temperature, uint64_t seed, const int* step, int64_t* out,
+                cudaStream_t s) {
+    if (rows <= 0) return UMV_OK;
+    sample_kernel<<<rows, 1024, 0, s>>>(logits, vocab, 1.0f / temperature, seed, step, out);
+    UMV_LAUNCH_CHECK("sample_kernel");
+    return UMV_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// Decode-loop state (device resident so a captured step can be replayed without host work).
+__global__ void decode_begin_kernel(const bf16* __restrict__ table, int D, int64_t vocab, DecodeState st,
+                                    const int64_t* __restrict__ forced, int64_t* __restrict__ tokens_out, int B,
+                                    bf16* __restrict__ x) {
+    const int b = blockIdx.x;
+    const int step = *st.step;
+    int64_t tok = forced ? forced[(size_t)step * B + b] : st.cur_tokens[b];
+    if (threadIdx.x == 0) tokens_out[(size_t)step * B + b] = tok;     // generated_sequence.append(curr_tokens)
+    if (tok < 0 || tok >= vocab) tok = 0;
+    const U4* src = reinterpret_cast<const U4*>(table + (size_t)tok * D);
+    U4* dst = reinterpret_cast<U4*>(x + (size_t)b * D);
+    for (int c = threadIdx.x; c < D / 8; c += blockDim.x) dst[c] = src[c];
+}
+int decode_begin_step(const bf16* table, int D, int64_t vocab, DecodeState st, const int64_t* forced, int64_t* tokens_out,
+                      int B, bf16* x, cudaStream_t s) {
+    decode_begin_kernel<<<B, 128, 0, s>>>(table, D, vocab, st, forced, tokens_out, B, x);
+    UMV_LAUNCH_CHECK("decode_begin_kernel");
+    return UMV_OK;
+}
+__global__ void decode_end_kernel(DecodeState st, int B) {
+    const int b = threadIdx.x;
+    if (b < B) {
+        st.positions[b] += 1;      // packed_query_position_ids + 1 (bagel.py:1310)
+        st.kv_len[b] += 1;         // key_values_lens + 1 (bagel.py:1309)
+        st.row_kvpos[b] += 1;
+    }
+    if (b == 0) *st.step += 1;
+}
+int decode_end_step(DecodeState st, int B, cudaStream_t s) {
+    decode_end_kernel<<<1, 64, 0, s>>>(st, B);
+    UMV_LAUNCH_CHECK("decode_end_kernel");
+    return UMV_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+__global__ void export_kv_kernel(KVPool pool, int layer, const int* __restrict__ pages, int len, bf16* __restrict__ k_out,
+                                 bf16* __restrict__ v_out) {
+    const int t = blockIdx.x, head = blockIdx.y;
+    const int page = pages[t / kPageTokens], slot = t % kPageTokens;
+    const bf16* ks = pool.base + pool.tile_offset(page, layer, 0, head) + (size_t)slot * pool.head_dim;
+    const bf16* vs = pool.base + pool.tile_offset(page, layer, 1, head) + (size_t)slot * pool.head_dim;
+    const size_t o = ((size_t)t * pool.kv_heads + head) * pool.head_dim;
+    for (int i = threadIdx.x; i < pool.head_dim; i += blockDim.x) {
+        k_out[o + i] = ks[i];
+        v_out[o + i] = vs[i];
+    }
+}
+int export_kv(KVPool pool, int layer, const int* pages, int len, bf16* k_out, bf16* v_out, cudaStream_t s) {
+    if (len <= 0) return UMV_OK;
+    export_kv_kernel<<<dim3(len, pool.kv_heads), 128, 0, s>>>(pool, layer, pages, len, k_out, v_out);
+    UMV_LAUNCH_CHECK("export_kv_kernel");
+    return UMV_OK;
+}
+
+__global__ void copy_page_kernel(KVPool pool, int src_page, int dst_page) {
+    const size_t n = (size_t)pool.layers * 2 * pool.kv_heads * pool.tile_elems() / 8;
+    const U4* s = reinterpret_cast<const U4*>(pool.base + pool.tile_offset(src_page, 0, 0, 0));
+    U4* d = reinterpret_cast<U4*>(pool.base + pool.tile_offset(dst_page, 0, 0, 0));
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) d[i] = s[i];
+}
+int copy_page(KVPool pool, int src_page, int dst_page, cudaStream_t s) {
+    copy_page_kernel<<<148, 256, 0, s>>>(pool, src_page, dst_page);
+    UMV_LAUNCH_CHECK("copy_page_kernel");
+    return UMV_OK;
+}
+
+// Synthetic weights: uniform(mean - bound, mean + bound) from a counter hash (benchmark random init).
+__global__ void fill_uniform_kernel(bf16* __restrict__ p, size_t n, uint64_t seed, float bound, float mean) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const uint64_t h = splitmix64(seed + i);
+        const float u = (float)(h >> 40) * (1.0f / 16777216.0f);
+        p[i] = f2b(mean + bound * (2.f * u - 1.f));
+    }
+}
+int fill_uniform_bf16(bf16* p, size_t n, uint64_t seed, float bound, float mean, cudaStream_t s) {
+    if (n == 0) return UMV_OK;
+    fill_uniform_kernel<<<148 * 8, 256, 0, s>>>(p, n, seed, bound, mean);
+    UMV_LAUNCH_CHECK("fill_uniform_kernel");
+    return UMV_OK;
+}
+
+}  // namespace umv

@@ -1,0 +1,109 @@
+// Host-side interface of the HBM-bound glue kernels (kernels.cu) and attention (attention.cu).
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+#include "common.cuh"
+
+namespace umv {
+
+constexpr int kPageTokens = 64;
+
+// Paged KV pool geometry: pool[page][layer][k|v][kv_head][slot][head_dim] bf16.
+struct KVPool {
+    bf16* base = nullptr;
+    int layers = 0, kv_heads = 0, head_dim = 0;
+    __host__ __device__ size_t tile_elems() const { return (size_t)kPageTokens * head_dim; }
+    __host__ __device__ size_t tile_offset(int page, int layer, int kv, int head) const {
+        return ((((size_t)page * layers + layer) * 2 + kv) * kv_heads + head) * tile_elems();
+    }
+};
+
+// ---- residual add + RMSNorm (Qwen2RMSNorm, modeling_qwen2.py:89-94; residual adds qwen2_navit.py:883,901)
+struct AddNormArgs {
+    bf16* h = nullptr;              // [M, D] residual stream; updated in place when a delta is given
+    const bf16* delta = nullptr;    // [M, D] bf16 linear output, or
+    const float* partial = nullptr; // [splits][M][D] fp32 split-K partials of that linear output
+    int splits = 0;
+    const bf16* w0 = nullptr;       // norm weight for rows with row_sel == 0 (understanding expert)
+    const bf16* w1 = nullptr;       // norm weight for rows with row_sel == 1 (generation expert)
+    const uint8_t* row_sel = nullptr;
+    bf16* y = nullptr;              // [M, D] normalised output (null: only the residual add)
+    int M = 0, D = 0;
+    float eps = 1e-6f;
+};
+int add_rmsnorm(const AddNormArgs& a, cudaStream_t s);
+
+// nn.LayerNorm under CUDA autocast (fp32 math) followed by the consumer Linear's cast: bf16 out.
+int layernorm_bf16(const bf16* x, const bf16* w, const bf16* b, bf16* y, int M, int D, float eps, cudaStream_t s);
+
+// ---- q/k RMSNorm + RoPE + KV append (qwen2_navit.py:544-545,568-600; modeling_qwen2.py:164-220)
+struct RopeAppendArgs {
+    const bf16* qkv = nullptr;       // [M, (H+2Hkv)*dh] bf16 (bias already applied), or
+    const float* partial = nullptr;  // [splits][M][(H+2Hkv)*dh] fp32 partials (+ bias below)
+    int splits = 0;
+    const bf16* bias = nullptr;      // used with `partial`
+    bf16* q_out = nullptr;           // [M, ldq] rotated queries (may alias qkv)
+    int ldq = 0;
+    const int* positions = nullptr;  // [M] rope position per row
+    const int* row_seq = nullptr;    // [M] index into the page table rows
+    const int* row_kvpos = nullptr;  // [M] absolute KV slot of the row within its sequence
+    const int* page_table = nullptr; // [n_seqs][max_pages]
+    int max_pages = 0;
+    const float* inv_freq = nullptr; // [dh/2] fp32
+    const bf16* qn0 = nullptr; const bf16* kn0 = nullptr;   // understanding q_norm / k_norm
+    const bf16* qn1 = nullptr; const bf16* kn1 = nullptr;   // *_moe_gen
+    const uint8_t* row_sel = nullptr;                        // null in "und" mode
+    int gen_mode = 0;                // 1: fp32 norm+rope, single rounding (qwen2_navit.py:568-583)
+    KVPool pool; int layer = 0;
+    int M = 0, H = 0, Hkv = 0, dh = 0;
+    float eps = 1e-6f;
+};
+int rope_append(const RopeAppendArgs& a, cudaStream_t s);
+
+// ---- attention (flash_attn_varlen_func call sites qwen2_navit.py:605-614, siglip_navit.py:232-241)
+struct AttnArgs {
+    const bf16* q = nullptr; int ldq = 0;     // row (token) stride in elements; head h at column h*dh
+    bf16* out = nullptr; int ldo = 0;
+    // un-paged K/V (ViT, op-level): [Tk, Hkv, dh] with row strides
+    const bf16* k = nullptr; const bf16* v = nullptr; int ldk = 0, ldv = 0;
+    // paged K/V (LLM)
+    int paged = 0; KVPool pool; int layer = 0; const int* page_table = nullptr; int max_pages = 0;
+    const int* q_start = nullptr;   // device [n+1] cumulative query offsets
+    const int* k_start = nullptr;   // device [n+1] cumulative key offsets (un-paged only)
+    const int* q_len = nullptr;     // device [n]
+    const int* kv_len = nullptr;    // device [n] keys visible to the sample (past + new)
+    int n = 0, H = 0, Hkv = 0, dh = 0, causal = 0;
+    int max_q_len = 0;              // host upper bound (grid sizing)
+    int max_kv_len = 0;             // host upper bound (split sizing)
+    int splits = 1;                 // split-KV factor (>1 needs ws)
+    float* ws = nullptr;            // [splits][total_q*H][dh+1] fp32 partial outputs + lse
+    int total_q = 0;
+};
+int attention_forward(const AttnArgs& a, cudaStream_t s);
+int attention_init();   // once per process, before any capture
+
+// ---- misc
+int embed_rows(const bf16* table, const int64_t* ids, int n, int D, int64_t vocab, bf16* out, cudaStream_t s);
+int gather_add_rows(bf16* x, const bf16* table, const int64_t* ids, int M, int D, cudaStream_t s);  // x[m] = bf16(x[m] + table[ids[m]])
+int f32_to_bf16_padded(const float* x, bf16* y, int M, int K, int Kpad, cudaStream_t s);
+int argmax_rows(const bf16* logits, int rows, int vocab, int64_t* out, cudaStream_t s);
+int copy_rows(const bf16* src, int lds, const int* rows, bf16* dst, int ldd, int n, int D, int scatter, cudaStream_t s);
+int fill_uniform_bf16(bf16* p, size_t n, uint64_t seed, float bound, float mean, cudaStream_t s);
+
+// decode-loop state kernels (Bagel.generate_text, bagel.py:1262-1311)
+struct DecodeState {
+    int64_t* cur_tokens;     // [B]
+    int* positions;          // [B] rope position of the next query
+    int* kv_len;             // [B] KV length including the token being processed this step
+    int* row_kvpos;          // [B] slot the new token's K/V go to (= kv_len - 1)
+    int* step;               // [1]
+};
+int decode_begin_step(const bf16* table, int D, int64_t vocab, DecodeState st, const int64_t* forced, int64_t* tokens_out,
+                      int B, bf16* x, cudaStream_t s);
+int decode_end_step(DecodeState st, int B, cudaStream_t s);
+int sample_rows(const bf16* logits, int rows, int vocab, float temperature, uint64_t seed, const int* step, int64_t* out,
+                cudaStream_t s);
+int export_kv(KVPool pool, int layer, const int* pages, int len, bf16* k_out, bf16* v_out, cudaStream_t s);
+int copy_page(KVPool pool, int src_page, int dst_page, cudaStream_t s);
+
+}  // namespace umv

@@ -1,0 +1,246 @@
+"""Python handle on the CUDA engine (libumv.so).  torch is used for device memory and streams only;
+every compute call goes through the C ABI of include/umv.h."""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Iterable, Sequence
+
+import torch
+
+from . import _lib
+from .config import BagelDims
+
+
+def _ptr(t: torch.Tensor | None):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _stream_ptr(stream: torch.cuda.Stream | None = None):
+    s = stream if stream is not None else torch.cuda.current_stream()
+    return C.c_void_p(s.cuda_stream)
+
+
+class Engine:
+    """One engine per GPU per process (matches the reference's single-device usage,
+    codes/interactive_vqa_inferencer.py:19-20).  Owns weights, the KV page pool and workspaces."""
+
+    def __init__(self, dims: BagelDims, max_tokens: int = 2048, max_seqs: int = 8, kv_pages: int = 256,
+                 enable_vit: bool = True, enable_gen: bool = True, device: int | None = None):
+        if not torch.cuda.is_available():
+            raise _lib.UmvError("unimedvl_b200 needs a CUDA device: the engine has no CPU fallback")
+        self.lib = _lib.load()
+        if device is not None:
+            torch.cuda.set_device(device)
+        self.device = torch.device("cuda", torch.cuda.current_device())
+        self.dims = dims
+        # the engine replays captured decode steps: use a non-default stream for all work
+        self.stream = torch.cuda.Stream(device=self.device)
+        l, v = dims.llm, dims.vit
+        d = _lib.Dims(
+            hidden=l.hidden, heads=l.heads, kv_heads=l.kv_heads, inter=l.inter, layers=l.layers, vocab=l.vocab,
+            rope_theta=l.rope_theta, rms_eps=l.eps,
+            vit_hidden=v.hidden, vit_heads=v.heads, vit_inter=v.inter, vit_layers=v.layers, vit_patch_dim=v.patch_dim,
+            vit_positions=v.num_positions, vit_eps=v.eps, vit_pos_table=dims.vit_max_num_patch_per_side ** 2,
+            latent_dim=dims.patch_latent_dim, latent_pos_table=dims.max_latent_size ** 2,
+            max_tokens=max_tokens, max_seqs=max_seqs, kv_pages=kv_pages,
+            enable_vit=int(enable_vit), enable_gen=int(enable_gen))
+        self._c_dims = d
+        h = C.c_void_p()
+        _lib.check(self.lib.umv_create(C.byref(d), C.byref(h)))
+        self.h = h
+        self.max_tokens, self.max_seqs = max_tokens, max_seqs
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.umv_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------ weights
+    def load_state_dict(self, sd: dict, strict: bool = True) -> None:
+        """Reference state_dict keys; tensors may live on CPU or the GPU."""
+        for name, t in sd.items():
+            t = t.detach()
+            if t.dtype not in (torch.bfloat16, torch.float32):
+                raise ValueError(f"{name}: dtype {t.dtype} (bf16 or fp32 expected)")
+            if t.dtype == torch.float32 and t.is_cuda:
+                t = t.to(torch.bfloat16)
+            t = t.contiguous()
+            shape = _lib.i64_array(t.shape)
+            rc = self.lib.umv_load_tensor(self.h, name.encode(), _ptr(t), _lib.BF16 if t.dtype == torch.bfloat16 else _lib.F32,
+                                          t.dim(), shape, int(t.is_cuda))
+            if rc == _lib.ERR_INVALID and not strict and "unknown tensor" in self.lib.umv_last_error().decode():
+                continue
+            _lib.check(rc)
+        torch.cuda.synchronize()
+
+    def fill_synthetic(self, seed: int = 0) -> None:
+        _lib.check(self.lib.umv_fill_synthetic(self.h, C.c_uint64(seed)))
+
+    def finalize(self) -> None:
+        _lib.check(self.lib.umv_finalize(self.h))
+
+    def export_tensor(self, name: str, shape: Sequence[int]) -> torch.Tensor:
+        out = torch.empty(tuple(shape), dtype=torch.bfloat16)
+        _lib.check(self.lib.umv_export_tensor(self.h, name.encode(), _ptr(out), out.numel() * 2))
+        return out
+
+    def weight_bytes(self) -> int:
+        n = C.c_int64()
+        _lib.check(self.lib.umv_weight_bytes(self.h, C.byref(n)))
+        return n.value
+
+    # ---------------------------------------------------------------- sequences
+    def seq_new(self) -> int:
+        s = C.c_int32()
+        _lib.check(self.lib.umv_seq_new(self.h, C.byref(s)))
+        return s.value
+
+    def seq_fork(self, src: int) -> int:
+        s = C.c_int32()
+        _lib.check(self.lib.umv_seq_fork(self.h, src, C.byref(s)))
+        return s.value
+
+    def seq_free(self, seq: int) -> None:
+        if self.h:
+            _lib.check(self.lib.umv_seq_free(self.h, seq))
+
+    def seq_len(self, seq: int) -> int:
+        n = C.c_int32()
+        _lib.check(self.lib.umv_seq_len(self.h, seq, C.byref(n)))
+        return n.value
+
+    def seq_truncate(self, seq: int, length: int) -> None:
+        _lib.check(self.lib.umv_seq_truncate(self.h, seq, length))
+
+    def pages_free(self) -> int:
+        n = C.c_int32()
+        _lib.check(self.lib.umv_pages_free(self.h, C.byref(n)))
+        return n.value
+
+    def seq_export(self, seq: int, layer: int):
+        """Packed [len, kv_heads, head_dim] K and V of one layer (NaiveCache layout)."""
+        n = self.seq_len(seq)
+        l = self.dims.llm
+        k = torch.empty((n, l.kv_heads, l.head_dim), dtype=torch.bfloat16, device=self.device)
+        v = torch.empty_like(k)
+        with torch.cuda.stream(self.stream):
+            _lib.check(self.lib.umv_seq_export(self.h, seq, layer, _ptr(k), _ptr(v), _stream_ptr(self.stream)))
+        self.stream.synchronize()
+        return k, v
+
+    # ------------------------------------------------------------------ forward
+    def _enter(self):
+        """Order the engine stream after whatever the caller queued on the current stream."""
+        self.stream.wait_stream(torch.cuda.current_stream())
+
+    def _exit(self):
+        torch.cuda.current_stream().wait_stream(self.stream)
+
+    def embed_tokens(self, ids: torch.Tensor) -> torch.Tensor:
+        ids = ids.to(self.device, torch.int64).contiguous()
+        out = torch.empty((ids.numel(), self.dims.llm.hidden), dtype=torch.bfloat16, device=self.device)
+        self._enter()
+        _lib.check(self.lib.umv_embed_tokens(self.h, _ptr(ids), ids.numel(), _ptr(out), _stream_ptr(self.stream)))
+        self._exit()
+        return out
+
+    def vit_embed(self, pixels: torch.Tensor, pos_ids: torch.Tensor, seqlens: Iterable[int]) -> torch.Tensor:
+        pixels = pixels.to(self.device, torch.float32).contiguous()
+        pos_ids = pos_ids.to(self.device, torch.int64).contiguous()
+        lens = [int(x) for x in seqlens]
+        out = torch.empty((pixels.shape[0], self.dims.llm.hidden), dtype=torch.bfloat16, device=self.device)
+        self._enter()
+        _lib.check(self.lib.umv_vit_embed(self.h, _ptr(pixels), _ptr(pos_ids), _lib.i32_array(lens), len(lens), _ptr(out),
+                                          _stream_ptr(self.stream)))
+        self._exit()
+        return out
+
+    def llm_forward(self, x: torch.Tensor, seqs: Sequence[int], q_lens: Sequence[int], positions: Sequence[int],
+                    row_is_gen=None, is_causal: bool = True, update_kv: bool = True, want_hidden: bool = True):
+        x = x.to(self.device, torch.bfloat16).contiguous()
+        M = x.shape[0]
+        assert len(positions) == M and sum(int(q) for q in q_lens) == M
+        out = torch.empty_like(x) if want_hidden else None
+        sel = None
+        if row_is_gen is not None:
+            sel = (C.c_uint8 * M)(*[int(b) for b in row_is_gen])
+        self._enter()
+        _lib.check(self.lib.umv_llm_forward(self.h, _ptr(x), len(seqs), _lib.i32_array(seqs), _lib.i32_array(q_lens),
+                                            _lib.i32_array(positions), sel, int(is_causal), int(update_kv), _ptr(out),
+                                            _stream_ptr(self.stream)))
+        self._exit()
+        return out
+
+    def lm_head(self, hidden: torch.Tensor) -> torch.Tensor:
+        hidden = hidden.to(self.device, torch.bfloat16).contiguous()
+        out = torch.empty((hidden.shape[0], self.dims.llm.vocab), dtype=torch.bfloat16, device=self.device)
+        self._enter()
+        _lib.check(self.lib.umv_lm_head(self.h, _ptr(hidden), hidden.shape[0], _ptr(out), _stream_ptr(self.stream)))
+        self._exit()
+        return out
+
+    def generate_text(self, seqs: Sequence[int], start_tokens: Sequence[int], positions: Sequence[int], n_steps: int,
+                      temperature: float = 0.0, seed: int = 0, forced_tokens: torch.Tensor | None = None,
+                      return_logits: bool = False):
+        """Bagel.generate_text (bagel.py:1236-1317) without the EOS early-exit: returns i64 [n_steps, B]
+        (row 0 = start tokens) and optionally bf16 logits [n_steps, B, vocab]."""
+        B = len(seqs)
+        toks = torch.empty((n_steps, B), dtype=torch.int64, device=self.device)
+        logits = torch.empty((n_steps, B, self.dims.llm.vocab), dtype=torch.bfloat16, device=self.device) if return_logits else None
+        if forced_tokens is not None:
+            forced_tokens = forced_tokens.to(self.device, torch.int64).contiguous()
+            assert tuple(forced_tokens.shape) == (n_steps, B)
+        self._enter()
+        _lib.check(self.lib.umv_generate_text(self.h, B, _lib.i32_array(seqs), _lib.i64_array(start_tokens),
+                                              _lib.i32_array(positions), n_steps, C.c_float(temperature), C.c_uint64(seed),
+                                              _ptr(forced_tokens), _ptr(toks), _ptr(logits), _stream_ptr(self.stream)))
+        self._exit()
+        return (toks, logits) if return_logits else toks
+
+    def launch_count(self) -> int:
+        return int(self.lib.umv_launch_count())
+
+
+# ------------------------------------------------------------------------ op-level (parity tests)
+def op_linear(x, w, bias=None, residual=None, epi: int = 0, impl: int = 0) -> torch.Tensor:
+    lib = _lib.load()
+    M, K = x.shape
+    N = w.shape[0]
+    y = torch.empty((M, N // 2 if epi == 2 else N), dtype=torch.bfloat16, device=x.device)
+    _lib.check(lib.umv_op_linear(_ptr(x), _ptr(w), _ptr(bias), _ptr(residual), _ptr(y), M, N, K, epi, impl, _stream_ptr()))
+    return y
+
+
+def op_rmsnorm(x, w, eps=1e-6) -> torch.Tensor:
+    lib = _lib.load()
+    y = torch.empty_like(x)
+    _lib.check(lib.umv_op_rmsnorm(_ptr(x), _ptr(w), _ptr(y), x.shape[0], x.shape[1], C.c_float(eps), _stream_ptr()))
+    return y
+
+
+def op_layernorm(x, w, b, eps=1e-6) -> torch.Tensor:
+    lib = _lib.load()
+    y = torch.empty_like(x)
+    _lib.check(lib.umv_op_layernorm(_ptr(x), _ptr(w), _ptr(b), _ptr(y), x.shape[0], x.shape[1], C.c_float(eps), _stream_ptr()))
+    return y
+
+
+def op_attention(q, k, v, q_lens, k_lens, causal: bool) -> torch.Tensor:
+    lib = _lib.load()
+    out = torch.empty_like(q)
+    _lib.check(lib.umv_op_attention(_ptr(q), _ptr(k), _ptr(v), _ptr(out), len(q_lens), _lib.i32_array(q_lens),
+                                    _lib.i32_array(k_lens), q.shape[1], k.shape[1], q.shape[2], int(causal), _stream_ptr()))
+    return out
+
+
+def op_argmax(logits) -> torch.Tensor:
+    lib = _lib.load()
+    out = torch.empty((logits.shape[0],), dtype=torch.int64, device=logits.device)
+    _lib.check(lib.umv_op_argmax(_ptr(logits), logits.shape[0], logits.shape[1], _ptr(out), _stream_ptr()))
+    return out
