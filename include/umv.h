@@ -118,10 +118,13 @@ int umv_lm_head(umv_engine* e, const void* hidden, int32_t m, void* logits, void
  * [n_steps, n_seqs] device, optional) teacher-forces the inputs; logits_out (bf16
  * [n_steps, n_seqs, vocab] device, optional) receives every step's logits.  temperature <= 0 ->
  * argmax (ties -> lowest index, torch.argmax); > 0 -> softmax(logits/T) sampling with the engine's
- * own counter-based RNG (seed).  KV lengths advance by n_steps. */
+ * own counter-based RNG (seed).  next_tokens_out (i64 [n_seqs] device, optional) receives the token
+ * computed by the last step (the reference discards it; a caller that continues the loop in chunks
+ * feeds it back as start_tokens).  KV lengths advance by n_steps. */
 int umv_generate_text(umv_engine* e, int32_t n_seqs, const int32_t* seqs, const int64_t* start_tokens,
                       const int32_t* positions, int32_t n_steps, float temperature, uint64_t seed,
-                      const int64_t* forced_tokens, int64_t* tokens_out, void* logits_out, void* stream);
+                      const int64_t* forced_tokens, int64_t* tokens_out, void* logits_out,
+                      int64_t* next_tokens_out, void* stream);
 
 /* ---- rectified-flow step: Bagel._forward_flow (bagel.py:989-1211) -------------------------
  * One velocity evaluation incl. up to three LLM forwards (main / cfg_text / cfg_img contexts) and
@@ -165,6 +168,12 @@ int umv_op_attention(const void* q, const void* k, const void* v, void* out, int
                      const int32_t* k_lens, int32_t heads, int32_t kv_heads, int32_t head_dim, int32_t causal,
                      void* stream);
 int umv_op_argmax(const void* logits, int32_t rows, int32_t vocab, int64_t* out, void* stream);
+
+/* Measurement hook (bench.py roofline): launch ONE weight-major decode linear of layer `layer` exactly
+ * as the decode step does, on m rows of the engine's activation workspace.  which: 0 qkv (split-K
+ * partials), 1 o_proj, 2 gate/up + SwiGLU, 3 down_proj, 4 lm_head.  *weight_bytes receives the bytes of
+ * weights the launch streams (the algorithmic HBM traffic besides the m activation rows). */
+int umv_bench_decode_linear(umv_engine* e, int32_t which, int32_t layer, int32_t m, int64_t* weight_bytes, void* stream);
 
 /* Kernel launches issued by this library since load (bench.py "gpu_launches"). */
 int64_t umv_launch_count(void);

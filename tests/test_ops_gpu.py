@@ -1,0 +1,100 @@
+"""Op-level parity on the B200, through the C ABI (umv_op_*): every kernel the model path launches vs the
+oracle / a plain torch fp32 restatement of the same op.  Tolerances: elementwise ops (norms, epilogue math)
+are bit-exact up to rare 1-ulp flips from fp32 reduction order; contractions accumulate in fp32 in a
+different order than the oracle, so results agree to <= 1 bf16 ulp on all but a small fraction."""
+import pytest
+import torch
+
+from oracle import numerics as nm
+from util import ulp_stats
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from unimedvl_b200 import engine
+    return engine
+
+
+def _ref_linear(x, w, b, res, epi):
+    M, N = x.shape[0], w.shape[0]
+    acc = x.float() @ w.float().T
+    if epi == 2:
+        v = acc.view(M, N // 128, 2, 64)
+        g, u = v[:, :, 0].reshape(M, N // 2).bfloat16(), v[:, :, 1].reshape(M, N // 2).bfloat16()
+        return torch.nn.functional.silu(g) * u
+    y = (acc + b.float()).bfloat16()
+    if epi == 1:
+        y = torch.nn.functional.gelu(y, approximate="tanh")
+    if epi == 3:
+        y = y + res
+    return y
+
+
+@pytest.mark.parametrize("M,N,K", [(8, 4608, 3584), (1, 896, 896), (16, 3584, 3584), (33, 1152, 896), (64, 2048, 896),
+                                   (8, 3584, 18944), (130, 896, 64), (300, 3456, 1152), (1000, 1152, 4304), (70, 64, 896),
+                                   (1026, 3072, 896), (257, 432, 144)])
+def test_linear_all_paths(ops, M, N, K):
+    torch.manual_seed(M * 7 + N)
+    x = torch.randn(M, K, device="cuda").bfloat16()
+    w = (torch.randn(N, K, device="cuda") / K ** 0.5).bfloat16()
+    b = (torch.randn(N, device="cuda") * 0.1).bfloat16()
+    res = torch.randn(M, N, device="cuda").bfloat16()
+    for epi in (0, 1, 3, 2):
+        if epi == 2 and N % 128:
+            continue
+        ref = _ref_linear(x, w, b, res, epi)
+        for impl in (3, 1, 2):                    # simple CUDA-core kernel, tcgen05 token-major, tcgen05 weight-major
+            if impl == 2 and M > 64:
+                continue
+            y = ops.op_linear(x, w, None if epi == 2 else b, res if epi == 3 else None, epi=epi, impl=impl)
+            s = ulp_stats(y, ref)
+            assert not torch.isnan(y.float()).any()
+            assert s["rel_l2"] < 1e-3 and s["frac_gt1"] < 2e-3, (M, N, K, epi, impl, s)
+
+
+def test_linear_rejects_unaligned_rows(ops):
+    x = torch.randn(4, 588, device="cuda").bfloat16()
+    w = torch.randn(64, 588, device="cuda").bfloat16()
+    y = ops.op_linear(x, w, impl=0)              # auto: falls to the CUDA-core kernel (588*2 B rows are not TMA-addressable)
+    assert ulp_stats(y, (x.float() @ w.float().T).bfloat16())["rel_l2"] < 1e-3
+    with pytest.raises(ValueError):
+        ops.op_linear(x, w, impl=1)
+
+
+@pytest.mark.parametrize("M,D", [(8, 3584), (100, 896), (3, 128), (1, 8), (17, 1152), (50, 144)])
+def test_norms(ops, M, D):
+    torch.manual_seed(D)
+    x = torch.randn(M, D).bfloat16()
+    w = (1 + 0.1 * torch.randn(D)).bfloat16()
+    b = (0.1 * torch.randn(D)).bfloat16()
+    s = ulp_stats(ops.op_rmsnorm(x.cuda(), w.cuda()), nm.rmsnorm(x, w, 1e-6))
+    assert s["max_ulp"] <= 1 and s["frac"] < 1e-3, s
+    s = ulp_stats(ops.op_layernorm(x.cuda(), w.cuda(), b.cuda()), nm.layernorm(x, w, b, 1e-6, nm.Semantics.cuda).bfloat16())
+    assert s["frac"] < 1e-3 and s["rel_l2"] < 1e-4, s
+
+
+def test_argmax_ties_go_to_lowest_index(ops):
+    torch.manual_seed(0)
+    for V in (2048, 152064):
+        lg = torch.randn(8, V).bfloat16()
+        lg[3, 100] = lg[3, 7] = 50.0
+        lg[5, V - 1] = lg[5, V - 2] = 60.0
+        assert torch.equal(ops.op_argmax(lg.cuda()).cpu(), torch.argmax(lg, -1))
+
+
+@pytest.mark.parametrize("dh,H,Hkv,ql,kl,causal", [
+    (128, 7, 1, [5, 70], [5, 70], True), (128, 7, 1, [1, 1], [100, 37], True), (128, 7, 1, [64], [64], False),
+    (72, 2, 2, [48, 20, 200], [48, 20, 200], False), (128, 28, 4, [130], [300], True), (128, 28, 4, [130], [300], False),
+    (72, 16, 16, [1024], [1024], False), (128, 28, 4, [1, 1, 1], [1058, 1185, 64], True), (128, 7, 1, [34, 12], [1060, 50], True),
+    (128, 4, 4, [1], [1], True), (72, 2, 2, [1], [1], False)])
+def test_attention_varlen(ops, dh, H, Hkv, ql, kl, causal):
+    torch.manual_seed(sum(kl))
+    q = torch.randn(sum(ql), H, dh).bfloat16()
+    k = torch.randn(sum(kl), Hkv, dh).bfloat16()
+    v = torch.randn(sum(kl), Hkv, dh).bfloat16()
+    o = ops.op_attention(q.cuda(), k.cuda(), v.cuda(), ql, kl, causal)
+    s = ulp_stats(o, nm.attention_varlen(q, k, v, ql, kl, causal))
+    # both sides round P to bf16 but the online softmax rescales per 64-key block: <= few ulp, tiny rel error
+    assert not torch.isnan(o.float()).any() and s["rel_l2"] < 4e-3, s

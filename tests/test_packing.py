@@ -1,0 +1,69 @@
+"""Host packing vs fixtures produced by the reference's Bagel.prepare_* (tests/golden/make_golden.py, G1).
+Integer / fp32 host work -> bit-exact."""
+import numpy as np
+import torch
+from PIL import Image
+
+from unimedvl_b200 import packing, synth
+from util import Golden, TOK
+
+
+class FakeTokenizer:
+    def encode(self, text):
+        return [(ord(c) * 7 + i * 13) % 2000 for i, c in enumerate(text)]
+
+
+def _imgs(sizes, base=0):
+    return [Image.fromarray(synth.synthetic_image(base + i, h, w)) for i, (h, w) in enumerate(sizes)]
+
+
+def _cmp(got: dict, g: Golden, prefix: str):
+    want = g.group(prefix)
+    for k, w in want.items():
+        if k in ("newlens", "new_rope"):
+            continue
+        v = got[k]
+        if not torch.is_tensor(v):
+            v = torch.as_tensor(np.asarray(v))
+        assert v.dtype == w.dtype, (prefix, k, v.dtype, w.dtype)
+        assert v.shape == w.shape, (prefix, k, v.shape, w.shape)
+        assert torch.equal(v, w), (prefix, k)
+    assert set(got) >= set(k for k in want if k not in ("newlens", "new_rope"))
+
+
+def test_packing_matches_reference():
+    g = Golden("packing")
+    tok = FakeTokenizer()
+    vit_tf = packing.ImageTransform(980, 28, 14)
+    vae_tf = packing.ImageTransform(1024, 32, 16)
+    imgs = _imgs([(84, 112), (56, 70), (100, 61)])
+    d, lens, rope = packing.prepare_vit_images([0, 5, 9], [0, 5, 3], imgs, vit_tf, TOK)
+    _cmp(d, g, "vit")
+    assert lens == g.t("vit.newlens").tolist() and rope == g.t("vit.new_rope").tolist()
+    d, lens2, rope2 = packing.prepare_prompts(lens, rope, ["What is shown?", "Describe.", "x"], tok, TOK)
+    _cmp(d, g, "prompts")
+    assert lens2 == g.t("prompts.newlens").tolist() and rope2 == g.t("prompts.new_rope").tolist()
+    _cmp(packing.prepare_start_tokens(lens2, rope2, TOK), g, "start")
+    d, lens3, rope3 = packing.prepare_vae_images(lens2, rope2, imgs, vae_tf, TOK)
+    shapes = d.pop("patchified_vae_latent_shapes")
+    assert [list(s) for s in shapes] == g.t("vaeimg.patchified_vae_latent_shapes").tolist()
+    _cmp({**d, "patchified_vae_latent_shapes": np.asarray(shapes)}, g, "vaeimg")
+    assert lens3 == g.t("vaeimg.newlens").tolist() and rope3 == g.t("vaeimg.new_rope").tolist()
+    torch.manual_seed(42)
+    _cmp(packing.prepare_vae_latent(lens2, rope2, [(64, 64), (64, 96), (32, 48)], TOK), g, "latent")
+    _cmp(packing.prepare_vae_latent_cfg([3, 0, 7], [3, 0, 2], [(64, 64), (64, 96), (32, 48)]), g, "latentcfg")
+
+
+def test_image_transform_matches_reference():
+    g = Golden("packing")
+    t = packing.ImageTransform(980, 378, 14)(Image.fromarray(synth.synthetic_image(7, 300, 500)))
+    assert torch.equal(t, g.t("transform.300x500"))
+    t = packing.ImageTransform(1024, 32, 16)(Image.fromarray(synth.synthetic_image(8, 50, 70)))
+    assert torch.equal(t, g.t("transform.vae.50x70"))
+
+
+def test_empty_and_single():
+    d, lens, rope = packing.prepare_prompts([0], [0], [""], FakeTokenizer(), TOK)
+    assert d["packed_text_ids"].tolist() == [TOK["bos_token_id"], TOK["eos_token_id"]] and lens == [2] and rope == [2]
+    s = packing.prepare_start_tokens([], [], TOK)
+    assert s["packed_start_tokens"].numel() == 0 and s["packed_key_value_indexes"].numel() == 0

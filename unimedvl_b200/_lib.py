@@ -64,7 +64,7 @@ SIGNATURES = {
     "umv_embed_tokens": (C.c_int, [_P, _P, _I, _P, _P]),
     "umv_llm_forward": (C.c_int, [_P, _P, _I, _IP, _IP, _IP, C.POINTER(C.c_uint8), _I, _I, _P, _P]),
     "umv_lm_head": (C.c_int, [_P, _P, _I, _P, _P]),
-    "umv_generate_text": (C.c_int, [_P, _I, _IP, _LP, _IP, _I, _F, _U64, _P, _P, _P, _P]),
+    "umv_generate_text": (C.c_int, [_P, _I, _IP, _LP, _IP, _I, _F, _U64, _P, _P, _P, _P, _P]),
     "umv_flow_velocity": (C.c_int, [_P, C.POINTER(FlowArgs), _P, _P, _P]),
     "umv_flow_euler": (C.c_int, [_P, _P, _P, C.c_int64, _F, _I, _P]),
     "umv_op_linear": (C.c_int, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P]),
@@ -72,6 +72,7 @@ SIGNATURES = {
     "umv_op_layernorm": (C.c_int, [_P, _P, _P, _P, _I, _I, _F, _P]),
     "umv_op_attention": (C.c_int, [_P, _P, _P, _P, _I, _IP, _IP, _I, _I, _I, _I, _P]),
     "umv_op_argmax": (C.c_int, [_P, _I, _I, _P, _P]),
+    "umv_bench_decode_linear": (C.c_int, [_P, _I, _I, _I, _LP, _P]),
     "umv_launch_count": (C.c_int64, []),
 }
 

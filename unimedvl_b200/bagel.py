@@ -1,0 +1,226 @@
+"""Drop-in stand-in for the reference's ``Bagel`` module (codes/modeling/unimedvl/bagel.py:91).
+
+Same method surface, argument names, dict keys and return types as the reference,
+so ``codes/inferencer.py:InterleaveInferencer`` and the two ``interactive_*`` entry scripts can hold this
+object instead of the torch module.  All device work goes to the CUDA engine through the C ABI; the
+``prepare_*`` methods are host packing (unimedvl_b200/packing.py).  No torch.nn compute, no fallback.
+"""
+from __future__ import annotations
+
+from types import SimpleNamespace
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+
+from . import packing
+from .cache import NaiveCache, paged_handle
+from .config import BagelDims
+from .engine import Engine
+
+
+class _DeviceProbe:
+    """``next(model.language_model.model.embed_tokens.parameters()).device`` (inferencer.py:99-101,
+    bagel.py:422,538) must resolve to the engine's device."""
+
+    def __init__(self, device):
+        self._t = torch.empty(0, device=device)
+
+    def parameters(self):
+        yield self._t
+
+
+def _canonical(indexes: torch.Tensor, expected: torch.Tensor, what: str):
+    """The engine addresses the cache by (sample, position); it accepts exactly the packed index layout
+    the reference's prepare_* methods emit and refuses anything else instead of mis-addressing."""
+    if indexes is None:
+        return
+    if indexes.numel() != expected.numel() or not torch.equal(indexes.to("cpu", torch.int64), expected):
+        raise NotImplementedError(f"{what}: only the index layout produced by Bagel.prepare_* is supported")
+
+
+class Bagel:
+    def __init__(self, engine: Engine, dims: BagelDims):
+        self.engine = engine
+        self.dims = dims
+        l = dims.llm
+        self.config = SimpleNamespace(
+            llm_config=SimpleNamespace(num_hidden_layers=l.layers, hidden_size=l.hidden, layer_module="Qwen2MoTDecoderLayer"),
+            vit_config=SimpleNamespace(patch_size=dims.vit.patch, hidden_size=dims.vit.hidden),
+            vae_config=SimpleNamespace(downsample=dims.vae.downsample, z_channels=dims.vae.z_channels),
+            visual_gen=True, visual_und=True, latent_patch_size=dims.latent_patch_size,
+            max_latent_size=dims.max_latent_size, vit_max_num_patch_per_side=dims.vit_max_num_patch_per_side)
+        self.hidden_size = l.hidden
+        self.use_moe = True
+        self.num_heads = l.heads
+        self.latent_patch_size = dims.latent_patch_size
+        self.latent_downsample = dims.latent_downsample
+        self.max_latent_size = dims.max_latent_size
+        self.latent_channel = dims.vae.z_channels
+        self.patch_latent_dim = dims.patch_latent_dim
+        self.vit_patch_size = dims.vit.patch
+        self.vit_max_num_patch_per_side = dims.vit_max_num_patch_per_side
+        self.vit_hidden_size = dims.vit.hidden
+        probe = _DeviceProbe(engine.device)
+        self.language_model = SimpleNamespace(model=SimpleNamespace(embed_tokens=probe))
+        self.device = engine.device
+
+    def eval(self):
+        return self
+
+    def parameters(self):
+        return self.language_model.model.embed_tokens.parameters()
+
+    # ------------------------------------------------------------------ host packing (reference signatures)
+    def prepare_prompts(self, curr_kvlens, curr_rope, prompts, tokenizer, new_token_ids):
+        return packing.prepare_prompts(curr_kvlens, curr_rope, prompts, tokenizer, new_token_ids)
+
+    def prepare_vit_images(self, curr_kvlens, curr_rope, images, transforms, new_token_ids):
+        return packing.prepare_vit_images(curr_kvlens, curr_rope, images, transforms, new_token_ids, self.vit_patch_size,
+                                          self.vit_max_num_patch_per_side)
+
+    def prepare_vae_images(self, curr_kvlens, curr_rope, images, transforms, new_token_ids, timestep=0):
+        return packing.prepare_vae_images(curr_kvlens, curr_rope, images, transforms, new_token_ids, self.latent_downsample,
+                                          self.max_latent_size, timestep)
+
+    def prepare_vae_latent(self, curr_kvlens, curr_rope, image_sizes, new_token_ids):
+        return packing.prepare_vae_latent(curr_kvlens, curr_rope, image_sizes, new_token_ids, self.latent_downsample,
+                                          self.max_latent_size, self.patch_latent_dim)
+
+    def prepare_vae_latent_cfg(self, curr_kvlens, curr_rope, image_sizes):
+        return packing.prepare_vae_latent_cfg(curr_kvlens, curr_rope, image_sizes, self.latent_downsample)
+
+    def prepare_start_tokens(self, curr_kvlens, curr_rope, new_token_ids):
+        return packing.prepare_start_tokens(curr_kvlens, curr_rope, new_token_ids, device=self.device)
+
+    # ------------------------------------------------------------------ helpers
+    @staticmethod
+    def _ints(t) -> List[int]:
+        return [int(v) for v in (t.tolist() if torch.is_tensor(t) else t)]
+
+    def _check_kv(self, handle, key_values_lens, packed_key_value_indexes, new_lens, packed_indexes, what):
+        kv = self._ints(key_values_lens)
+        have = handle.lens()
+        if have != kv:
+            raise ValueError(f"{what}: key_values_lens {kv} do not match the cache ({have})")
+        exp_kv, starts = packing._layout(kv, new_lens)
+        _canonical(packed_key_value_indexes, torch.as_tensor(exp_kv), what + ".packed_key_value_indexes")
+        if packed_indexes is not None:
+            import numpy as np
+            exp_q = np.concatenate([np.arange(s, s + n) for s, n in zip(starts, new_lens)]) if new_lens else np.zeros(0, "int64")
+            _canonical(packed_indexes, torch.as_tensor(exp_q), what + ".packed_indexes")
+
+    # ------------------------------------------------------------------ prefill
+    @torch.no_grad()
+    def forward_cache_update_text(self, past_key_values, packed_text_ids, packed_text_position_ids, text_token_lens,
+                                  packed_text_indexes, packed_key_value_indexes, key_values_lens):
+        """bagel.py:412-458: embed -> LLM forward (mode und, causal) -> cache update."""
+        lens = self._ints(text_token_lens)
+        h = paged_handle(past_key_values, self.engine, len(lens))
+        self._check_kv(h, key_values_lens, packed_key_value_indexes, lens, packed_text_indexes, "forward_cache_update_text")
+        x = self.engine.embed_tokens(packed_text_ids)
+        self.engine.llm_forward(x, h.seqs, lens, self._ints(packed_text_position_ids), is_causal=True, update_kv=True,
+                                want_hidden=False)
+        return past_key_values
+
+    @torch.no_grad()
+    def forward_cache_update_vit(self, past_key_values, packed_text_ids, packed_text_indexes, packed_vit_tokens,
+                                 packed_vit_token_indexes, packed_vit_position_ids, vit_token_seqlens, packed_position_ids,
+                                 packed_seqlens, packed_indexes, packed_key_value_indexes, key_values_lens):
+        """bagel.py:523-615: markers + ViT/connector embeddings -> LLM forward (mode und, full attention)."""
+        lens = self._ints(packed_seqlens)
+        h = paged_handle(past_key_values, self.engine, len(lens))
+        self._check_kv(h, key_values_lens, packed_key_value_indexes, lens, packed_indexes, "forward_cache_update_vit")
+        dev = self.device
+        seq = torch.zeros((sum(lens), self.hidden_size), dtype=torch.bfloat16, device=dev)
+        seq[packed_text_indexes.to(dev)] = self.engine.embed_tokens(packed_text_ids)
+        seq[packed_vit_token_indexes.to(dev)] = self.engine.vit_embed(packed_vit_tokens, packed_vit_position_ids,
+                                                                      self._ints(vit_token_seqlens))
+        self.engine.llm_forward(seq, h.seqs, lens, self._ints(packed_position_ids), is_causal=False, update_kv=True,
+                                want_hidden=False)
+        return past_key_values
+
+    # ------------------------------------------------------------------ decode
+    @torch.no_grad()
+    def generate_text(self, past_key_values, packed_key_value_indexes, key_values_lens, packed_start_tokens,
+                      packed_query_position_ids, max_length: int, do_sample: bool = False, temperature: float = 1.0,
+                      end_token_id: Optional[int] = None, seed: int = 0, chunk: int = 32):
+        """bagel.py:1236-1317.  Returns LongTensor [steps, B] whose row 0 is the start tokens.  The loop runs
+        on the device; with ``end_token_id`` set it proceeds in chunks and stops -- as the reference does --
+        when SAMPLE 0 produces the end token (bagel.py:1313), trimming the cache to the steps the reference
+        would have executed."""
+        B = len(self._ints(key_values_lens))
+        h = paged_handle(past_key_values, self.engine, B)
+        self._check_kv(h, key_values_lens, packed_key_value_indexes, [0] * B, None, "generate_text")
+        start_lens = h.lens()
+        tokens = self._ints(packed_start_tokens)
+        pos = self._ints(packed_query_position_ids)
+        temp = float(temperature) if do_sample else 0.0
+        rows, done = [], 0
+        while done < max_length:
+            n = max_length - done if end_token_id is None else min(chunk, max_length - done)
+            toks, nxt = self.engine.generate_text(h.seqs, tokens, pos, n, temperature=temp, seed=seed + done,
+                                                  return_next=True)
+            rows.append(toks)
+            done += n
+            if end_token_id is not None:
+                fed = torch.cat([toks[1:, 0], nxt[:1]]).tolist()      # token computed at each executed step, sample 0
+                if end_token_id in fed:
+                    executed = done - n + fed.index(end_token_id) + 1
+                    out = torch.cat(rows, dim=0)[:executed]
+                    for s, l0 in zip(h.seqs, start_lens):
+                        self.engine.seq_truncate(s, l0 + executed)
+                    return out
+            tokens = nxt.tolist()
+            pos = [p + n for p in pos]
+        return torch.cat(rows, dim=0)
+
+    @torch.no_grad()
+    def chat(self, tokenizer, new_token_ids, image_transform, images, prompt, max_length: int, do_sample: bool = False,
+             temperature: float = 1.0):
+        """bagel.py:1321-1392 (single-sample VQA helper)."""
+        past_key_values = NaiveCache(self.config.llm_config.num_hidden_layers)
+        newlens, new_rope = [0], [0]
+        for image in images:
+            g, newlens, new_rope = self.prepare_vit_images(newlens, new_rope, [image], image_transform, new_token_ids)
+            past_key_values = self.forward_cache_update_vit(past_key_values, **g)
+        g, newlens, new_rope = self.prepare_prompts(newlens, new_rope, [prompt], tokenizer, new_token_ids)
+        past_key_values = self.forward_cache_update_text(past_key_values, **g)
+        g = self.prepare_start_tokens(newlens, new_rope, new_token_ids)
+        toks = self.generate_text(past_key_values=past_key_values, max_length=max_length, do_sample=do_sample,
+                                  temperature=temperature, end_token_id=new_token_ids["eos_token_id"], **g)
+        output = tokenizer.decode(toks[:, 0])
+        return output.split("<|im_end|>")[0].split("<|im_start|>")[1]
+
+    # ------------------------------------------------------------------ batched VQA job (bench / serving)
+    @torch.no_grad()
+    def vqa_generate(self, pixels: torch.Tensor, vit_pos_ids: torch.Tensor, vit_seqlens: Sequence[int],
+                     prompt_ids: Sequence[Sequence[int]], new_token_ids: dict, max_length: int) -> torch.Tensor:
+        """One packed VQA job for B samples (one image each): host (pinned) tensors in, host tokens out.
+        The same sequence of calls the reference's chat() makes, batched over samples as
+        InterleaveInferencer's packed API allows: ViT prefill -> prompt prefill -> greedy decode."""
+        B = len(vit_seqlens)
+        dev = self.device
+        cache = NaiveCache(self.config.llm_config.num_hidden_layers)
+        zeros = [0] * B
+        # image block: [<vision_start>, patches, <vision_end>] per sample, one rope position
+        L = packing._image_block_layout(zeros, zeros, [int(n) for n in vit_seqlens], new_token_ids)
+        g = dict(packed_text_ids=torch.as_tensor(L["text_ids"]), packed_text_indexes=torch.as_tensor(L["text_idx"]),
+                 packed_vit_tokens=pixels.to(dev, non_blocking=True), packed_vit_token_indexes=torch.as_tensor(L["img_idx"]),
+                 packed_vit_position_ids=vit_pos_ids.to(dev, non_blocking=True), vit_token_seqlens=list(vit_seqlens),
+                 packed_position_ids=torch.as_tensor(L["pos"]), packed_seqlens=L["seqlens"],
+                 packed_indexes=torch.as_tensor(L["packed_idx"]), packed_key_value_indexes=torch.as_tensor(L["kv_indexes"]),
+                 key_values_lens=zeros)
+        cache = self.forward_cache_update_vit(cache, **g)
+        lens, rope = L["seqlens"], [1] * B
+
+        class _Ids:
+            def __init__(self, table): self.t = table
+            def encode(self, i): return list(self.t[i])
+        g, lens, rope = packing.prepare_prompts(lens, rope, list(range(B)), _Ids(prompt_ids), new_token_ids)
+        cache = self.forward_cache_update_text(cache, **g)
+        g = packing.prepare_start_tokens(lens, rope, new_token_ids)
+        toks = self.generate_text(past_key_values=cache, max_length=max_length, end_token_id=None, **g)
+        out = torch.empty(toks.shape, dtype=toks.dtype, pin_memory=True)
+        out.copy_(toks, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return out

@@ -793,7 +793,8 @@ int umv_vit_embed(umv_engine* e, const float* pixels, const int64_t* pos_ids, co
 
 int umv_generate_text(umv_engine* e, int32_t n_seqs, const int32_t* seqs, const int64_t* start_tokens,
                       const int32_t* positions, int32_t n_steps, float temperature, uint64_t seed,
-                      const int64_t* forced_tokens, int64_t* tokens_out, void* logits_out, void* stream) {
+                      const int64_t* forced_tokens, int64_t* tokens_out, void* logits_out, int64_t* next_tokens_out,
+                      void* stream) {
     UMV_REQUIRE(e && e->finalized, UMV_ERR_STATE, "engine not finalized");
     UMV_REQUIRE(seqs && start_tokens && positions && tokens_out && n_seqs > 0 && n_steps > 0, UMV_ERR_INVALID,
                 "umv_generate_text: null/empty argument");
@@ -850,7 +851,9 @@ int umv_generate_text(umv_engine* e, int32_t n_seqs, const int32_t* seqs, const 
         cudaGraph_t graph = nullptr;
         cudaGraphExec_t exec = nullptr;
         UMV_CUDA_OK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+        const long long launches_before = g_launches;
         int rc = step(st, e->logits);
+        g_launches += (g_launches - launches_before) * (n_steps - 1);    // every replay launches the captured kernels
         cudaError_t ce = cudaStreamEndCapture(st, &graph);
         if (rc != UMV_OK) { if (graph) cudaGraphDestroy(graph); return rc; }
         UMV_CUDA_OK(ce);
@@ -871,6 +874,8 @@ int umv_generate_text(umv_engine* e, int32_t n_seqs, const int32_t* seqs, const 
             UMV_TRY(step(st, lg));
         }
     }
+    if (next_tokens_out)
+        UMV_CUDA_OK(cudaMemcpyAsync(next_tokens_out, e->dec_tokens, B * sizeof(int64_t), cudaMemcpyDeviceToDevice, st));
     for (int b = 0; b < B; ++b) sq[b]->len += n_steps;
     return UMV_OK;
 }
@@ -883,6 +888,39 @@ int umv_flow_velocity(umv_engine*, const umv_flow_args*, const float*, float*, v
 int umv_flow_euler(umv_engine*, float*, const float*, int64_t, float, int32_t, void*) {
     set_error("umv_flow_euler: not built yet");
     return UMV_ERR_UNSUPPORTED;
+}
+
+int umv_bench_decode_linear(umv_engine* e, int32_t which, int32_t layer, int32_t m, int64_t* weight_bytes, void* stream) {
+    UMV_REQUIRE(e && e->finalized, UMV_ERR_STATE, "engine not finalized");
+    UMV_REQUIRE(layer >= 0 && layer < e->d.layers && m > 0 && m <= 64 && which >= 0 && which <= 4, UMV_ERR_INVALID,
+                "umv_bench_decode_linear: bad argument");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const umv_dims& d = e->d;
+    const int D = d.hidden, I = d.inter, QN = e->qkvn;
+    const LayerW& L = e->layers[layer];
+    int64_t wb = 0;
+    int rc = UMV_OK;
+    switch (which) {
+        case 0: wb = (int64_t)QN * D * 2;
+            rc = lin(e, e->xn, D, L.wqkv[0], nullptr, nullptr, nullptr, 0, m, QN, D, EPI_PARTIAL, st, GEMM_WEIGHT_MAJOR, e->ws,
+                     pick_splits(QN, D, e->sm_count));
+            break;
+        case 1: wb = (int64_t)D * D * 2;
+            rc = lin(e, e->attn, D, L.wo[0], nullptr, nullptr, nullptr, 0, m, D, D, EPI_PARTIAL, st, GEMM_WEIGHT_MAJOR, e->ws,
+                     pick_splits(D, D, e->sm_count));
+            break;
+        case 2: wb = (int64_t)2 * I * D * 2;
+            rc = lin(e, e->xn, D, L.wgu[0], nullptr, nullptr, e->act, I, m, 2 * I, D, EPI_SWIGLU, st, GEMM_WEIGHT_MAJOR);
+            break;
+        case 3: wb = (int64_t)D * I * 2;
+            rc = lin(e, e->act, I, L.wdown[0], nullptr, nullptr, nullptr, 0, m, D, I, EPI_PARTIAL, st, GEMM_WEIGHT_MAJOR, e->ws,
+                     pick_splits(D, I, e->sm_count));
+            break;
+        default: wb = (int64_t)d.vocab * D * 2;
+            rc = lin(e, e->xn, D, e->lm_head, nullptr, nullptr, e->logits, d.vocab, m, d.vocab, D, EPI_BF16, st, GEMM_WEIGHT_MAJOR);
+    }
+    if (weight_bytes) *weight_bytes = wb;
+    return rc;
 }
 
 // ------------------------------------------------------------------------------ op-level entry points

@@ -187,7 +187,7 @@ class Engine:
 
     def generate_text(self, seqs: Sequence[int], start_tokens: Sequence[int], positions: Sequence[int], n_steps: int,
                       temperature: float = 0.0, seed: int = 0, forced_tokens: torch.Tensor | None = None,
-                      return_logits: bool = False):
+                      return_logits: bool = False, return_next: bool = False):
         """Bagel.generate_text (bagel.py:1236-1317) without the EOS early-exit: returns i64 [n_steps, B]
         (row 0 = start tokens) and optionally bf16 logits [n_steps, B, vocab]."""
         B = len(seqs)
@@ -196,12 +196,15 @@ class Engine:
         if forced_tokens is not None:
             forced_tokens = forced_tokens.to(self.device, torch.int64).contiguous()
             assert tuple(forced_tokens.shape) == (n_steps, B)
+        nxt = torch.empty((B,), dtype=torch.int64, device=self.device) if return_next else None
         self._enter()
         _lib.check(self.lib.umv_generate_text(self.h, B, _lib.i32_array(seqs), _lib.i64_array(start_tokens),
                                               _lib.i32_array(positions), n_steps, C.c_float(temperature), C.c_uint64(seed),
-                                              _ptr(forced_tokens), _ptr(toks), _ptr(logits), _stream_ptr(self.stream)))
+                                              _ptr(forced_tokens), _ptr(toks), _ptr(logits), _ptr(nxt),
+                                              _stream_ptr(self.stream)))
         self._exit()
-        return (toks, logits) if return_logits else toks
+        out = (toks,) + ((logits,) if return_logits else ()) + ((nxt,) if return_next else ())
+        return out if len(out) > 1 else toks
 
     def launch_count(self) -> int:
         return int(self.lib.umv_launch_count())
