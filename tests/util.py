@@ -79,6 +79,7 @@ def bf16_ordinal(t: torch.Tensor) -> torch.Tensor:
 
 def ulp_stats(a: torch.Tensor, b: torch.Tensor) -> dict:
     """a, b: same shape; compared as bf16.  Returns mismatch fraction, max ulp distance, rel-L2."""
+    a, b = a.detach().cpu(), b.detach().cpu()
     da = (bf16_ordinal(a) - bf16_ordinal(b)).abs()
     af, bf = a.float(), b.float()
     denom = bf.norm().item() or 1.0

@@ -45,7 +45,12 @@ class _LayerView:
     access (parity tests); ``None`` for an empty cache exactly as the reference."""
 
     def __init__(self, cache: "NaiveCache", which: int):
-        self._cache, self._which = cache, which
+        import weakref
+        self._ref, self._which = weakref.ref(cache), which      # no reference cycle: pages are freed by refcount
+
+    @property
+    def _cache(self):
+        return self._ref()
 
     def __getitem__(self, layer: int):
         h = self._cache._umv
