@@ -42,6 +42,8 @@ __device__ __forceinline__ uint32_t tile_off(int row, int chunk) {
 template <int HD>
 __global__ void __launch_bounds__(kAttnThreads) attn_fwd_kernel(AttnArgs a, float scale_log2) {
     using Cfg = AttnCfg<HD>;
+    pdl_launch_dependents();
+    pdl_wait();
     extern __shared__ __align__(128) uint8_t smem[];
     uint8_t* sQ = smem;
     uint8_t* sK = smem + Cfg::kTileBytes;
@@ -250,6 +252,8 @@ __global__ void __launch_bounds__(kAttnThreads) attn_fwd_kernel(AttnArgs a, floa
 // Split-KV combine: out = sum_s w_s O_s / sum_s w_s, w_s = 2^(lse_s - max lse).   one warp per (token, head)
 template <int HD>
 __global__ void attn_combine_kernel(AttnArgs a) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     const int rows = a.total_q * a.H;
     if (gw >= rows) return;
@@ -298,18 +302,18 @@ static int launch_attn(const AttnArgs& a, cudaStream_t s) {
     const int row_tiles = (a.max_q_len * G + kTileRows - 1) / kTileRows;
     const float scale_log2 = (1.0f / sqrtf((float)HD)) * 1.4426950408889634f;
     dim3 grid(row_tiles, a.n * a.Hkv, a.splits);
-    attn_fwd_kernel<HD><<<grid, kAttnThreads, AttnCfg<HD>::kSmemBytes, s>>>(a, scale_log2);
+    cudaError_t e = launch_k(attn_fwd_kernel<HD>, grid, dim3(kAttnThreads), AttnCfg<HD>::kSmemBytes, s, a, scale_log2);
     ++g_launches;
-    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaGetLastError();
     if (e != cudaSuccess) {
         set_error("attn_fwd_kernel<%d> launch failed: %s", HD, cudaGetErrorString(e));
         return UMV_ERR_CUDA;
     }
     if (a.splits > 1) {
         const int rows = a.total_q * a.H;
-        attn_combine_kernel<HD><<<(rows * 32 + 127) / 128, 128, 0, s>>>(a);
+        e = launch_k(attn_combine_kernel<HD>, dim3((rows * 32 + 127) / 128), dim3(128), 0, s, a);
         ++g_launches;
-        e = cudaGetLastError();
+        if (e == cudaSuccess) e = cudaGetLastError();
         if (e != cudaSuccess) {
             set_error("attn_combine_kernel launch failed: %s", cudaGetErrorString(e));
             return UMV_ERR_CUDA;

@@ -2,6 +2,7 @@
 #pragma once
 #include <cstdint>
 #include <cstdio>
+#include <utility>
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 
@@ -74,6 +75,25 @@ __device__ __forceinline__ float block_sum(float v, float* red) {
     float t = (lane < nw) ? red[lane] : 0.0f;
     t = warp_sum(t);
     return t;
+}
+
+// Programmatic dependent launch: every kernel of the engine starts with pdl_launch_dependents() +
+// pdl_wait() (ptx.cuh), so back-to-back launches overlap their launch latency / prologue -- and, for the
+// weight-major linear, the first weight tiles -- with the tail of the previous kernel.  UMV_PDL=0 disables.
+extern bool g_pdl;
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args&&... args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = g_pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
 }
 
 struct alignas(16) U4 {

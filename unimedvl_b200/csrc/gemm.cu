@@ -16,6 +16,7 @@
 // siglip_navit.py:190,216-218,243,256-258; modeling_utils.py:108,120-122.
 #include <cuda.h>
 #include <cstdarg>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 
@@ -27,6 +28,7 @@
 namespace umv {
 
 long long g_launches = 0;
+bool g_pdl = true;
 
 constexpr int BM = 128;   // UMMA M (TMEM lanes)
 constexpr int BK = 64;    // 64 bf16 = one 128-byte swizzle row
@@ -80,6 +82,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     float* sExch = reinterpret_cast<float*>(smem + kStages * Cfg::kStageBytes + Cfg::kBarBytes);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    pdl_launch_dependents();
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmA);
         tma_prefetch_desc(&tmB);
@@ -113,6 +116,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const uint64_t hintB = SWAP ? kEvictLast : kEvictNormal;
             int stage = 0;
             uint32_t phase = 0;
+            // Weight-major: the A operand (weights) does not depend on the previous kernel, so the first
+            // kStages weight tiles are requested BEFORE griddepcontrol.wait and stream in while the
+            // predecessor (a norm / rope / attention kernel on a handful of SMs) is still running; the
+            // activation tiles of those stages are requested right after the wait.
+            bool waited = !SWAP;
+            int n_deferred = 0;
+            int def_kb[kStages], def_bt[kStages];
+            if (!SWAP) pdl_wait();
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
                 const int split = tile % p.splits;
                 const int t2 = tile / p.splits;
@@ -120,12 +131,29 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 const int kb0 = split * p.kb_per_split;
                 const int kb1 = min(p.kb_total, kb0 + p.kb_per_split);
                 for (int kb = kb0; kb < kb1; ++kb) {
+                    if (!waited && n_deferred == kStages) {
+                        pdl_wait();
+                        waited = true;
+                        for (int i = 0; i < n_deferred; ++i)
+                            tma_load_2d(sB + i * Cfg::kBTile, &tmB, &full[i], def_kb[i] * BK, def_bt[i] * BN, hintB);
+                    }
                     mbar_wait(&empty[stage], phase ^ 1u);
                     mbar_expect_tx(&full[stage], Cfg::kStageBytes);
                     tma_load_2d(sA + stage * kATile, &tmA, &full[stage], kb * BK, a_tile * BM, hintA);
-                    tma_load_2d(sB + stage * Cfg::kBTile, &tmB, &full[stage], kb * BK, b_tile * BN, hintB);
+                    if (waited) {
+                        tma_load_2d(sB + stage * Cfg::kBTile, &tmB, &full[stage], kb * BK, b_tile * BN, hintB);
+                    } else {
+                        def_kb[n_deferred] = kb;          // stage index == n_deferred during the first ring pass
+                        def_bt[n_deferred] = b_tile;
+                        ++n_deferred;
+                    }
                     if (++stage == kStages) { stage = 0; phase ^= 1u; }
                 }
+            }
+            if (!waited) {
+                pdl_wait();
+                for (int i = 0; i < n_deferred; ++i)
+                    tma_load_2d(sB + i * Cfg::kBTile, &tmB, &full[i], def_kb[i] * BK, def_bt[i] * BN, hintB);
             }
         }
     } else if (warp == 1) {
@@ -162,6 +190,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         // ------------------------------------------------------------ epilogue (4 warps)
         const int quarter = warp & 3;                  // TMEM lane quarter this warp may read
         const int lrow = quarter * 32 + lane;          // lane within the 128-row tile
+        pdl_wait();                                    // outputs / bias / residual belong to the dependency chain
         int acc = 0;
         uint32_t acc_phase = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -311,6 +340,8 @@ __global__ void gemm_simple_kernel(const bf16* __restrict__ x, int ldx, const bf
     const int n_out = (epi == EPI_SWIGLU) ? N / 2 : N;
     const int n = blockIdx.x * blockDim.x + threadIdx.x;
     const int m = blockIdx.y * blockDim.y + threadIdx.y;
+    pdl_launch_dependents();
+    pdl_wait();
     if (m >= M || n >= n_out) return;
     const bf16* xr = x + (size_t)m * ldx;
     if (epi == EPI_SWIGLU) {
@@ -360,6 +391,7 @@ int gemm_init() {
             return;
         }
         g_encode = reinterpret_cast<EncodeTiledFn>(fn);
+        if (const char* v = getenv("UMV_PDL")) g_pdl = atoi(v) != 0;
         int dev = 0;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev);
@@ -440,9 +472,9 @@ static int launch_tc(const LinearCall& c, cudaStream_t stream) {
     if (rc) return rc;
     const int tiles = p.a_tiles * p.b_tiles * p.splits;
     const int grid = tiles < g_sm_count ? tiles : g_sm_count;
-    gemm_tc_kernel<BN, MODE, SWAP><<<grid, 192, TcCfg<BN, SWAP>::kSmemBytes, stream>>>(tmA, tmB, p);
+    cudaError_t e = launch_k(gemm_tc_kernel<BN, MODE, SWAP>, dim3(grid), dim3(192), TcCfg<BN, SWAP>::kSmemBytes, stream, tmA, tmB, p);
     ++g_launches;
-    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaGetLastError();
     if (e != cudaSuccess) {
         set_error("gemm_tc_kernel<%d,%d,%d> launch failed: %s", BN, MODE, (int)SWAP, cudaGetErrorString(e));
         return UMV_ERR_CUDA;
@@ -482,10 +514,10 @@ int linear_forward(const LinearCall& c, cudaStream_t stream) {
         dim3 block(32, 8);
         const int n_out = c.epi == EPI_SWIGLU ? c.N / 2 : c.N;
         dim3 grid((n_out + 31) / 32, (c.M + 7) / 8);
-        gemm_simple_kernel<<<grid, block, 0, stream>>>(c.x, c.ldx, c.w, c.bias, c.residual, c.y, c.ldy, c.M, c.N, c.K,
-                                                       c.epi);
+        cudaError_t e = launch_k(gemm_simple_kernel, grid, block, 0, stream, c.x, c.ldx, c.w, c.bias, c.residual, c.y, c.ldy,
+                                 c.M, c.N, c.K, c.epi);
         ++g_launches;
-        cudaError_t e = cudaGetLastError();
+        if (e == cudaSuccess) e = cudaGetLastError();
         if (e != cudaSuccess) {
             set_error("gemm_simple_kernel launch failed: %s", cudaGetErrorString(e));
             return UMV_ERR_CUDA;

@@ -6,6 +6,7 @@
 #include "common.cuh"
 #include "gemm.cuh"
 #include "kernels.cuh"
+#include "ptx.cuh"
 
 namespace umv {
 
@@ -25,6 +26,8 @@ constexpr int kNormThreads = 256;
 constexpr int kNormMaxChunks = 8;   // 8 chunks * 8 elems * 256 threads = D <= 16384
 
 __global__ void __launch_bounds__(kNormThreads) add_rmsnorm_kernel(AddNormArgs a) {
+    pdl_launch_dependents();
+    pdl_wait();
     __shared__ float red[32];
     const int row = blockIdx.x;
     const int nchunk = a.D / 8;
@@ -105,7 +108,7 @@ int add_rmsnorm(const AddNormArgs& a, cudaStream_t s) {
     if (a.M <= 0) return UMV_OK;
     UMV_REQUIRE(a.D % 8 == 0 && a.D <= 8 * kNormThreads * kNormMaxChunks, UMV_ERR_UNSUPPORTED,
                 "add_rmsnorm: D=%d must be a multiple of 8 and <= %d", a.D, 8 * kNormThreads * kNormMaxChunks);
-    add_rmsnorm_kernel<<<a.M, kNormThreads, 0, s>>>(a);
+    launch_k(add_rmsnorm_kernel, dim3(a.M), dim3(kNormThreads), 0, s, a);
     UMV_LAUNCH_CHECK("add_rmsnorm_kernel");
     return UMV_OK;
 }
@@ -115,6 +118,8 @@ int add_rmsnorm(const AddNormArgs& a, cudaStream_t s) {
 __global__ void __launch_bounds__(kNormThreads) layernorm_kernel(const bf16* __restrict__ x, const bf16* __restrict__ w,
                                                                   const bf16* __restrict__ b, bf16* __restrict__ y, int D,
                                                                   float eps) {
+    pdl_launch_dependents();
+    pdl_wait();
     __shared__ float red[32];
     const int row = blockIdx.x;
     const int nchunk = D / 8;
@@ -171,7 +176,7 @@ __global__ void __launch_bounds__(kNormThreads) layernorm_kernel(const bf16* __r
 int layernorm_bf16(const bf16* x, const bf16* w, const bf16* b, bf16* y, int M, int D, float eps, cudaStream_t s) {
     if (M <= 0) return UMV_OK;
     UMV_REQUIRE(D % 8 == 0 && D <= 8 * kNormThreads * kNormMaxChunks, UMV_ERR_UNSUPPORTED, "layernorm: bad D=%d", D);
-    layernorm_kernel<<<M, kNormThreads, 0, s>>>(x, w, b, y, D, eps);
+    launch_k(layernorm_kernel, dim3(M), dim3(kNormThreads), 0, s, x, w, b, y, D, eps);
     UMV_LAUNCH_CHECK("layernorm_kernel");
     return UMV_OK;
 }
@@ -180,6 +185,8 @@ int layernorm_bf16(const bf16* x, const bf16* w, const bf16* b, bf16* y, int M, 
 // One warp per (row, head-slot): slots [0,H) = q heads, [H,H+Hkv) = k heads, [H+Hkv,H+2Hkv) = v heads.
 // head_dim 128: lane l owns elements 4l..4l+3; the rotate_half partner (i +- 64) lives in lane l^16.
 __global__ void __launch_bounds__(256) rope_append_kernel(RopeAppendArgs a) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     const int slots = a.H + 2 * a.Hkv;
@@ -256,7 +263,7 @@ int rope_append(const RopeAppendArgs& a, cudaStream_t s) {
     UMV_REQUIRE(a.dh == 128, UMV_ERR_UNSUPPORTED, "rope_append: head_dim %d (only 128 is built)", a.dh);
     const long long warps = (long long)a.M * (a.H + 2 * a.Hkv);
     const int blocks = (int)((warps * 32 + 255) / 256);
-    rope_append_kernel<<<blocks, 256, 0, s>>>(a);
+    launch_k(rope_append_kernel, dim3(blocks), dim3(256), 0, s, a);
     UMV_LAUNCH_CHECK("rope_append_kernel");
     return UMV_OK;
 }
@@ -264,6 +271,8 @@ int rope_append(const RopeAppendArgs& a, cudaStream_t s) {
 // ------------------------------------------------------------------------------------------
 __global__ void embed_rows_kernel(const bf16* __restrict__ table, const int64_t* __restrict__ ids, int D, int64_t vocab,
                                   bf16* __restrict__ out) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int row = blockIdx.x;
     int64_t id = ids[row];
     if (id < 0 || id >= vocab) id = 0;      // host validates ids; never read out of bounds
@@ -273,13 +282,15 @@ __global__ void embed_rows_kernel(const bf16* __restrict__ table, const int64_t*
 }
 int embed_rows(const bf16* table, const int64_t* ids, int n, int D, int64_t vocab, bf16* out, cudaStream_t s) {
     if (n <= 0) return UMV_OK;
-    embed_rows_kernel<<<n, 128, 0, s>>>(table, ids, D, vocab, out);
+    launch_k(embed_rows_kernel, dim3(n), dim3(128), 0, s, table, ids, D, vocab, out);
     UMV_LAUNCH_CHECK("embed_rows_kernel");
     return UMV_OK;
 }
 
 __global__ void gather_add_rows_kernel(bf16* __restrict__ x, const bf16* __restrict__ table, const int64_t* __restrict__ ids,
                                        int D) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int row = blockIdx.x;
     const bf16* t = table + (size_t)ids[row] * D;
     bf16* xr = x + (size_t)row * D;
@@ -298,19 +309,21 @@ __global__ void gather_add_rows_kernel(bf16* __restrict__ x, const bf16* __restr
 }
 int gather_add_rows(bf16* x, const bf16* table, const int64_t* ids, int M, int D, cudaStream_t s) {
     if (M <= 0) return UMV_OK;
-    gather_add_rows_kernel<<<M, 128, 0, s>>>(x, table, ids, D);
+    launch_k(gather_add_rows_kernel, dim3(M), dim3(128), 0, s, x, table, ids, D);
     UMV_LAUNCH_CHECK("gather_add_rows_kernel");
     return UMV_OK;
 }
 
 __global__ void f32_to_bf16_padded_kernel(const float* __restrict__ x, bf16* __restrict__ y, int K, int Kpad) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int row = blockIdx.x;
     for (int c = threadIdx.x; c < Kpad; c += blockDim.x)
         y[(size_t)row * Kpad + c] = c < K ? f2b(x[(size_t)row * K + c]) : f2b(0.f);
 }
 int f32_to_bf16_padded(const float* x, bf16* y, int M, int K, int Kpad, cudaStream_t s) {
     if (M <= 0) return UMV_OK;
-    f32_to_bf16_padded_kernel<<<M, 128, 0, s>>>(x, y, K, Kpad);
+    launch_k(f32_to_bf16_padded_kernel, dim3(M), dim3(128), 0, s, x, y, K, Kpad);
     UMV_LAUNCH_CHECK("f32_to_bf16_padded_kernel");
     return UMV_OK;
 }
@@ -318,6 +331,8 @@ int f32_to_bf16_padded(const float* x, bf16* y, int M, int K, int Kpad, cudaStre
 // rows[]: scatter==0: dst[i] = src[rows[i]] ; scatter==1: dst[rows[i]] = src[i]
 __global__ void copy_rows_kernel(const bf16* __restrict__ src, int lds, const int* __restrict__ rows, bf16* __restrict__ dst,
                                  int ldd, int D, int scatter) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int i = blockIdx.x;
     const int r = rows[i];
     const bf16* s = src + (size_t)(scatter ? i : r) * lds;
@@ -326,7 +341,7 @@ __global__ void copy_rows_kernel(const bf16* __restrict__ src, int lds, const in
 }
 int copy_rows(const bf16* src, int lds, const int* rows, bf16* dst, int ldd, int n, int D, int scatter, cudaStream_t s) {
     if (n <= 0) return UMV_OK;
-    copy_rows_kernel<<<n, 128, 0, s>>>(src, lds, rows, dst, ldd, D, scatter);
+    launch_k(copy_rows_kernel, dim3(n), dim3(128), 0, s, src, lds, rows, dst, ldd, D, scatter);
     UMV_LAUNCH_CHECK("copy_rows_kernel");
     return UMV_OK;
 }
@@ -334,6 +349,8 @@ int copy_rows(const bf16* src, int lds, const int* rows, bf16* dst, int ldd, int
 // ------------------------------------------------------------------------------------------
 // torch.argmax over bf16 logits: maximum value, ties -> lowest index (R8).  One CTA per row.
 __global__ void __launch_bounds__(1024) argmax_kernel(const bf16* __restrict__ logits, int vocab, int64_t* __restrict__ out) {
+    pdl_launch_dependents();
+    pdl_wait();
     __shared__ float sval[32];
     __shared__ int sidx[32];
     const bf16* row = logits + (size_t)blockIdx.x * vocab;
@@ -381,7 +398,7 @@ int argmax_rows(const bf16* logits, int rows, int vocab, int64_t* out, cudaStrea
     if (rows <= 0) return UMV_OK;
     UMV_REQUIRE((reinterpret_cast<uintptr_t>(logits) & 15) == 0 && vocab % 8 == 0, UMV_ERR_INVALID,
                 "argmax: logits must be 16-byte aligned with vocab %% 8 == 0 (vocab=%d)", vocab);
-    argmax_kernel<<<rows, 1024, 0, s>>>(logits, vocab, out);
+    launch_k(argmax_kernel, dim3(rows), dim3(1024), 0, s, logits, vocab, out);
     UMV_LAUNCH_CHECK("argmax_kernel");
     return UMV_OK;
 }
@@ -396,6 +413,8 @@ __device__ __forceinline__ uint64_t splitmix64(uint64_t x) {
 }
 __global__ void __launch_bounds__(1024) sample_kernel(const bf16* __restrict__ logits, int vocab, float inv_t, uint64_t seed,
                                                        const int* __restrict__ step, int64_t* __restrict__ out) {
+    pdl_launch_dependents();
+    pdl_wait();
     __shared__ float red[32];
     __shared__ float s_prefix[1024];
     const bf16* row = logits + (size_t)blockIdx.x * vocab;
@@ -437,7 +456,7 @@ __global__ void __launch_bounds__(1024) sample_kernel(const bf16* __restrict__ l
 int sample_rows(const bf16* logits, int rows, int vocab, float temperature, uint64_t seed, const int* step, int64_t* out,
                 cudaStream_t s) {
     if (rows <= 0) return UMV_OK;
-    sample_kernel<<<rows, 1024, 0, s>>>(logits, vocab, 1.0f / temperature, seed, step, out);
+    launch_k(sample_kernel, dim3(rows), dim3(1024), 0, s, logits, vocab, 1.0f / temperature, seed, step, out);
     UMV_LAUNCH_CHECK("sample_kernel");
     return UMV_OK;
 }
@@ -447,6 +466,8 @@ int sample_rows(const bf16* logits, int rows, int vocab, float temperature, uint
 __global__ void decode_begin_kernel(const bf16* __restrict__ table, int D, int64_t vocab, DecodeState st,
                                     const int64_t* __restrict__ forced, int64_t* __restrict__ tokens_out, int B,
                                     bf16* __restrict__ x) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int b = blockIdx.x;
     const int step = *st.step;
     int64_t tok = forced ? forced[(size_t)step * B + b] : st.cur_tokens[b];
@@ -458,11 +479,13 @@ __global__ void decode_begin_kernel(const bf16* __restrict__ table, int D, int64
 }
 int decode_begin_step(const bf16* table, int D, int64_t vocab, DecodeState st, const int64_t* forced, int64_t* tokens_out,
                       int B, bf16* x, cudaStream_t s) {
-    decode_begin_kernel<<<B, 128, 0, s>>>(table, D, vocab, st, forced, tokens_out, B, x);
+    launch_k(decode_begin_kernel, dim3(B), dim3(128), 0, s, table, D, vocab, st, forced, tokens_out, B, x);
     UMV_LAUNCH_CHECK("decode_begin_kernel");
     return UMV_OK;
 }
 __global__ void decode_end_kernel(DecodeState st, int B) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int b = threadIdx.x;
     if (b < B) {
         st.positions[b] += 1;      // packed_query_position_ids + 1 (bagel.py:1310)
@@ -472,7 +495,7 @@ __global__ void decode_end_kernel(DecodeState st, int B) {
     if (b == 0) *st.step += 1;
 }
 int decode_end_step(DecodeState st, int B, cudaStream_t s) {
-    decode_end_kernel<<<1, 64, 0, s>>>(st, B);
+    launch_k(decode_end_kernel, dim3(1), dim3(64), 0, s, st, B);
     UMV_LAUNCH_CHECK("decode_end_kernel");
     return UMV_OK;
 }
@@ -480,6 +503,8 @@ int decode_end_step(DecodeState st, int B, cudaStream_t s) {
 // ------------------------------------------------------------------------------------------
 __global__ void export_kv_kernel(KVPool pool, int layer, const int* __restrict__ pages, int len, bf16* __restrict__ k_out,
                                  bf16* __restrict__ v_out) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int t = blockIdx.x, head = blockIdx.y;
     const int page = pages[t / kPageTokens], slot = t % kPageTokens;
     const bf16* ks = pool.base + pool.tile_offset(page, layer, 0, head) + (size_t)slot * pool.head_dim;
@@ -492,25 +517,29 @@ __global__ void export_kv_kernel(KVPool pool, int layer, const int* __restrict__
 }
 int export_kv(KVPool pool, int layer, const int* pages, int len, bf16* k_out, bf16* v_out, cudaStream_t s) {
     if (len <= 0) return UMV_OK;
-    export_kv_kernel<<<dim3(len, pool.kv_heads), 128, 0, s>>>(pool, layer, pages, len, k_out, v_out);
+    launch_k(export_kv_kernel, dim3(dim3(len, pool.kv_heads)), dim3(128), 0, s, pool, layer, pages, len, k_out, v_out);
     UMV_LAUNCH_CHECK("export_kv_kernel");
     return UMV_OK;
 }
 
 __global__ void copy_page_kernel(KVPool pool, int src_page, int dst_page) {
+    pdl_launch_dependents();
+    pdl_wait();
     const size_t n = (size_t)pool.layers * 2 * pool.kv_heads * pool.tile_elems() / 8;
     const U4* s = reinterpret_cast<const U4*>(pool.base + pool.tile_offset(src_page, 0, 0, 0));
     U4* d = reinterpret_cast<U4*>(pool.base + pool.tile_offset(dst_page, 0, 0, 0));
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) d[i] = s[i];
 }
 int copy_page(KVPool pool, int src_page, int dst_page, cudaStream_t s) {
-    copy_page_kernel<<<148, 256, 0, s>>>(pool, src_page, dst_page);
+    launch_k(copy_page_kernel, dim3(148), dim3(256), 0, s, pool, src_page, dst_page);
     UMV_LAUNCH_CHECK("copy_page_kernel");
     return UMV_OK;
 }
 
 // Synthetic weights: uniform(mean - bound, mean + bound) from a counter hash (benchmark random init).
 __global__ void fill_uniform_kernel(bf16* __restrict__ p, size_t n, uint64_t seed, float bound, float mean) {
+    pdl_launch_dependents();
+    pdl_wait();
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
         const uint64_t h = splitmix64(seed + i);
         const float u = (float)(h >> 40) * (1.0f / 16777216.0f);
@@ -519,7 +548,7 @@ __global__ void fill_uniform_kernel(bf16* __restrict__ p, size_t n, uint64_t see
 }
 int fill_uniform_bf16(bf16* p, size_t n, uint64_t seed, float bound, float mean, cudaStream_t s) {
     if (n == 0) return UMV_OK;
-    fill_uniform_kernel<<<148 * 8, 256, 0, s>>>(p, n, seed, bound, mean);
+    launch_k(fill_uniform_kernel, dim3(148 * 8), dim3(256), 0, s, p, n, seed, bound, mean);
     UMV_LAUNCH_CHECK("fill_uniform_kernel");
     return UMV_OK;
 }
