@@ -139,6 +139,84 @@ class Bagel:
                                 want_hidden=False)
         return past_key_values
 
+    # ------------------------------------------------------------------ image generation (rectified flow)
+    _RENORM = {"global": 0, "channel": 1, "text_channel": 2}
+
+    def _flow_geometry(self, packed_seqlens, packed_position_ids):
+        lens = self._ints(packed_seqlens)
+        lat_lens = [n - 2 for n in lens]
+        pos = self._ints(packed_position_ids)
+        first, starts = 0, []
+        for n in lens:
+            starts.append(first)
+            first += n
+        return lens, lat_lens, [pos[s] for s in starts]
+
+    @torch.no_grad()
+    def generate_image(self, packed_text_ids, packed_text_indexes, packed_init_noises, packed_vae_position_ids,
+                       packed_vae_token_indexes, packed_seqlens, packed_position_ids, packed_indexes, past_key_values,
+                       key_values_lens, packed_key_value_indexes, num_timesteps: int = 24, timestep_shift: float = 1.0,
+                       cfg_renorm_min: float = 0.0, cfg_renorm_type: str = "global", cfg_interval=(0, 1),
+                       cfg_text_scale: float = 1.0, cfg_text_packed_query_indexes=None, cfg_text_packed_position_ids=None,
+                       cfg_text_past_key_values=None, cfg_text_key_values_lens=None, cfg_text_packed_key_value_indexes=None,
+                       cfg_img_scale: float = 1.0, cfg_img_packed_query_indexes=None, cfg_img_packed_position_ids=None,
+                       cfg_img_past_key_values=None, cfg_img_key_values_lens=None, cfg_img_packed_key_value_indexes=None,
+                       cfg_type: str = "parallel"):
+        """bagel.py:901-986: shifted-time Euler integration of the guided velocity; returns a tuple of fp32
+        [h*w, patch_latent_dim] latents (one per image, on the device).  Batching rule: the "global"
+        renorm is taken per image, which equals the reference for its only supported case (batch 1, bagel.py:1196)."""
+        if cfg_renorm_type not in self._RENORM:
+            raise NotImplementedError(f"{cfg_renorm_type} is not suppoprted")
+        lens, lat_lens, pos = self._flow_geometry(packed_seqlens, packed_position_ids)
+        B = len(lens)
+        ids = self._ints(packed_text_ids)
+        if ids[0::2] != [ids[0]] * B or ids[1::2] != [ids[1]] * B:
+            raise NotImplementedError("generate_image: every image must use the same start/end marker ids")
+        h = paged_handle(past_key_values, self.engine, B)
+        self._check_kv(h, key_values_lens, packed_key_value_indexes, lens, packed_indexes, "generate_image")
+
+        used, temps = set(h.seqs), []
+
+        def branch(cache, kv_lens, kv_idx, q_idx, pos_ids, what):
+            if cache is None:
+                return None
+            hb = paged_handle(cache, self.engine, B)
+            self._check_kv(hb, kv_lens, kv_idx, lens, q_idx, what)
+            if used & set(hb.seqs):          # the same context object passed for two branches: give it its own pages
+                hb = hb.fork()
+                temps.append(hb)
+            used.update(hb.seqs)
+            return hb.seqs, self._flow_geometry(packed_seqlens, pos_ids)[2]
+        cfg_text = branch(cfg_text_past_key_values, cfg_text_key_values_lens, cfg_text_packed_key_value_indexes,
+                          cfg_text_packed_query_indexes, cfg_text_packed_position_ids, "generate_image.cfg_text")
+        cfg_img = branch(cfg_img_past_key_values, cfg_img_key_values_lens, cfg_img_packed_key_value_indexes,
+                         cfg_img_packed_query_indexes, cfg_img_packed_position_ids, "generate_image.cfg_img")
+        dev = self.device
+        x_t = packed_init_noises.to(dev, torch.float32).contiguous().clone()
+        pos_ids = packed_vae_position_ids.to(dev)
+        v = torch.empty_like(x_t)
+        # schedule exactly as the reference computes it (fp32 tensors, bagel.py:937-940)
+        timesteps = torch.linspace(1, 0, num_timesteps)
+        timesteps = timestep_shift * timesteps / (1 + (timestep_shift - 1) * timesteps)
+        dts = timesteps[:-1] - timesteps[1:]
+        timesteps = timesteps[:-1]
+        renorm = self._RENORM[cfg_renorm_type]
+        for i, t in enumerate(timesteps):
+            on = bool(t > cfg_interval[0] and t <= cfg_interval[1])
+            ts_, is_ = (cfg_text_scale, cfg_img_scale) if on else (1.0, 1.0)
+            use_text = cfg_text if ts_ > 1.0 else None
+            use_img = cfg_img if is_ > 1.0 else None
+            if ts_ > 1.0 and use_text is None:
+                raise ValueError("cfg_text_scale > 1 needs cfg_text_past_key_values")
+            if is_ > 1.0 and use_img is None:
+                raise ValueError("cfg_img_scale > 1 needs cfg_img_past_key_values")
+            self.engine.flow_velocity(x_t, pos_ids, lat_lens, h.seqs, pos, ids[:2], float(t), use_text, use_img, ts_, is_,
+                                      cfg_renorm_min, renorm, out=v)
+            # velocity dtype in the reference: bf16 unless a per-token (fp32) norm scaled it (SURVEY.md R9)
+            v_is_bf16 = not (ts_ > 1.0 and renorm in (1, 2))
+            self.engine.flow_euler(x_t, v, float(dts[i]), v_is_bf16)
+        return x_t.split(lat_lens)
+
     # ------------------------------------------------------------------ decode
     @torch.no_grad()
     def generate_text(self, past_key_values, packed_key_value_indexes, key_values_lens, packed_start_tokens,

@@ -205,6 +205,14 @@ static int build_runtime(umv_engine* e) {
         UMV_TRY(dev_alloc(e, &e->meta_dev[i], e->meta_bytes));
         cudaEventCreateWithFlags(&e->meta_ev[i], cudaEventDisableTiming);
     }
+    // flow scratch: timestep frequencies exp(-ln(10000) * i / 128) in fp32 (modeling_utils.py:96-99)
+    UMV_TRY(dev_alloc(e, &e->flow_small, (size_t)4 * std::max(d.hidden, 256)));
+    {
+        std::vector<float> f(128);
+        for (int i = 0; i < 128; ++i) f[i] = expf(-logf(10000.0f) * (float)i / 128.0f);
+        UMV_TRY(dev_alloc(e, &e->t_freqs, f.size()));
+        cudaMemcpy(e->t_freqs, f.data(), f.size() * sizeof(float), cudaMemcpyHostToDevice);
+    }
     // decode state
     UMV_TRY(dev_alloc(e, &e->dec_tokens, 64));
     UMV_TRY(dev_alloc(e, &e->dec_pos, 64));
@@ -316,8 +324,8 @@ struct LlmRun {
     CallMeta m;
 };
 
-static int lin(umv_engine* e, const bf16* x, int ldx, const bf16* w, const bf16* bias, const bf16* res, bf16* y, int ldy, int M,
-               int N, int K, int epi, cudaStream_t st, int impl = GEMM_AUTO, float* ws = nullptr, int splits = 1) {
+int lin(umv_engine* e, const bf16* x, int ldx, const bf16* w, const bf16* bias, const bf16* res, bf16* y, int ldy, int M,
+               int N, int K, int epi, cudaStream_t st, int impl, float* ws, int splits) {
     LinearCall c;
     c.x = x; c.ldx = ldx; c.w = w; c.bias = bias; c.residual = res; c.y = y; c.ldy = ldy;
     c.M = M; c.N = N; c.K = K; c.epi = epi; c.ws = ws; c.splits = splits;
@@ -663,10 +671,20 @@ int umv_llm_forward(umv_engine* e, const void* x, int32_t n_seqs, const int32_t*
                     const int32_t* positions, const uint8_t* row_is_gen, int32_t is_causal, int32_t update_kv, void* out,
                     void* stream) {
     UMV_REQUIRE(e && e->finalized, UMV_ERR_STATE, "engine not finalized");
-    UMV_REQUIRE(x && seqs && q_lens && positions && n_seqs > 0, UMV_ERR_INVALID, "umv_llm_forward: null/empty argument");
+    UMV_REQUIRE(x, UMV_ERR_INVALID, "umv_llm_forward: null x");
+    return umv::llm_run(e, static_cast<const bf16*>(x), n_seqs, seqs, q_lens, positions, row_is_gen, is_causal, update_kv,
+                        static_cast<bf16*>(out), static_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"
+
+namespace umv {
+// Packed forward over n_seqs sequences; x == nullptr means the packed query sequence is already in e->h.
+int llm_run(umv_engine* e, const bf16* x, int n_seqs, const int32_t* seqs, const int32_t* q_lens, const int32_t* positions,
+            const uint8_t* row_is_gen, int is_causal, int update_kv, bf16* out, cudaStream_t st) {
+    UMV_REQUIRE(seqs && q_lens && positions && n_seqs > 0, UMV_ERR_INVALID, "umv_llm_forward: null/empty argument");
     UMV_REQUIRE(n_seqs <= 3 * e->d.max_seqs, UMV_ERR_INVALID, "umv_llm_forward: %d sequences > 3*max_seqs", n_seqs);
     UMV_REQUIRE(!row_is_gen || e->d.enable_gen, UMV_ERR_STATE, "generation expert weights were not enabled");
-    cudaStream_t st = static_cast<cudaStream_t>(stream);
     const int D = e->d.hidden;
     LlmRun r;
     r.n_seqs = n_seqs;
@@ -725,13 +743,16 @@ int umv_llm_forward(umv_engine* e, const void* x, int32_t n_seqs, const int32_t*
         m.n_text = (int)text.size();
     }
     UMV_TRY(meta_commit(e, &mb, st));
-    UMV_CUDA_OK(cudaMemcpy2DAsync(e->h, (size_t)D * 2, x, (size_t)D * 2, (size_t)D * 2, M, cudaMemcpyDeviceToDevice, st));
+    if (x) UMV_CUDA_OK(cudaMemcpy2DAsync(e->h, (size_t)D * 2, x, (size_t)D * 2, (size_t)D * 2, M, cudaMemcpyDeviceToDevice, st));
     r.weight_major = M <= 64;
-    UMV_TRY(llm_layers(e, r, static_cast<bf16*>(out), st));
+    UMV_TRY(llm_layers(e, r, out, st));
     if (update_kv)
         for (int b = 0; b < n_seqs; ++b) sq[b]->len += q_lens[b];
     return UMV_OK;
 }
+}  // namespace umv
+
+extern "C" {
 
 int umv_lm_head(umv_engine* e, const void* hidden, int32_t m, void* logits, void* stream) {
     UMV_REQUIRE(e && e->finalized, UMV_ERR_STATE, "engine not finalized");
@@ -880,14 +901,95 @@ int umv_generate_text(umv_engine* e, int32_t n_seqs, const int32_t* seqs, const 
     return UMV_OK;
 }
 
-// ------------------------------------------------------------------------------ flow (next milestone)
-int umv_flow_velocity(umv_engine*, const umv_flow_args*, const float*, float*, void*) {
-    set_error("umv_flow_velocity: not built yet");
-    return UMV_ERR_UNSUPPORTED;
+
+// ------------------------------------------------------------------------------ rectified flow
+int umv_flow_velocity(umv_engine* e, const umv_flow_args* a, const float* x_t, float* v_out, void* stream) {
+    UMV_REQUIRE(e && e->finalized, UMV_ERR_STATE, "engine not finalized");
+    UMV_REQUIRE(e->d.enable_gen, UMV_ERR_STATE, "generation expert weights were not enabled");
+    UMV_REQUIRE(a && x_t && v_out && a->seqs && a->lat_lens && a->positions && a->marker_ids && a->lat_pos_ids && a->n_seqs > 0,
+                UMV_ERR_INVALID, "umv_flow_velocity: null/empty argument");
+    UMV_REQUIRE(a->renorm_type >= 0 && a->renorm_type <= 2, UMV_ERR_UNSUPPORTED, "cfg_renorm_type %d is not supported", a->renorm_type);
+    const bool has_text = a->cfg_text_scale > 1.0f, has_img = a->cfg_img_scale > 1.0f;
+    UMV_REQUIRE(!has_text || (a->cfg_text_seqs && a->cfg_text_positions), UMV_ERR_INVALID, "cfg_text context missing");
+    UMV_REQUIRE(!has_img || (a->cfg_img_seqs && a->cfg_img_positions), UMV_ERR_INVALID, "cfg_img context missing");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const umv_dims& d = e->d;
+    const int D = d.hidden, C = d.latent_dim, B = a->n_seqs;
+    int n_lat = 0;
+    for (int b = 0; b < B; ++b) {
+        UMV_REQUIRE(a->lat_lens[b] > 0, UMV_ERR_INVALID, "empty image %d", b);
+        n_lat += a->lat_lens[b];
+    }
+    const int Mb = n_lat + 2 * B;
+    const int text_branch = has_text ? 1 : -1, img_branch = has_img ? (has_text ? 2 : 1) : -1;
+    const int nb = 1 + (has_text ? 1 : 0) + (has_img ? 1 : 0);
+    UMV_REQUIRE(nb * Mb <= d.max_tokens, UMV_ERR_NOMEM, "flow step needs %d rows > max_tokens %d", nb * Mb, d.max_tokens);
+    // the reference evaluates cfg_img only inside the cfg_text branch (bagel.py:1173-1207): img without text is ignored
+    // per-image geometry
+    MetaBuilder mb;
+    UMV_TRY(meta_begin(e, &mb, (size_t)Mb * 4 + (size_t)B * 16 + 64));
+    int *d_row_src, *d_row0, *d_lat0, *d_n;
+    int* h_src = mb.put<int>(nullptr, Mb, &d_row_src);
+    int* h_row0 = mb.put<int>(nullptr, B, &d_row0);
+    int* h_lat0 = mb.put<int>(nullptr, B, &d_lat0);
+    mb.put<int>(a->lat_lens, B, &d_n);
+    int r = 0, l = 0;
+    for (int b = 0; b < B; ++b) {
+        h_src[r++] = -1;
+        h_row0[b] = r;
+        h_lat0[b] = l;
+        for (int j = 0; j < a->lat_lens[b]; ++j) h_src[r++] = l++;
+        h_src[r++] = -2;
+    }
+    UMV_TRY(meta_commit(e, &mb, st));
+    // 1. vae2llm(x_t): fp32 latents enter the autocast Linear as bf16
+    bf16* xtb = e->attn;
+    bf16* lat = e->act;
+    UMV_TRY(f32_to_bf16_padded(x_t, xtb, n_lat, C, C, st));
+    UMV_TRY(lin(e, xtb, C, e->vae2llm_w, e->vae2llm_b, nullptr, lat, D, n_lat, D, C, EPI_BF16, st));
+    // 2. timestep embedding, once per step (the reference recomputes it per token for an identical t)
+    bf16* tf = e->flow_small;
+    bf16* th = e->flow_small + std::max(D, 256);
+    bf16* temb = e->flow_small + 2 * std::max(D, 256);
+    UMV_TRY(timestep_freq(a->timestep, e->t_freqs, 128, tf, st));
+    UMV_TRY(lin(e, tf, 256, e->t_w0, e->t_b0, nullptr, th, D, 1, D, 256, EPI_BF16, st));
+    UMV_TRY(silu_inplace(th, D, st));
+    UMV_TRY(lin(e, th, D, e->t_w2, e->t_b2, nullptr, temb, D, 1, D, D, EPI_BF16, st));
+    // 3. packed query sequence for every branch
+    UMV_REQUIRE(a->marker_ids[0] >= 0 && a->marker_ids[0] < d.vocab && a->marker_ids[1] >= 0 && a->marker_ids[1] < d.vocab,
+                UMV_ERR_INVALID, "marker token id out of range");
+    UMV_TRY(flow_compose(lat, temb, e->latent_pos, a->lat_pos_ids, e->embed, a->marker_ids[0], a->marker_ids[1], d_row_src, Mb, nb,
+                         D, e->h, st));
+    // 4. one packed gen-mode forward over all branches (rows are independent; contexts / rope positions differ)
+    std::vector<int32_t> seqs, qlens, pos;
+    std::vector<uint8_t> is_gen;
+    const int32_t* bseq[3] = {a->seqs, nullptr, nullptr};
+    const int32_t* bpos[3] = {a->positions, nullptr, nullptr};
+    if (has_text) { bseq[text_branch] = a->cfg_text_seqs; bpos[text_branch] = a->cfg_text_positions; }
+    if (has_img) { bseq[img_branch] = a->cfg_img_seqs; bpos[img_branch] = a->cfg_img_positions; }
+    for (int br = 0; br < nb; ++br)
+        for (int b = 0; b < B; ++b) {
+            seqs.push_back(bseq[br][b]);
+            qlens.push_back(a->lat_lens[b] + 2);
+            for (int j = 0; j < a->lat_lens[b] + 2; ++j) {
+                pos.push_back(bpos[br][b]);
+                is_gen.push_back(j > 0 && j < a->lat_lens[b] + 1 ? 1 : 0);
+            }
+        }
+    UMV_TRY(llm_run(e, nullptr, nb * B, seqs.data(), qlens.data(), pos.data(), is_gen.data(), 0, 0, e->xn, st));
+    // 5. llm2vae on every row, then CFG on the latent rows
+    bf16* vall = e->qkv;
+    UMV_TRY(lin(e, e->xn, D, e->llm2vae_w, e->llm2vae_b, nullptr, vall, C, nb * Mb, C, D, EPI_BF16, st));
+    CfgArgs c;
+    c.v = vall; c.rows_per_branch = Mb; c.C = C; c.text_branch = text_branch; c.img_branch = has_text ? img_branch : -1;
+    c.text_scale = a->cfg_text_scale; c.img_scale = a->cfg_img_scale; c.renorm_min = a->cfg_renorm_min;
+    c.renorm_type = a->renorm_type; c.img_row0 = d_row0; c.img_lat0 = d_lat0; c.img_n = d_n; c.out = v_out;
+    return cfg_combine(c, B, st);
 }
-int umv_flow_euler(umv_engine*, float*, const float*, int64_t, float, int32_t, void*) {
-    set_error("umv_flow_euler: not built yet");
-    return UMV_ERR_UNSUPPORTED;
+
+int umv_flow_euler(umv_engine* e, float* x_t, const float* v, int64_t n, float dt, int32_t v_is_bf16, void* stream) {
+    UMV_REQUIRE(e && x_t && v, UMV_ERR_INVALID, "umv_flow_euler: null argument");
+    return euler_step(x_t, v, n, dt, v_is_bf16, static_cast<cudaStream_t>(stream));
 }
 
 int umv_bench_decode_linear(umv_engine* e, int32_t which, int32_t layer, int32_t m, int64_t* weight_bytes, void* stream) {

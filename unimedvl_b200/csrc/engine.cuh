@@ -54,6 +54,15 @@ struct CallMeta {
 
 }  // namespace umv
 
+struct umv_engine;
+namespace umv {
+// engine.cu internals shared with flow.cu / vae.cu
+int lin(umv_engine* e, const bf16* x, int ldx, const bf16* w, const bf16* bias, const bf16* res, bf16* y, int ldy, int M, int N,
+        int K, int epi, cudaStream_t st, int impl = 0, float* ws = nullptr, int splits = 1);
+int llm_run(umv_engine* e, const bf16* x, int n_seqs, const int32_t* seqs, const int32_t* q_lens, const int32_t* positions,
+            const uint8_t* row_is_gen, int is_causal, int update_kv, bf16* out, cudaStream_t st);
+}  // namespace umv
+
 struct umv_engine {
     umv_dims d{};
     int dh = 0, qkvn = 0, vit_kpad = 0, sm_count = 148;
@@ -100,6 +109,9 @@ struct umv_engine {
 
     // decode state
     int64_t* dec_tokens = nullptr;
+    // flow scratch
+    umv::bf16 *flow_small = nullptr;   // [4, hidden]: timestep frequencies / hidden / embedding
+    float* t_freqs = nullptr;          // [128] exp(-ln(1e4) i / 128)
     int *dec_pos = nullptr, *dec_kvlen = nullptr, *dec_kvpos = nullptr, *dec_step = nullptr, *dec_rowseq = nullptr,
         *dec_qstart = nullptr, *dec_qlen = nullptr, *dec_pages = nullptr;
     int dec_pages_cap = 0;

@@ -106,4 +106,24 @@ int sample_rows(const bf16* logits, int rows, int vocab, float temperature, uint
 int export_kv(KVPool pool, int layer, const int* pages, int len, bf16* k_out, bf16* v_out, cudaStream_t s);
 int copy_page(KVPool pool, int src_page, int dst_page, cudaStream_t s);
 
+// ---- rectified-flow glue (flow.cu)
+struct CfgArgs {
+    const bf16* v;
+    int rows_per_branch, C;
+    int text_branch, img_branch;       // branch index or -1
+    float text_scale, img_scale, renorm_min;
+    int renorm_type;                   // 0 global (per image), 1 channel, 2 text_channel
+    const int* img_row0;               // [B] packed row of the image's first latent token
+    const int* img_lat0;               // [B] first latent index
+    const int* img_n;                  // [B] latent tokens
+    float* out;                        // [n_lat, C] fp32
+};
+int timestep_freq(float t, const float* freqs, int half, bf16* out, cudaStream_t s);
+int silu_inplace(bf16* x, int n, cudaStream_t s);
+int flow_compose(const bf16* lat, const bf16* temb, const bf16* pos_table, const int64_t* pos_ids, const bf16* embed,
+                 int64_t id_start, int64_t id_end, const int* row_src, int rows_per_branch, int branches, int D, bf16* out,
+                 cudaStream_t s);
+int cfg_combine(const CfgArgs& a, int n_images, cudaStream_t s);
+int euler_step(float* x, const float* v, int64_t n, float dt, int v_is_bf16, cudaStream_t s);
+
 }  // namespace umv

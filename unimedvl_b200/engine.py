@@ -206,6 +206,38 @@ class Engine:
         out = (toks,) + ((logits,) if return_logits else ()) + ((nxt,) if return_next else ())
         return out if len(out) > 1 else toks
 
+    def flow_velocity(self, x_t: torch.Tensor, lat_pos_ids: torch.Tensor, lat_lens, seqs, positions, marker_ids, timestep: float,
+                      cfg_text=None, cfg_img=None, cfg_text_scale: float = 1.0, cfg_img_scale: float = 1.0,
+                      cfg_renorm_min: float = 0.0, renorm_type: int = 0, out: torch.Tensor | None = None) -> torch.Tensor:
+        """Bagel._forward_flow (bagel.py:989-1211).  x_t fp32 [n_lat, latent_dim] on the device; cfg_text / cfg_img are
+        (seqs, positions) of the alternate contexts.  Returns the guided velocity as fp32 values [n_lat, latent_dim]."""
+        assert x_t.is_cuda and x_t.dtype == torch.float32 and x_t.is_contiguous()
+        lat_pos_ids = lat_pos_ids.to(self.device, torch.int64).contiguous()
+        v = out if out is not None else torch.empty_like(x_t)
+        keep = [_lib.i32_array(seqs), _lib.i32_array(lat_lens), _lib.i32_array(positions), _lib.i64_array(marker_ids)]
+        a = _lib.FlowArgs()
+        a.n_seqs = len(seqs)
+        a.seqs, a.lat_lens, a.positions, a.marker_ids = keep[0], keep[1], keep[2], keep[3]
+        if cfg_text is not None:
+            keep += [_lib.i32_array(cfg_text[0]), _lib.i32_array(cfg_text[1])]
+            a.cfg_text_seqs, a.cfg_text_positions = keep[-2], keep[-1]
+        if cfg_img is not None:
+            keep += [_lib.i32_array(cfg_img[0]), _lib.i32_array(cfg_img[1])]
+            a.cfg_img_seqs, a.cfg_img_positions = keep[-2], keep[-1]
+        a.lat_pos_ids = lat_pos_ids.data_ptr()
+        a.timestep, a.cfg_text_scale, a.cfg_img_scale = float(timestep), float(cfg_text_scale), float(cfg_img_scale)
+        a.cfg_renorm_min, a.renorm_type = float(cfg_renorm_min), int(renorm_type)
+        self._enter()
+        _lib.check(self.lib.umv_flow_velocity(self.h, C.byref(a), _ptr(x_t), _ptr(v), _stream_ptr(self.stream)))
+        self._exit()
+        return v
+
+    def flow_euler(self, x_t: torch.Tensor, v: torch.Tensor, dt: float, v_is_bf16: bool) -> None:
+        self._enter()
+        _lib.check(self.lib.umv_flow_euler(self.h, _ptr(x_t), _ptr(v), x_t.numel(), C.c_float(dt), int(v_is_bf16),
+                                           _stream_ptr(self.stream)))
+        self._exit()
+
     def launch_count(self) -> int:
         return int(self.lib.umv_launch_count())
 
