@@ -53,6 +53,7 @@ typedef struct umv_dims {
     int32_t max_seqs;             /* largest number of samples in one call         */
     int32_t kv_pages;             /* KV page pool size (pages of UMV_PAGE_TOKENS tokens) */
     int32_t enable_vit, enable_gen;   /* allocate ViT / generation-expert weights  */
+    int32_t enable_vae;               /* allocate the FLUX-style autoencoder (autoencoder.py:338-349 geometry) */
 } umv_dims;
 
 #define UMV_PAGE_TOKENS 64
@@ -151,6 +152,18 @@ typedef struct umv_flow_args {
 int umv_flow_velocity(umv_engine* e, const umv_flow_args* a, const float* x_t, float* v_out, void* stream);
 /* x_t <- x_t - bf16(v * dt) (bagel.py:983; v*dt rounds to bf16 when v is bf16-valued). */
 int umv_flow_euler(umv_engine* e, float* x_t, const float* v, int64_t n, float dt, int32_t v_is_bf16, void* stream);
+
+/* Latent tokens entering the LLM (bagel.py:777-781, 1100-1107): bf16(bf16(vae2llm(x) + time_embedder(t)) +
+ * latent_pos_embed[pos]).  x: f32 [n, latent_dim] device; pos_ids: i64 [n] device; out: bf16 [n, hidden]. */
+int umv_latent_embed(umv_engine* e, const float* x, const int64_t* pos_ids, int32_t n, float timestep, void* out, void* stream);
+
+/* ---- VAE: AutoEncoder.decode / Encoder (autoencoder.py:300-307, 122-257).  Weight names are the
+ * reference's with the prefix "vae_model." (the submodule name inside Bagel, bagel.py:102).
+ * decode: z bf16 [n, z_channels, h, w] (NCHW, the scaled latent decode_image builds, inferencer.py:239-241)
+ *   -> bf16 image [n, 3, 8h, 8w].  encode_moments: x bf16 [n, 3, H, W] -> bf16 [n, 2*z_channels, H/8, W/8]
+ *   (mean | logvar); the caller draws DiagonalGaussian's noise and applies scale/shift (autoencoder.py:266-303). */
+int umv_vae_decode(umv_engine* e, const void* z, int32_t n, int32_t h, int32_t w, void* out, void* stream);
+int umv_vae_encode_moments(umv_engine* e, const void* x, int32_t n, int32_t H, int32_t W, void* out, void* stream);
 
 /* ---- op-level entry points (parity tests; each is the kernel the model path uses) ---------- */
 /* y[M,N] = x[M,K] @ w[N,K]^T (+bias) with epilogue `epi`: 0 bf16, 1 gelu_tanh, 2 swiglu (w rows

@@ -21,7 +21,7 @@ class Dims(C.Structure):
         ("vit_patch_dim", C.c_int32), ("vit_positions", C.c_int32), ("vit_eps", C.c_float),
         ("vit_pos_table", C.c_int32), ("latent_dim", C.c_int32), ("latent_pos_table", C.c_int32),
         ("max_tokens", C.c_int32), ("max_seqs", C.c_int32), ("kv_pages", C.c_int32),
-        ("enable_vit", C.c_int32), ("enable_gen", C.c_int32),
+        ("enable_vit", C.c_int32), ("enable_gen", C.c_int32), ("enable_vae", C.c_int32),
     ]
 
 
@@ -67,6 +67,9 @@ SIGNATURES = {
     "umv_generate_text": (C.c_int, [_P, _I, _IP, _LP, _IP, _I, _F, _U64, _P, _P, _P, _P, _P]),
     "umv_flow_velocity": (C.c_int, [_P, C.POINTER(FlowArgs), _P, _P, _P]),
     "umv_flow_euler": (C.c_int, [_P, _P, _P, C.c_int64, _F, _I, _P]),
+    "umv_latent_embed": (C.c_int, [_P, _P, _P, _I, _F, _P, _P]),
+    "umv_vae_decode": (C.c_int, [_P, _P, _I, _I, _I, _P, _P]),
+    "umv_vae_encode_moments": (C.c_int, [_P, _P, _I, _I, _I, _P, _P]),
     "umv_op_linear": (C.c_int, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P]),
     "umv_op_rmsnorm": (C.c_int, [_P, _P, _P, _I, _I, _F, _P]),
     "umv_op_layernorm": (C.c_int, [_P, _P, _P, _P, _I, _I, _F, _P]),

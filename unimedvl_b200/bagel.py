@@ -139,6 +139,34 @@ class Bagel:
                                 want_hidden=False)
         return past_key_values
 
+    @torch.no_grad()
+    def forward_cache_update_vae(self, vae_model, past_key_values, padded_images, patchified_vae_latent_shapes,
+                                 packed_vae_position_ids, packed_timesteps, packed_vae_token_indexes, packed_text_ids,
+                                 packed_text_indexes, packed_position_ids, packed_seqlens, packed_indexes, key_values_lens,
+                                 packed_key_value_indexes):
+        """bagel.py:697-806: VAE-encode the image, patchify the latent (chpwq->hwpqc), embed the latent tokens at
+        timestep `packed_timesteps` and prefill them through the GENERATION expert (mode gen, full attention)."""
+        lens = self._ints(packed_seqlens)
+        h = paged_handle(past_key_values, self.engine, len(lens))
+        self._check_kv(h, key_values_lens, packed_key_value_indexes, lens, packed_indexes, "forward_cache_update_vae")
+        dev = self.device
+        p, C = self.latent_patch_size, self.latent_channel
+        latent = vae_model.encode(padded_images.to(dev))                         # [B, C, Hp/8, Wp/8] bf16
+        rows = []
+        for z, (hh, ww) in zip(latent, patchified_vae_latent_shapes):
+            z = z[:, :hh * p, :ww * p].reshape(C, hh, p, ww, p)
+            rows.append(z.permute(1, 3, 2, 4, 0).reshape(-1, p * p * C))
+        packed_latent = torch.cat(rows, dim=0)
+        t = float(self._ints(packed_timesteps)[0]) if torch.is_tensor(packed_timesteps) else float(packed_timesteps[0])
+        seq = torch.zeros((sum(lens), self.hidden_size), dtype=torch.bfloat16, device=dev)
+        seq[packed_text_indexes.to(dev)] = self.engine.embed_tokens(packed_text_ids)
+        seq[packed_vae_token_indexes.to(dev)] = self.engine.latent_embed(packed_latent.float(), packed_vae_position_ids, t)
+        is_gen = torch.zeros(sum(lens), dtype=torch.uint8)
+        is_gen[packed_vae_token_indexes.cpu()] = 1
+        self.engine.llm_forward(seq, h.seqs, lens, self._ints(packed_position_ids), row_is_gen=is_gen.tolist(), is_causal=False,
+                                update_kv=True, want_hidden=False)
+        return past_key_values
+
     # ------------------------------------------------------------------ image generation (rectified flow)
     _RENORM = {"global": 0, "channel": 1, "text_channel": 2}
 

@@ -54,6 +54,19 @@ static void reg(umv_engine* e, const std::string& name, bf16* dst, int64_t rows,
     e->slots[name] = s;
 }
 
+int engine_alloc(umv_engine* e, void** out, size_t bytes) {
+    uint8_t* p = nullptr;
+    UMV_TRY(dev_alloc(e, &p, bytes));
+    *out = p;
+    return UMV_OK;
+}
+void engine_reg(umv_engine* e, const std::string& name, bf16* dst, int64_t rows, int64_t cols, int ndim, int conv_k, int conv_cin,
+                float bound, float mean) {
+    reg(e, name, dst, rows, cols, cols, ndim, SLOT_PLAIN, bound, mean);
+    e->slots[name].conv_k = conv_k;
+    e->slots[name].conv_cin = conv_cin;
+}
+
 // Allocates one linear layer [rows, cols] (+ optional bias) and registers its reference names.
 static int alloc_linear(umv_engine* e, const std::string& name, int64_t rows, int64_t cols, bool bias, bf16** w, bf16** b,
                         int64_t ld = 0) {
@@ -472,6 +485,7 @@ int umv_create(const umv_dims* dims, umv_engine** out) {
     if (rc == UMV_OK) rc = attention_init();
     if (rc == UMV_OK) rc = build_weights(e);
     if (rc == UMV_OK) rc = build_runtime(e);
+    if (rc == UMV_OK && d.enable_vae) rc = vae_build(e);
     if (rc != UMV_OK) {
         umv_destroy(e);
         return rc;
@@ -484,6 +498,7 @@ int umv_destroy(umv_engine* e) {
     if (!e) return UMV_OK;
     cudaDeviceSynchronize();
     for (void* p : e->allocs) cudaFree(p);
+    delete e->vae;
     for (int i = 0; i < umv_engine::kMetaRing; ++i) {
         if (e->meta_host[i]) cudaFreeHost(e->meta_host[i]);
         if (e->meta_ev[i]) cudaEventDestroy(e->meta_ev[i]);
@@ -516,6 +531,23 @@ int umv_load_tensor(umv_engine* e, const char* name, const void* data, int dtype
     auto it = e->slots.find(name);
     UMV_REQUIRE(it != e->slots.end(), UMV_ERR_INVALID, "umv_load_tensor: unknown tensor '%s'", name);
     Slot& s = it->second;
+    if (s.conv_k > 0) {
+        // conv weight [cout, cin, k, k] -> engine layout [cout, k, k, cin] (tap-major, matches the NHWC im2col)
+        UMV_REQUIRE(ndim == 4 && shape[0] == s.rows && shape[1] == s.conv_cin && shape[2] == s.conv_k && shape[3] == s.conv_k,
+                    UMV_ERR_INVALID, "umv_load_tensor: '%s' expects a conv weight [%lld,%d,%d,%d]", name, (long long)s.rows,
+                    s.conv_cin, s.conv_k, s.conv_k);
+        UMV_REQUIRE(dtype == UMV_BF16, UMV_ERR_UNSUPPORTED, "conv weights must be bf16");
+        const size_t n = (size_t)s.rows * s.cols;
+        std::vector<bf16> src(n), dst(n);
+        UMV_CUDA_OK(cudaMemcpy(src.data(), data, n * 2, cudaMemcpyDefault));
+        const int kk = s.conv_k * s.conv_k, cin = s.conv_cin;
+        for (int64_t o = 0; o < s.rows; ++o)
+            for (int c = 0; c < cin; ++c)
+                for (int t = 0; t < kk; ++t) dst[(o * kk + t) * cin + c] = src[(o * cin + c) * kk + t];
+        int rc2 = slot_copy(e, s, dst.data(), true);
+        if (rc2 == UMV_OK) s.loaded = true;
+        return rc2;
+    }
     const int64_t rows = ndim == 2 ? shape[0] : 1, cols = ndim == 2 ? shape[1] : shape[0];
     UMV_REQUIRE(ndim == s.ndim && rows == s.rows && cols == s.cols, UMV_ERR_INVALID,
                 "umv_load_tensor: '%s' expects shape [%lld,%lld] (ndim %d), got ndim %d [%lld,%lld]", name, (long long)s.rows,
@@ -544,6 +576,17 @@ int umv_export_tensor(umv_engine* e, const char* name, void* host_dst, size_t by
     Slot& s = it->second;
     UMV_REQUIRE(bytes == (size_t)s.rows * s.cols * 2, UMV_ERR_INVALID, "umv_export_tensor: '%s' needs %zu bytes", name,
                 (size_t)s.rows * s.cols * 2);
+    if (s.conv_k > 0) {
+        const size_t n = (size_t)s.rows * s.cols;
+        std::vector<bf16> tmp(n);
+        UMV_TRY(slot_copy(e, s, tmp.data(), false));
+        bf16* out = static_cast<bf16*>(host_dst);
+        const int kk = s.conv_k * s.conv_k, cin = s.conv_cin;
+        for (int64_t o = 0; o < s.rows; ++o)
+            for (int c = 0; c < cin; ++c)
+                for (int t = 0; t < kk; ++t) out[(o * cin + c) * kk + t] = tmp[(o * kk + t) * cin + c];
+        return UMV_OK;
+    }
     return slot_copy(e, s, host_dst, false);
 }
 
@@ -985,6 +1028,32 @@ int umv_flow_velocity(umv_engine* e, const umv_flow_args* a, const float* x_t, f
     c.text_scale = a->cfg_text_scale; c.img_scale = a->cfg_img_scale; c.renorm_min = a->cfg_renorm_min;
     c.renorm_type = a->renorm_type; c.img_row0 = d_row0; c.img_lat0 = d_lat0; c.img_n = d_n; c.out = v_out;
     return cfg_combine(c, B, st);
+}
+
+int umv_latent_embed(umv_engine* e, const float* x, const int64_t* pos_ids, int32_t n, float timestep, void* out, void* stream) {
+    UMV_REQUIRE(e && e->finalized, UMV_ERR_STATE, "engine not finalized");
+    UMV_REQUIRE(e->d.enable_gen, UMV_ERR_STATE, "generation expert weights were not enabled");
+    UMV_REQUIRE(x && pos_ids && out && n > 0 && n <= e->d.max_tokens, UMV_ERR_INVALID, "umv_latent_embed: bad argument");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int D = e->d.hidden, C = e->d.latent_dim;
+    MetaBuilder mb;
+    UMV_TRY(meta_begin(e, &mb, (size_t)n * 4 + 64));
+    int* d_src;
+    int* h_src = mb.put<int>(nullptr, n, &d_src);
+    for (int i = 0; i < n; ++i) h_src[i] = i;
+    UMV_TRY(meta_commit(e, &mb, st));
+    bf16* xtb = e->attn;
+    bf16* lat = e->act;
+    UMV_TRY(f32_to_bf16_padded(x, xtb, n, C, C, st));
+    UMV_TRY(lin(e, xtb, C, e->vae2llm_w, e->vae2llm_b, nullptr, lat, D, n, D, C, EPI_BF16, st));
+    bf16* tf = e->flow_small;
+    bf16* th = e->flow_small + std::max(D, 256);
+    bf16* temb = e->flow_small + 2 * std::max(D, 256);
+    UMV_TRY(timestep_freq(timestep, e->t_freqs, 128, tf, st));
+    UMV_TRY(lin(e, tf, 256, e->t_w0, e->t_b0, nullptr, th, D, 1, D, 256, EPI_BF16, st));
+    UMV_TRY(silu_inplace(th, D, st));
+    UMV_TRY(lin(e, th, D, e->t_w2, e->t_b2, nullptr, temb, D, 1, D, D, EPI_BF16, st));
+    return flow_compose(lat, temb, e->latent_pos, pos_ids, e->embed, 0, 0, d_src, n, 1, D, static_cast<bf16*>(out), st);
 }
 
 int umv_flow_euler(umv_engine* e, float* x_t, const float* v, int64_t n, float dt, int32_t v_is_bf16, void* stream) {

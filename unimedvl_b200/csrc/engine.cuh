@@ -20,6 +20,7 @@ struct Slot {
     int64_t dst_ld = 0;      // destination row stride in elements
     int kind = SLOT_PLAIN;
     int ndim = 2;
+    int conv_k = 0, conv_cin = 0;   // >0: reference tensor is a conv weight [rows, conv_cin, k, k]; stored [rows, k, k, conv_cin]
     bool loaded = false;
     float synth_bound = 0.02f * 1.7320508f, synth_mean = 0.f;
 };
@@ -56,7 +57,28 @@ struct CallMeta {
 
 struct umv_engine;
 namespace umv {
+// ---- VAE (autoencoder.py:38-257) weights, NHWC / tap-major conv layout
+struct VaeConv { bf16* w = nullptr; bf16* b = nullptr; int cin = 0, cout = 0, k = 0; };
+struct VaeNorm { bf16* w = nullptr; bf16* b = nullptr; int c = 0; };
+struct VaeRes { VaeNorm n1, n2; VaeConv c1, c2, sc; int cin = 0, cout = 0; };
+struct VaeAttn { VaeNorm n; VaeConv q, k, v, o; int c = 0; };
+struct VaeLevel { std::vector<VaeRes> blocks; VaeConv resample; bool has_resample = false; };
+struct VaeHalf { VaeConv conv_in, conv_out; VaeRes mid1, mid2; VaeAttn attn; std::vector<VaeLevel> levels; VaeNorm norm_out; };
+struct VaeState {
+    VaeHalf enc, dec;
+    int ch = 128, z = 16, nlev = 4, nres = 2;
+    int mult[4] = {1, 2, 4, 4};
+    float scale = 0.3611f, shift = 0.1159f;
+    // workspaces (grown on demand)
+    bf16 *a0 = nullptr, *a1 = nullptr, *a2 = nullptr, *col = nullptr, *p = nullptr, *vt = nullptr;
+    float *s = nullptr, *stats = nullptr;
+    size_t act_elems = 0, col_elems = 0, s_elems = 0;
+};
+int vae_build(umv_engine* e);
 // engine.cu internals shared with flow.cu / vae.cu
+int engine_alloc(umv_engine* e, void** out, size_t bytes);
+void engine_reg(umv_engine* e, const std::string& name, bf16* dst, int64_t rows, int64_t cols, int ndim, int conv_k, int conv_cin,
+                float bound, float mean);
 int lin(umv_engine* e, const bf16* x, int ldx, const bf16* w, const bf16* bias, const bf16* res, bf16* y, int ldy, int M, int N,
         int K, int epi, cudaStream_t st, int impl = 0, float* ws = nullptr, int splits = 1);
 int llm_run(umv_engine* e, const bf16* x, int n_seqs, const int32_t* seqs, const int32_t* q_lens, const int32_t* positions,
@@ -109,6 +131,7 @@ struct umv_engine {
 
     // decode state
     int64_t* dec_tokens = nullptr;
+    umv::VaeState* vae = nullptr;
     // flow scratch
     umv::bf16 *flow_small = nullptr;   // [4, hidden]: timestep frequencies / hidden / embedding
     float* t_freqs = nullptr;          // [128] exp(-ln(1e4) i / 128)

@@ -25,7 +25,7 @@ class Engine:
     codes/interactive_vqa_inferencer.py:19-20).  Owns weights, the KV page pool and workspaces."""
 
     def __init__(self, dims: BagelDims, max_tokens: int = 2048, max_seqs: int = 8, kv_pages: int = 256,
-                 enable_vit: bool = True, enable_gen: bool = True, device: int | None = None):
+                 enable_vit: bool = True, enable_gen: bool = True, enable_vae: bool = False, device: int | None = None):
         if not torch.cuda.is_available():
             raise _lib.UmvError("unimedvl_b200 needs a CUDA device: the engine has no CPU fallback")
         self.lib = _lib.load()
@@ -43,7 +43,7 @@ class Engine:
             vit_positions=v.num_positions, vit_eps=v.eps, vit_pos_table=dims.vit_max_num_patch_per_side ** 2,
             latent_dim=dims.patch_latent_dim, latent_pos_table=dims.max_latent_size ** 2,
             max_tokens=max_tokens, max_seqs=max_seqs, kv_pages=kv_pages,
-            enable_vit=int(enable_vit), enable_gen=int(enable_gen))
+            enable_vit=int(enable_vit), enable_gen=int(enable_gen), enable_vae=int(enable_vae))
         self._c_dims = d
         h = C.c_void_p()
         _lib.check(self.lib.umv_create(C.byref(d), C.byref(h)))
@@ -231,6 +231,36 @@ class Engine:
         _lib.check(self.lib.umv_flow_velocity(self.h, C.byref(a), _ptr(x_t), _ptr(v), _stream_ptr(self.stream)))
         self._exit()
         return v
+
+    def latent_embed(self, x: torch.Tensor, pos_ids: torch.Tensor, timestep: float) -> torch.Tensor:
+        x = x.to(self.device, torch.float32).contiguous()
+        pos_ids = pos_ids.to(self.device, torch.int64).contiguous()
+        out = torch.empty((x.shape[0], self.dims.llm.hidden), dtype=torch.bfloat16, device=self.device)
+        self._enter()
+        _lib.check(self.lib.umv_latent_embed(self.h, _ptr(x), _ptr(pos_ids), x.shape[0], C.c_float(timestep), _ptr(out),
+                                             _stream_ptr(self.stream)))
+        self._exit()
+        return out
+
+    def vae_decode(self, z: torch.Tensor) -> torch.Tensor:
+        """AutoEncoder.decode: bf16 [n, 16, h, w] -> bf16 [n, 3, 8h, 8w]."""
+        z = z.to(self.device, torch.bfloat16).contiguous()
+        n, c, h, w = z.shape
+        out = torch.empty((n, 3, 8 * h, 8 * w), dtype=torch.bfloat16, device=self.device)
+        self._enter()
+        _lib.check(self.lib.umv_vae_decode(self.h, _ptr(z), n, h, w, _ptr(out), _stream_ptr(self.stream)))
+        self._exit()
+        return out
+
+    def vae_encode_moments(self, x: torch.Tensor) -> torch.Tensor:
+        """Encoder.forward: bf16 [n, 3, H, W] -> bf16 moments [n, 32, H/8, W/8]."""
+        x = x.to(self.device, torch.bfloat16).contiguous()
+        n, c, H, W = x.shape
+        out = torch.empty((n, 2 * self.dims.vae.z_channels, H // 8, W // 8), dtype=torch.bfloat16, device=self.device)
+        self._enter()
+        _lib.check(self.lib.umv_vae_encode_moments(self.h, _ptr(x), n, H, W, _ptr(out), _stream_ptr(self.stream)))
+        self._exit()
+        return out
 
     def flow_euler(self, x_t: torch.Tensor, v: torch.Tensor, dt: float, v_is_bf16: bool) -> None:
         self._enter()
