@@ -1,0 +1,36 @@
+import os, sys, subprocess, json
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+if len(sys.argv) > 1:
+    stop = int(sys.argv[1])
+    import torch, torch.nn.functional as F
+    from util import make_oracle, tiny_weights, Semantics, ulp_stats
+    from oracle import vae as ovae
+    from unimedvl_b200.autoencoder import AutoEncoder
+    from unimedvl_b200.engine import Engine
+    dims, sd, vsd = tiny_weights(vae=True)
+    eng = Engine(dims, max_tokens=512, max_seqs=4, kv_pages=64, enable_vae=True)
+    eng.load_state_dict(sd); vae = AutoEncoder(eng); vae.load_state_dict(vsd); eng.finalize()
+    o = make_oracle(Semantics.cuda, vae=True)
+    torch.manual_seed(0)
+    x = (torch.rand(1, 3, 32, 48) * 2 - 1).bfloat16()
+    # oracle stages
+    D = o.dims.vae; S = Semantics.cuda; P = "encoder."
+    stages = []
+    h = ovae.conv(o.vae_sd, P + "conv_in", x); stages.append(h)
+    in_mult = (1,) + tuple(D.ch_mult)
+    for lvl in range(4):
+        bi_, bo = D.ch * in_mult[lvl], D.ch * D.ch_mult[lvl]
+        for b in range(2):
+            h = ovae.resnet_block(o.vae_sd, f"{P}down.{lvl}.block.{b}.", h, bi_, bo, D, S); bi_ = bo; stages.append(h)
+        if lvl != 3:
+            h = F.pad(h, (0, 1, 0, 1)); h = ovae.conv(o.vae_sd, f"{P}down.{lvl}.downsample.conv", h, stride=2, padding=0); stages.append(h)
+    ref = stages[stop]
+    out = eng.vae_encode_moments(x.cuda())   # debug build writes the NHWC tap into the output buffer
+    torch.cuda.synchronize()
+    C, Hh, Ww = ref.shape[1], ref.shape[2], ref.shape[3]
+    got = out.flatten()[: Hh * Ww * C].view(Hh, Ww, C).permute(2, 0, 1)[None].cpu()
+    print("stage", stop, tuple(ref.shape), {k: round(v, 5) for k, v in ulp_stats(got, ref).items()})
+else:
+    for s in range(0, 12):
+        subprocess.run([sys.executable, __file__, str(s)], env={**os.environ, "UMV_VAE_STOP": str(s)})
