@@ -26,7 +26,12 @@ if len(sys.argv) > 1:
         if lvl != 3:
             h = F.pad(h, (0, 1, 0, 1)); h = ovae.conv(o.vae_sd, f"{P}down.{lvl}.downsample.conv", h, stride=2, padding=0); stages.append(h)
     ref = stages[stop]
-    out = eng.vae_encode_moments(x.cuda())   # debug build writes the NHWC tap into the output buffer
+    import ctypes as C
+    from unimedvl_b200 import _lib
+    out = torch.zeros(32 * 48 * 512, dtype=torch.bfloat16, device="cuda")   # the debug tap (NHWC) lands here
+    xc = x.cuda().contiguous()
+    torch.cuda.synchronize()
+    _lib.check(eng.lib.umv_vae_encode_moments(eng.h, C.c_void_p(xc.data_ptr()), 1, 32, 48, C.c_void_p(out.data_ptr()), None))
     torch.cuda.synchronize()
     C, Hh, Ww = ref.shape[1], ref.shape[2], ref.shape[3]
     got = out.flatten()[: Hh * Ww * C].view(Hh, Ww, C).permute(2, 0, 1)[None].cpu()
