@@ -25,6 +25,9 @@ if len(sys.argv) > 1:
             h = ovae.resnet_block(o.vae_sd, f"{P}down.{lvl}.block.{b}.", h, bi_, bo, D, S); bi_ = bo; stages.append(h)
         if lvl != 3:
             h = F.pad(h, (0, 1, 0, 1)); h = ovae.conv(o.vae_sd, f"{P}down.{lvl}.downsample.conv", h, stride=2, padding=0); stages.append(h)
+    h = ovae.resnet_block(o.vae_sd, P + "mid.block_1.", h, 512, 512, D, S); stages.append(h)
+    h = ovae.attn_block(o.vae_sd, P + "mid.attn_1.", h, D, S); stages.append(h)
+    h = ovae.resnet_block(o.vae_sd, P + "mid.block_2.", h, 512, 512, D, S); stages.append(h)
     ref = stages[stop]
     import ctypes as C
     from unimedvl_b200 import _lib
@@ -37,5 +40,5 @@ if len(sys.argv) > 1:
     got = out.flatten()[: Hh * Ww * C].view(Hh, Ww, C).permute(2, 0, 1)[None].cpu()
     print("stage", stop, tuple(ref.shape), {k: round(v, 5) for k, v in ulp_stats(got, ref).items()})
 else:
-    for s in range(0, 12):
+    for s in range(11, 15):
         subprocess.run([sys.executable, __file__, str(s)], env={**os.environ, "UMV_VAE_STOP": str(s)})

@@ -521,8 +521,11 @@ int umv_vae_encode_moments(umv_engine* e, const void* x, int32_t n, int32_t Hh, 
             }
         }
         UMV_TRY(res_block(e, H.mid1, im, st));
+        UMV_DBG_STAGE(H.mid1.cout)
         UMV_TRY(attn_block(e, H.attn, im, st));
+        UMV_DBG_STAGE(H.attn.c)
         UMV_TRY(res_block(e, H.mid2, im, st));
+        UMV_DBG_STAGE(H.mid2.cout)
         UMV_TRY(gn(e, H.norm_out, V.a0, im, V.a1, 1, st));
         UMV_TRY(conv(e, H.conv_out, V.a1, im, V.a2, nullptr, 0, 1, nullptr, st));
         const int HW = im.H * im.W, C = 2 * V.z;
