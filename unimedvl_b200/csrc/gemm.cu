@@ -44,6 +44,7 @@ struct GemmParams {
     const bf16* residual;
     float* ws;
     int epi;
+    int early_a;    // weight-major: A (weights) is constant data and may be fetched before griddepcontrol.wait
 };
 
 template <int BN, bool SWAP>
@@ -120,10 +121,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             // kStages weight tiles are requested BEFORE griddepcontrol.wait and stream in while the
             // predecessor (a norm / rope / attention kernel on a handful of SMs) is still running; the
             // activation tiles of those stages are requested right after the wait.
-            bool waited = !SWAP;
+            bool waited = !SWAP || !p.early_a;
             int n_deferred = 0;
             int def_kb[kStages], def_bt[kStages];
-            if (!SWAP) pdl_wait();
+            if (waited) pdl_wait();
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
                 const int split = tile % p.splits;
                 const int t2 = tile / p.splits;
@@ -465,6 +466,7 @@ static int launch_tc(const LinearCall& c, cudaStream_t stream) {
     p.residual = c.residual;
     p.ws = c.ws;
     p.epi = c.epi;
+    p.early_a = c.w_static ? 1 : 0;
     CUtensorMap tmA, tmB;
     int rc = make_tmap(&tmA, A, p.a_rows, c.K, lda, BM);
     if (rc) return rc;

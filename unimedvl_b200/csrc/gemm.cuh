@@ -29,6 +29,7 @@ struct LinearCall {
     int M = 0, N = 0, K = 0;
     int epi = EPI_BF16;
     int impl = GEMM_AUTO;
+    bool w_static = true;           // false: `w` is produced by the preceding kernel (activation x activation product)
 };
 
 // Returns 0 or a umv_status.  For EPI_PARTIAL the caller sums ws[0..splits) in a fixed order.

@@ -432,7 +432,11 @@ static int attn_block(umv_engine* e, const VaeAttn& a, Img im, cudaStream_t st) 
     UMV_LAUNCH_CHECK("softmax_rows_kernel");
     launch_k(transpose_kernel, dim3((C + 31) / 32, (L + 31) / 32), dim3(256), 0, st, (const bf16*)v, V.vt, L, C);
     UMV_LAUNCH_CHECK("transpose_kernel");
-    UMV_TRY(lin(e, V.p, L, V.vt, nullptr, nullptr, V.a1, C, L, C, L, EPI_BF16, st));          // O = P V
+    {   // O = P V: the "weight" operand V^T was written by the transpose just above -> no early weight prefetch
+        LinearCall c;
+        c.x = V.p; c.ldx = L; c.w = V.vt; c.y = V.a1; c.ldy = C; c.M = L; c.N = C; c.K = L; c.epi = EPI_BF16; c.w_static = false;
+        UMV_TRY(linear_forward(c, st));
+    }
     return lin(e, V.a1, C, a.o.w, a.o.b, V.a0, V.a0, C, L, C, C, EPI_RESID, st);               // x + proj_out(O)
 }
 
