@@ -282,6 +282,24 @@ def golden_edit(model, vae, out):
         cache_arrays("edit.after_vae", cache, out)
 
 
+def golden_e2e(model, vae, out):
+    """G6: the caller-level workflows through the reference's own InterleaveInferencer.__call__ (inferencer.py:640-680)."""
+    tok = FakeTokenizer()
+    inf = InterleaveInferencer(model, vae, tok, ImageTransform(1024, 32, 16), ImageTransform(980, 28, 14), TOK)
+    img = make_images([(70, 98)], base=30)[0]
+    with torch.no_grad(), torch.autocast("cpu", dtype=torch.bfloat16):
+        r = inf(image=img, text="What is shown in this image?", understanding_output=True, max_think_token_n=9, do_sample=False)
+        out["e2e.i2t_text"] = np.asarray(r["text"])
+        torch.manual_seed(42)
+        r = inf(text="a chest x-ray with cardiomegaly", understanding_output=False, num_timesteps=5, image_shapes=(64, 64),
+                cfg_text_scale=4.0, cfg_img_scale=1.5)
+        out["e2e.t2i_image"] = np.asarray(r["image"])
+        torch.manual_seed(43)
+        r = inf(image=img, text="make it brighter", understanding_output=False, num_timesteps=4, image_shapes=(64, 80),
+                cfg_text_scale=4.0, cfg_img_scale=2.0, cfg_interval=[0, 1.0], cfg_renorm_type="text_channel")
+        out["e2e.edit_image"] = np.asarray(r["image"])
+
+
 def main():
     torch.manual_seed(0)
     torch.set_num_threads(8)
@@ -290,7 +308,8 @@ def main():
     for name, fn in (("packing", lambda o: golden_packing(model, o)),
                      ("vqa", lambda o: golden_vqa(model, o)),
                      ("t2i", lambda o: golden_t2i(model, vae, o)),
-                     ("edit", lambda o: golden_edit(model, vae, o))):
+                     ("edit", lambda o: golden_edit(model, vae, o)),
+                     ("e2e", lambda o: golden_e2e(model, vae, o))):
         out = {}
         fn(out)
         path = os.path.join(HERE, f"{name}.npz")

@@ -1,0 +1,182 @@
+"""Session driver with the reference's ``InterleaveInferencer`` surface (codes/inferencer.py:31-680):
+same constructor, context dict (``kv_lens`` / ``ropes`` / ``past_key_values``), method names, keyword
+arguments and return types, so scripts written against the reference keep working.  The reference's own
+class also runs unmodified on top of ``unimedvl_b200.Bagel``; this restatement exists so the
+path has no dependency on the reference tree and so the two wasteful steps SURVEY.md section 8a (a14) notes
+-- prefilling prompts into a CFG context that an understanding request never reads, and deep-copying the
+whole KV for ``gen_text`` -- become no-ops (lazy context, page fork) without changing any output.
+"""
+from __future__ import annotations
+
+from copy import deepcopy
+from typing import Any, Dict, List, Optional, Union
+
+import torch
+from PIL import Image
+
+from .cache import NaiveCache
+from .packing import pil_img2rgb
+
+VLM_THINK_SYSTEM_PROMPT = '''You should first think about the reasoning process in the mind and then provide the user with the answer.
+The reasoning process is enclosed within <think> </think> tags, i.e. <think> reasoning process here </think> answer here'''
+
+GEN_THINK_SYSTEM_PROMPT = '''You should first think about the planning process in your mind, and then generate the image.
+The planning process is enclosed within <think> </think> tags; that is, <think> planning process here </think> image here.
+'''
+
+
+class InterleaveInferencer:
+    def __init__(self, model, vae_model, tokenizer, vae_transform, vit_transform, new_token_ids):
+        self.model = model
+        self.vae_model = vae_model
+        self.tokenizer = tokenizer
+        self.vae_transform = vae_transform
+        self.vit_transform = vit_transform
+        self.new_token_ids = new_token_ids
+
+    # ------------------------------------------------------------------ contexts
+    def init_gen_context(self) -> Dict[str, Any]:
+        """inferencer.py:73-80."""
+        return {"kv_lens": [0], "ropes": [0],
+                "past_key_values": NaiveCache(self.model.config.llm_config.num_hidden_layers)}
+
+    @torch.no_grad()
+    def update_context_text(self, text: str, gen_context: Dict[str, Any]) -> Dict[str, Any]:
+        """inferencer.py:82-128."""
+        g, kv_lens, ropes = self.model.prepare_prompts(curr_kvlens=gen_context["kv_lens"], curr_rope=gen_context["ropes"],
+                                                       prompts=[text], tokenizer=self.tokenizer,
+                                                       new_token_ids=self.new_token_ids)
+        pkv = self.model.forward_cache_update_text(gen_context["past_key_values"], **g)
+        gen_context.update(kv_lens=kv_lens, ropes=ropes, past_key_values=pkv)
+        return gen_context
+
+    @torch.no_grad()
+    def update_context_image(self, image, gen_context: Dict[str, Any], vae: bool = True, vit: bool = True) -> Dict[str, Any]:
+        """inferencer.py:130-162: VAE latent tokens (generation expert) and / or ViT tokens (understanding expert)."""
+        assert vae or vit
+        pkv, kv_lens, ropes = gen_context["past_key_values"], gen_context["kv_lens"], gen_context["ropes"]
+        if vae:
+            g, kv_lens, ropes = self.model.prepare_vae_images(curr_kvlens=kv_lens, curr_rope=ropes, images=[image],
+                                                              transforms=self.vae_transform, new_token_ids=self.new_token_ids)
+            pkv = self.model.forward_cache_update_vae(self.vae_model, pkv, **g)
+        if vit:
+            g, kv_lens, ropes = self.model.prepare_vit_images(curr_kvlens=kv_lens, curr_rope=ropes, images=[image],
+                                                              transforms=self.vit_transform, new_token_ids=self.new_token_ids)
+            pkv = self.model.forward_cache_update_vit(pkv, **g)
+        gen_context.update(kv_lens=kv_lens, ropes=ropes, past_key_values=pkv)
+        return gen_context
+
+    # ------------------------------------------------------------------ generation
+    @torch.no_grad()
+    def gen_image(self, image_shape, gen_context, cfg_text_scale=4.0, cfg_img_scale=1.5, cfg_text_precontext=None,
+                  cfg_img_precontext=None, cfg_interval=(0.4, 1.0), cfg_renorm_min=0.0, cfg_renorm_type="global",
+                  num_timesteps=50, timestep_shift=3.0):
+        """inferencer.py:164-232."""
+        g = self.model.prepare_vae_latent(curr_kvlens=gen_context["kv_lens"], curr_rope=gen_context["ropes"],
+                                          image_sizes=[image_shape], new_token_ids=self.new_token_ids)
+        ct = self.model.prepare_vae_latent_cfg(curr_kvlens=cfg_text_precontext["kv_lens"], curr_rope=cfg_text_precontext["ropes"],
+                                               image_sizes=[image_shape])
+        ci = self.model.prepare_vae_latent_cfg(curr_kvlens=cfg_img_precontext["kv_lens"], curr_rope=cfg_img_precontext["ropes"],
+                                               image_sizes=[image_shape])
+        latents = self.model.generate_image(
+            past_key_values=gen_context["past_key_values"], cfg_text_past_key_values=cfg_text_precontext["past_key_values"],
+            cfg_img_past_key_values=cfg_img_precontext["past_key_values"], num_timesteps=num_timesteps,
+            cfg_text_scale=cfg_text_scale, cfg_img_scale=cfg_img_scale, cfg_interval=cfg_interval,
+            cfg_renorm_min=cfg_renorm_min, cfg_renorm_type=cfg_renorm_type, timestep_shift=timestep_shift, **g,
+            cfg_text_packed_position_ids=ct["cfg_packed_position_ids"], cfg_text_packed_query_indexes=ct["cfg_packed_query_indexes"],
+            cfg_text_key_values_lens=ct["cfg_key_values_lens"], cfg_text_packed_key_value_indexes=ct["cfg_packed_key_value_indexes"],
+            cfg_img_packed_position_ids=ci["cfg_packed_position_ids"], cfg_img_packed_query_indexes=ci["cfg_packed_query_indexes"],
+            cfg_img_key_values_lens=ci["cfg_key_values_lens"], cfg_img_packed_key_value_indexes=ci["cfg_packed_key_value_indexes"])
+        return self.decode_image(latents[0], image_shape)
+
+    def decode_image(self, latent: torch.Tensor, image_shape) -> Image.Image:
+        """inferencer.py:234-256: un-patchify (nhwpqc -> nchpwq), VAE decode, (x*0.5+0.5).clamp(0,1)*255 -> uint8 PIL."""
+        H, W = image_shape
+        m = self.model
+        h, w = H // m.latent_downsample, W // m.latent_downsample
+        p, c = m.latent_patch_size, m.latent_channel
+        z = latent.reshape(1, h, w, p, p, c).permute(0, 5, 1, 3, 2, 4).reshape(1, c, h * p, w * p)
+        probe = next(self.vae_model.parameters())
+        z = z.to(device=probe.device, dtype=probe.dtype)
+        image = self.vae_model.decode(z)
+        image = (image * 0.5 + 0.5).clamp(0, 1)[0].permute(1, 2, 0) * 255
+        return Image.fromarray(image.to(torch.uint8).cpu().numpy())
+
+    @torch.no_grad()
+    def gen_text(self, gen_context, max_length: int = 500, do_sample: bool = True, temperature: float = 1.0) -> str:
+        """inferencer.py:258-279.  deepcopy == page fork: the caller's context is not advanced."""
+        ctx = deepcopy(gen_context)
+        g = self.model.prepare_start_tokens(ctx["kv_lens"], ctx["ropes"], self.new_token_ids)
+        toks = self.model.generate_text(past_key_values=ctx["past_key_values"], max_length=max_length, do_sample=do_sample,
+                                        temperature=temperature, end_token_id=self.new_token_ids["eos_token_id"], **g)
+        out = self.tokenizer.decode(toks[:, 0])
+        return out.split("<|im_end|>")[0].split("<|im_start|>")[1]
+
+    # ------------------------------------------------------------------ workflows
+    @torch.no_grad()
+    def interleave_inference(self, input_lists: List[Union[str, Image.Image]], think=False, understanding_output=False,
+                             max_think_token_n=1000, do_sample=False, text_temperature=0.3, cfg_text_scale=3.0,
+                             cfg_img_scale=1.5, cfg_interval=(0.4, 1.0), timestep_shift=3.0, num_timesteps=50,
+                             cfg_renorm_min=0.0, cfg_renorm_type="global", image_shapes=(1024, 1024)) -> List[Union[str, Image.Image]]:
+        """inferencer.py:551-638.  The cfg_img context (text only) is maintained only when an image will be generated:
+        an understanding request never reads it, so its prefills are skipped."""
+        output_list: List[Union[str, Image.Image]] = []
+        gen_context = self.init_gen_context()
+        need_cfg = not understanding_output
+        cfg_img_context = deepcopy(gen_context) if need_cfg else None
+        cfg_text_context = None
+        if think:
+            system_prompt = VLM_THINK_SYSTEM_PROMPT if understanding_output else GEN_THINK_SYSTEM_PROMPT
+            gen_context = self.update_context_text(system_prompt, gen_context)
+            if need_cfg:
+                cfg_img_context = self.update_context_text(system_prompt, cfg_img_context)
+        for term in input_lists:
+            if isinstance(term, str):
+                if need_cfg:
+                    cfg_text_context = deepcopy(gen_context)           # the context WITHOUT this text
+                gen_context = self.update_context_text(term, gen_context)
+                if need_cfg:
+                    cfg_img_context = self.update_context_text(term, cfg_img_context)
+            elif isinstance(term, Image.Image):
+                term = self.vae_transform.resize_transform(pil_img2rgb(term))
+                gen_context = self.update_context_image(term, gen_context, vae=not understanding_output)
+                if need_cfg:
+                    cfg_text_context = deepcopy(gen_context)
+            else:
+                raise ValueError(f"Unsupported input type: {type(term)}")
+        if understanding_output:
+            output_list.append(self.gen_text(gen_context, do_sample=do_sample, temperature=text_temperature,
+                                             max_length=max_think_token_n))
+            return output_list
+        if think:
+            text = self.gen_text(gen_context, do_sample=do_sample, temperature=text_temperature, max_length=max_think_token_n)
+            gen_context = self.update_context_text(text, gen_context)
+            output_list.append(text)
+        output_list.append(self.gen_image(image_shapes, gen_context, cfg_text_precontext=cfg_text_context,
+                                          cfg_img_precontext=cfg_img_context, cfg_text_scale=cfg_text_scale,
+                                          cfg_img_scale=cfg_img_scale, cfg_interval=cfg_interval, timestep_shift=timestep_shift,
+                                          num_timesteps=num_timesteps, cfg_renorm_min=cfg_renorm_min,
+                                          cfg_renorm_type=cfg_renorm_type))
+        return output_list
+
+    def __call__(self, image: Optional[Union[Image.Image, List[Image.Image]]] = None, text: Optional[str] = None,
+                 inference_ver=0, **kargs) -> Dict[str, Any]:
+        """inferencer.py:640-680."""
+        out: Dict[str, Any] = {"image": None, "text": None}
+        if image is None and text is None:
+            return out
+        inputs: list = []
+        if image is not None:
+            inputs.extend(image if isinstance(image, list) else [image])
+        if text is not None:
+            inputs.append(text)
+        if inference_ver != 0:
+            raise ValueError(f"Unsupported inference_ver: {inference_ver}")   # VQA-reconstruction variants: SURVEY.md section 8f rank 4
+        for item in self.interleave_inference(inputs, **kargs):
+            if isinstance(item, Image.Image):
+                out["image"] = (out["image"] or []) + [item]
+            elif isinstance(item, str):
+                out["text"] = item
+        if isinstance(out["image"], list) and len(out["image"]) == 1:
+            out["image"] = out["image"][0]
+        return out
