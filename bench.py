@@ -183,6 +183,59 @@ def run_reference(args, rank: int, world: int):
 
 
 # ------------------------------------------------------------------------------------------------
+def t2i_secondary(eng, model, dims, tok, n_images: int = 4, H: int = 256, W: int = 256):
+    """Secondary metric (BASELINE.json configs[3] per-GPU share): text -> 256x256 image, 4 images per GPU, 50 timesteps,
+    dual CFG 4.0 / 1.5 on (0.4, 1], per-image "global" renorm (defaults of inferencer.py:165-178): 131 LLM forwards per
+    image batched as 3 CFG branches per step.  Device-timed generate_image (the VAE decode is not resident in this engine
+    instance: it adds 0.62 of ~446 TFLOP per image)."""
+    import torch
+    from unimedvl_b200 import packing, synth
+    from unimedvl_b200.cache import NaiveCache
+    B = n_images
+
+    class _Ids:
+        def encode(self, i): return synth.synthetic_prompt_ids(100 + i, 30)
+    g, lens, rope = packing.prepare_prompts([0] * B, [0] * B, list(range(B)), _Ids(), tok)
+    ctx = model.forward_cache_update_text(NaiveCache(dims.llm.layers), **g)
+    cfg_text = NaiveCache(dims.llm.layers)                      # context without the prompt: empty
+    from unimedvl_b200.cache import paged_handle
+    paged_handle(cfg_text, eng, B)
+    cfg_img = NaiveCache(dims.llm.layers)
+    cfg_img = model.forward_cache_update_text(cfg_img, **g)     # text-only context (no image in a pure T2I request)
+    torch.manual_seed(42)
+    gi = model.prepare_vae_latent(lens, rope, [(H, W)] * B, tok)
+    ct = model.prepare_vae_latent_cfg([0] * B, [0] * B, [(H, W)] * B)
+    ci = model.prepare_vae_latent_cfg(lens, rope, [(H, W)] * B)
+
+    def run(steps):
+        return model.generate_image(
+            past_key_values=ctx, cfg_text_past_key_values=cfg_text, cfg_img_past_key_values=cfg_img, num_timesteps=steps,
+            timestep_shift=3.0, cfg_text_scale=4.0, cfg_img_scale=1.5, cfg_interval=(0.4, 1.0), cfg_renorm_min=0.0,
+            cfg_renorm_type="global", **gi,
+            cfg_text_packed_position_ids=ct["cfg_packed_position_ids"], cfg_text_packed_query_indexes=ct["cfg_packed_query_indexes"],
+            cfg_text_key_values_lens=ct["cfg_key_values_lens"], cfg_text_packed_key_value_indexes=ct["cfg_packed_key_value_indexes"],
+            cfg_img_packed_position_ids=ci["cfg_packed_position_ids"], cfg_img_packed_query_indexes=ci["cfg_packed_query_indexes"],
+            cfg_img_key_values_lens=ci["cfg_key_values_lens"], cfg_img_packed_key_value_indexes=ci["cfg_packed_key_value_indexes"])
+    run(4)
+    torch.cuda.synchronize()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    lat = run(50)
+    ev1.record()
+    torch.cuda.synchronize()
+    ms = ev0.elapsed_time(ev1)
+    flops = 0.0
+    for t_on, branches in ((41, 3), (8, 1)):
+        flops += t_on * branches * B * (2 * 258 * 6.5253e9 + 4 * 258 * (32 + 258) * 3584 * 28)
+    peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["bf16_tflops_sustained"] if os.path.exists(
+        os.path.join(ROOT, "MEASURED_PEAKS.json")) else 1400.0
+    return {"metric": "T2I img/s @14B, 256x256, 50 steps, dual CFG", "value": round(B / (ms / 1e3), 4), "unit": "img/s",
+            "images_per_gpu": B, "ms_per_batch": round(ms, 1), "algorithmic_tflop_per_image": round(flops / B / 1e12, 1),
+            "roofline": {"bound": "tensor", "achieved": round(flops / (ms / 1e3) / 1e12, 1), "peak": peak, "unit": "TFLOP/s",
+                         "frac": round(flops / (ms / 1e3) / 1e12 / peak, 4), "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained"},
+            "finite": bool(all(torch.isfinite(x).all().item() for x in lat))}
+
+
 def run_engine(args, rank: int, local_rank: int, world: int):
     import torch
     import torch.distributed as dist
@@ -304,6 +357,7 @@ def run_engine(args, rank: int, local_rank: int, world: int):
     step_ms = ms / args.steps / DECODE_STEPS
     step_achieved = step_bytes / (step_ms / 1e3) / 1e9
 
+    t2i = t2i_secondary(eng, model, dims, tok) if (world == 1 and args.t2i) else None
     cpu = cpu_decode_baseline() if world == 1 else None
     line = {
         "metric": "VQA decode tok/s @14B (B=8/GPU, 448x448, 128-token greedy)", "value": round(value, 1), "unit": "tok/s",
@@ -327,6 +381,8 @@ def run_engine(args, rank: int, local_rank: int, world: int):
                           "roofline_tok_s_per_gpu": round(B / (step_bytes / (peak * 1e9)), 1)},
         "clocks": clocks,
     }
+    if t2i is not None:
+        line["t2i"] = t2i
     if cpu is not None:
         line["cpu_baseline"] = cpu
     print(json.dumps(line), flush=True)
@@ -340,6 +396,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="engine", choices=["engine", "reference"])
+    ap.add_argument("--t2i", type=int, default=1, help="also time the secondary metric (text-to-image img/s) at N=1")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
