@@ -247,51 +247,41 @@ __global__ void __launch_bounds__(kAttnThreads) attn_fwd_kernel(AttnArgs a, floa
             }
         }
     }
-    if (a.splits == 1) return;
-    // ---- split-KV combine by the last CTA of this (row tile, sample, kv head) group to finish: no extra launch.
-    __shared__ int s_last;
-    __threadfence();
-    __syncthreads();
-    int* counter = a.counters + (blockIdx.y * gridDim.x + blockIdx.x);
-    if (tid == 0) {
-        const int ticket = atomicAdd(counter, 1);
-        s_last = (ticket == a.splits - 1) ? 1 : 0;
-        if (s_last) *counter = 0;                        // self-resetting for the next launch
-    }
-    __syncthreads();
-    if (!s_last) return;
-    __threadfence();
-    const size_t rows_total = (size_t)a.total_q * a.H;
-    const float* lse = a.ws + (size_t)a.splits * rows_total * HD;
-    const int nvalid = min(kTileRows, nrows - r0);
-    for (int r = warp; r < nvalid; r += kAttnThreads / 32) {
-        const int R = r0 + r;
-        const int tok = R / G, head = kvh * G + R % G;
-        const size_t ridx = (size_t)(qs + tok) * a.H + head;
-        float mx = -INFINITY;
-        for (int sp = 0; sp < a.splits; ++sp) mx = fmaxf(mx, __ldcg(lse + (size_t)sp * rows_total + ridx));
-        float acc[(HD + 31) / 32];
+}
+
+// Split-KV combine: out = sum_s w_s O_s / sum_s w_s, w_s = 2^(lse_s - max lse).   one warp per (token, head)
+template <int HD>
+__global__ void attn_combine_kernel(AttnArgs a) {
+    pdl_launch_dependents();
+    pdl_wait();
+    const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    const int rows = a.total_q * a.H;
+    if (gw >= rows) return;
+    const float* lse = a.ws + (size_t)a.splits * rows * HD;
+    float mx = -INFINITY;
+    for (int s = 0; s < a.splits; ++s) mx = fmaxf(mx, lse[(size_t)s * rows + gw]);
+    float acc[(HD + 31) / 32];
 #pragma unroll
-        for (int i = 0; i < (HD + 31) / 32; ++i) acc[i] = 0.f;
-        float wsum = 0.f;
-        for (int sp = 0; sp < a.splits; ++sp) {              // fixed order: deterministic
-            const float l = __ldcg(lse + (size_t)sp * rows_total + ridx);
-            const float w = (l == -INFINITY) ? 0.f : exp2f(l - mx);
-            wsum += w;
-            const float* src = a.ws + ((size_t)sp * rows_total + ridx) * HD;
-#pragma unroll
-            for (int i = 0; i < (HD + 31) / 32; ++i) {
-                const int d = lane + i * 32;
-                if (d < HD) acc[i] += w * __ldcg(src + d);
-            }
-        }
-        const float inv = wsum > 0.f ? 1.f / wsum : 0.f;
-        bf16* dst = a.out + (size_t)(qs + tok) * a.ldo + head * HD;
+    for (int i = 0; i < (HD + 31) / 32; ++i) acc[i] = 0.f;
+    float wsum = 0.f;
+    for (int s = 0; s < a.splits; ++s) {
+        const float l = lse[(size_t)s * rows + gw];
+        const float w = (l == -INFINITY) ? 0.f : exp2f(l - mx);
+        wsum += w;
+        const float* src = a.ws + ((size_t)s * rows + gw) * HD;
 #pragma unroll
         for (int i = 0; i < (HD + 31) / 32; ++i) {
             const int d = lane + i * 32;
-            if (d < HD) dst[d] = f2b(acc[i] * inv);
+            if (d < HD) acc[i] += w * src[d];
         }
+    }
+    const float inv = wsum > 0.f ? 1.f / wsum : 0.f;
+    const int tok = gw / a.H, head = gw % a.H;
+    bf16* dst = a.out + (size_t)tok * a.ldo + head * HD;
+#pragma unroll
+    for (int i = 0; i < (HD + 31) / 32; ++i) {
+        const int d = lane + i * 32;
+        if (d < HD) dst[d] = f2b(acc[i] * inv);
     }
 }
 
@@ -319,14 +309,23 @@ static int launch_attn(const AttnArgs& a, cudaStream_t s) {
         set_error("attn_fwd_kernel<%d> launch failed: %s", HD, cudaGetErrorString(e));
         return UMV_ERR_CUDA;
     }
+    if (a.splits > 1) {
+        const int rows = a.total_q * a.H;
+        e = launch_k(attn_combine_kernel<HD>, dim3((rows * 32 + 127) / 128), dim3(128), 0, s, a);
+        ++g_launches;
+        if (e == cudaSuccess) e = cudaGetLastError();
+        if (e != cudaSuccess) {
+            set_error("attn_combine_kernel launch failed: %s", cudaGetErrorString(e));
+            return UMV_ERR_CUDA;
+        }
+    }
     return UMV_OK;
 }
 
 int attention_forward(const AttnArgs& a, cudaStream_t s) {
     if (a.n <= 0 || a.max_q_len <= 0) return UMV_OK;
     UMV_REQUIRE(a.H % a.Hkv == 0, UMV_ERR_INVALID, "attention: heads %d not a multiple of kv heads %d", a.H, a.Hkv);
-    UMV_REQUIRE(a.splits == 1 || (a.ws != nullptr && a.counters != nullptr), UMV_ERR_INVALID,
-                "attention: split-KV needs a workspace and arrival counters");
+    UMV_REQUIRE(a.splits == 1 || a.ws != nullptr, UMV_ERR_INVALID, "attention: split-KV needs a workspace");
     UMV_REQUIRE(a.ldq % 8 == 0 && a.ldo % 2 == 0, UMV_ERR_INVALID, "attention: q/out row strides must keep 16-byte rows");
     if (a.dh == 128) return launch_attn<128>(a, s);
     if (a.dh == 72) return launch_attn<72>(a, s);

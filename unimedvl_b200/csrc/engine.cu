@@ -191,8 +191,6 @@ static int build_runtime(umv_engine* e) {
     UMV_TRY(dev_alloc(e, &e->ws, e->ws_elems));
     e->attn_ws_elems = (size_t)16 * 64 * d.heads * (e->dh + 1);
     UMV_TRY(dev_alloc(e, &e->attn_ws, e->attn_ws_elems));
-    UMV_TRY(dev_alloc(e, &e->attn_counters, (size_t)4096));
-    cudaMemset(e->attn_counters, 0, 4096 * sizeof(int));
     // RoPE inverse frequencies: ROPE_INIT_FUNCTIONS['default'] -> 1 / theta^(2i/dh), fp32 (never bf16)
     std::vector<float> inv(e->dh / 2);
     for (int i = 0; i < e->dh / 2; ++i) {
@@ -373,19 +371,6 @@ static int llm_layers(umv_engine* e, const LlmRun& r, bf16* out, cudaStream_t st
         attn_splits = std::max(1, std::min(std::min(16, blocks), (2 * e->sm_count + r.n_seqs * Hkv - 1) / (r.n_seqs * Hkv)));
     }
 
-    // decode: while the small norm / rope / attention kernels of layer li run, a side stream pulls the head of that
-    // layer's gate/up weights into L2 (forked after the previous down-proj so it does not compete with it)
-    const bool prefetch = partial && e->l2_prefetch_bytes > 0 && st != nullptr;
-    bool forked = false;
-    auto fork_prefetch = [&](int layer) -> int {
-        if (!prefetch || layer >= d.layers) return UMV_OK;
-        UMV_CUDA_OK(cudaEventRecord(e->ev_fork, st));
-        UMV_CUDA_OK(cudaStreamWaitEvent(e->side, e->ev_fork, 0));
-        forked = true;
-        return l2_prefetch(e->layers[layer].wgu[0], std::min(e->l2_prefetch_bytes, (size_t)2 * I * D * 2), e->side);
-    };
-    UMV_TRY(fork_prefetch(0));
-
     for (int li = 0; li < d.layers; ++li) {
         const LayerW& L = e->layers[li];
         UMV_TRY(norm(L.ln1[0], L.ln1[1], e->xn));
@@ -417,7 +402,7 @@ static int llm_layers(umv_engine* e, const LlmRun& r, bf16* out, cudaStream_t st
         aa.paged = 1; aa.pool = e->pool; aa.layer = li; aa.page_table = r.m.page_table; aa.max_pages = r.m.max_pages;
         aa.q_start = r.m.q_start; aa.q_len = r.m.q_len; aa.kv_len = r.m.kv_len;
         aa.n = r.n_seqs; aa.H = H; aa.Hkv = Hkv; aa.dh = dh; aa.causal = r.causal ? 1 : 0;
-        aa.max_q_len = r.max_q_len; aa.max_kv_len = r.max_kv_len; aa.splits = attn_splits; aa.ws = e->attn_ws; aa.counters = e->attn_counters; aa.total_q = M;
+        aa.max_q_len = r.max_q_len; aa.max_kv_len = r.max_kv_len; aa.splits = attn_splits; aa.ws = e->attn_ws; aa.total_q = M;
         UMV_TRY(attention_forward(aa, st));
         // ---- output projection + residual
         if (partial) {
@@ -446,15 +431,10 @@ static int llm_layers(umv_engine* e, const LlmRun& r, bf16* out, cudaStream_t st
             const int s = pick_splits(D, I, e->sm_count);
             UMV_TRY(lin(e, e->act, I, L.wdown[0], nullptr, nullptr, nullptr, 0, M, D, I, EPI_PARTIAL, st, GEMM_WEIGHT_MAJOR, e->ws, s));
             pending_splits = s;
-            UMV_TRY(fork_prefetch(li + 1));
         } else {
             UMV_TRY(lin(e, e->act, I, L.wdown[E], nullptr, e->h, e->h, D, M, D, I, EPI_RESID, st));
             if (T > 0) UMV_TRY(copy_rows(e->yt, D, r.m.text_rows, e->h, D, T, D, 1, st));
         }
-    }
-    if (forked) {      // join the side stream (required inside a capture; harmless otherwise)
-        UMV_CUDA_OK(cudaEventRecord(e->ev_join, e->side));
-        UMV_CUDA_OK(cudaStreamWaitEvent(st, e->ev_join, 0));
     }
     // final norm (norm / norm_moe_gen, qwen2_navit.py:1162-1169); also folds the last down-proj partials
     return norm(e->final_norm[0], e->final_norm[1], out ? out : e->xn);
@@ -501,10 +481,6 @@ int umv_create(const umv_dims* dims, umv_engine** out) {
     if (const char* v = getenv("UMV_SPLITK")) e->use_splitk = atoi(v) != 0;
     if (const char* v = getenv("UMV_GRAPH")) e->use_graph = atoi(v) != 0;
     if (const char* v = getenv("UMV_GEMM_IMPL")) e->gemm_impl = atoi(v);
-    if (const char* v = getenv("UMV_L2_PREFETCH_MB")) e->l2_prefetch_bytes = (size_t)atoi(v) << 20;
-    cudaStreamCreateWithFlags(&e->side, cudaStreamNonBlocking);
-    cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming);
-    cudaEventCreateWithFlags(&e->ev_join, cudaEventDisableTiming);
     int rc = gemm_init();
     if (rc == UMV_OK) rc = attention_init();
     if (rc == UMV_OK) rc = build_weights(e);
@@ -523,9 +499,6 @@ int umv_destroy(umv_engine* e) {
     cudaDeviceSynchronize();
     for (void* p : e->allocs) cudaFree(p);
     delete e->vae;
-    if (e->side) cudaStreamDestroy(e->side);
-    if (e->ev_fork) cudaEventDestroy(e->ev_fork);
-    if (e->ev_join) cudaEventDestroy(e->ev_join);
     for (int i = 0; i < umv_engine::kMetaRing; ++i) {
         if (e->meta_host[i]) cudaFreeHost(e->meta_host[i]);
         if (e->meta_ev[i]) cudaEventDestroy(e->meta_ev[i]);

@@ -90,9 +90,6 @@ struct umv_engine {
     int dh = 0, qkvn = 0, vit_kpad = 0, sm_count = 148;
     bool finalized = false;
     bool use_splitk = true, use_graph = true;
-    size_t l2_prefetch_bytes = (size_t)80 << 20;   // UMV_L2_PREFETCH_MB: next layer's gate/up weights pulled into L2 during decode
-    cudaStream_t side = nullptr;
-    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     int gemm_impl = 0;
 
     std::vector<void*> allocs;
@@ -120,7 +117,6 @@ struct umv_engine {
     umv::bf16 *xt = nullptr, *ht = nullptr, *yt = nullptr, *actt = nullptr;   // text-row (understanding expert) staging, gen mode
     float* ws = nullptr;          // split-K partials
     size_t ws_elems = 0;
-    int* attn_counters = nullptr; // split-KV arrival counters (zeroed once, self-resetting)
     float* attn_ws = nullptr;     // split-KV partials
     size_t attn_ws_elems = 0;
     int w_h = 0, w_qkv = 0, w_act = 0;   // workspace row widths

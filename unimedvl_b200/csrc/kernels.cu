@@ -536,24 +536,6 @@ int copy_page(KVPool pool, int src_page, int dst_page, cudaStream_t s) {
     return UMV_OK;
 }
 
-// Fire-and-forget L2 prefetch of a weight range (cp.async.bulk.prefetch.L2): issued on a side stream while the
-// latency-bound norm / rope / attention kernels leave HBM idle, so the next weight-major linear finds part of its
-// weights in the 126 MB L2.
-__global__ void l2_prefetch_kernel(const uint8_t* __restrict__ p, size_t bytes, int chunk) {
-    const size_t off = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * (size_t)chunk;
-    if (off >= bytes) return;
-    const uint32_t n = (uint32_t)min((size_t)chunk, bytes - off) & ~15u;
-    if (n) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p + off), "r"(n) : "memory");
-}
-int l2_prefetch(const void* p, size_t bytes, cudaStream_t s) {
-    if (bytes == 0) return UMV_OK;
-    const int chunk = 32 * 1024;
-    const size_t n = (bytes + chunk - 1) / chunk;
-    l2_prefetch_kernel<<<(unsigned)((n + 127) / 128), 128, 0, s>>>(static_cast<const uint8_t*>(p), bytes, chunk);
-    UMV_LAUNCH_CHECK("l2_prefetch_kernel");
-    return UMV_OK;
-}
-
 // Synthetic weights: uniform(mean - bound, mean + bound) from a counter hash (benchmark random init).
 __global__ void fill_uniform_kernel(bf16* __restrict__ p, size_t n, uint64_t seed, float bound, float mean) {
     pdl_launch_dependents();

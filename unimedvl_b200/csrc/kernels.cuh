@@ -77,7 +77,6 @@ struct AttnArgs {
     int max_kv_len = 0;             // host upper bound (split sizing)
     int splits = 1;                 // split-KV factor (>1 needs ws)
     float* ws = nullptr;            // [splits][total_q*H][dh+1] fp32 partial outputs + lse
-    int* counters = nullptr;        // [row_tiles * n * Hkv] zero-initialised, self-resetting arrival counters (split-KV)
     int total_q = 0;
 };
 int attention_forward(const AttnArgs& a, cudaStream_t s);
@@ -89,7 +88,6 @@ int gather_add_rows(bf16* x, const bf16* table, const int64_t* ids, int M, int D
 int f32_to_bf16_padded(const float* x, bf16* y, int M, int K, int Kpad, cudaStream_t s);
 int argmax_rows(const bf16* logits, int rows, int vocab, int64_t* out, cudaStream_t s);
 int copy_rows(const bf16* src, int lds, const int* rows, bf16* dst, int ldd, int n, int D, int scatter, cudaStream_t s);
-int l2_prefetch(const void* p, size_t bytes, cudaStream_t s);
 int fill_uniform_bf16(bf16* p, size_t n, uint64_t seed, float bound, float mean, cudaStream_t s);
 
 // decode-loop state kernels (Bagel.generate_text, bagel.py:1262-1311)
