@@ -189,7 +189,7 @@ static int build_runtime(umv_engine* e) {
     UMV_TRY(dev_alloc(e, &e->actt, (size_t)Tmax * d.inter));
     e->ws_elems = (size_t)16 * 64 * std::max(e->qkvn, D);
     UMV_TRY(dev_alloc(e, &e->ws, e->ws_elems));
-    e->attn_ws_elems = (size_t)16 * 64 * d.heads * (e->dh + 1);
+    e->attn_ws_elems = (size_t)32 * 64 * d.heads * (e->dh + 1);
     UMV_TRY(dev_alloc(e, &e->attn_ws, e->attn_ws_elems));
     // RoPE inverse frequencies: ROPE_INIT_FUNCTIONS['default'] -> 1 / theta^(2i/dh), fp32 (never bf16)
     std::vector<float> inv(e->dh / 2);
@@ -370,7 +370,9 @@ static int llm_layers(umv_engine* e, const LlmRun& r, bf16* out, cudaStream_t st
     int attn_splits = 1;
     if (r.weight_major && r.max_q_len == 1) {
         const int blocks = (r.max_kv_len + kPageTokens - 1) / kPageTokens;
-        attn_splits = std::max(1, std::min(std::min(16, blocks), (2 * e->sm_count + r.n_seqs * Hkv - 1) / (r.n_seqs * Hkv)));
+        static const int max_splits = getenv("UMV_ATTN_SPLITS") ? atoi(getenv("UMV_ATTN_SPLITS")) : 16;
+        static const int waves = getenv("UMV_ATTN_WAVES") ? atoi(getenv("UMV_ATTN_WAVES")) : 2;
+        attn_splits = std::max(1, std::min(std::min(max_splits, blocks), (waves * e->sm_count + r.n_seqs * Hkv - 1) / (r.n_seqs * Hkv)));
     }
 
     for (int li = 0; li < d.layers; ++li) {
