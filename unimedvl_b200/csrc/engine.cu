@@ -355,9 +355,7 @@ static int llm_layers(umv_engine* e, const LlmRun& r, bf16* out, cudaStream_t st
     const int T = r.gen ? r.m.n_text : 0;
     int pending_splits = 0;     // >0: e->ws holds split-K partials of the last residual-branch linear
 
-    static const int ablate = getenv("UMV_ABLATE") ? atoi(getenv("UMV_ABLATE")) : 0;   // timing experiments only (wrong results)
     auto norm = [&](const bf16* w0, const bf16* w1, bf16* y) {
-        if (ablate & 4) { pending_splits = 0; return (int)UMV_OK; }
         AddNormArgs a;
         a.h = e->h; a.M = M; a.D = D; a.eps = d.rms_eps; a.w0 = w0; a.w1 = w1 ? w1 : w0;
         a.row_sel = r.gen ? r.m.row_sel : nullptr;
@@ -399,7 +397,7 @@ static int llm_layers(umv_engine* e, const LlmRun& r, bf16* out, cudaStream_t st
         ra.qn0 = L.qn[0]; ra.kn0 = L.kn[0]; ra.qn1 = L.qn[E]; ra.kn1 = L.kn[E];
         ra.row_sel = r.gen ? r.m.row_sel : nullptr; ra.gen_mode = r.gen ? 1 : 0;
         ra.pool = e->pool; ra.layer = li; ra.M = M; ra.H = H; ra.Hkv = Hkv; ra.dh = dh; ra.eps = d.rms_eps;
-        if (!(ablate & 1)) UMV_TRY(rope_append(ra, st));
+        UMV_TRY(rope_append(ra, st));
         // ---- attention over the paged cache (past + the rows just appended)
         AttnArgs aa;
         aa.q = e->qkv; aa.ldq = QN; aa.out = e->attn; aa.ldo = D;
@@ -407,8 +405,7 @@ static int llm_layers(umv_engine* e, const LlmRun& r, bf16* out, cudaStream_t st
         aa.q_start = r.m.q_start; aa.q_len = r.m.q_len; aa.kv_len = r.m.kv_len;
         aa.n = r.n_seqs; aa.H = H; aa.Hkv = Hkv; aa.dh = dh; aa.causal = r.causal ? 1 : 0;
         aa.max_q_len = r.max_q_len; aa.max_kv_len = r.max_kv_len; aa.splits = attn_splits; aa.ws = e->attn_ws; aa.total_q = M;
-        if (ablate & 8) aa.splits = 1;
-        if (!(ablate & 2)) UMV_TRY(attention_forward(aa, st));
+        UMV_TRY(attention_forward(aa, st));
         // ---- output projection + residual
         if (partial) {
             const int s = pick_splits(D, D, e->sm_count);
