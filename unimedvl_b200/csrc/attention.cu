@@ -10,6 +10,8 @@
 // Replaces flash_attn_varlen_func (flash-attn 2.x, external to the reference) at
 // qwen2_navit.py:605-614 (causal = bottom-right aligned, or full) and siglip_navit.py:232-241, and the
 // per-step full KV re-materialisation of qwen2_navit.py:589-600 (the cache is read in place).
+#include <cooperative_groups.h>
+
 #include "../../include/umv.h"
 #include "common.cuh"
 #include "gemm.cuh"
@@ -285,9 +287,266 @@ __global__ void attn_combine_kernel(AttnArgs a) {
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Fused decode attention: ONE launch per layer for the chain
+//   split-K reduce (+bias) of the q/k/v projection -> q/k RMSNorm -> RoPE -> KV append -> attention over the paged
+//   cache -> split-KV combine.
+// A thread-block cluster of `S` CTAs owns one (sample, kv head): CTA r covers key blocks [r*bps, (r+1)*bps); inside a
+// CTA the 4 warps split each 64-key block (16 keys each) since only G <= 8 query rows exist; the CTA whose range holds
+// the newest position rotates and stores the new K/V row before its block is staged; partial (m, l, O) are merged
+// first across warps in shared memory, then across the cluster through distributed shared memory (no global round
+// trip, no second kernel).  Numerics identical to rope_append_kernel + attn_fwd_kernel (und mode, R4-R6).
+namespace cg = cooperative_groups;
+constexpr int kDecQBytes = 16 * 256;
+constexpr int kDecSmemBytes = kDecQBytes + 4 * kTileKeys * 256;
+
+__global__ void __launch_bounds__(kAttnThreads) attn_decode_kernel(DecodeAttnArgs a, float scale_log2) {
+    constexpr int HD = 128;
+    pdl_launch_dependents();
+    pdl_wait();
+    cg::cluster_group cluster = cg::this_cluster();
+    extern __shared__ __align__(128) uint8_t smem[];
+    uint8_t* sQ = smem;
+    uint8_t* sK = smem + kDecQBytes;
+    uint8_t* sV = sK + 2 * kTileKeys * 256;
+    __shared__ float red_m[4][8], red_l[4][8];
+    __shared__ float red_o[4][8][HD];
+    __shared__ float fin_o[8][HD];
+    __shared__ float fin_m[8], fin_l[8];
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int S = (int)cluster.num_blocks(), rank = (int)cluster.block_rank();
+    const int b = blockIdx.y / a.Hkv, kvh = blockIdx.y % a.Hkv;
+    const int G = a.H / a.Hkv;
+    const int ncols = (a.H + 2 * a.Hkv) * HD;
+    const int kvlen = a.kv_len[b];
+    const int blocks_total = (kvlen + kTileKeys - 1) / kTileKeys;
+    const int bps = (blocks_total + S - 1) / S;
+    const int kb_begin = rank * bps, kb_end = min(blocks_total, kb_begin + bps);
+    const int last_block = (kvlen - 1) / kTileKeys;
+    const bool owner = kb_begin <= last_block && last_block < kb_end;
+
+    auto load_kv = [&](int kb, int stage) {
+        const int page = a.page_table[(size_t)b * a.max_pages + kb];
+        const bf16* kbase = a.pool.base + a.pool.tile_offset(page, a.layer, 0, kvh);
+        const bf16* vbase = a.pool.base + a.pool.tile_offset(page, a.layer, 1, kvh);
+        uint8_t* dk = sK + stage * kTileKeys * 256;
+        uint8_t* dv = sV + stage * kTileKeys * 256;
+        for (int i = tid; i < kTileKeys * 16; i += kAttnThreads) {
+            const int r = i >> 4, ch = i & 15;
+            const bool ok = kb * kTileKeys + r < kvlen;
+            cp_async16(dk + tile_off<HD>(r, ch), kbase + (size_t)(ok ? r : 0) * HD + ch * 8, ok);
+            cp_async16(dv + tile_off<HD>(r, ch), vbase + (size_t)(ok ? r : 0) * HD + ch * 8, ok);
+        }
+    };
+    // stage the first block right away unless it is the one that receives the new token
+    const bool pre = kb_begin < kb_end && !(owner && kb_begin == last_block);
+    if (pre) load_kv(kb_begin, 0);
+    cp_async_commit();
+
+    // ---- rows of this step: G query heads (-> sQ) and, on the owner CTA, the new K and V rows (-> page)
+    for (int i = tid; i < 16 * 16; i += kAttnThreads) {
+        const int r = i >> 4, ch = i & 15;
+        if (r >= G) *reinterpret_cast<U4*>(sQ + tile_off<HD>(r, ch)) = U4{0, 0, 0, 0};
+    }
+    const float pos = (float)a.positions[b];
+    const int n_tasks = G + (owner ? 2 : 0);
+    for (int task = warp; task < n_tasks; task += kAttnThreads / 32) {
+        const bool is_q = task < G, is_v = task == G + 1;
+        const int col = (is_q ? (kvh * G + task) : (is_v ? a.H + a.Hkv + kvh : a.H + kvh)) * HD + lane * 4;
+        float x[4];
+        if (a.partial) {
+            float acc[4] = {0.f, 0.f, 0.f, 0.f};
+            for (int sp = 0; sp < a.ksplits; ++sp) {
+                const float4 p4 = *reinterpret_cast<const float4*>(a.partial + ((size_t)sp * a.M + b) * ncols + col);
+                acc[0] += p4.x; acc[1] += p4.y; acc[2] += p4.z; acc[3] += p4.w;
+            }
+            const uint2 bv = *reinterpret_cast<const uint2*>(a.bias + col);
+            const float2 b0 = unpack2(bv.x), b1 = unpack2(bv.y);
+            x[0] = rbf(acc[0] + b0.x); x[1] = rbf(acc[1] + b0.y); x[2] = rbf(acc[2] + b1.x); x[3] = rbf(acc[3] + b1.y);
+        } else {
+            const uint2 qv = *reinterpret_cast<const uint2*>(a.qkv + (size_t)b * ncols + col);
+            const float2 f0 = unpack2(qv.x), f1 = unpack2(qv.y);
+            x[0] = f0.x; x[1] = f0.y; x[2] = f1.x; x[3] = f1.y;
+        }
+        float o4[4];
+        if (is_v) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) o4[j] = x[j];
+        } else {
+            const bf16* nw = is_q ? a.qn : a.kn;
+            float ss = x[0] * x[0] + x[1] * x[1] + x[2] * x[2] + x[3] * x[3];
+            ss = warp_sum(ss);
+            const float inv = 1.0f / sqrtf(ss / (float)HD + a.eps);
+            const uint2 wv = *reinterpret_cast<const uint2*>(nw + lane * 4);
+            const float2 w0 = unpack2(wv.x), w1 = unpack2(wv.y);
+            const float w[4] = {w0.x, w0.y, w1.x, w1.y};
+            float n[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) n[j] = rbf(w[j] * rbf(x[j] * inv));
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int i = lane * 4 + j;
+                const float ang = __fmul_rn(pos, a.inv_freq[i % (HD / 2)]);
+                const float c = rbf(cosf(ang)), sn = rbf(sinf(ang));
+                const float partner = __shfl_xor_sync(0xffffffffu, n[j], 16);
+                const float rot = (i < HD / 2) ? -partner : partner;
+                o4[j] = rbf(rbf(n[j] * c) + rbf(rot * sn));
+            }
+        }
+        const uint2 packed = make_uint2(pack2(o4[0], o4[1]), pack2(o4[2], o4[3]));
+        if (is_q) {
+            *reinterpret_cast<uint2*>(sQ + tile_off<HD>(task, lane >> 1) + (lane & 1) * 8) = packed;
+        } else {
+            const int slot = (kvlen - 1) % kTileKeys;
+            const int page = a.page_table[(size_t)b * a.max_pages + last_block];
+            bf16* dst = a.pool.base + a.pool.tile_offset(page, a.layer, is_v ? 1 : 0, kvh) + (size_t)slot * HD + lane * 4;
+            *reinterpret_cast<uint2*>(dst) = packed;
+        }
+    }
+    __syncthreads();                       // sQ complete; the owner's K/V row is visible to the CTA's later cp.async
+    if (!pre && kb_begin < kb_end) load_kv(kb_begin, 0);
+    cp_async_commit();
+
+    const int g = lane >> 2, t = lane & 3;
+    uint32_t qf[8][4];
+#pragma unroll
+    for (int ks = 0; ks < 8; ++ks)
+        ldmatrix_x4(qf[ks][0], qf[ks][1], qf[ks][2], qf[ks][3], smem_u32(sQ + tile_off<HD>(lane & 15, ks * 2 + (lane >> 4))));
+    float o[16][2];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) o[i][0] = o[i][1] = 0.f;
+    float m_a = -INFINITY, l_a = 0.f;
+
+    for (int kb = kb_begin; kb < kb_end; ++kb) {
+        const int stage = (kb - kb_begin) & 1;
+        if (kb + 1 < kb_end) {
+            load_kv(kb + 1, stage ^ 1);
+            cp_async_commit();
+            cp_async_wait<1>();
+        } else {
+            cp_async_wait<0>();
+        }
+        __syncthreads();
+        const uint8_t* cK = sK + stage * kTileKeys * 256;
+        const uint8_t* cV = sV + stage * kTileKeys * 256;
+        float s0[4] = {0.f, 0.f, 0.f, 0.f}, s1[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int ks = 0; ks < 8; ++ks) {
+            uint32_t b0, b1, b2, b3;
+            ldmatrix_x4(b0, b1, b2, b3,
+                        smem_u32(cK + tile_off<HD>(warp * 16 + (lane & 7) + ((lane >> 4) << 3), ks * 2 + ((lane >> 3) & 1))));
+            mma_bf16_16816(s0, qf[ks], b0, b1);
+            mma_bf16_16816(s1, qf[ks], b2, b3);
+        }
+        const int key0 = kb * kTileKeys + warp * 16 + 2 * t;
+        float v00 = key0 < kvlen ? s0[0] * scale_log2 : -INFINITY;
+        float v01 = key0 + 1 < kvlen ? s0[1] * scale_log2 : -INFINITY;
+        float v10 = key0 + 8 < kvlen ? s1[0] * scale_log2 : -INFINITY;
+        float v11 = key0 + 9 < kvlen ? s1[1] * scale_log2 : -INFINITY;
+        float mx = fmaxf(fmaxf(v00, v01), fmaxf(v10, v11));
+        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+        const float mn = fmaxf(m_a, mx);
+        const float ms = mn == -INFINITY ? 0.f : mn;
+        const float al = exp2f(m_a - ms);
+        m_a = mn;
+        const float p00 = exp2f(v00 - ms), p01 = exp2f(v01 - ms), p10 = exp2f(v10 - ms), p11 = exp2f(v11 - ms);
+        l_a = l_a * al + (p00 + p01 + p10 + p11);
+        const uint32_t pf[4] = {pack2(p00, p01), 0u, pack2(p10, p11), 0u};      // rows 8..15 of the tile are padding
+#pragma unroll
+        for (int dt = 0; dt < 16; ++dt) { o[dt][0] *= al; o[dt][1] *= al; }
+#pragma unroll
+        for (int dp = 0; dp < 16; dp += 2) {
+            uint32_t b0, b1, b2, b3;
+            asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+                         : "=r"(b0), "=r"(b1), "=r"(b2), "=r"(b3)
+                         : "r"(smem_u32(cV + tile_off<HD>(warp * 16 + (lane & 7) + (((lane >> 3) & 1) << 3), dp + (lane >> 4)))));
+            float acc0[4] = {o[dp][0], o[dp][1], 0.f, 0.f}, acc1[4] = {o[dp + 1][0], o[dp + 1][1], 0.f, 0.f};
+            mma_bf16_16816(acc0, pf, b0, b1);
+            mma_bf16_16816(acc1, pf, b2, b3);
+            o[dp][0] = acc0[0]; o[dp][1] = acc0[1];
+            o[dp + 1][0] = acc1[0]; o[dp + 1][1] = acc1[1];
+        }
+        __syncthreads();
+    }
+    cp_async_wait<0>();
+    l_a += __shfl_xor_sync(0xffffffffu, l_a, 1);
+    l_a += __shfl_xor_sync(0xffffffffu, l_a, 2);
+
+    // ---- merge the 4 key-quarters of this CTA
+    if (t == 0) { red_m[warp][g] = m_a; red_l[warp][g] = l_a; }
+#pragma unroll
+    for (int dt = 0; dt < 16; ++dt) *reinterpret_cast<float2*>(&red_o[warp][g][dt * 8 + 2 * t]) = make_float2(o[dt][0], o[dt][1]);
+    __syncthreads();
+    {
+        const int row = tid >> 4, d0 = (tid & 15) * 8;
+        float M = -INFINITY;
+#pragma unroll
+        for (int w = 0; w < 4; ++w) M = fmaxf(M, red_m[w][row]);
+        float L = 0.f, acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int w = 0; w < 4; ++w) {
+            const float mw = red_m[w][row];
+            const float wg = (mw == -INFINITY) ? 0.f : exp2f(mw - M);
+            L += wg * red_l[w][row];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[j] += wg * red_o[w][row][d0 + j];
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) fin_o[row][d0 + j] = acc[j];
+        if ((tid & 15) == 0) { fin_m[row] = M; fin_l[row] = L; }
+    }
+    cluster.sync();
+    // ---- merge the key ranges of the cluster: CTA `rank` finishes heads rank, rank+S, ...
+    for (int head = rank; head < G; head += S) {
+        float M = -INFINITY;
+        for (int r = 0; r < S; ++r) M = fmaxf(M, cluster.map_shared_rank(fin_m, r)[head]);
+        float L = 0.f, acc = 0.f;
+        for (int r = 0; r < S; ++r) {                      // fixed order: deterministic
+            const float mr = cluster.map_shared_rank(fin_m, r)[head];
+            const float wg = (mr == -INFINITY) ? 0.f : exp2f(mr - M);
+            L += wg * cluster.map_shared_rank(fin_l, r)[head];
+            acc += wg * cluster.map_shared_rank(&fin_o[0][0], r)[head * HD + tid];
+        }
+        a.out[(size_t)b * a.ldo + (kvh * G + head) * HD + tid] = f2b(L > 0.f ? acc / L : 0.f);
+    }
+    cluster.sync();                        // peers may still be reading this CTA's shared memory
+}
+
+int decode_attention(const DecodeAttnArgs& a, cudaStream_t s) {
+    UMV_REQUIRE(a.H % a.Hkv == 0 && a.H / a.Hkv <= 8, UMV_ERR_UNSUPPORTED, "decode_attention: GQA group %d > 8", a.H / a.Hkv);
+    UMV_REQUIRE(a.cluster >= 1 && a.cluster <= 8, UMV_ERR_INVALID, "decode_attention: cluster size %d", a.cluster);
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(a.cluster, a.M * a.Hkv);
+    cfg.blockDim = dim3(kAttnThreads);
+    cfg.dynamicSmemBytes = kDecSmemBytes;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[2];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = a.cluster;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = g_pdl ? 2 : 1;
+    const float scale_log2 = (1.0f / sqrtf(128.0f)) * 1.4426950408889634f;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, attn_decode_kernel, a, scale_log2);
+    ++g_launches;
+    if (e == cudaSuccess) e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        set_error("attn_decode_kernel launch failed: %s", cudaGetErrorString(e));
+        return UMV_ERR_CUDA;
+    }
+    return UMV_OK;
+}
+
 int attention_init() {
     cudaFuncSetAttribute(attn_fwd_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnCfg<128>::kSmemBytes);
     cudaFuncSetAttribute(attn_fwd_kernel<72>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnCfg<72>::kSmemBytes);
+    cudaFuncSetAttribute(attn_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kDecSmemBytes);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) {
         set_error("attention_init: %s", cudaGetErrorString(e));

@@ -391,6 +391,21 @@ static int llm_layers(umv_engine* e, const LlmRun& r, bf16* out, cudaStream_t st
             }
             ra.qkv = e->qkv;
         }
+        // decode (one query token per sample, understanding expert): the whole rope -> append -> attention -> combine
+        // chain is one cluster launch
+        static const bool fused_attn = !(getenv("UMV_FUSED_ATTN") && atoi(getenv("UMV_FUSED_ATTN")) == 0);
+        const bool fuse = fused_attn && r.weight_major && r.max_q_len == 1 && !r.gen && dh == 128 && H / Hkv <= 8;
+        if (fuse) {
+            DecodeAttnArgs da;
+            da.qkv = ra.qkv; da.partial = ra.partial; da.ksplits = ra.splits; da.bias = ra.bias;
+            da.out = e->attn; da.ldo = D; da.positions = r.m.positions; da.kv_len = r.m.kv_len;
+            da.page_table = r.m.page_table; da.max_pages = r.m.max_pages; da.inv_freq = e->inv_freq;
+            da.qn = L.qn[0]; da.kn = L.kn[0]; da.pool = e->pool; da.layer = li; da.M = M; da.H = H; da.Hkv = Hkv;
+            da.eps = d.rms_eps;
+            const int blocks = (r.max_kv_len + kPageTokens - 1) / kPageTokens;
+            da.cluster = std::max(1, std::min(8, blocks));
+            UMV_TRY(decode_attention(da, st));
+        } else {
         ra.q_out = e->qkv; ra.ldq = QN;
         ra.positions = r.m.positions; ra.row_seq = r.m.row_seq; ra.row_kvpos = r.m.row_kvpos;
         ra.page_table = r.m.page_table; ra.max_pages = r.m.max_pages; ra.inv_freq = e->inv_freq;
@@ -406,6 +421,7 @@ static int llm_layers(umv_engine* e, const LlmRun& r, bf16* out, cudaStream_t st
         aa.n = r.n_seqs; aa.H = H; aa.Hkv = Hkv; aa.dh = dh; aa.causal = r.causal ? 1 : 0;
         aa.max_q_len = r.max_q_len; aa.max_kv_len = r.max_kv_len; aa.splits = attn_splits; aa.ws = e->attn_ws; aa.total_q = M;
         UMV_TRY(attention_forward(aa, st));
+        }
         // ---- output projection + residual
         if (partial) {
             const int s = pick_splits(D, D, e->sm_count);

@@ -530,7 +530,17 @@ int linear_forward(const LinearCall& c, cudaStream_t stream) {
         if (c.epi == EPI_SWIGLU) {
             return (c.N % 256 == 0) ? launch_tc<256, 2, false>(c, stream) : launch_tc<128, 2, false>(c, stream);
         }
-        if (c.N > 128) return launch_tc<256, 0, false>(c, stream);
+        if (c.N > 128) {
+            // 128x256 tiles unless wave quantisation on the 148 persistent CTAs costs more than the narrower tile's
+            // lower efficiency (128x128: half the work per tile, B tile re-read twice as often: ~8 % slower per flop)
+            static const int force_bn = getenv("UMV_BN") ? atoi(getenv("UMV_BN")) : 0;
+            const long m_tiles = (c.M + BM - 1) / BM;
+            const long t256 = m_tiles * ((c.N + 255) / 256), t128 = m_tiles * ((c.N + 127) / 128);
+            const double cost256 = (double)((t256 + g_sm_count - 1) / g_sm_count);
+            const double cost128 = (double)((t128 + g_sm_count - 1) / g_sm_count) * 0.5 * 1.08;
+            const bool use128 = force_bn ? force_bn == 128 : cost128 < cost256;
+            return use128 ? launch_tc<128, 0, false>(c, stream) : launch_tc<256, 0, false>(c, stream);
+        }
         if (c.N > 64) return launch_tc<128, 0, false>(c, stream);
         return launch_tc<64, 0, false>(c, stream);
     }

@@ -127,3 +127,25 @@ int cfg_combine(const CfgArgs& a, int n_images, cudaStream_t s);
 int euler_step(float* x, const float* v, int64_t n, float dt, int v_is_bf16, cudaStream_t s);
 
 }  // namespace umv
+
+namespace umv {
+// ---- fused decode attention (attention.cu): split-K reduce + bias + q/k RMSNorm + RoPE + KV append + split-KV
+// attention + combine through distributed shared memory of a thread-block cluster, one launch per layer.
+struct DecodeAttnArgs {
+    const bf16* qkv = nullptr;        // [M, ncols] bf16 (bias applied), or
+    const float* partial = nullptr;   // [ksplits][M][ncols] fp32 split-K partials (+ bias)
+    int ksplits = 0;
+    const bf16* bias = nullptr;
+    bf16* out = nullptr; int ldo = 0; // [M, H*dh]
+    const int* positions = nullptr;   // [M] rope position of the (single) query token of each sample
+    const int* kv_len = nullptr;      // [M] keys visible, including the token being appended
+    const int* page_table = nullptr; int max_pages = 0;
+    const float* inv_freq = nullptr;
+    const bf16* qn = nullptr; const bf16* kn = nullptr;
+    KVPool pool; int layer = 0;
+    int M = 0, H = 0, Hkv = 0;
+    int cluster = 8;                  // CTAs (key ranges) per (sample, kv head)
+    float eps = 1e-6f;
+};
+int decode_attention(const DecodeAttnArgs& a, cudaStream_t s);
+}  // namespace umv
