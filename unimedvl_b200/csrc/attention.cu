@@ -301,7 +301,8 @@ namespace cg = cooperative_groups;
 constexpr int kDecQBytes = 16 * 256;
 constexpr int kDecSmemBytes = kDecQBytes + 4 * kTileKeys * 256;
 
-__global__ void __launch_bounds__(kAttnThreads) attn_decode_kernel(DecodeAttnArgs a, float scale_log2) {
+constexpr int kDecThreads = 256;   // warps 0-3: one 16-key quarter of every block each; all 8 warps: rope rows + staging
+__global__ void __launch_bounds__(kDecThreads, 2) attn_decode_kernel(DecodeAttnArgs a, float scale_log2) {
     constexpr int HD = 128;
     pdl_launch_dependents();
     pdl_wait();
@@ -333,7 +334,7 @@ __global__ void __launch_bounds__(kAttnThreads) attn_decode_kernel(DecodeAttnArg
         const bf16* vbase = a.pool.base + a.pool.tile_offset(page, a.layer, 1, kvh);
         uint8_t* dk = sK + stage * kTileKeys * 256;
         uint8_t* dv = sV + stage * kTileKeys * 256;
-        for (int i = tid; i < kTileKeys * 16; i += kAttnThreads) {
+        for (int i = tid; i < kTileKeys * 16; i += kDecThreads) {
             const int r = i >> 4, ch = i & 15;
             const bool ok = kb * kTileKeys + r < kvlen;
             cp_async16(dk + tile_off<HD>(r, ch), kbase + (size_t)(ok ? r : 0) * HD + ch * 8, ok);
@@ -346,13 +347,13 @@ __global__ void __launch_bounds__(kAttnThreads) attn_decode_kernel(DecodeAttnArg
     cp_async_commit();
 
     // ---- rows of this step: G query heads (-> sQ) and, on the owner CTA, the new K and V rows (-> page)
-    for (int i = tid; i < 16 * 16; i += kAttnThreads) {
+    for (int i = tid; i < 16 * 16; i += kDecThreads) {
         const int r = i >> 4, ch = i & 15;
         if (r >= G) *reinterpret_cast<U4*>(sQ + tile_off<HD>(r, ch)) = U4{0, 0, 0, 0};
     }
     const float pos = (float)a.positions[b];
     const int n_tasks = G + (owner ? 2 : 0);
-    for (int task = warp; task < n_tasks; task += kAttnThreads / 32) {
+    for (int task = warp; task < n_tasks; task += kDecThreads / 32) {
         const bool is_q = task < G, is_v = task == G + 1;
         const int col = (is_q ? (kvh * G + task) : (is_v ? a.H + a.Hkv + kvh : a.H + kvh)) * HD + lane * 4;
         float x[4];
@@ -431,6 +432,7 @@ __global__ void __launch_bounds__(kAttnThreads) attn_decode_kernel(DecodeAttnArg
         __syncthreads();
         const uint8_t* cK = sK + stage * kTileKeys * 256;
         const uint8_t* cV = sV + stage * kTileKeys * 256;
+        if (warp < 4) {
         float s0[4] = {0.f, 0.f, 0.f, 0.f}, s1[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
         for (int ks = 0; ks < 8; ++ks) {
@@ -469,6 +471,7 @@ __global__ void __launch_bounds__(kAttnThreads) attn_decode_kernel(DecodeAttnArg
             o[dp][0] = acc0[0]; o[dp][1] = acc0[1];
             o[dp + 1][0] = acc1[0]; o[dp + 1][1] = acc1[1];
         }
+        }
         __syncthreads();
     }
     cp_async_wait<0>();
@@ -476,11 +479,13 @@ __global__ void __launch_bounds__(kAttnThreads) attn_decode_kernel(DecodeAttnArg
     l_a += __shfl_xor_sync(0xffffffffu, l_a, 2);
 
     // ---- merge the 4 key-quarters of this CTA
-    if (t == 0) { red_m[warp][g] = m_a; red_l[warp][g] = l_a; }
+    if (warp < 4) {
+        if (t == 0) { red_m[warp][g] = m_a; red_l[warp][g] = l_a; }
 #pragma unroll
-    for (int dt = 0; dt < 16; ++dt) *reinterpret_cast<float2*>(&red_o[warp][g][dt * 8 + 2 * t]) = make_float2(o[dt][0], o[dt][1]);
+        for (int dt = 0; dt < 16; ++dt) *reinterpret_cast<float2*>(&red_o[warp][g][dt * 8 + 2 * t]) = make_float2(o[dt][0], o[dt][1]);
+    }
     __syncthreads();
-    {
+    if (tid < 128) {
         const int row = tid >> 4, d0 = (tid & 15) * 8;
         float M = -INFINITY;
 #pragma unroll
@@ -500,7 +505,7 @@ __global__ void __launch_bounds__(kAttnThreads) attn_decode_kernel(DecodeAttnArg
     }
     cluster.sync();
     // ---- merge the key ranges of the cluster: CTA `rank` finishes heads rank, rank+S, ...
-    for (int head = rank; head < G; head += S) {
+    for (int head = rank; head < G && tid < HD; head += S) {
         float M = -INFINITY;
         for (int r = 0; r < S; ++r) M = fmaxf(M, cluster.map_shared_rank(fin_m, r)[head]);
         float L = 0.f, acc = 0.f;
@@ -520,7 +525,7 @@ int decode_attention(const DecodeAttnArgs& a, cudaStream_t s) {
     UMV_REQUIRE(a.cluster >= 1 && a.cluster <= 8, UMV_ERR_INVALID, "decode_attention: cluster size %d", a.cluster);
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(a.cluster, a.M * a.Hkv);
-    cfg.blockDim = dim3(kAttnThreads);
+    cfg.blockDim = dim3(kDecThreads);
     cfg.dynamicSmemBytes = kDecSmemBytes;
     cfg.stream = s;
     cudaLaunchAttribute attr[2];
