@@ -188,6 +188,15 @@ int umv_op_argmax(const void* logits, int32_t rows, int32_t vocab, int64_t* out,
  * weights the launch streams (the algorithmic HBM traffic besides the m activation rows). */
 int umv_bench_decode_linear(umv_engine* e, int32_t which, int32_t layer, int32_t m, int64_t* weight_bytes, void* stream);
 
+/* Diagnostic timeline: after umv_trace_begin(max_slots) every traced kernel launch (linears, norms, attention) gets a
+ * slot in launch order and stamps %globaltimer (ns) into it: [0] first CTA started, [1] it passed the dependency wait
+ * (linears: all weight tiles requested), [2] first CTA ended, [3] last CTA ended.  Launches captured into a CUDA graph
+ * keep their slot, so after a replayed decode loop the slots hold the timeline of the last step.  umv_trace_read
+ * synchronises the device and copies min(n, max_slots) slots (12 x uint64 each: the 4 stamps + 8 kernel-specific ones) and kernel names (name_len bytes each).
+ * umv_trace_begin(0) turns tracing off.  No reference counterpart (tools/decode_trace.py). */
+int umv_trace_begin(int32_t max_slots);
+int umv_trace_read(uint64_t* stamps, char* names, int32_t name_len, int32_t max_slots, int32_t* n);
+
 /* Kernel launches issued by this library since load (bench.py "gpu_launches"). */
 int64_t umv_launch_count(void);
 

@@ -77,6 +77,8 @@ SIGNATURES = {
     "umv_op_argmax": (C.c_int, [_P, _I, _I, _P, _P]),
     "umv_bench_decode_linear": (C.c_int, [_P, _I, _I, _I, _LP, _P]),
     "umv_launch_count": (C.c_int64, []),
+    "umv_trace_begin": (C.c_int, [_I]),
+    "umv_trace_read": (C.c_int, [_P, _P, _I, _I, _P]),
 }
 
 _lib = None

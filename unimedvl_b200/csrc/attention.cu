@@ -10,8 +10,6 @@
 // Replaces flash_attn_varlen_func (flash-attn 2.x, external to the reference) at
 // qwen2_navit.py:605-614 (causal = bottom-right aligned, or full) and siglip_navit.py:232-241, and the
 // per-step full KV re-materialisation of qwen2_navit.py:589-600 (the cache is read in place).
-#include <cooperative_groups.h>
-
 #include "../../include/umv.h"
 #include "common.cuh"
 #include "gemm.cuh"
@@ -45,7 +43,9 @@ template <int HD>
 __global__ void __launch_bounds__(kAttnThreads) attn_fwd_kernel(AttnArgs a, float scale_log2) {
     using Cfg = AttnCfg<HD>;
     pdl_launch_dependents();
+    trace_start(a.trace);
     pdl_wait();
+    trace_wait(a.trace);
     extern __shared__ __align__(128) uint8_t smem[];
     uint8_t* sQ = smem;
     uint8_t* sK = smem + Cfg::kTileBytes;
@@ -249,13 +249,16 @@ __global__ void __launch_bounds__(kAttnThreads) attn_fwd_kernel(AttnArgs a, floa
             }
         }
     }
+    trace_end<false>(a.trace);
 }
 
 // Split-KV combine: out = sum_s w_s O_s / sum_s w_s, w_s = 2^(lse_s - max lse).   one warp per (token, head)
 template <int HD>
 __global__ void attn_combine_kernel(AttnArgs a) {
     pdl_launch_dependents();
+    trace_start(a.trace_combine);
     pdl_wait();
+    trace_wait(a.trace_combine);
     const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     const int rows = a.total_q * a.H;
     if (gw >= rows) return;
@@ -285,6 +288,7 @@ __global__ void attn_combine_kernel(AttnArgs a) {
         const int d = lane + i * 32;
         if (d < HD) dst[d] = f2b(acc[i] * inv);
     }
+    trace_end<false>(a.trace_combine);
 }
 
 
@@ -292,48 +296,155 @@ __global__ void attn_combine_kernel(AttnArgs a) {
 // Fused decode attention: ONE launch per layer for the chain
 //   split-K reduce (+bias) of the q/k/v projection -> q/k RMSNorm -> RoPE -> KV append -> attention over the paged
 //   cache -> split-KV combine.
-// A thread-block cluster of `S` CTAs owns one (sample, kv head): CTA r covers key blocks [r*bps, (r+1)*bps); inside a
-// CTA the 4 warps split each 64-key block (16 keys each) since only G <= 8 query rows exist; the CTA whose range holds
-// the newest position rotates and stores the new K/V row before its block is staged; partial (m, l, O) are merged
-// first across warps in shared memory, then across the cluster through distributed shared memory (no global round
-// trip, no second kernel).  Numerics identical to rope_append_kernel + attn_fwd_kernel (und mode, R4-R6).
-namespace cg = cooperative_groups;
+// A thread-block cluster of `S` CTAs owns one (sample, kv head); CTA r covers a contiguous range of 64-key blocks.
+// The kernel is on the critical path of the decode chain and moves little data (18 MB per layer at B=8, ctx 1.1k), so
+// it is organised around the number of DEPENDENT memory round trips, not around bandwidth:
+//   1. after griddepcontrol.wait every load that does not depend on another load is issued at once: kv_len, position,
+//      the sample's page-table row (-> shared memory), all split-K partials of this CTA's q/k/v rows, bias, norm
+//      weights, inv_freq;
+//   2. as soon as the page row is known, the K/V tiles of up to three blocks (the CTA's whole range at ctx <= 1.5k) are
+//      in flight together (cp.async ring), while the warps normalise / rotate the G query rows and the new K/V row;
+//   3. inside a CTA the 4 compute warps split each 64-key block (only G <= 8 query rows exist); partial (m, l, O) are
+//      merged across warps in shared memory and then PUSHED to the CTA that finishes the head through distributed
+//      shared memory (remote stores, no remote round trip), one cluster barrier, local combine, store.
+// Numerics identical to rope_append_kernel + attn_fwd_kernel + attn_combine_kernel (und mode, R4-R6).
+constexpr int kDecThreads = 256;
+constexpr int kDecStages = 6;                                           // 64-key blocks in flight per CTA (one CTA per SM)
 constexpr int kDecQBytes = 16 * 256;
-constexpr int kDecSmemBytes = kDecQBytes + 4 * kTileKeys * 256;
+constexpr int kDecStageBytes = 2 * kTileKeys * 256;                    // K tile + V tile
+constexpr int kDecSmemBytes = kDecQBytes + kDecStages * kDecStageBytes;
+constexpr int kDecMaxPages = 512;                                       // page-table row staged in shared memory
+constexpr int kDecMaxSplits = 8;                                        // split-K partials summed with all loads in flight
+constexpr int kDecRecvRows = 16;                                        // >= S * ceil(G / S) for G <= 8, S <= 8
 
-constexpr int kDecThreads = 256;   // warps 0-3: one 16-key quarter of every block each; all 8 warps: rope rows + staging
-__global__ void __launch_bounds__(kDecThreads, 2) attn_decode_kernel(DecodeAttnArgs a, float scale_log2) {
+__device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
+__device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
+__device__ __forceinline__ uint32_t map_to_rank(const void* smem_ptr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_u32(smem_ptr)), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void st_cluster_f4(uint32_t addr, float4 v) {
+    asm volatile("st.shared::cluster.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ void st_cluster_f1(uint32_t addr, float v) {
+    asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
+}
+
+__global__ void __launch_bounds__(kDecThreads, 1) attn_decode_kernel(DecodeAttnArgs a, float scale_log2) {
     constexpr int HD = 128;
     pdl_launch_dependents();
-    pdl_wait();
-    cg::cluster_group cluster = cg::this_cluster();
+    trace_start(a.trace);
+    cluster_arrive();                      // phase 1: "this CTA runs" (its shared memory may be written by peers later)
     extern __shared__ __align__(128) uint8_t smem[];
     uint8_t* sQ = smem;
-    uint8_t* sK = smem + kDecQBytes;
-    uint8_t* sV = sK + 2 * kTileKeys * 256;
-    __shared__ float red_m[4][8], red_l[4][8];
-    __shared__ float red_o[4][8][HD];
-    __shared__ float fin_o[8][HD];
-    __shared__ float fin_m[8], fin_l[8];
+    uint8_t* sKV = smem + kDecQBytes;
+    __shared__ int s_pages[kDecMaxPages];
+    __shared__ __align__(16) float recv_o[kDecRecvRows][HD];
+    __shared__ float recv_m[kDecRecvRows], recv_l[kDecRecvRows];
+    // after the key loop the stage ring is dead: the cross-warp merge buffers live there
+    float* red_o = reinterpret_cast<float*>(sKV);                     // [8 warps][8 rows][HD]
+    float* red_m = red_o + 8 * 8 * HD;                                // [8][8]
+    float* red_l = red_m + 64;                                        // [8][8]
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int S = (int)cluster.num_blocks(), rank = (int)cluster.block_rank();
+    uint32_t S, rank;
+    asm volatile("mov.u32 %0, %%cluster_nctaid.x;" : "=r"(S));
+    asm volatile("mov.u32 %0, %%cluster_ctaid.x;" : "=r"(rank));
     const int b = blockIdx.y / a.Hkv, kvh = blockIdx.y % a.Hkv;
     const int G = a.H / a.Hkv;
+    const int hpc = (G + (int)S - 1) / (int)S;                        // heads finished per CTA
     const int ncols = (a.H + 2 * a.Hkv) * HD;
+
+    // ---- constants (weights): before the dependency wait
+    for (int i = tid; i < 16 * 16; i += kDecThreads) {                // padding rows of the Q tile
+        const int r = i >> 4, ch = i & 15;
+        if (r >= G) *reinterpret_cast<U4*>(sQ + tile_off<HD>(r, ch)) = U4{0, 0, 0, 0};
+    }
+    // row tasks: warps 0..G-1 one query head each, warp G the new K row and the new V row
+    const bool is_q = warp < G, is_kv = warp == G;
+    const int col_a = (is_q ? kvh * G + warp : a.H + kvh) * HD + lane * 4;          // q head / k row
+    const int col_v = (a.H + a.Hkv + kvh) * HD + lane * 4;
+    uint2 wv = make_uint2(0u, 0u), ba = make_uint2(0u, 0u), bv = make_uint2(0u, 0u);
+    if (is_q || is_kv) {
+        wv = *reinterpret_cast<const uint2*>((is_q ? a.qn : a.kn) + lane * 4);
+        if (a.partial) {
+            ba = *reinterpret_cast<const uint2*>(a.bias + col_a);
+            if (is_kv) bv = *reinterpret_cast<const uint2*>(a.bias + col_v);
+        }
+    }
+    pdl_wait();
+    trace_wait(a.trace);
+
+    // ---- round trip 1: everything that needs no other load
     const int kvlen = a.kv_len[b];
+    for (int i = tid; i < a.max_pages; i += kDecThreads) s_pages[i] = a.page_table[(size_t)b * a.max_pages + i];
+    float xa[4] = {0.f, 0.f, 0.f, 0.f}, xv[4] = {0.f, 0.f, 0.f, 0.f};
+    float4 rc = make_float4(0.f, 0.f, 0.f, 0.f), rs = rc;            // bf16-rounded cos / sin of this lane's 4 elements
+    if (is_q || is_kv) {
+        if (a.rope_cs) {
+            rc = *reinterpret_cast<const float4*>(a.rope_cs + (size_t)b * HD + (lane * 4) % (HD / 2));
+            rs = *reinterpret_cast<const float4*>(a.rope_cs + (size_t)b * HD + HD / 2 + (lane * 4) % (HD / 2));
+        } else {
+            const float pos = (float)a.positions[b];
+            const float4 fr = *reinterpret_cast<const float4*>(a.inv_freq + (lane * 4) % (HD / 2));
+            const float f[4] = {fr.x, fr.y, fr.z, fr.w};
+            float c[4], sn[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float ang = __fmul_rn(pos, f[j]);
+                c[j] = rbf(cosf(ang));
+                sn[j] = rbf(sinf(ang));
+            }
+            rc = make_float4(c[0], c[1], c[2], c[3]);
+            rs = make_float4(sn[0], sn[1], sn[2], sn[3]);
+        }
+        if (a.partial) {
+            float4 pa[kDecMaxSplits], pv[kDecMaxSplits];
+#pragma unroll
+            for (int sp = 0; sp < kDecMaxSplits; ++sp) {
+                pa[sp] = pv[sp] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (sp < a.ksplits) {
+                    const float* rowp = a.partial + ((size_t)sp * a.M + b) * ncols;
+                    pa[sp] = *reinterpret_cast<const float4*>(rowp + col_a);
+                    if (is_kv) pv[sp] = *reinterpret_cast<const float4*>(rowp + col_v);
+                }
+            }
+            float sa[4] = {0.f, 0.f, 0.f, 0.f}, sv[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int sp = 0; sp < kDecMaxSplits; ++sp) {            // fixed order; +0.f beyond ksplits is exact
+                if (sp < a.ksplits) {
+                    sa[0] += pa[sp].x; sa[1] += pa[sp].y; sa[2] += pa[sp].z; sa[3] += pa[sp].w;
+                    sv[0] += pv[sp].x; sv[1] += pv[sp].y; sv[2] += pv[sp].z; sv[3] += pv[sp].w;
+                }
+            }
+            const float2 a0 = unpack2(ba.x), a1 = unpack2(ba.y), v0 = unpack2(bv.x), v1 = unpack2(bv.y);
+            xa[0] = rbf(sa[0] + a0.x); xa[1] = rbf(sa[1] + a0.y); xa[2] = rbf(sa[2] + a1.x); xa[3] = rbf(sa[3] + a1.y);
+            xv[0] = rbf(sv[0] + v0.x); xv[1] = rbf(sv[1] + v0.y); xv[2] = rbf(sv[2] + v1.x); xv[3] = rbf(sv[3] + v1.y);
+        } else {
+            const uint2 qa = *reinterpret_cast<const uint2*>(a.qkv + (size_t)b * ncols + col_a);
+            uint2 qv = make_uint2(0u, 0u);
+            if (is_kv) qv = *reinterpret_cast<const uint2*>(a.qkv + (size_t)b * ncols + col_v);
+            const float2 f0 = unpack2(qa.x), f1 = unpack2(qa.y), g0 = unpack2(qv.x), g1 = unpack2(qv.y);
+            xa[0] = f0.x; xa[1] = f0.y; xa[2] = f1.x; xa[3] = f1.y;
+            xv[0] = g0.x; xv[1] = g0.y; xv[2] = g1.x; xv[3] = g1.y;
+        }
+    }
+
+    // key-block range of this CTA (balanced: sizes differ by at most one)
     const int blocks_total = (kvlen + kTileKeys - 1) / kTileKeys;
-    const int bps = (blocks_total + S - 1) / S;
-    const int kb_begin = rank * bps, kb_end = min(blocks_total, kb_begin + bps);
-    const int last_block = (kvlen - 1) / kTileKeys;
-    const bool owner = kb_begin <= last_block && last_block < kb_end;
+    const int kb_begin = (int)(((long long)blocks_total * rank) / S), kb_end = (int)(((long long)blocks_total * (rank + 1)) / S);
+    const int last_block = (kvlen - 1) / kTileKeys, new_slot = (kvlen - 1) % kTileKeys;
+    const bool owner = kb_begin <= last_block && last_block < kb_end;     // this CTA appends the new K/V row
+    __syncthreads();                                                      // s_pages (and the Q padding) visible
+    trace_dbg(a.trace, 0);
 
     auto load_kv = [&](int kb, int stage) {
-        const int page = a.page_table[(size_t)b * a.max_pages + kb];
+        const int page = s_pages[kb];
         const bf16* kbase = a.pool.base + a.pool.tile_offset(page, a.layer, 0, kvh);
         const bf16* vbase = a.pool.base + a.pool.tile_offset(page, a.layer, 1, kvh);
-        uint8_t* dk = sK + stage * kTileKeys * 256;
-        uint8_t* dv = sV + stage * kTileKeys * 256;
+        uint8_t* dk = sKV + stage * kDecStageBytes;
+        uint8_t* dv = dk + kTileKeys * 256;
         for (int i = tid; i < kTileKeys * 16; i += kDecThreads) {
             const int r = i >> 4, ch = i & 15;
             const bool ok = kb * kTileKeys + r < kvlen;
@@ -341,76 +452,51 @@ __global__ void __launch_bounds__(kDecThreads, 2) attn_decode_kernel(DecodeAttnA
             cp_async16(dv + tile_off<HD>(r, ch), vbase + (size_t)(ok ? r : 0) * HD + ch * 8, ok);
         }
     };
-    // stage the first block right away unless it is the one that receives the new token
-    const bool pre = kb_begin < kb_end && !(owner && kb_begin == last_block);
-    if (pre) load_kv(kb_begin, 0);
-    cp_async_commit();
-
-    // ---- rows of this step: G query heads (-> sQ) and, on the owner CTA, the new K and V rows (-> page)
-    for (int i = tid; i < 16 * 16; i += kDecThreads) {
-        const int r = i >> 4, ch = i & 15;
-        if (r >= G) *reinterpret_cast<U4*>(sQ + tile_off<HD>(r, ch)) = U4{0, 0, 0, 0};
+    // ---- round trip 2: up to kDecStages blocks (the CTA's whole range at B = 8, ctx <= 1.5k) go out together, one commit
+    // group per ring slot.  The block that receives the new token is loaded like the others; its new row is patched in
+    // shared memory from the registers of the K/V warp once the tile has landed.
+#pragma unroll
+    for (int j = 0; j < kDecStages; ++j) {
+        if (kb_begin + j < kb_end) load_kv(kb_begin + j, j);
+        cp_async_commit();
     }
-    const float pos = (float)a.positions[b];
-    const int n_tasks = G + (owner ? 2 : 0);
-    for (int task = warp; task < n_tasks; task += kDecThreads / 32) {
-        const bool is_q = task < G, is_v = task == G + 1;
-        const int col = (is_q ? (kvh * G + task) : (is_v ? a.H + a.Hkv + kvh : a.H + kvh)) * HD + lane * 4;
-        float x[4];
-        if (a.partial) {
-            float acc[4] = {0.f, 0.f, 0.f, 0.f};
-            for (int sp = 0; sp < a.ksplits; ++sp) {
-                const float4 p4 = *reinterpret_cast<const float4*>(a.partial + ((size_t)sp * a.M + b) * ncols + col);
-                acc[0] += p4.x; acc[1] += p4.y; acc[2] += p4.z; acc[3] += p4.w;
-            }
-            const uint2 bv = *reinterpret_cast<const uint2*>(a.bias + col);
-            const float2 b0 = unpack2(bv.x), b1 = unpack2(bv.y);
-            x[0] = rbf(acc[0] + b0.x); x[1] = rbf(acc[1] + b0.y); x[2] = rbf(acc[2] + b1.x); x[3] = rbf(acc[3] + b1.y);
-        } else {
-            const uint2 qv = *reinterpret_cast<const uint2*>(a.qkv + (size_t)b * ncols + col);
-            const float2 f0 = unpack2(qv.x), f1 = unpack2(qv.y);
-            x[0] = f0.x; x[1] = f0.y; x[2] = f1.x; x[3] = f1.y;
-        }
-        float o4[4];
-        if (is_v) {
+
+    // ---- rows of this step: RMSNorm + RoPE of the query heads (-> sQ) and of the new K row, V row as is (-> page)
+    uint2 k_new = make_uint2(0u, 0u), v_new = make_uint2(0u, 0u);
+    if (is_q || is_kv) {
+        const float2 w0 = unpack2(wv.x), w1 = unpack2(wv.y);
+        const float nw[4] = {w0.x, w0.y, w1.x, w1.y};
+        const float c[4] = {rc.x, rc.y, rc.z, rc.w}, sn[4] = {rs.x, rs.y, rs.z, rs.w};
+        float ss = xa[0] * xa[0] + xa[1] * xa[1] + xa[2] * xa[2] + xa[3] * xa[3];
+        ss = warp_sum(ss);
+        const float inv = 1.0f / sqrtf(ss / (float)HD + a.eps);
+        float n[4], o4[4];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) o4[j] = x[j];
-        } else {
-            const bf16* nw = is_q ? a.qn : a.kn;
-            float ss = x[0] * x[0] + x[1] * x[1] + x[2] * x[2] + x[3] * x[3];
-            ss = warp_sum(ss);
-            const float inv = 1.0f / sqrtf(ss / (float)HD + a.eps);
-            const uint2 wv = *reinterpret_cast<const uint2*>(nw + lane * 4);
-            const float2 w0 = unpack2(wv.x), w1 = unpack2(wv.y);
-            const float w[4] = {w0.x, w0.y, w1.x, w1.y};
-            float n[4];
+        for (int j = 0; j < 4; ++j) n[j] = rbf(nw[j] * rbf(xa[j] * inv));
 #pragma unroll
-            for (int j = 0; j < 4; ++j) n[j] = rbf(w[j] * rbf(x[j] * inv));
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const int i = lane * 4 + j;
-                const float ang = __fmul_rn(pos, a.inv_freq[i % (HD / 2)]);
-                const float c = rbf(cosf(ang)), sn = rbf(sinf(ang));
-                const float partner = __shfl_xor_sync(0xffffffffu, n[j], 16);
-                const float rot = (i < HD / 2) ? -partner : partner;
-                o4[j] = rbf(rbf(n[j] * c) + rbf(rot * sn));
-            }
+        for (int j = 0; j < 4; ++j) {
+            const float partner = __shfl_xor_sync(0xffffffffu, n[j], 16);
+            const float rot = (lane < 16) ? -partner : partner;
+            o4[j] = rbf(rbf(n[j] * c[j]) + rbf(rot * sn[j]));
         }
         const uint2 packed = make_uint2(pack2(o4[0], o4[1]), pack2(o4[2], o4[3]));
         if (is_q) {
-            *reinterpret_cast<uint2*>(sQ + tile_off<HD>(task, lane >> 1) + (lane & 1) * 8) = packed;
-        } else {
-            const int slot = (kvlen - 1) % kTileKeys;
-            const int page = a.page_table[(size_t)b * a.max_pages + last_block];
-            bf16* dst = a.pool.base + a.pool.tile_offset(page, a.layer, is_v ? 1 : 0, kvh) + (size_t)slot * HD + lane * 4;
-            *reinterpret_cast<uint2*>(dst) = packed;
+            *reinterpret_cast<uint2*>(sQ + tile_off<HD>(warp, lane >> 1) + (lane & 1) * 8) = packed;
+        } else if (owner) {
+            k_new = packed;
+            v_new = make_uint2(pack2(xv[0], xv[1]), pack2(xv[2], xv[3]));
+            const int page = s_pages[last_block];
+            bf16* kdst = a.pool.base + a.pool.tile_offset(page, a.layer, 0, kvh) + (size_t)new_slot * HD + lane * 4;
+            bf16* vdst = a.pool.base + a.pool.tile_offset(page, a.layer, 1, kvh) + (size_t)new_slot * HD + lane * 4;
+            *reinterpret_cast<uint2*>(kdst) = k_new;
+            *reinterpret_cast<uint2*>(vdst) = v_new;
         }
     }
-    __syncthreads();                       // sQ complete; the owner's K/V row is visible to the CTA's later cp.async
-    if (!pre && kb_begin < kb_end) load_kv(kb_begin, 0);
-    cp_async_commit();
+    __syncthreads();                       // sQ complete
+    trace_dbg(a.trace, 1);
 
     const int g = lane >> 2, t = lane & 3;
+    const int quarter = warp & 3, sub = warp >> 2;      // warp = (16-key quarter, which block of the round's pair)
     uint32_t qf[8][4];
 #pragma unroll
     for (int ks = 0; ks < 8; ++ks)
@@ -420,109 +506,148 @@ __global__ void __launch_bounds__(kDecThreads, 2) attn_decode_kernel(DecodeAttnA
     for (int i = 0; i < 16; ++i) o[i][0] = o[i][1] = 0.f;
     float m_a = -INFINITY, l_a = 0.f;
 
-    for (int kb = kb_begin; kb < kb_end; ++kb) {
-        const int stage = (kb - kb_begin) & 1;
-        if (kb + 1 < kb_end) {
-            load_kv(kb + 1, stage ^ 1);
-            cp_async_commit();
-            cp_async_wait<1>();
-        } else {
-            cp_async_wait<0>();
-        }
+    const int nblk = kb_end - kb_begin;
+    for (int rd = 0; 2 * rd < nblk; ++rd) {
+        // commit groups, in order: kDecStages first-pass slots, then one refill group per finished round (two blocks).
+        // Round rd needs blocks 2rd, 2rd+1: first-pass groups <= 2rd+1 (rd < 3) or refill group rd-3.
+        if (rd == 0) cp_async_wait<kDecStages - 2>();
+        else if (rd == 1) cp_async_wait<kDecStages - 3>();
+        else cp_async_wait<kDecStages - 4>();
         __syncthreads();
-        const uint8_t* cK = sK + stage * kTileKeys * 256;
-        const uint8_t* cV = sV + stage * kTileKeys * 256;
-        if (warp < 4) {
-        float s0[4] = {0.f, 0.f, 0.f, 0.f}, s1[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-        for (int ks = 0; ks < 8; ++ks) {
-            uint32_t b0, b1, b2, b3;
-            ldmatrix_x4(b0, b1, b2, b3,
-                        smem_u32(cK + tile_off<HD>(warp * 16 + (lane & 7) + ((lane >> 4) << 3), ks * 2 + ((lane >> 3) & 1))));
-            mma_bf16_16816(s0, qf[ks], b0, b1);
-            mma_bf16_16816(s1, qf[ks], b2, b3);
+        const int j = 2 * rd + sub, kb = kb_begin + j, stage = j % kDecStages;
+        if (owner && (last_block == kb_begin + 2 * rd || last_block == kb_begin + 2 * rd + 1)) {      // CTA-uniform
+            if (is_kv) {
+                uint8_t* tk = sKV + ((last_block - kb_begin) % kDecStages) * kDecStageBytes;
+                *reinterpret_cast<uint2*>(tk + tile_off<HD>(new_slot, lane >> 1) + (lane & 1) * 8) = k_new;
+                *reinterpret_cast<uint2*>(tk + kTileKeys * 256 + tile_off<HD>(new_slot, lane >> 1) + (lane & 1) * 8) = v_new;
+            }
+            __syncthreads();
         }
-        const int key0 = kb * kTileKeys + warp * 16 + 2 * t;
-        float v00 = key0 < kvlen ? s0[0] * scale_log2 : -INFINITY;
-        float v01 = key0 + 1 < kvlen ? s0[1] * scale_log2 : -INFINITY;
-        float v10 = key0 + 8 < kvlen ? s1[0] * scale_log2 : -INFINITY;
-        float v11 = key0 + 9 < kvlen ? s1[1] * scale_log2 : -INFINITY;
-        float mx = fmaxf(fmaxf(v00, v01), fmaxf(v10, v11));
-        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
-        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
-        const float mn = fmaxf(m_a, mx);
-        const float ms = mn == -INFINITY ? 0.f : mn;
-        const float al = exp2f(m_a - ms);
-        m_a = mn;
-        const float p00 = exp2f(v00 - ms), p01 = exp2f(v01 - ms), p10 = exp2f(v10 - ms), p11 = exp2f(v11 - ms);
-        l_a = l_a * al + (p00 + p01 + p10 + p11);
-        const uint32_t pf[4] = {pack2(p00, p01), 0u, pack2(p10, p11), 0u};      // rows 8..15 of the tile are padding
+        if (rd < 3) trace_dbg(a.trace, 2 + rd);
+        const uint8_t* cK = sKV + stage * kDecStageBytes;
+        const uint8_t* cV = cK + kTileKeys * 256;
+        if (j < nblk) {
+            float s0[4] = {0.f, 0.f, 0.f, 0.f}, s1[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-        for (int dt = 0; dt < 16; ++dt) { o[dt][0] *= al; o[dt][1] *= al; }
+            for (int ks = 0; ks < 8; ++ks) {
+                uint32_t b0, b1, b2, b3;
+                ldmatrix_x4(b0, b1, b2, b3,
+                            smem_u32(cK + tile_off<HD>(quarter * 16 + (lane & 7) + ((lane >> 4) << 3), ks * 2 + ((lane >> 3) & 1))));
+                mma_bf16_16816(s0, qf[ks], b0, b1);
+                mma_bf16_16816(s1, qf[ks], b2, b3);
+            }
+            const int key0 = kb * kTileKeys + quarter * 16 + 2 * t;
+            float v00 = key0 < kvlen ? s0[0] * scale_log2 : -INFINITY;
+            float v01 = key0 + 1 < kvlen ? s0[1] * scale_log2 : -INFINITY;
+            float v10 = key0 + 8 < kvlen ? s1[0] * scale_log2 : -INFINITY;
+            float v11 = key0 + 9 < kvlen ? s1[1] * scale_log2 : -INFINITY;
+            float mx = fmaxf(fmaxf(v00, v01), fmaxf(v10, v11));
+            mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+            mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+            const float mn = fmaxf(m_a, mx);
+            const float ms = mn == -INFINITY ? 0.f : mn;
+            const float al = exp2f(m_a - ms);
+            m_a = mn;
+            const float p00 = exp2f(v00 - ms), p01 = exp2f(v01 - ms), p10 = exp2f(v10 - ms), p11 = exp2f(v11 - ms);
+            l_a = l_a * al + (p00 + p01 + p10 + p11);
+            const uint32_t pf[4] = {pack2(p00, p01), 0u, pack2(p10, p11), 0u};      // rows 8..15 of the tile are padding
 #pragma unroll
-        for (int dp = 0; dp < 16; dp += 2) {
-            uint32_t b0, b1, b2, b3;
-            asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
-                         : "=r"(b0), "=r"(b1), "=r"(b2), "=r"(b3)
-                         : "r"(smem_u32(cV + tile_off<HD>(warp * 16 + (lane & 7) + (((lane >> 3) & 1) << 3), dp + (lane >> 4)))));
-            float acc0[4] = {o[dp][0], o[dp][1], 0.f, 0.f}, acc1[4] = {o[dp + 1][0], o[dp + 1][1], 0.f, 0.f};
-            mma_bf16_16816(acc0, pf, b0, b1);
-            mma_bf16_16816(acc1, pf, b2, b3);
-            o[dp][0] = acc0[0]; o[dp][1] = acc0[1];
-            o[dp + 1][0] = acc1[0]; o[dp + 1][1] = acc1[1];
+            for (int dt = 0; dt < 16; ++dt) { o[dt][0] *= al; o[dt][1] *= al; }
+#pragma unroll
+            for (int dp = 0; dp < 16; dp += 2) {
+                uint32_t b0, b1, b2, b3;
+                asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+                             : "=r"(b0), "=r"(b1), "=r"(b2), "=r"(b3)
+                             : "r"(smem_u32(cV + tile_off<HD>(quarter * 16 + (lane & 7) + (((lane >> 3) & 1) << 3), dp + (lane >> 4)))));
+                float acc0[4] = {o[dp][0], o[dp][1], 0.f, 0.f}, acc1[4] = {o[dp + 1][0], o[dp + 1][1], 0.f, 0.f};
+                mma_bf16_16816(acc0, pf, b0, b1);
+                mma_bf16_16816(acc1, pf, b2, b3);
+                o[dp][0] = acc0[0]; o[dp][1] = acc0[1];
+                o[dp + 1][0] = acc1[0]; o[dp + 1][1] = acc1[1];
+            }
         }
+        if (2 * rd + kDecStages < nblk) {       // long contexts only: refill the two slots just consumed
+            __syncthreads();
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                const int jn = 2 * rd + u + kDecStages;
+                if (jn < nblk) load_kv(kb_begin + jn, jn % kDecStages);
+            }
         }
-        __syncthreads();
+        cp_async_commit();
     }
     cp_async_wait<0>();
     l_a += __shfl_xor_sync(0xffffffffu, l_a, 1);
     l_a += __shfl_xor_sync(0xffffffffu, l_a, 2);
 
-    // ---- merge the 4 key-quarters of this CTA
-    if (warp < 4) {
-        if (t == 0) { red_m[warp][g] = m_a; red_l[warp][g] = l_a; }
-#pragma unroll
-        for (int dt = 0; dt < 16; ++dt) *reinterpret_cast<float2*>(&red_o[warp][g][dt * 8 + 2 * t]) = make_float2(o[dt][0], o[dt][1]);
-    }
+    // ---- merge the 8 (key-quarter, block parity) partials of this CTA (buffers alias the dead stage ring)
     __syncthreads();
+    trace_dbg(a.trace, 5);
+    if (t == 0) { red_m[warp * 8 + g] = m_a; red_l[warp * 8 + g] = l_a; }
+#pragma unroll
+    for (int dt = 0; dt < 16; ++dt)
+        *reinterpret_cast<float2*>(&red_o[(warp * 8 + g) * HD + dt * 8 + 2 * t]) = make_float2(o[dt][0], o[dt][1]);
+    __syncthreads();
+    cluster_wait();                        // phase 1 complete: every CTA of the cluster is running
+    trace_dbg(a.trace, 6);
     if (tid < 128) {
         const int row = tid >> 4, d0 = (tid & 15) * 8;
-        float M = -INFINITY;
+        if (row < G) {
+            float M = -INFINITY;
 #pragma unroll
-        for (int w = 0; w < 4; ++w) M = fmaxf(M, red_m[w][row]);
-        float L = 0.f, acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+            for (int w = 0; w < 8; ++w) M = fmaxf(M, red_m[w * 8 + row]);
+            float L = 0.f, acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-        for (int w = 0; w < 4; ++w) {
-            const float mw = red_m[w][row];
-            const float wg = (mw == -INFINITY) ? 0.f : exp2f(mw - M);
-            L += wg * red_l[w][row];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) acc[j] += wg * red_o[w][row][d0 + j];
+            for (int w = 0; w < 8; ++w) {
+                const float mw = red_m[w * 8 + row];
+                const float wg = (mw == -INFINITY) ? 0.f : exp2f(mw - M);
+                L += wg * red_l[w * 8 + row];
+                const float4 x0 = *reinterpret_cast<const float4*>(&red_o[(w * 8 + row) * HD + d0]);
+                const float4 x1 = *reinterpret_cast<const float4*>(&red_o[(w * 8 + row) * HD + d0 + 4]);
+                acc[0] += wg * x0.x; acc[1] += wg * x0.y; acc[2] += wg * x0.z; acc[3] += wg * x0.w;
+                acc[4] += wg * x1.x; acc[5] += wg * x1.y; acc[6] += wg * x1.z; acc[7] += wg * x1.w;
+            }
+            // push this key range's partial of head `row` to the CTA that finishes the head
+            const uint32_t dst = (uint32_t)row % S;
+            const int slot = (int)rank * hpc + row / (int)S;
+            const uint32_t ro = map_to_rank(&recv_o[slot][d0], dst);
+            st_cluster_f4(ro, make_float4(acc[0], acc[1], acc[2], acc[3]));
+            st_cluster_f4(ro + 16, make_float4(acc[4], acc[5], acc[6], acc[7]));
+            if ((tid & 15) == 0) {
+                st_cluster_f1(map_to_rank(&recv_m[slot], dst), M);
+                st_cluster_f1(map_to_rank(&recv_l[slot], dst), L);
+            }
         }
-#pragma unroll
-        for (int j = 0; j < 8; ++j) fin_o[row][d0 + j] = acc[j];
-        if ((tid & 15) == 0) { fin_m[row] = M; fin_l[row] = L; }
     }
-    cluster.sync();
-    // ---- merge the key ranges of the cluster: CTA `rank` finishes heads rank, rank+S, ...
-    for (int head = rank; head < G && tid < HD; head += S) {
+    cluster_arrive();                      // phase 2: pushes released ...
+    cluster_wait();                        // ... and everyone's pushes into this CTA acquired
+    trace_dbg(a.trace, 7);
+    // ---- finish heads rank, rank + S, ...: merge the S key ranges in a fixed order (deterministic)
+    for (int hi = tid >> 7; hi < hpc; hi += kDecThreads / 128) {
+        const int head = (int)rank + hi * (int)S, d = tid & 127;
+        if (head >= G) break;
         float M = -INFINITY;
-        for (int r = 0; r < S; ++r) M = fmaxf(M, cluster.map_shared_rank(fin_m, r)[head]);
+        for (int r = 0; r < (int)S; ++r) M = fmaxf(M, recv_m[r * hpc + hi]);
         float L = 0.f, acc = 0.f;
-        for (int r = 0; r < S; ++r) {                      // fixed order: deterministic
-            const float mr = cluster.map_shared_rank(fin_m, r)[head];
+        for (int r = 0; r < (int)S; ++r) {
+            const float mr = recv_m[r * hpc + hi];
             const float wg = (mr == -INFINITY) ? 0.f : exp2f(mr - M);
-            L += wg * cluster.map_shared_rank(fin_l, r)[head];
-            acc += wg * cluster.map_shared_rank(&fin_o[0][0], r)[head * HD + tid];
+            L += wg * recv_l[r * hpc + hi];
+            acc += wg * recv_o[r * hpc + hi][d];
         }
-        a.out[(size_t)b * a.ldo + (kvh * G + head) * HD + tid] = f2b(L > 0.f ? acc / L : 0.f);
+        a.out[(size_t)b * a.ldo + (kvh * G + head) * HD + d] = f2b(L > 0.f ? acc / L : 0.f);
     }
-    cluster.sync();                        // peers may still be reading this CTA's shared memory
+    trace_end(a.trace);
 }
 
 int decode_attention(const DecodeAttnArgs& a, cudaStream_t s) {
-    UMV_REQUIRE(a.H % a.Hkv == 0 && a.H / a.Hkv <= 8, UMV_ERR_UNSUPPORTED, "decode_attention: GQA group %d > 8", a.H / a.Hkv);
+    const int G = a.Hkv > 0 ? a.H / a.Hkv : 0;
+    UMV_REQUIRE(a.H % a.Hkv == 0 && G <= 7, UMV_ERR_UNSUPPORTED, "decode_attention: GQA group %d > 7", G);
     UMV_REQUIRE(a.cluster >= 1 && a.cluster <= 8, UMV_ERR_INVALID, "decode_attention: cluster size %d", a.cluster);
+    UMV_REQUIRE(a.cluster * ((G + a.cluster - 1) / a.cluster) <= kDecRecvRows, UMV_ERR_UNSUPPORTED, "decode_attention: G=%d S=%d", G, a.cluster);
+    UMV_REQUIRE(a.max_pages <= kDecMaxPages, UMV_ERR_UNSUPPORTED, "decode_attention: %d pages per sample > %d", a.max_pages, kDecMaxPages);
+    UMV_REQUIRE(a.partial == nullptr || a.ksplits <= kDecMaxSplits, UMV_ERR_UNSUPPORTED, "decode_attention: %d split-K partials > %d",
+                a.ksplits, kDecMaxSplits);
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(a.cluster, a.M * a.Hkv);
     cfg.blockDim = dim3(kDecThreads);
@@ -538,7 +663,9 @@ int decode_attention(const DecodeAttnArgs& a, cudaStream_t s) {
     cfg.attrs = attr;
     cfg.numAttrs = g_pdl ? 2 : 1;
     const float scale_log2 = (1.0f / sqrtf(128.0f)) * 1.4426950408889634f;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, attn_decode_kernel, a, scale_log2);
+    DecodeAttnArgs at = a;
+    at.trace = trace_next("attn_decode");
+    cudaError_t e = cudaLaunchKernelEx(&cfg, attn_decode_kernel, at, scale_log2);
     ++g_launches;
     if (e == cudaSuccess) e = cudaGetLastError();
     if (e != cudaSuccess) {
@@ -546,6 +673,11 @@ int decode_attention(const DecodeAttnArgs& a, cudaStream_t s) {
         return UMV_ERR_CUDA;
     }
     return UMV_OK;
+}
+
+// Shapes the fused decode kernel covers (else: rope_append + attn_fwd + attn_combine).
+bool decode_attention_supported(int H, int Hkv, int dh, int max_pages, int ksplits) {
+    return dh == 128 && Hkv > 0 && H % Hkv == 0 && H / Hkv <= 7 && max_pages <= kDecMaxPages && ksplits <= kDecMaxSplits;
 }
 
 int attention_init() {
@@ -561,7 +693,10 @@ int attention_init() {
 }
 
 template <int HD>
-static int launch_attn(const AttnArgs& a, cudaStream_t s) {
+static int launch_attn(const AttnArgs& a0, cudaStream_t s) {
+    AttnArgs a = a0;
+    a.trace = trace_next("attn_fwd");
+    if (a.splits > 1) a.trace_combine = trace_next("attn_combine");
     const int G = a.H / a.Hkv;
     const int row_tiles = (a.max_q_len * G + kTileRows - 1) / kTileRows;
     const float scale_log2 = (1.0f / sqrtf((float)HD)) * 1.4426950408889634f;

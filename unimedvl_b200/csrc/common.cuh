@@ -96,6 +96,36 @@ inline cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, siz
     return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
 }
 
+// ---- timeline trace (diagnostic; umv_trace_begin / umv_trace_read): with a non-null slot a kernel stamps %globaltimer
+// when its first CTA starts, when that CTA passes griddepcontrol.wait, when it ends, and the latest end over all CTAs.
+struct TraceSlot {
+    unsigned long long t_start, t_wait, t_end_first, t_end_last;
+    unsigned long long dbg[8];      // kernel-specific intermediate stamps of the first CTA
+};
+TraceSlot* trace_next(const char* kernel_name);     // host: next slot of the active trace, or nullptr (tracing off)
+#ifdef __CUDACC__
+__device__ __forceinline__ unsigned long long gtime() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+__device__ __forceinline__ bool trace_lead() { return threadIdx.x == 0 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0; }
+__device__ __forceinline__ void trace_start(TraceSlot* s) { if (s && trace_lead()) s->t_start = gtime(); }
+__device__ __forceinline__ void trace_dbg(TraceSlot* s, int i) { if (s && trace_lead()) s->dbg[i] = gtime(); }
+__device__ __forceinline__ void trace_wait(TraceSlot* s) { if (s && trace_lead()) s->t_wait = gtime(); }
+// kSync = false for kernels whose threads may have returned early (thread 0's own end is stamped)
+template <bool kSync = true>
+__device__ __forceinline__ void trace_end(TraceSlot* s) {
+    if (!s) return;
+    if (kSync) __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned long long t = gtime();
+        atomicMax(&s->t_end_last, t);
+        if (trace_lead()) s->t_end_first = t;
+    }
+}
+#endif
+
 struct alignas(16) U4 {
     uint32_t x, y, z, w;
 };

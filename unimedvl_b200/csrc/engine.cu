@@ -231,6 +231,7 @@ static int build_runtime(umv_engine* e) {
     UMV_TRY(dev_alloc(e, &e->dec_pos, 64));
     UMV_TRY(dev_alloc(e, &e->dec_kvlen, 64));
     UMV_TRY(dev_alloc(e, &e->dec_kvpos, 64));
+    UMV_TRY(dev_alloc(e, &e->dec_rope, (size_t)64 * e->dh));
     UMV_TRY(dev_alloc(e, &e->dec_rowseq, 64));
     UMV_TRY(dev_alloc(e, &e->dec_qstart, 65));
     UMV_TRY(dev_alloc(e, &e->dec_qlen, 64));
@@ -338,8 +339,9 @@ struct LlmRun {
 };
 
 int lin(umv_engine* e, const bf16* x, int ldx, const bf16* w, const bf16* bias, const bf16* res, bf16* y, int ldy, int M,
-               int N, int K, int epi, cudaStream_t st, int impl, float* ws, int splits) {
+               int N, int K, int epi, cudaStream_t st, int impl, float* ws, int splits, int stages) {
     LinearCall c;
+    c.stages = stages;
     c.x = x; c.ldx = ldx; c.w = w; c.bias = bias; c.residual = res; c.y = y; c.ldy = ldy;
     c.M = M; c.N = N; c.K = K; c.epi = epi; c.ws = ws; c.splits = splits;
     c.impl = e->gemm_impl ? e->gemm_impl : impl;
@@ -355,8 +357,33 @@ static int llm_layers(umv_engine* e, const LlmRun& r, bf16* out, cudaStream_t st
     const int T = r.gen ? r.m.n_text : 0;
     int pending_splits = 0;     // >0: e->ws holds split-K partials of the last residual-branch linear
 
+    // Decode: the latency-bound kernels of the chain (norm, attention) ask the L2 for weights of the linears that follow
+    // them, so HBM keeps streaming while they run.  Units: 64-element k-blocks (128 B per weight row).
+    static const int pf_wo = getenv("UMV_PF_WO") ? atoi(getenv("UMV_PF_WO")) : 1;
+    static const int pf_gu_kb = getenv("UMV_PF_GU_KB") ? atoi(getenv("UMV_PF_GU_KB")) : 20;
+    static const int pf_n2_kb = getenv("UMV_PF_N2_KB") ? atoi(getenv("UMV_PF_N2_KB")) : 0;
+    static const int pf_n1_kb = getenv("UMV_PF_N1_KB") ? atoi(getenv("UMV_PF_N1_KB")) : 0;
+    const int ring_kb = 10;                       // k-blocks the weight-major linear itself requests before its wait
+    auto region = [&](const bf16* w, int rows, int K, int kb0, int nkb) {
+        L2Region g;
+        const int kbt = K / 64;
+        if (kb0 >= kbt || nkb <= 0) return g;
+        g.base = w; g.pitch = (long long)K * 2; g.rows = rows; g.seg_off = kb0 * 128; g.seg_bytes = std::min(nkb, kbt - kb0) * 128;
+        return g;
+    };
+    // The two linears next to the decode-attention kernel run with a shallow TMA ring so that their CTA and the attention
+    // CTA of the same SM fit in shared memory together: the attention CTAs are then resident (waiting) when the q/k/v
+    // projection ends, and the o_proj CTAs stream their weights while attention runs.
+    static const int near_attn_stages = getenv("UMV_NEAR_ATTN_STAGES") ? atoi(getenv("UMV_NEAR_ATTN_STAGES")) : 6;
+    static const int attn_cluster_max = getenv("UMV_ATTN_CLUSTER") ? atoi(getenv("UMV_ATTN_CLUSTER")) : 4;
+    static const int attn_ctas_per_sm = getenv("UMV_ATTN_CTAS_PER_SM") ? atoi(getenv("UMV_ATTN_CTAS_PER_SM")) : 1;
+    const int gu_rows = std::min(2 * I, e->sm_count * 128);      // rows of the first wave of gate/up tiles
+    L2Region norm_pf;
+
     auto norm = [&](const bf16* w0, const bf16* w1, bf16* y) {
         AddNormArgs a;
+        a.prefetch = norm_pf;
+        norm_pf = L2Region();
         a.h = e->h; a.M = M; a.D = D; a.eps = d.rms_eps; a.w0 = w0; a.w1 = w1 ? w1 : w0;
         a.row_sel = r.gen ? r.m.row_sel : nullptr;
         a.y = y;
@@ -375,12 +402,13 @@ static int llm_layers(umv_engine* e, const LlmRun& r, bf16* out, cudaStream_t st
 
     for (int li = 0; li < d.layers; ++li) {
         const LayerW& L = e->layers[li];
+        if (partial && pf_n1_kb > 0) norm_pf = region(L.wqkv[0], QN, D, 0, pf_n1_kb);
         UMV_TRY(norm(L.ln1[0], L.ln1[1], e->xn));
         // ---- q/k/v projections
         RopeAppendArgs ra;
         if (partial) {
             const int s = pick_splits(QN, D, e->sm_count);
-            UMV_TRY(lin(e, e->xn, D, L.wqkv[0], nullptr, nullptr, nullptr, 0, M, QN, D, EPI_PARTIAL, st, GEMM_WEIGHT_MAJOR, e->ws, s));
+            UMV_TRY(lin(e, e->xn, D, L.wqkv[0], nullptr, nullptr, nullptr, 0, M, QN, D, EPI_PARTIAL, st, GEMM_WEIGHT_MAJOR, e->ws, s, near_attn_stages));
             ra.partial = e->ws; ra.splits = s; ra.bias = L.bqkv[0];
         } else {
             UMV_TRY(lin(e, e->xn, D, L.wqkv[E], L.bqkv[E], nullptr, e->qkv, QN, M, QN, D, EPI_BF16, st));
@@ -394,16 +422,22 @@ static int llm_layers(umv_engine* e, const LlmRun& r, bf16* out, cudaStream_t st
         // decode (one query token per sample, understanding expert): the whole rope -> append -> attention -> combine
         // chain is one cluster launch
         static const bool fused_attn = !(getenv("UMV_FUSED_ATTN") && atoi(getenv("UMV_FUSED_ATTN")) == 0);
-        const bool fuse = fused_attn && r.weight_major && r.max_q_len == 1 && !r.gen && dh == 128 && H / Hkv <= 8;
+        const bool fuse = fused_attn && r.weight_major && r.max_q_len == 1 && !r.gen &&
+                          decode_attention_supported(H, Hkv, dh, r.m.max_pages, ra.splits);
         if (fuse) {
             DecodeAttnArgs da;
             da.qkv = ra.qkv; da.partial = ra.partial; da.ksplits = ra.splits; da.bias = ra.bias;
             da.out = e->attn; da.ldo = D; da.positions = r.m.positions; da.kv_len = r.m.kv_len;
-            da.page_table = r.m.page_table; da.max_pages = r.m.max_pages; da.inv_freq = e->inv_freq;
+            da.page_table = r.m.page_table; da.max_pages = r.m.max_pages; da.inv_freq = e->inv_freq; da.rope_cs = r.m.rope_cs;
             da.qn = L.qn[0]; da.kn = L.kn[0]; da.pool = e->pool; da.layer = li; da.M = M; da.H = H; da.Hkv = Hkv;
             da.eps = d.rms_eps;
             const int blocks = (r.max_kv_len + kPageTokens - 1) / kPageTokens;
-            da.cluster = std::max(1, std::min(8, blocks));
+            // key ranges per (sample, kv head): as many as fit one wave of 2 CTAs per SM, at most one per 64-key block
+            da.cluster = std::max(1, std::min(std::min(attn_cluster_max, blocks), attn_ctas_per_sm * e->sm_count / std::max(1, M * Hkv)));
+            if (partial) {
+                if (pf_wo) da.prefetch[0] = region(L.wo[0], D, D, 0, D / 64);
+                da.prefetch[1] = region(L.wgu[0], gu_rows, D, ring_kb, pf_gu_kb);
+            }
             UMV_TRY(decode_attention(da, st));
         } else {
         ra.q_out = e->qkv; ra.ldq = QN;
@@ -425,7 +459,7 @@ static int llm_layers(umv_engine* e, const LlmRun& r, bf16* out, cudaStream_t st
         // ---- output projection + residual
         if (partial) {
             const int s = pick_splits(D, D, e->sm_count);
-            UMV_TRY(lin(e, e->attn, D, L.wo[0], nullptr, nullptr, nullptr, 0, M, D, D, EPI_PARTIAL, st, GEMM_WEIGHT_MAJOR, e->ws, s));
+            UMV_TRY(lin(e, e->attn, D, L.wo[0], nullptr, nullptr, nullptr, 0, M, D, D, EPI_PARTIAL, st, GEMM_WEIGHT_MAJOR, e->ws, s, near_attn_stages));
             pending_splits = s;
         } else {
             if (T > 0) {
@@ -436,6 +470,7 @@ static int llm_layers(umv_engine* e, const LlmRun& r, bf16* out, cudaStream_t st
             UMV_TRY(lin(e, e->attn, D, L.wo[E], nullptr, e->h, e->h, D, M, D, D, EPI_RESID, st));
             if (T > 0) UMV_TRY(copy_rows(e->yt, D, r.m.text_rows, e->h, D, T, D, 1, st));
         }
+        if (partial && pf_n2_kb > 0) norm_pf = region(L.wgu[0], gu_rows, D, ring_kb + pf_gu_kb, pf_n2_kb);
         UMV_TRY(norm(L.ln2[0], L.ln2[1], e->xn));
         // ---- SwiGLU MLP + residual
         if (T > 0) {
@@ -470,6 +505,14 @@ extern "C" {
 const char* umv_last_error(void) { return get_error(); }
 int umv_abi_version(void) { return UMV_ABI_VERSION; }
 int64_t umv_launch_count(void) { return g_launches; }
+int umv_trace_begin(int32_t max_slots) { return trace_begin(max_slots); }
+int umv_trace_read(uint64_t* stamps, char* names, int32_t name_len, int32_t max_slots, int32_t* n) {
+    UMV_REQUIRE(stamps && names && n && name_len > 0, UMV_ERR_INVALID, "umv_trace_read: null argument");
+    int k = 0;
+    int rc = trace_read(reinterpret_cast<unsigned long long*>(stamps), names, name_len, max_slots, &k);
+    *n = k;
+    return rc;
+}
 
 int umv_create(const umv_dims* dims, umv_engine** out) {
     UMV_REQUIRE(dims && out, UMV_ERR_INVALID, "umv_create: null argument");
@@ -917,7 +960,8 @@ int umv_generate_text(umv_engine* e, int32_t n_seqs, const int32_t* seqs, const 
     UMV_CUDA_OK(cudaStreamSynchronize(st));     // host vectors above go out of scope; also a clean capture start
     r.m.q_start = e->dec_qstart; r.m.q_len = e->dec_qlen; r.m.kv_len = e->dec_kvlen; r.m.positions = e->dec_pos;
     r.m.row_seq = e->dec_rowseq; r.m.row_kvpos = e->dec_kvpos; r.m.page_table = e->dec_pages; r.m.max_pages = max_pages;
-    DecodeState ds{e->dec_tokens, e->dec_pos, e->dec_kvlen, e->dec_kvpos, e->dec_step};
+    DecodeState ds{e->dec_tokens, e->dec_pos, e->dec_kvlen, e->dec_kvpos, e->dec_step, e->dec_rope, e->inv_freq, e->dh};
+    r.m.rope_cs = e->dec_rope;
 
     auto step = [&](cudaStream_t s, bf16* logits) -> int {
         UMV_TRY(decode_begin_step(e->embed, D, V, ds, forced_tokens, tokens_out, B, e->h, s));

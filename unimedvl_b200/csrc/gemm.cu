@@ -19,6 +19,8 @@
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
+#include <string>
+#include <vector>
 
 #include "../../include/umv.h"
 #include "common.cuh"
@@ -29,6 +31,38 @@ namespace umv {
 
 long long g_launches = 0;
 bool g_pdl = true;
+
+// ---- timeline trace state (one trace per process; slots are handed out in launch order)
+static TraceSlot* g_trace_dev = nullptr;
+static int g_trace_cap = 0, g_trace_n = 0;
+static std::vector<std::string> g_trace_names;
+TraceSlot* trace_next(const char* kernel_name) {
+    if (!g_trace_dev || g_trace_n >= g_trace_cap) return nullptr;
+    g_trace_names.emplace_back(kernel_name);
+    return g_trace_dev + g_trace_n++;
+}
+int trace_begin(int max_slots) {
+    if (g_trace_dev) cudaFree(g_trace_dev);
+    g_trace_dev = nullptr;
+    g_trace_cap = g_trace_n = 0;
+    g_trace_names.clear();
+    if (max_slots <= 0) return UMV_OK;
+    UMV_CUDA_OK(cudaMalloc(&g_trace_dev, sizeof(TraceSlot) * max_slots));
+    UMV_CUDA_OK(cudaMemset(g_trace_dev, 0, sizeof(TraceSlot) * max_slots));
+    g_trace_cap = max_slots;
+    return UMV_OK;
+}
+int trace_read(unsigned long long* out, char* names, int name_len, int max_slots, int* n) {
+    UMV_CUDA_OK(cudaDeviceSynchronize());
+    const int k = g_trace_n < max_slots ? g_trace_n : max_slots;
+    if (k > 0) UMV_CUDA_OK(cudaMemcpy(out, g_trace_dev, sizeof(TraceSlot) * k, cudaMemcpyDeviceToHost));
+    for (int i = 0; i < k; ++i) {
+        strncpy(names + (size_t)i * name_len, g_trace_names[i].c_str(), name_len - 1);
+        names[(size_t)i * name_len + name_len - 1] = 0;
+    }
+    *n = k;
+    return UMV_OK;
+}
 
 constexpr int BM = 128;   // UMMA M (TMEM lanes)
 constexpr int BK = 64;    // 64 bf16 = one 128-byte swizzle row
@@ -45,6 +79,8 @@ struct GemmParams {
     float* ws;
     int epi;
     int early_a;    // weight-major: A (weights) is constant data and may be fetched before griddepcontrol.wait
+    TraceSlot* trace;
+    int stages;     // ring depth of this launch (<= TcCfg::kStages); a shallow ring leaves shared memory for a neighbour CTA
 };
 
 template <int BN, bool SWAP>
@@ -57,6 +93,7 @@ struct TcCfg {
     static constexpr int kBarBytes = 256;
     static constexpr int kExchBytes = SWAP ? 64 * BN * 4 : 0;   // swiglu gate/up exchange (weight-major only)
     static constexpr int kSmemBytes = 1024 + kStages * kStageBytes + kBarBytes + kExchBytes;
+    static constexpr int smem_bytes(int stages) { return 1024 + stages * kStageBytes + kBarBytes + kExchBytes; }
 };
 
 __device__ __forceinline__ float epi_value(int epi, float acc, float bias) {
@@ -70,20 +107,22 @@ template <int BN, int MODE, bool SWAP>
 __global__ void __launch_bounds__(192, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
     using Cfg = TcCfg<BN, SWAP>;
-    constexpr int kStages = Cfg::kStages;
+    constexpr int kMaxStages = Cfg::kStages;
+    const int kStages = p.stages;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     uint8_t* sA = smem;
     uint8_t* sB = smem + kStages * kATile;
     uint64_t* full = reinterpret_cast<uint64_t*>(smem + kStages * Cfg::kStageBytes);
-    uint64_t* empty = full + kStages;
-    uint64_t* tfull = empty + kStages;
+    uint64_t* empty = full + kMaxStages;
+    uint64_t* tfull = empty + kMaxStages;
     uint64_t* tempty = tfull + 2;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
     float* sExch = reinterpret_cast<float*>(smem + kStages * Cfg::kStageBytes + Cfg::kBarBytes);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     pdl_launch_dependents();
+    trace_start(p.trace);
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmA);
         tma_prefetch_desc(&tmB);
@@ -123,7 +162,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             // activation tiles of those stages are requested right after the wait.
             bool waited = !SWAP || !p.early_a;
             int n_deferred = 0;
-            int def_kb[kStages], def_bt[kStages];
+            int def_kb[kMaxStages], def_bt[kMaxStages];
             if (waited) pdl_wait();
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
                 const int split = tile % p.splits;
@@ -151,6 +190,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     if (++stage == kStages) { stage = 0; phase ^= 1u; }
                 }
             }
+            if (p.trace && blockIdx.x == 0) p.trace->t_wait = gtime();     // all tiles requested (short jobs: == after the wait)
             if (!waited) {
                 pdl_wait();
                 for (int i = 0; i < n_deferred; ++i)
@@ -330,6 +370,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     tc_fence_before();
     __syncthreads();
     if (warp == 1) tmem_dealloc<Cfg::kTmemCols>(tmem_base);
+    trace_end(p.trace);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -467,6 +508,12 @@ static int launch_tc(const LinearCall& c, cudaStream_t stream) {
     p.ws = c.ws;
     p.epi = c.epi;
     p.early_a = c.w_static ? 1 : 0;
+    {
+        char nm[32];
+        snprintf(nm, sizeof nm, "gemm<%d,%d,%d> N%d K%d", BN, MODE, (int)SWAP, c.N, c.K);
+        p.trace = trace_next(nm);
+    }
+    p.stages = (c.stages > 0 && c.stages < TcCfg<BN, SWAP>::kStages) ? (c.stages < 2 ? 2 : c.stages) : TcCfg<BN, SWAP>::kStages;
     CUtensorMap tmA, tmB;
     int rc = make_tmap(&tmA, A, p.a_rows, c.K, lda, BM);
     if (rc) return rc;
@@ -474,7 +521,7 @@ static int launch_tc(const LinearCall& c, cudaStream_t stream) {
     if (rc) return rc;
     const int tiles = p.a_tiles * p.b_tiles * p.splits;
     const int grid = tiles < g_sm_count ? tiles : g_sm_count;
-    cudaError_t e = launch_k(gemm_tc_kernel<BN, MODE, SWAP>, dim3(grid), dim3(192), TcCfg<BN, SWAP>::kSmemBytes, stream, tmA, tmB, p);
+    cudaError_t e = launch_k(gemm_tc_kernel<BN, MODE, SWAP>, dim3(grid), dim3(192), TcCfg<BN, SWAP>::smem_bytes(p.stages), stream, tmA, tmB, p);
     ++g_launches;
     if (e == cudaSuccess) e = cudaGetLastError();
     if (e != cudaSuccess) {

@@ -29,6 +29,7 @@ struct LinearCall {
     int M = 0, N = 0, K = 0;
     int epi = EPI_BF16;
     int impl = GEMM_AUTO;
+    int stages = 0;                 // 0: deepest TMA ring that fits; else ring depth (shared memory left for a co-resident kernel)
     bool w_static = true;           // false: `w` is produced by the preceding kernel (activation x activation product)
 };
 
@@ -38,6 +39,9 @@ int linear_forward(const LinearCall& c, cudaStream_t stream);
 int pick_splits(int N, int K, int sm_count);
 // Must be called once before the first tcgen05 launch (resolves cuTensorMapEncodeTiled, sets smem attrs).
 int gemm_init();
+
+int trace_begin(int max_slots);       // diagnostic timeline (umv_trace_begin / umv_trace_read)
+int trace_read(unsigned long long* out, char* names, int name_len, int max_slots, int* n);
 
 extern long long g_launches;   // kernel launch counter (umv_launch_count)
 

@@ -27,7 +27,10 @@ constexpr int kNormMaxChunks = 8;   // 8 chunks * 8 elems * 256 threads = D <= 1
 
 __global__ void __launch_bounds__(kNormThreads) add_rmsnorm_kernel(AddNormArgs a) {
     pdl_launch_dependents();
+    trace_start(a.trace);
+    l2_prefetch_region(a.prefetch, threadIdx.x * gridDim.x + blockIdx.x, gridDim.x * kNormThreads);
     pdl_wait();
+    trace_wait(a.trace);
     __shared__ float red[32];
     const int row = blockIdx.x;
     const int nchunk = a.D / 8;
@@ -102,12 +105,91 @@ __global__ void __launch_bounds__(kNormThreads) add_rmsnorm_kernel(AddNormArgs a
             stg16(yrow + ch * 8, U4{o[0], o[1], o[2], o[3]});
         }
     }
+    trace_end<false>(a.trace);
 }
 
-int add_rmsnorm(const AddNormArgs& a, cudaStream_t s) {
-    if (a.M <= 0) return UMV_OK;
+// Decode variant (split-K partials of the preceding weight-major linear, a handful of rows): the kernel sits on the
+// critical path of the decode chain and is pure latency, so one thread owns one 8-element chunk and EVERY global load
+// (norm weight before griddepcontrol.wait -- it is constant --, residual row and all split partials right after it) is
+// issued before the first use: one memory round trip instead of one per split.  Same arithmetic and summation order as
+// add_rmsnorm_kernel.
+constexpr int kNormDecThreads = 512;
+constexpr int kNormDecMaxSplits = 8;
+__global__ void __launch_bounds__(kNormDecThreads) add_rmsnorm_splitk_kernel(AddNormArgs a) {
+    pdl_launch_dependents();
+    trace_start(a.trace);
+    __shared__ float red[32];
+    const int row = blockIdx.x, ch = threadIdx.x;
+    const bool active = ch < a.D / 8;
+    U4 wv = {0, 0, 0, 0};
+    if (active && a.y) wv = ldg16(a.w0 + ch * 8);
+    pdl_wait();
+    trace_wait(a.trace);
+    bf16* hrow = a.h + (size_t)row * a.D;
+    float ss = 0.f;
+    float v[8];
+    if (active) {
+        const U4 hv = ldg16(hrow + ch * 8);
+        float4 p[kNormDecMaxSplits][2];
+#pragma unroll
+        for (int s = 0; s < kNormDecMaxSplits; ++s) {
+            if (s < a.splits) {
+                const float4* pp = reinterpret_cast<const float4*>(a.partial + ((size_t)s * a.M + row) * a.D + ch * 8);
+                p[s][0] = pp[0];
+                p[s][1] = pp[1];
+            } else {
+                p[s][0] = p[s][1] = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        }
+        float d[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int s = 0; s < kNormDecMaxSplits; ++s) {      // fixed order -> deterministic; adding +0.f for s >= splits is exact
+            if (s < a.splits) {
+                d[0] += p[s][0].x; d[1] += p[s][0].y; d[2] += p[s][0].z; d[3] += p[s][0].w;
+                d[4] += p[s][1].x; d[5] += p[s][1].y; d[6] += p[s][1].z; d[7] += p[s][1].w;
+            }
+        }
+        const uint32_t* hw = &hv.x;
+        uint32_t o[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float2 f = unpack2(hw[j]);
+            v[2 * j] = rbf(f.x + rbf(d[2 * j]));               // Linear output rounded (R3), residual add in bf16 (R7)
+            v[2 * j + 1] = rbf(f.y + rbf(d[2 * j + 1]));
+            o[j] = pack2(v[2 * j], v[2 * j + 1]);
+        }
+        stg16(hrow + ch * 8, U4{o[0], o[1], o[2], o[3]});
+#pragma unroll
+        for (int j = 0; j < 8; ++j) ss += v[j] * v[j];
+    }
+    trace_dbg(a.trace, 0);
+    if (a.y == nullptr) return;
+    ss = block_sum(ss, red);
+    trace_dbg(a.trace, 1);
+    if (!active) return;
+    const float inv = 1.0f / sqrtf(ss / (float)a.D + a.eps);
+    const uint32_t* ww = &wv.x;
+    uint32_t o[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const float2 wf = unpack2(ww[j]);
+        o[j] = pack2(wf.x * rbf(v[2 * j] * inv), wf.y * rbf(v[2 * j + 1] * inv));   // R2
+    }
+    stg16(a.y + (size_t)row * a.D + ch * 8, U4{o[0], o[1], o[2], o[3]});
+    trace_end<false>(a.trace);
+}
+
+int add_rmsnorm(const AddNormArgs& a0, cudaStream_t s) {
+    if (a0.M <= 0) return UMV_OK;
+    AddNormArgs a = a0;
+    a.trace = trace_next("add_rmsnorm");
     UMV_REQUIRE(a.D % 8 == 0 && a.D <= 8 * kNormThreads * kNormMaxChunks, UMV_ERR_UNSUPPORTED,
                 "add_rmsnorm: D=%d must be a multiple of 8 and <= %d", a.D, 8 * kNormThreads * kNormMaxChunks);
+    if (a.partial && !a.delta && !a.row_sel && a.splits <= kNormDecMaxSplits && a.D <= 8 * kNormDecThreads && a.M <= 64) {
+        launch_k(add_rmsnorm_splitk_kernel, dim3(a.M), dim3(kNormDecThreads), 0, s, a);
+        UMV_LAUNCH_CHECK("add_rmsnorm_splitk_kernel");
+        return UMV_OK;
+    }
     launch_k(add_rmsnorm_kernel, dim3(a.M), dim3(kNormThreads), 0, s, a);
     UMV_LAUNCH_CHECK("add_rmsnorm_kernel");
     return UMV_OK;
@@ -186,7 +268,9 @@ int layernorm_bf16(const bf16* x, const bf16* w, const bf16* b, bf16* y, int M, 
 // head_dim 128: lane l owns elements 4l..4l+3; the rotate_half partner (i +- 64) lives in lane l^16.
 __global__ void __launch_bounds__(256) rope_append_kernel(RopeAppendArgs a) {
     pdl_launch_dependents();
+    trace_start(a.trace);
     pdl_wait();
+    trace_wait(a.trace);
     const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     const int slots = a.H + 2 * a.Hkv;
@@ -256,10 +340,13 @@ __global__ void __launch_bounds__(256) rope_append_kernel(RopeAppendArgs a) {
         bf16* dst = a.pool.base + a.pool.tile_offset(page, a.layer, kv, head) + (size_t)(pos_kv % kPageTokens) * a.dh + lane * 4;
         *reinterpret_cast<uint2*>(dst) = packed;
     }
+    trace_end<false>(a.trace);
 }
 
-int rope_append(const RopeAppendArgs& a, cudaStream_t s) {
-    if (a.M <= 0) return UMV_OK;
+int rope_append(const RopeAppendArgs& a0, cudaStream_t s) {
+    if (a0.M <= 0) return UMV_OK;
+    RopeAppendArgs a = a0;
+    a.trace = trace_next("rope_append");
     UMV_REQUIRE(a.dh == 128, UMV_ERR_UNSUPPORTED, "rope_append: head_dim %d (only 128 is built)", a.dh);
     const long long warps = (long long)a.M * (a.H + 2 * a.Hkv);
     const int blocks = (int)((warps * 32 + 255) / 256);
@@ -476,6 +563,12 @@ __global__ void decode_begin_kernel(const bf16* __restrict__ table, int D, int64
     const U4* src = reinterpret_cast<const U4*>(table + (size_t)tok * D);
     U4* dst = reinterpret_cast<U4*>(x + (size_t)b * D);
     for (int c = threadIdx.x; c < D / 8; c += blockDim.x) dst[c] = src[c];
+    // rope angles of this step (modeling_qwen2.py:164-181): the same for every layer, so they are evaluated once here
+    if (st.rope_cs && threadIdx.x < st.dh / 2) {
+        const float ang = __fmul_rn((float)st.positions[b], st.inv_freq[threadIdx.x]);
+        st.rope_cs[(size_t)b * st.dh + threadIdx.x] = rbf(cosf(ang));                  // cos/sin cast to bf16 (R5)
+        st.rope_cs[(size_t)b * st.dh + st.dh / 2 + threadIdx.x] = rbf(sinf(ang));
+    }
 }
 int decode_begin_step(const bf16* table, int D, int64_t vocab, DecodeState st, const int64_t* forced, int64_t* tokens_out,
                       int B, bf16* x, cudaStream_t s) {

@@ -18,6 +18,23 @@ struct KVPool {
     }
 };
 
+// A strided region of constant data (weights of a LATER kernel of the decode chain) that a latency-bound kernel asks the
+// L2 to fetch while HBM would otherwise idle: `rows` segments of `seg_bytes` at base + r * pitch + seg_off.
+struct L2Region {
+    const void* base = nullptr;
+    long long pitch = 0;
+    int rows = 0, seg_off = 0, seg_bytes = 0;     // seg_off, seg_bytes, pitch: multiples of 16
+};
+#ifdef __CUDACC__
+// Called by every thread of the grid with its global thread index / the grid's thread count, BEFORE griddepcontrol.wait.
+__device__ __forceinline__ void l2_prefetch_region(const L2Region& r, int gtid, int gthreads) {
+    if (r.seg_bytes <= 0) return;
+    for (int row = gtid; row < r.rows; row += gthreads)
+        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(static_cast<const char*>(r.base) + (size_t)row * r.pitch + r.seg_off),
+                     "r"(r.seg_bytes) : "memory");
+}
+#endif
+
 // ---- residual add + RMSNorm (Qwen2RMSNorm, modeling_qwen2.py:89-94; residual adds qwen2_navit.py:883,901)
 struct AddNormArgs {
     bf16* h = nullptr;              // [M, D] residual stream; updated in place when a delta is given
@@ -30,6 +47,8 @@ struct AddNormArgs {
     bf16* y = nullptr;              // [M, D] normalised output (null: only the residual add)
     int M = 0, D = 0;
     float eps = 1e-6f;
+    L2Region prefetch;              // optional: weights of a following linear
+    TraceSlot* trace = nullptr;
 };
 int add_rmsnorm(const AddNormArgs& a, cudaStream_t s);
 
@@ -57,6 +76,7 @@ struct RopeAppendArgs {
     KVPool pool; int layer = 0;
     int M = 0, H = 0, Hkv = 0, dh = 0;
     float eps = 1e-6f;
+    TraceSlot* trace = nullptr;
 };
 int rope_append(const RopeAppendArgs& a, cudaStream_t s);
 
@@ -78,6 +98,7 @@ struct AttnArgs {
     int splits = 1;                 // split-KV factor (>1 needs ws)
     float* ws = nullptr;            // [splits][total_q*H][dh+1] fp32 partial outputs + lse
     int total_q = 0;
+    TraceSlot* trace = nullptr; TraceSlot* trace_combine = nullptr;
 };
 int attention_forward(const AttnArgs& a, cudaStream_t s);
 int attention_init();   // once per process, before any capture
@@ -97,6 +118,9 @@ struct DecodeState {
     int* kv_len;             // [B] KV length including the token being processed this step
     int* row_kvpos;          // [B] slot the new token's K/V go to (= kv_len - 1)
     int* step;               // [1]
+    float* rope_cs;          // [B][dh] cos | sin of the step's rope angles (bf16-rounded), shared by all layers; may be null
+    const float* inv_freq;   // [dh/2]
+    int dh;
 };
 int decode_begin_step(const bf16* table, int D, int64_t vocab, DecodeState st, const int64_t* forced, int64_t* tokens_out,
                       int B, bf16* x, cudaStream_t s);
@@ -141,11 +165,15 @@ struct DecodeAttnArgs {
     const int* kv_len = nullptr;      // [M] keys visible, including the token being appended
     const int* page_table = nullptr; int max_pages = 0;
     const float* inv_freq = nullptr;
+    const float* rope_cs = nullptr;   // optional [M][dh]: bf16-rounded cos (first dh/2) and sin of position * inv_freq, per sample
     const bf16* qn = nullptr; const bf16* kn = nullptr;
     KVPool pool; int layer = 0;
     int M = 0, H = 0, Hkv = 0;
     int cluster = 8;                  // CTAs (key ranges) per (sample, kv head)
     float eps = 1e-6f;
+    L2Region prefetch[2];             // optional: weights of the following linears (o_proj, head of gate/up)
+    TraceSlot* trace = nullptr;
 };
 int decode_attention(const DecodeAttnArgs& a, cudaStream_t s);
+bool decode_attention_supported(int H, int Hkv, int dh, int max_pages, int ksplits);
 }  // namespace umv
