@@ -30,6 +30,9 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 B_PER_GPU = 8
+# DRAM traffic of one weight-major gate/up + SwiGLU launch at M=8 (ncu --set full, profiles/r1_decode_kernels_full.md):
+# 271,748,096 B read + 3,301,632 B written; the algorithmic figure is 271,941,632 B.
+NCU_TRAFFIC_GATE_UP = 275_049_728
 DECODE_STEPS = 128
 PROMPT_TOKENS = 30
 IMG = 448
@@ -374,7 +377,9 @@ def run_engine(args, rank: int, local_rank: int, world: int):
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "kernel": "gemm_tc_kernel<16,2,true> (weight-major gate/up + SwiGLU, M=8)",
                      "achieved": round(achieved, 1), "peak": peak, "peak_source": peak_src, "unit": "GB/s",
-                     "frac": round(achieved / peak, 4), "traffic": None, "algorithmic_bytes_per_launch": int(alg_bytes),
+                     "frac": round(achieved / peak, 4), "traffic": NCU_TRAFFIC_GATE_UP, "traffic_source": "profiles/r1_decode_kernels_full.md "
+                     "(ncu --set full: dram__bytes_read.sum + dram__bytes_write.sum of this kernel, per launch)",
+                     "algorithmic_bytes_per_launch": int(alg_bytes),
                      "us_per_launch": round(k_ms * 1e3, 2)},
         "step_roofline": {"bound": "hbm", "algorithmic_bytes_per_decode_forward": int(step_bytes),
                           "achieved": round(step_achieved, 1), "unit": "GB/s", "frac": round(step_achieved / peak, 4),

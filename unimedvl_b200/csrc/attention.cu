@@ -18,19 +18,22 @@
 
 namespace umv {
 
-constexpr int kAttnThreads = 128;
-constexpr int kTileRows = 64;   // query rows per CTA (4 warps x 16)
 constexpr int kTileKeys = 64;   // keys per block == KV page size
+// ROWS = query rows per CTA (16 per warp).  64 is what is built: at 128 rows the kernel needs > 128 registers per thread
+// (64 O + 32 S + 32 Q fragments), i.e. one CTA per SM and no more resident warps than two 64-row CTAs.
 
-template <int HD>
+template <int HD, int ROWS = 64>
 struct AttnCfg {
+    static constexpr int kThreads = ROWS * 2;                       // 16 rows per warp
     static constexpr int kChunks = HD / 8;                          // 16-byte chunks of real data per row
     static constexpr int kKSteps = (HD + 15) / 16;                  // QK^T k-steps (HD padded to 16)
     static constexpr int kDTiles = HD / 8;                          // PV n-tiles
     static constexpr bool kSwizzle = (HD == 128);
     static constexpr int kRowBytes = kSwizzle ? 256 : (kKSteps * 32 + 16);   // 72 -> 176 B (conflict-free ldmatrix)
-    static constexpr int kTileBytes = kTileRows * kRowBytes;
-    static constexpr int kSmemBytes = 5 * kTileBytes;               // Q + 2 x (K, V)
+    static constexpr int kTileBytes = kTileKeys * kRowBytes;        // one K or V block
+    static constexpr int kQBytes = ROWS * kRowBytes;
+    static constexpr int kStages = 3;                               // K/V blocks in flight (two 112 KB CTAs fit one SM)
+    static constexpr int kSmemBytes = kQBytes + 2 * kStages * kTileBytes;     // Q + kStages x (K, V)
 };
 
 template <int HD>
@@ -39,17 +42,18 @@ __device__ __forceinline__ uint32_t tile_off(int row, int chunk) {
     return row * AttnCfg<HD>::kRowBytes + (chunk << 4);
 }
 
-template <int HD>
-__global__ void __launch_bounds__(kAttnThreads) attn_fwd_kernel(AttnArgs a, float scale_log2) {
-    using Cfg = AttnCfg<HD>;
+template <int HD, int ROWS>
+__global__ void __launch_bounds__(ROWS * 2) attn_fwd_kernel(AttnArgs a, float scale_log2) {
+    using Cfg = AttnCfg<HD, ROWS>;
+    constexpr int kTileRows = ROWS, kAttnThreads = ROWS * 2;
     pdl_launch_dependents();
     trace_start(a.trace);
     pdl_wait();
     trace_wait(a.trace);
     extern __shared__ __align__(128) uint8_t smem[];
     uint8_t* sQ = smem;
-    uint8_t* sK = smem + Cfg::kTileBytes;
-    uint8_t* sV = smem + 3 * Cfg::kTileBytes;
+    uint8_t* sK = smem + Cfg::kQBytes;
+    uint8_t* sV = sK + Cfg::kStages * Cfg::kTileBytes;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int b = blockIdx.y / a.Hkv, kvh = blockIdx.y % a.Hkv;
@@ -71,8 +75,8 @@ __global__ void __launch_bounds__(kAttnThreads) attn_fwd_kernel(AttnArgs a, floa
 
     if (!Cfg::kSwizzle) {
         // zero the padding chunk (columns HD..HD+7) that the last QK^T k-step reads
-        for (int i = tid; i < 5 * kTileRows; i += kAttnThreads)
-            *reinterpret_cast<U4*>(smem + (i / kTileRows) * Cfg::kTileBytes + tile_off<HD>(i % kTileRows, Cfg::kChunks)) = U4{0, 0, 0, 0};
+        for (int i = tid; i < kTileRows + 2 * Cfg::kStages * kTileKeys; i += kAttnThreads)      // rows of Q, then of the K/V stage tiles
+            *reinterpret_cast<U4*>(smem + tile_off<HD>(i, Cfg::kChunks)) = U4{0, 0, 0, 0};
     }
 
     // ---- stage Q
@@ -107,8 +111,12 @@ __global__ void __launch_bounds__(kAttnThreads) attn_fwd_kernel(AttnArgs a, floa
             cp_async16(dv + tile_off<HD>(r, ch), vbase + (size_t)(ok ? r : 0) * vstride + ch * 8, ok);
         }
     };
-    if (kb_begin < kb_end) load_kv(kb_begin, 0);
-    cp_async_commit();
+    // ring of kStages blocks, one commit group per slot (group 0 also carries Q); a refill group per finished block
+#pragma unroll
+    for (int j = 0; j < Cfg::kStages; ++j) {
+        if (kb_begin + j < kb_end) load_kv(kb_begin + j, j);
+        cp_async_commit();
+    }
 
     const int g = lane >> 2, t = lane & 3;
     const int Ra = r0 + warp * 16 + g, Rb = Ra + 8;
@@ -123,14 +131,8 @@ __global__ void __launch_bounds__(kAttnThreads) attn_fwd_kernel(AttnArgs a, floa
     float m_a = -INFINITY, m_b = -INFINITY, l_a = 0.f, l_b = 0.f;
 
     for (int kb = kb_begin; kb < kb_end; ++kb) {
-        const int stage = (kb - kb_begin) & 1;
-        if (kb + 1 < kb_end) {
-            load_kv(kb + 1, stage ^ 1);
-            cp_async_commit();
-            cp_async_wait<1>();
-        } else {
-            cp_async_wait<0>();
-        }
+        const int stage = (kb - kb_begin) % Cfg::kStages;
+        cp_async_wait<Cfg::kStages - 1>();       // kStages + i groups committed at iteration i: group i has landed
         __syncthreads();
         if (kb == kb_begin) {
 #pragma unroll
@@ -215,7 +217,9 @@ __global__ void __launch_bounds__(kAttnThreads) attn_fwd_kernel(AttnArgs a, floa
                 mma_bf16_16816(o[Cfg::kDTiles - 1], pf[kk], b0, b1);
             }
         }
-        __syncthreads();
+        __syncthreads();                          // the slot is free: refill it
+        if (kb + Cfg::kStages < kb_end) load_kv(kb + Cfg::kStages, stage);
+        cp_async_commit();
     }
     cp_async_wait<0>();
 
@@ -681,8 +685,8 @@ bool decode_attention_supported(int H, int Hkv, int dh, int max_pages, int kspli
 }
 
 int attention_init() {
-    cudaFuncSetAttribute(attn_fwd_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnCfg<128>::kSmemBytes);
-    cudaFuncSetAttribute(attn_fwd_kernel<72>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnCfg<72>::kSmemBytes);
+    cudaFuncSetAttribute(attn_fwd_kernel<128, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnCfg<128, 64>::kSmemBytes);
+    cudaFuncSetAttribute(attn_fwd_kernel<72, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnCfg<72, 64>::kSmemBytes);
     cudaFuncSetAttribute(attn_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kDecSmemBytes);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) {
@@ -692,20 +696,20 @@ int attention_init() {
     return UMV_OK;
 }
 
-template <int HD>
+template <int HD, int ROWS>
 static int launch_attn(const AttnArgs& a0, cudaStream_t s) {
     AttnArgs a = a0;
     a.trace = trace_next("attn_fwd");
     if (a.splits > 1) a.trace_combine = trace_next("attn_combine");
     const int G = a.H / a.Hkv;
-    const int row_tiles = (a.max_q_len * G + kTileRows - 1) / kTileRows;
+    const int row_tiles = (a.max_q_len * G + ROWS - 1) / ROWS;
     const float scale_log2 = (1.0f / sqrtf((float)HD)) * 1.4426950408889634f;
     dim3 grid(row_tiles, a.n * a.Hkv, a.splits);
-    cudaError_t e = launch_k(attn_fwd_kernel<HD>, grid, dim3(kAttnThreads), AttnCfg<HD>::kSmemBytes, s, a, scale_log2);
+    cudaError_t e = launch_k(attn_fwd_kernel<HD, ROWS>, grid, dim3(ROWS * 2), AttnCfg<HD, ROWS>::kSmemBytes, s, a, scale_log2);
     ++g_launches;
     if (e == cudaSuccess) e = cudaGetLastError();
     if (e != cudaSuccess) {
-        set_error("attn_fwd_kernel<%d> launch failed: %s", HD, cudaGetErrorString(e));
+        set_error("attn_fwd_kernel<%d,%d> launch failed: %s", HD, ROWS, cudaGetErrorString(e));
         return UMV_ERR_CUDA;
     }
     if (a.splits > 1) {
@@ -726,8 +730,8 @@ int attention_forward(const AttnArgs& a, cudaStream_t s) {
     UMV_REQUIRE(a.H % a.Hkv == 0, UMV_ERR_INVALID, "attention: heads %d not a multiple of kv heads %d", a.H, a.Hkv);
     UMV_REQUIRE(a.splits == 1 || a.ws != nullptr, UMV_ERR_INVALID, "attention: split-KV needs a workspace");
     UMV_REQUIRE(a.ldq % 8 == 0 && a.ldo % 2 == 0, UMV_ERR_INVALID, "attention: q/out row strides must keep 16-byte rows");
-    if (a.dh == 128) return launch_attn<128>(a, s);
-    if (a.dh == 72) return launch_attn<72>(a, s);
+    if (a.dh == 128) return launch_attn<128, 64>(a, s);
+    if (a.dh == 72) return launch_attn<72, 64>(a, s);
     set_error("attention: head_dim %d is not built (128 and 72 are)", a.dh);
     return UMV_ERR_UNSUPPORTED;
 }

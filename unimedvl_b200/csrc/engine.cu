@@ -180,6 +180,7 @@ static int build_runtime(umv_engine* e) {
     UMV_TRY(dev_alloc(e, &e->xn, (size_t)Mmax * e->w_h));
     UMV_TRY(dev_alloc(e, &e->qkv, (size_t)Mmax * e->w_qkv));
     UMV_TRY(dev_alloc(e, &e->attn, (size_t)Mmax * e->w_h));
+    UMV_TRY(dev_alloc(e, &e->rope_tab, (size_t)Mmax * e->dh));
     UMV_TRY(dev_alloc(e, &e->act, (size_t)Mmax * e->w_act));
     UMV_TRY(dev_alloc(e, &e->logits, (size_t)64 * d.vocab));
     const int Tmax = std::min(Mmax, 8 * d.max_seqs);
@@ -346,6 +347,21 @@ int lin(umv_engine* e, const bf16* x, int ldx, const bf16* w, const bf16* bias, 
     c.M = M; c.N = N; c.K = K; c.epi = epi; c.ws = ws; c.splits = splits;
     c.impl = e->gemm_impl ? e->gemm_impl : impl;
     if (c.impl == GEMM_SIMPLE && epi == EPI_PARTIAL) c.impl = GEMM_WEIGHT_MAJOR;
+    // A few rows against a weight matrix with far fewer 128-row tiles than SMs (o_proj / down_proj / q,k,v of the
+    // understanding-expert rows in a generation-mode forward, the time-embedding MLP): the weights would stream through a
+    // fraction of the SMs.  Split K across the machine into fp32 partials and finish with a tiny reduce + epilogue kernel.
+    if ((c.impl == GEMM_AUTO || c.impl == GEMM_WEIGHT_MAJOR) && M <= 64 && e->use_splitk && e->ws && ws == nullptr &&
+        (epi == EPI_BF16 || epi == EPI_GELU || epi == EPI_RESID) && K % 8 == 0 && ldx % 8 == 0 && N % 8 == 0 && ldy % 8 == 0 &&
+        ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(w) | reinterpret_cast<uintptr_t>(y)) & 15) == 0 &&
+        (N + 127) / 128 <= e->sm_count / 2) {
+        const int s = pick_splits(N, K, e->sm_count);
+        if (s > 1 && (size_t)s * M * N <= e->ws_elems) {
+            c.impl = GEMM_WEIGHT_MAJOR; c.epi = EPI_PARTIAL; c.ws = e->ws; c.splits = s;
+            c.bias = nullptr; c.residual = nullptr; c.y = nullptr;
+            UMV_TRY(linear_forward(c, st));
+            return splitk_finish(e->ws, s, M, N, bias, res, y, ldy, epi, st);
+        }
+    }
     return linear_forward(c, st);
 }
 
@@ -357,33 +373,14 @@ static int llm_layers(umv_engine* e, const LlmRun& r, bf16* out, cudaStream_t st
     const int T = r.gen ? r.m.n_text : 0;
     int pending_splits = 0;     // >0: e->ws holds split-K partials of the last residual-branch linear
 
-    // Decode: the latency-bound kernels of the chain (norm, attention) ask the L2 for weights of the linears that follow
-    // them, so HBM keeps streaming while they run.  Units: 64-element k-blocks (128 B per weight row).
-    static const int pf_wo = getenv("UMV_PF_WO") ? atoi(getenv("UMV_PF_WO")) : 1;
-    static const int pf_gu_kb = getenv("UMV_PF_GU_KB") ? atoi(getenv("UMV_PF_GU_KB")) : 20;
-    static const int pf_n2_kb = getenv("UMV_PF_N2_KB") ? atoi(getenv("UMV_PF_N2_KB")) : 0;
-    static const int pf_n1_kb = getenv("UMV_PF_N1_KB") ? atoi(getenv("UMV_PF_N1_KB")) : 0;
-    const int ring_kb = 10;                       // k-blocks the weight-major linear itself requests before its wait
-    auto region = [&](const bf16* w, int rows, int K, int kb0, int nkb) {
-        L2Region g;
-        const int kbt = K / 64;
-        if (kb0 >= kbt || nkb <= 0) return g;
-        g.base = w; g.pitch = (long long)K * 2; g.rows = rows; g.seg_off = kb0 * 128; g.seg_bytes = std::min(nkb, kbt - kb0) * 128;
-        return g;
-    };
-    // The two linears next to the decode-attention kernel run with a shallow TMA ring so that their CTA and the attention
-    // CTA of the same SM fit in shared memory together: the attention CTAs are then resident (waiting) when the q/k/v
-    // projection ends, and the o_proj CTAs stream their weights while attention runs.
-    static const int near_attn_stages = getenv("UMV_NEAR_ATTN_STAGES") ? atoi(getenv("UMV_NEAR_ATTN_STAGES")) : 6;
-    static const int attn_cluster_max = getenv("UMV_ATTN_CLUSTER") ? atoi(getenv("UMV_ATTN_CLUSTER")) : 4;
-    static const int attn_ctas_per_sm = getenv("UMV_ATTN_CTAS_PER_SM") ? atoi(getenv("UMV_ATTN_CTAS_PER_SM")) : 1;
-    const int gu_rows = std::min(2 * I, e->sm_count * 128);      // rows of the first wave of gate/up tiles
-    L2Region norm_pf;
+    // Tuning knobs (measured on B200, profiles/r1_decode_timeline.md): a shallower TMA ring for the linears next to the
+    // decode-attention kernel (co-residency in shared memory) costs more streaming rate than the overlap returns -> 0 = full.
+    static const int near_attn_stages = getenv("UMV_NEAR_ATTN_STAGES") ? atoi(getenv("UMV_NEAR_ATTN_STAGES")) : 0;
+    static const int attn_cluster_max = getenv("UMV_ATTN_CLUSTER") ? atoi(getenv("UMV_ATTN_CLUSTER")) : 8;
 
     auto norm = [&](const bf16* w0, const bf16* w1, bf16* y) {
         AddNormArgs a;
-        a.prefetch = norm_pf;
-        norm_pf = L2Region();
+
         a.h = e->h; a.M = M; a.D = D; a.eps = d.rms_eps; a.w0 = w0; a.w1 = w1 ? w1 : w0;
         a.row_sel = r.gen ? r.m.row_sel : nullptr;
         a.y = y;
@@ -402,7 +399,6 @@ static int llm_layers(umv_engine* e, const LlmRun& r, bf16* out, cudaStream_t st
 
     for (int li = 0; li < d.layers; ++li) {
         const LayerW& L = e->layers[li];
-        if (partial && pf_n1_kb > 0) norm_pf = region(L.wqkv[0], QN, D, 0, pf_n1_kb);
         UMV_TRY(norm(L.ln1[0], L.ln1[1], e->xn));
         // ---- q/k/v projections
         RopeAppendArgs ra;
@@ -433,16 +429,12 @@ static int llm_layers(umv_engine* e, const LlmRun& r, bf16* out, cudaStream_t st
             da.eps = d.rms_eps;
             const int blocks = (r.max_kv_len + kPageTokens - 1) / kPageTokens;
             // key ranges per (sample, kv head): as many as fit one wave of 2 CTAs per SM, at most one per 64-key block
-            da.cluster = std::max(1, std::min(std::min(attn_cluster_max, blocks), attn_ctas_per_sm * e->sm_count / std::max(1, M * Hkv)));
-            if (partial) {
-                if (pf_wo) da.prefetch[0] = region(L.wo[0], D, D, 0, D / 64);
-                da.prefetch[1] = region(L.wgu[0], gu_rows, D, ring_kb, pf_gu_kb);
-            }
+            da.cluster = std::max(1, std::min(std::min(attn_cluster_max, blocks), e->sm_count / std::max(1, M * Hkv)));
             UMV_TRY(decode_attention(da, st));
         } else {
         ra.q_out = e->qkv; ra.ldq = QN;
         ra.positions = r.m.positions; ra.row_seq = r.m.row_seq; ra.row_kvpos = r.m.row_kvpos;
-        ra.page_table = r.m.page_table; ra.max_pages = r.m.max_pages; ra.inv_freq = e->inv_freq;
+        ra.page_table = r.m.page_table; ra.max_pages = r.m.max_pages; ra.inv_freq = e->inv_freq; ra.rope_cs = r.m.rope_cs;
         ra.qn0 = L.qn[0]; ra.kn0 = L.kn[0]; ra.qn1 = L.qn[E]; ra.kn1 = L.kn[E];
         ra.row_sel = r.gen ? r.m.row_sel : nullptr; ra.gen_mode = r.gen ? 1 : 0;
         ra.pool = e->pool; ra.layer = li; ra.M = M; ra.H = H; ra.Hkv = Hkv; ra.dh = dh; ra.eps = d.rms_eps;
@@ -470,7 +462,6 @@ static int llm_layers(umv_engine* e, const LlmRun& r, bf16* out, cudaStream_t st
             UMV_TRY(lin(e, e->attn, D, L.wo[E], nullptr, e->h, e->h, D, M, D, D, EPI_RESID, st));
             if (T > 0) UMV_TRY(copy_rows(e->yt, D, r.m.text_rows, e->h, D, T, D, 1, st));
         }
-        if (partial && pf_n2_kb > 0) norm_pf = region(L.wgu[0], gu_rows, D, ring_kb + pf_gu_kb, pf_n2_kb);
         UMV_TRY(norm(L.ln2[0], L.ln2[1], e->xn));
         // ---- SwiGLU MLP + residual
         if (T > 0) {
@@ -849,6 +840,8 @@ int llm_run(umv_engine* e, const bf16* x, int n_seqs, const int32_t* seqs, const
     UMV_TRY(meta_commit(e, &mb, st));
     if (x) UMV_CUDA_OK(cudaMemcpy2DAsync(e->h, (size_t)D * 2, x, (size_t)D * 2, (size_t)D * 2, M, cudaMemcpyDeviceToDevice, st));
     r.weight_major = M <= 64;
+    UMV_TRY(rope_table(m.positions, e->inv_freq, M, e->dh, e->rope_tab, st));
+    r.m.rope_cs = e->rope_tab;
     UMV_TRY(llm_layers(e, r, out, st));
     if (update_kv)
         for (int b = 0; b < n_seqs; ++b) sq[b]->len += q_lens[b];

@@ -138,6 +138,7 @@ struct umv_engine {
     float* t_freqs = nullptr;          // [128] exp(-ln(1e4) i / 128)
     int *dec_pos = nullptr, *dec_kvlen = nullptr, *dec_kvpos = nullptr, *dec_step = nullptr, *dec_rowseq = nullptr,
         *dec_qstart = nullptr, *dec_qlen = nullptr, *dec_pages = nullptr;
+    float* rope_tab = nullptr;         // [max_tokens][dh] per-forward rope cos | sin
     float* dec_rope = nullptr;         // [64][dh] per-step rope cos | sin
     int dec_pages_cap = 0;
 };

@@ -103,8 +103,14 @@ __device__ __forceinline__ float epi_value(int epi, float acc, float bias) {
 }
 
 // MODE 0: bf16 / gelu / +residual (runtime p.epi), 1: fp32 split-K partials, 2: swiglu
+// Threads: warp 0 TMA producer, warp 1 MMA issuer, then the epilogue warps: 4 on the weight-major path (its epilogue is
+// a few columns), 8 on the token-major path -- two warps per TMEM lane quarter, each draining half of the tile's columns,
+// so that short-K tiles (ViT K = 1152, VAE) are not paced by the epilogue.
+template <bool SWAP>
+constexpr int gemm_threads() { return SWAP ? 192 : 320; }
+
 template <int BN, int MODE, bool SWAP>
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(gemm_threads<SWAP>(), 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
     using Cfg = TcCfg<BN, SWAP>;
     constexpr int kMaxStages = Cfg::kStages;
@@ -135,7 +141,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
             for (int i = 0; i < 2; ++i) {
                 mbar_init(&tfull[i], 1);
-                mbar_init(&tempty[i], 4);
+                mbar_init(&tempty[i], SWAP ? 4 : 8);
             }
             fence_mbar_init();
         }
@@ -228,8 +234,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
         }
     } else {
-        // ------------------------------------------------------------ epilogue (4 warps)
+        // ------------------------------------------------------------ epilogue (4 or 8 warps)
         const int quarter = warp & 3;                  // TMEM lane quarter this warp may read
+        const int chalf = SWAP ? 0 : (warp - 2) >> 2;  // token-major: which half of the tile's columns this warp drains
         const int lrow = quarter * 32 + lane;          // lane within the 128-row tile
         pdl_wait();                                    // outputs / bias / residual belong to the dependency chain
         int acc = 0;
@@ -246,7 +253,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 const int row = a_tile * BM + lrow;            // token
                 const bool row_ok = row < p.tokens;
 #pragma unroll 1
-                for (int c0 = 0; c0 < BN; c0 += 16) {
+                for (int c0 = chalf * (BN / 2); c0 < (chalf + 1) * (BN / 2); c0 += 16) {
                     uint32_t r[16];
                     tmem_ld16(taddr + c0, r);
                     tmem_ld_wait();
@@ -283,10 +290,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 // weight rows interleaved [64 gate | 64 up] -> tile columns [blk*128 + c] / [blk*128 + 64 + c]
                 const int row = a_tile * BM + lrow;
                 const bool row_ok = row < p.tokens;
+                constexpr int kUnits = (BN / 128) * 4;             // 16-column gate/up chunk pairs of the tile
 #pragma unroll 1
-                for (int blk = 0; blk < BN / 128; ++blk) {
-#pragma unroll 1
-                    for (int c0 = 0; c0 < 64; c0 += 16) {
+                for (int unit = chalf * (kUnits / 2); unit < (chalf + 1) * (kUnits / 2); ++unit) {
+                    const int blk = unit >> 2, c0 = (unit & 3) * 16;
+                    {
                         uint32_t g[16], u[16];
                         tmem_ld16(taddr + blk * 128 + c0, g);
                         tmem_ld16(taddr + blk * 128 + 64 + c0, u);
@@ -407,6 +415,78 @@ __global__ void gemm_simple_kernel(const bf16* __restrict__ x, int ldx, const bf
 }
 
 // ---------------------------------------------------------------------------------------------
+// Finish of a split-K weight-major linear whose consumer is not fused with the reduction (the few understanding-expert
+// rows of a generation-mode forward, the time-embedding MLP): y = epilogue(sum_s ws[s] + bias) [+ residual], partials
+// summed in split order (deterministic), every partial load of a thread in flight together.  One thread per 8 features.
+constexpr int kFinishMaxSplits = 16;
+__global__ void __launch_bounds__(256) splitk_finish_kernel(const float* __restrict__ ws, int splits, int M, int N,
+                                                            const bf16* __restrict__ bias, const bf16* __restrict__ residual,
+                                                            bf16* __restrict__ y, int ldy, int epi, TraceSlot* trace) {
+    pdl_launch_dependents();
+    trace_start(trace);
+    pdl_wait();
+    trace_wait(trace);
+    const int nch = N / 8;
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx < M * nch) {
+        const int row = idx / nch, n = (idx % nch) * 8;
+        float4 p[kFinishMaxSplits][2];
+#pragma unroll
+        for (int sp = 0; sp < kFinishMaxSplits; ++sp) {
+            if (sp < splits) {
+                const float4* pp = reinterpret_cast<const float4*>(ws + ((size_t)sp * M + row) * N + n);
+                p[sp][0] = pp[0];
+                p[sp][1] = pp[1];
+            }
+        }
+        U4 bv = {0, 0, 0, 0}, rv = {0, 0, 0, 0};
+        if (bias) bv = ldg16(bias + n);
+        if (epi == EPI_RESID) rv = ldg16(residual + (size_t)row * ldy + n);
+        float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int sp = 0; sp < kFinishMaxSplits; ++sp) {
+            if (sp < splits) {
+                acc[0] += p[sp][0].x; acc[1] += p[sp][0].y; acc[2] += p[sp][0].z; acc[3] += p[sp][0].w;
+                acc[4] += p[sp][1].x; acc[5] += p[sp][1].y; acc[6] += p[sp][1].z; acc[7] += p[sp][1].w;
+            }
+        }
+        const uint32_t* bw = &bv.x;
+        const uint32_t* rw = &rv.x;
+        uint32_t o[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float2 b2 = unpack2(bw[j]);
+            float v0 = epi_value(epi, acc[2 * j], b2.x), v1 = epi_value(epi, acc[2 * j + 1], b2.y);
+            if (epi == EPI_RESID) {
+                const float2 r2 = unpack2(rw[j]);
+                v0 += r2.x;
+                v1 += r2.y;
+            }
+            o[j] = pack2(v0, v1);
+        }
+        stg16(y + (size_t)row * ldy + n, U4{o[0], o[1], o[2], o[3]});
+    }
+    trace_end<false>(trace);
+}
+
+int splitk_finish(const float* ws, int splits, int M, int N, const bf16* bias, const bf16* residual, bf16* y, int ldy, int epi,
+                  cudaStream_t stream) {
+    UMV_REQUIRE(splits >= 1 && splits <= kFinishMaxSplits && N % 8 == 0 && ldy % 8 == 0, UMV_ERR_INVALID,
+                "splitk_finish: splits=%d N=%d ldy=%d", splits, N, ldy);
+    UMV_REQUIRE(epi == EPI_BF16 || epi == EPI_GELU || epi == EPI_RESID, UMV_ERR_INVALID, "splitk_finish: epilogue %d", epi);
+    const int total = M * (N / 8);
+    cudaError_t e = launch_k(splitk_finish_kernel, dim3((total + 255) / 256), dim3(256), 0, stream, ws, splits, M, N, bias, residual, y,
+                             ldy, epi, trace_next("splitk_finish"));
+    ++g_launches;
+    if (e == cudaSuccess) e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        set_error("splitk_finish_kernel launch failed: %s", cudaGetErrorString(e));
+        return UMV_ERR_CUDA;
+    }
+    return UMV_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -521,7 +601,7 @@ static int launch_tc(const LinearCall& c, cudaStream_t stream) {
     if (rc) return rc;
     const int tiles = p.a_tiles * p.b_tiles * p.splits;
     const int grid = tiles < g_sm_count ? tiles : g_sm_count;
-    cudaError_t e = launch_k(gemm_tc_kernel<BN, MODE, SWAP>, dim3(grid), dim3(192), TcCfg<BN, SWAP>::smem_bytes(p.stages), stream, tmA, tmB, p);
+    cudaError_t e = launch_k(gemm_tc_kernel<BN, MODE, SWAP>, dim3(grid), dim3(gemm_threads<SWAP>()), TcCfg<BN, SWAP>::smem_bytes(p.stages), stream, tmA, tmB, p);
     ++g_launches;
     if (e == cudaSuccess) e = cudaGetLastError();
     if (e != cudaSuccess) {

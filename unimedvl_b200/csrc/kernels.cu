@@ -25,23 +25,28 @@ namespace umv {
 constexpr int kNormThreads = 256;
 constexpr int kNormMaxChunks = 8;   // 8 chunks * 8 elems * 256 threads = D <= 16384
 
+// NC = 8-element chunks per thread (D <= 2048 NC): keeps the register footprint -- and with it the number of resident
+// CTAs per SM on many-row (prefill / flow) calls -- proportional to the row width actually used.
+template <int NC>
 __global__ void __launch_bounds__(kNormThreads) add_rmsnorm_kernel(AddNormArgs a) {
     pdl_launch_dependents();
     trace_start(a.trace);
-    l2_prefetch_region(a.prefetch, threadIdx.x * gridDim.x + blockIdx.x, gridDim.x * kNormThreads);
     pdl_wait();
     trace_wait(a.trace);
     __shared__ float red[32];
     const int row = blockIdx.x;
     const int nchunk = a.D / 8;
     bf16* hrow = a.h + (size_t)row * a.D;
-    float v[kNormMaxChunks][8];
+    const bf16* w = (a.row_sel && a.row_sel[row]) ? a.w1 : a.w0;
+    float v[NC][8];
+    U4 wv[NC];
     float ss = 0.f;
 #pragma unroll
-    for (int c = 0; c < kNormMaxChunks; ++c) {
+    for (int c = 0; c < NC; ++c) {
         const int ch = threadIdx.x + c * kNormThreads;
         if (ch < nchunk) {
             const U4 hv = ldg16(hrow + ch * 8);
+            if (a.y) wv[c] = ldg16(w + ch * 8);
             const uint32_t* hw = &hv.x;
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
@@ -88,14 +93,12 @@ __global__ void __launch_bounds__(kNormThreads) add_rmsnorm_kernel(AddNormArgs a
     if (a.y == nullptr) return;
     ss = block_sum(ss, red);
     const float inv = 1.0f / sqrtf(ss / (float)a.D + a.eps);
-    const bf16* w = (a.row_sel && a.row_sel[row]) ? a.w1 : a.w0;
     bf16* yrow = a.y + (size_t)row * a.D;
 #pragma unroll
-    for (int c = 0; c < kNormMaxChunks; ++c) {
+    for (int c = 0; c < NC; ++c) {
         const int ch = threadIdx.x + c * kNormThreads;
         if (ch < nchunk) {
-            const U4 wv = ldg16(w + ch * 8);
-            const uint32_t* ww = &wv.x;
+            const uint32_t* ww = &wv[c].x;
             uint32_t o[4];
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
@@ -190,7 +193,11 @@ int add_rmsnorm(const AddNormArgs& a0, cudaStream_t s) {
         UMV_LAUNCH_CHECK("add_rmsnorm_splitk_kernel");
         return UMV_OK;
     }
-    launch_k(add_rmsnorm_kernel, dim3(a.M), dim3(kNormThreads), 0, s, a);
+    const int nc = (a.D / 8 + kNormThreads - 1) / kNormThreads;
+    if (nc <= 1) launch_k(add_rmsnorm_kernel<1>, dim3(a.M), dim3(kNormThreads), 0, s, a);
+    else if (nc <= 2) launch_k(add_rmsnorm_kernel<2>, dim3(a.M), dim3(kNormThreads), 0, s, a);
+    else if (nc <= 4) launch_k(add_rmsnorm_kernel<4>, dim3(a.M), dim3(kNormThreads), 0, s, a);
+    else launch_k(add_rmsnorm_kernel<kNormMaxChunks>, dim3(a.M), dim3(kNormThreads), 0, s, a);
     UMV_LAUNCH_CHECK("add_rmsnorm_kernel");
     return UMV_OK;
 }
@@ -266,81 +273,131 @@ int layernorm_bf16(const bf16* x, const bf16* w, const bf16* b, bf16* y, int M, 
 // ------------------------------------------------------------------------------------------
 // One warp per (row, head-slot): slots [0,H) = q heads, [H,H+Hkv) = k heads, [H+Hkv,H+2Hkv) = v heads.
 // head_dim 128: lane l owns elements 4l..4l+3; the rotate_half partner (i +- 64) lives in lane l^16.
-__global__ void __launch_bounds__(256) rope_append_kernel(RopeAppendArgs a) {
+// One CTA per row: the rope angles (and their bf16-rounded cos / sin), the row's norm-weight choice and its KV slot are
+// evaluated once and reused by the H + 2 Hkv head slots the CTA's 8 warps walk over (one warp per slot, lane = 4 columns).
+__global__ void __launch_bounds__(256, 4) rope_append_kernel(RopeAppendArgs a) {
     pdl_launch_dependents();
     trace_start(a.trace);
     pdl_wait();
     trace_wait(a.trace);
-    const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int lane = threadIdx.x & 31;
+    constexpr int kBatch = 5;                        // loads of a warp's next 5 head slots in flight together
+    const int row = blockIdx.x;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int slots = a.H + 2 * a.Hkv;
-    if (gw >= a.M * slots) return;
-    const int row = gw / slots, slot = gw % slots;
     const int ncols = slots * a.dh;
-    const int col = slot * a.dh + lane * 4;
-
-    float x[4];
+    const int half = a.dh / 2;
+    // every load that needs no other load goes out first (the kernel is a chain of a few memory round trips per row)
+    uint2 raw[kBatch];
+    if (!a.partial) {
+#pragma unroll
+        for (int i = 0; i < kBatch; ++i) {
+            const int slot = warp + 8 * i;
+            raw[i] = make_uint2(0u, 0u);
+            if (slot < slots) raw[i] = *reinterpret_cast<const uint2*>(a.qkv + (size_t)row * ncols + slot * a.dh + lane * 4);
+        }
+    }
+    const bool gen_row = a.row_sel && a.row_sel[row];
+    const int pos_kv = a.row_kvpos[row];
+    const int seq = a.row_seq[row];
+    const float4 c4 = *reinterpret_cast<const float4*>(a.rope_cs + (size_t)row * a.dh + (lane * 4) % half);
+    const float4 s4 = *reinterpret_cast<const float4*>(a.rope_cs + (size_t)row * a.dh + half + (lane * 4) % half);
+    const float c[4] = {c4.x, c4.y, c4.z, c4.w}, sn[4] = {s4.x, s4.y, s4.z, s4.w};
+    const int page = a.page_table[(size_t)seq * a.max_pages + pos_kv / kPageTokens];
+    // norm weights of this row (q heads / k heads), loaded once
+    const uint2 wq2 = *reinterpret_cast<const uint2*>((gen_row ? a.qn1 : a.qn0) + lane * 4);
+    const uint2 wk2 = *reinterpret_cast<const uint2*>((gen_row ? a.kn1 : a.kn0) + lane * 4);
+    auto process = [&](int slot, const float (&x)[4]) {
+        const int col = slot * a.dh + lane * 4;
+        const bool is_q = slot < a.H;
+        const bool is_v = slot >= a.H + a.Hkv;
+        float o[4];
+        if (is_v) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) o[j] = x[j];
+        } else {
+            float ss = x[0] * x[0] + x[1] * x[1] + x[2] * x[2] + x[3] * x[3];
+            ss = warp_sum(ss);
+            const float inv = 1.0f / sqrtf(ss / (float)a.dh + a.eps);
+            const uint2 wv = is_q ? wq2 : wk2;
+            const float2 w0 = unpack2(wv.x), w1 = unpack2(wv.y);
+            const float w[4] = {w0.x, w0.y, w1.x, w1.y};
+            float n[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                if (a.gen_mode) n[j] = __fmul_rn(w[j], __fmul_rn(x[j], inv));          // fp32 throughout
+                else n[j] = rbf(w[j] * rbf(x[j] * inv));                               // R4: two bf16 roundings
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float partner = __shfl_xor_sync(0xffffffffu, n[j], 16);
+                const float rot = (lane < 16) ? -partner : partner;
+                if (a.gen_mode) o[j] = rbf(__fadd_rn(__fmul_rn(n[j], c[j]), __fmul_rn(rot, sn[j])));
+                else o[j] = rbf(rbf(n[j] * c[j]) + rbf(rot * sn[j]));                   // R5: three roundings
+            }
+        }
+        const uint2 packed = make_uint2(pack2(o[0], o[1]), pack2(o[2], o[3]));
+        if (is_q) {
+            *reinterpret_cast<uint2*>(a.q_out + (size_t)row * a.ldq + col) = packed;
+        } else {
+            const int kv = is_v ? 1 : 0;
+            const int head = slot - a.H - (is_v ? a.Hkv : 0);
+            bf16* dst = a.pool.base + a.pool.tile_offset(page, a.layer, kv, head) + (size_t)(pos_kv % kPageTokens) * a.dh + lane * 4;
+            *reinterpret_cast<uint2*>(dst) = packed;
+        }
+    };
     if (a.partial) {
-        float acc[4] = {0.f, 0.f, 0.f, 0.f};
-        for (int s = 0; s < a.splits; ++s) {
-            const float4 p = *reinterpret_cast<const float4*>(a.partial + ((size_t)s * a.M + row) * ncols + col);
-            acc[0] += p.x; acc[1] += p.y; acc[2] += p.z; acc[3] += p.w;
+        for (int slot = warp; slot < slots; slot += 8) {
+            const int col = slot * a.dh + lane * 4;
+            float acc[4] = {0.f, 0.f, 0.f, 0.f};
+            for (int s = 0; s < a.splits; ++s) {
+                const float4 p = *reinterpret_cast<const float4*>(a.partial + ((size_t)s * a.M + row) * ncols + col);
+                acc[0] += p.x; acc[1] += p.y; acc[2] += p.z; acc[3] += p.w;
+            }
+            const uint2 bv = *reinterpret_cast<const uint2*>(a.bias + col);
+            const float2 b0 = unpack2(bv.x), b1 = unpack2(bv.y);
+            const float x[4] = {rbf(acc[0] + b0.x), rbf(acc[1] + b0.y), rbf(acc[2] + b1.x), rbf(acc[3] + b1.y)};
+            process(slot, x);
         }
-        const uint2 bv = *reinterpret_cast<const uint2*>(a.bias + col);
-        const float2 b0 = unpack2(bv.x), b1 = unpack2(bv.y);
-        x[0] = rbf(acc[0] + b0.x); x[1] = rbf(acc[1] + b0.y); x[2] = rbf(acc[2] + b1.x); x[3] = rbf(acc[3] + b1.y);
     } else {
-        const uint2 qv = *reinterpret_cast<const uint2*>(a.qkv + (size_t)row * ncols + col);
-        const float2 f0 = unpack2(qv.x), f1 = unpack2(qv.y);
-        x[0] = f0.x; x[1] = f0.y; x[2] = f1.x; x[3] = f1.y;
-    }
-
-    const bool is_q = slot < a.H;
-    const bool is_v = slot >= a.H + a.Hkv;
-    float o[4];
-    if (is_v) {
+        for (int s0 = warp; s0 < slots; s0 += 8 * kBatch) {
+            if (s0 != warp) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) o[j] = x[j];
-    } else {
-        const bool gen_row = a.row_sel && a.row_sel[row];
-        const bf16* nw = is_q ? (gen_row ? a.qn1 : a.qn0) : (gen_row ? a.kn1 : a.kn0);
-        float ss = x[0] * x[0] + x[1] * x[1] + x[2] * x[2] + x[3] * x[3];
-        ss = warp_sum(ss);
-        const float inv = 1.0f / sqrtf(ss / (float)a.dh + a.eps);
-        const uint2 wv = *reinterpret_cast<const uint2*>(nw + lane * 4);
-        const float2 w0 = unpack2(wv.x), w1 = unpack2(wv.y);
-        const float w[4] = {w0.x, w0.y, w1.x, w1.y};
-        float n[4];
+                for (int i = 0; i < kBatch; ++i) {
+                    const int slot = s0 + 8 * i;
+                    if (slot < slots) raw[i] = *reinterpret_cast<const uint2*>(a.qkv + (size_t)row * ncols + slot * a.dh + lane * 4);
+                }
+            }
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            if (a.gen_mode) n[j] = __fmul_rn(w[j], __fmul_rn(x[j], inv));          // fp32 throughout
-            else n[j] = rbf(w[j] * rbf(x[j] * inv));                               // R4: two bf16 roundings
+            for (int i = 0; i < kBatch; ++i) {
+                const int slot = s0 + 8 * i;
+                if (slot < slots) {
+                    const float2 f0 = unpack2(raw[i].x), f1 = unpack2(raw[i].y);
+                    const float x[4] = {f0.x, f0.y, f1.x, f1.y};
+                    process(slot, x);
+                }
+            }
         }
-        const float pos = (float)a.positions[row];
-        const int half = a.dh / 2;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const int i = lane * 4 + j;
-            const float ang = __fmul_rn(pos, a.inv_freq[i % half]);
-            const float c = rbf(cosf(ang)), sn = rbf(sinf(ang));                    // cos/sin cast to bf16 (R5)
-            const float partner = __shfl_xor_sync(0xffffffffu, n[j], 16);
-            const float rot = (i < half) ? -partner : partner;
-            if (a.gen_mode) o[j] = rbf(__fadd_rn(__fmul_rn(n[j], c), __fmul_rn(rot, sn)));
-            else o[j] = rbf(rbf(n[j] * c) + rbf(rot * sn));                         // R5: three roundings
-        }
-    }
-    const uint2 packed = make_uint2(pack2(o[0], o[1]), pack2(o[2], o[3]));
-    if (is_q) {
-        *reinterpret_cast<uint2*>(a.q_out + (size_t)row * a.ldq + col) = packed;
-    } else {
-        const int kv = is_v ? 1 : 0;
-        const int head = slot - a.H - (is_v ? a.Hkv : 0);
-        const int pos_kv = a.row_kvpos[row];
-        const int page = a.page_table[(size_t)a.row_seq[row] * a.max_pages + pos_kv / kPageTokens];
-        bf16* dst = a.pool.base + a.pool.tile_offset(page, a.layer, kv, head) + (size_t)(pos_kv % kPageTokens) * a.dh + lane * 4;
-        *reinterpret_cast<uint2*>(dst) = packed;
     }
     trace_end<false>(a.trace);
+}
+
+__global__ void rope_table_kernel(const int* __restrict__ positions, const float* __restrict__ inv_freq, int M, int dh,
+                                  float* __restrict__ cs) {
+    pdl_launch_dependents();
+    pdl_wait();
+    const int half = dh / 2;
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= M * half) return;
+    const int m = idx / half, i = idx % half;
+    const float ang = __fmul_rn((float)positions[m], inv_freq[i]);
+    cs[(size_t)m * dh + i] = rbf(cosf(ang));                       // cos/sin cast to bf16 (R5)
+    cs[(size_t)m * dh + half + i] = rbf(sinf(ang));
+}
+int rope_table(const int* positions, const float* inv_freq, int M, int dh, float* cs, cudaStream_t s) {
+    if (M <= 0) return UMV_OK;
+    launch_k(rope_table_kernel, dim3((M * (dh / 2) + 255) / 256), dim3(256), 0, s, positions, inv_freq, M, dh, cs);
+    UMV_LAUNCH_CHECK("rope_table_kernel");
+    return UMV_OK;
 }
 
 int rope_append(const RopeAppendArgs& a0, cudaStream_t s) {
@@ -348,8 +405,8 @@ int rope_append(const RopeAppendArgs& a0, cudaStream_t s) {
     RopeAppendArgs a = a0;
     a.trace = trace_next("rope_append");
     UMV_REQUIRE(a.dh == 128, UMV_ERR_UNSUPPORTED, "rope_append: head_dim %d (only 128 is built)", a.dh);
-    const long long warps = (long long)a.M * (a.H + 2 * a.Hkv);
-    const int blocks = (int)((warps * 32 + 255) / 256);
+    UMV_REQUIRE(a.rope_cs != nullptr, UMV_ERR_INVALID, "rope_append: the per-forward cos/sin table (rope_table) is required");
+    const int blocks = a.M;
     launch_k(rope_append_kernel, dim3(blocks), dim3(256), 0, s, a);
     UMV_LAUNCH_CHECK("rope_append_kernel");
     return UMV_OK;
@@ -417,18 +474,21 @@ int f32_to_bf16_padded(const float* x, bf16* y, int M, int K, int Kpad, cudaStre
 
 // rows[]: scatter==0: dst[i] = src[rows[i]] ; scatter==1: dst[rows[i]] = src[i]
 __global__ void copy_rows_kernel(const bf16* __restrict__ src, int lds, const int* __restrict__ rows, bf16* __restrict__ dst,
-                                 int ldd, int D, int scatter) {
+                                 int ldd, int D, int scatter, TraceSlot* trace) {
     pdl_launch_dependents();
+    trace_start(trace);
     pdl_wait();
+    trace_wait(trace);
     const int i = blockIdx.x;
     const int r = rows[i];
     const bf16* s = src + (size_t)(scatter ? i : r) * lds;
     bf16* d = dst + (size_t)(scatter ? r : i) * ldd;
     for (int c = threadIdx.x; c < D / 8; c += blockDim.x) stg16(d + c * 8, ldg16(s + c * 8));
+    trace_end<false>(trace);
 }
 int copy_rows(const bf16* src, int lds, const int* rows, bf16* dst, int ldd, int n, int D, int scatter, cudaStream_t s) {
     if (n <= 0) return UMV_OK;
-    launch_k(copy_rows_kernel, dim3(n), dim3(128), 0, s, src, lds, rows, dst, ldd, D, scatter);
+    launch_k(copy_rows_kernel, dim3(n), dim3(128), 0, s, src, lds, rows, dst, ldd, D, scatter, trace_next("copy_rows"));
     UMV_LAUNCH_CHECK("copy_rows_kernel");
     return UMV_OK;
 }

@@ -18,23 +18,6 @@ struct KVPool {
     }
 };
 
-// A strided region of constant data (weights of a LATER kernel of the decode chain) that a latency-bound kernel asks the
-// L2 to fetch while HBM would otherwise idle: `rows` segments of `seg_bytes` at base + r * pitch + seg_off.
-struct L2Region {
-    const void* base = nullptr;
-    long long pitch = 0;
-    int rows = 0, seg_off = 0, seg_bytes = 0;     // seg_off, seg_bytes, pitch: multiples of 16
-};
-#ifdef __CUDACC__
-// Called by every thread of the grid with its global thread index / the grid's thread count, BEFORE griddepcontrol.wait.
-__device__ __forceinline__ void l2_prefetch_region(const L2Region& r, int gtid, int gthreads) {
-    if (r.seg_bytes <= 0) return;
-    for (int row = gtid; row < r.rows; row += gthreads)
-        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(static_cast<const char*>(r.base) + (size_t)row * r.pitch + r.seg_off),
-                     "r"(r.seg_bytes) : "memory");
-}
-#endif
-
 // ---- residual add + RMSNorm (Qwen2RMSNorm, modeling_qwen2.py:89-94; residual adds qwen2_navit.py:883,901)
 struct AddNormArgs {
     bf16* h = nullptr;              // [M, D] residual stream; updated in place when a delta is given
@@ -47,7 +30,6 @@ struct AddNormArgs {
     bf16* y = nullptr;              // [M, D] normalised output (null: only the residual add)
     int M = 0, D = 0;
     float eps = 1e-6f;
-    L2Region prefetch;              // optional: weights of a following linear
     TraceSlot* trace = nullptr;
 };
 int add_rmsnorm(const AddNormArgs& a, cudaStream_t s);
@@ -69,6 +51,7 @@ struct RopeAppendArgs {
     const int* page_table = nullptr; // [n_seqs][max_pages]
     int max_pages = 0;
     const float* inv_freq = nullptr; // [dh/2] fp32
+    const float* rope_cs = nullptr;  // optional [M][dh]: bf16-rounded cos | sin of positions[m] * inv_freq (rope_table)
     const bf16* qn0 = nullptr; const bf16* kn0 = nullptr;   // understanding q_norm / k_norm
     const bf16* qn1 = nullptr; const bf16* kn1 = nullptr;   // *_moe_gen
     const uint8_t* row_sel = nullptr;                        // null in "und" mode
@@ -79,6 +62,9 @@ struct RopeAppendArgs {
     TraceSlot* trace = nullptr;
 };
 int rope_append(const RopeAppendArgs& a, cudaStream_t s);
+// cs[m][0:dh/2] = bf16(cos(positions[m] * inv_freq)), cs[m][dh/2:dh] = bf16(sin(..)) as fp32 values: the angles are the same
+// for every layer of a forward, so they are evaluated once (modeling_qwen2.py:164-181 recomputes them per layer).
+int rope_table(const int* positions, const float* inv_freq, int M, int dh, float* cs, cudaStream_t s);
 
 // ---- attention (flash_attn_varlen_func call sites qwen2_navit.py:605-614, siglip_navit.py:232-241)
 struct AttnArgs {
@@ -171,7 +157,6 @@ struct DecodeAttnArgs {
     int M = 0, H = 0, Hkv = 0;
     int cluster = 8;                  // CTAs (key ranges) per (sample, kv head)
     float eps = 1e-6f;
-    L2Region prefetch[2];             // optional: weights of the following linears (o_proj, head of gate/up)
     TraceSlot* trace = nullptr;
 };
 int decode_attention(const DecodeAttnArgs& a, cudaStream_t s);
