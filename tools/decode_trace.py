@@ -66,6 +66,14 @@ if ia:
     out.append("\n## inside attn_decode (first CTA; us after the dependency wait): " +
                ", ".join(f"dbg{k}={(t[i, 4 + k] - t[i, 1]) / 1e3:.1f}" for k in range(8) if t[i, 4 + k] > 0) +
                f", end={(t[i, 2] - t[i, 1]) / 1e3:.1f}\n")
+for pref in ("dec<1,1>", "dec<1,2>", "dec<0,3> N3584 K3584"):
+    ib = [i for i in range(n) if nm[i].startswith(pref)]
+    if ib:
+        i = ib[len(ib) // 2]
+        out.append(f"\n## inside {nm[i]} (first CTA; us after its start): " +
+                   ", ".join(f"dbg{k}={(t[i, 4 + k] - t[i, 0]) / 1e3:.1f}" for k in range(8) if t[i, 4 + k] > 0) +
+                   f", all tiles requested={(t[i, 1] - t[i, 0]) / 1e3:.1f}, first CTA end={(t[i, 2] - t[i, 0]) / 1e3:.1f}, "
+                   f"last CTA end={(t[i, 3] - t[i, 0]) / 1e3:.1f}; previous kernel's last CTA ended at {(t[i - 1, 3] - t[i, 0]) / 1e3:.1f}\n")
 ia = [i for i in range(n) if nm[i] == "add_rmsnorm"]
 if ia:
     i = ia[len(ia) // 2]

@@ -377,6 +377,20 @@ static int llm_layers(umv_engine* e, const LlmRun& r, bf16* out, cudaStream_t st
     // decode-attention kernel (co-residency in shared memory) costs more streaming rate than the overlap returns -> 0 = full.
     static const int near_attn_stages = getenv("UMV_NEAR_ATTN_STAGES") ? atoi(getenv("UMV_NEAR_ATTN_STAGES")) : 0;
     static const int attn_cluster_max = getenv("UMV_ATTN_CLUSTER") ? atoi(getenv("UMV_ATTN_CLUSTER")) : 8;
+    // Decode with <= 8 rows: the two RMSNorm links of every layer are folded into the linears around them (gemm_decode.cu)
+    static const bool fuse_norm_on = !(getenv("UMV_FUSE_NORM") && atoi(getenv("UMV_FUSE_NORM")) == 0);
+    const bool fuse_norm = fuse_norm_on && partial && r.max_q_len == 1 && decode_linear_supported(M, D) && I % 64 == 0;
+    auto dec_norm_lin = [&](const bf16* w, const bf16* nw, int N, int epi, bf16* y, int ldy, int splits) {
+        DecodeLinear c;
+        c.w = w; c.N = N; c.K = D; c.M = M; c.epi = epi; c.y = y; c.ldy = ldy; c.ws = e->ws; c.splits = splits;
+        c.norm_h = e->h; c.norm_w = nw; c.eps = d.rms_eps;
+        return decode_linear(c, st);
+    };
+    auto dec_resid_lin = [&](const bf16* x, int K, const bf16* w) {      // h += x W^T, split-K over a 4-CTA cluster
+        DecodeLinear c;
+        c.x = x; c.ldx = K; c.w = w; c.N = D; c.K = K; c.M = M; c.epi = EPI_CLUSTER_RESID; c.y = e->h; c.ldy = D; c.splits = 4;
+        return decode_linear(c, st);
+    };
 
     auto norm = [&](const bf16* w0, const bf16* w1, bf16* y) {
         AddNormArgs a;
@@ -399,10 +413,14 @@ static int llm_layers(umv_engine* e, const LlmRun& r, bf16* out, cudaStream_t st
 
     for (int li = 0; li < d.layers; ++li) {
         const LayerW& L = e->layers[li];
-        UMV_TRY(norm(L.ln1[0], L.ln1[1], e->xn));
+        if (!fuse_norm) UMV_TRY(norm(L.ln1[0], L.ln1[1], e->xn));
         // ---- q/k/v projections
         RopeAppendArgs ra;
-        if (partial) {
+        if (fuse_norm) {
+            const int s = pick_splits(QN, D, e->sm_count);
+            UMV_TRY(dec_norm_lin(L.wqkv[0], L.ln1[0], QN, EPI_PARTIAL, nullptr, 0, s));
+            ra.partial = e->ws; ra.splits = s; ra.bias = L.bqkv[0];
+        } else if (partial) {
             const int s = pick_splits(QN, D, e->sm_count);
             UMV_TRY(lin(e, e->xn, D, L.wqkv[0], nullptr, nullptr, nullptr, 0, M, QN, D, EPI_PARTIAL, st, GEMM_WEIGHT_MAJOR, e->ws, s, near_attn_stages));
             ra.partial = e->ws; ra.splits = s; ra.bias = L.bqkv[0];
@@ -449,8 +467,11 @@ static int llm_layers(umv_engine* e, const LlmRun& r, bf16* out, cudaStream_t st
         UMV_TRY(attention_forward(aa, st));
         }
         // ---- output projection + residual
-        if (partial) {
-            const int s = pick_splits(D, D, e->sm_count);
+        if (fuse_norm) {
+            UMV_TRY(dec_resid_lin(e->attn, D, L.wo[0]));
+        } else if (partial) {
+            static const int force_s = getenv("UMV_SPLITS_RES") ? atoi(getenv("UMV_SPLITS_RES")) : 0;
+            const int s = force_s ? force_s : pick_splits(D, D, e->sm_count);
             UMV_TRY(lin(e, e->attn, D, L.wo[0], nullptr, nullptr, nullptr, 0, M, D, D, EPI_PARTIAL, st, GEMM_WEIGHT_MAJOR, e->ws, s, near_attn_stages));
             pending_splits = s;
         } else {
@@ -462,6 +483,11 @@ static int llm_layers(umv_engine* e, const LlmRun& r, bf16* out, cudaStream_t st
             UMV_TRY(lin(e, e->attn, D, L.wo[E], nullptr, e->h, e->h, D, M, D, D, EPI_RESID, st));
             if (T > 0) UMV_TRY(copy_rows(e->yt, D, r.m.text_rows, e->h, D, T, D, 1, st));
         }
+        if (fuse_norm) {
+            UMV_TRY(dec_norm_lin(L.wgu[0], L.ln2[0], 2 * I, EPI_SWIGLU, e->act, I, 1));
+            UMV_TRY(dec_resid_lin(e->act, I, L.wdown[0]));
+            continue;
+        }
         UMV_TRY(norm(L.ln2[0], L.ln2[1], e->xn));
         // ---- SwiGLU MLP + residual
         if (T > 0) {
@@ -472,7 +498,8 @@ static int llm_layers(umv_engine* e, const LlmRun& r, bf16* out, cudaStream_t st
         }
         UMV_TRY(lin(e, e->xn, D, L.wgu[E], nullptr, nullptr, e->act, I, M, 2 * I, D, EPI_SWIGLU, st));
         if (partial) {
-            const int s = pick_splits(D, I, e->sm_count);
+            static const int force_s = getenv("UMV_SPLITS_RES") ? atoi(getenv("UMV_SPLITS_RES")) : 0;
+            const int s = force_s ? force_s : pick_splits(D, I, e->sm_count);
             UMV_TRY(lin(e, e->act, I, L.wdown[0], nullptr, nullptr, nullptr, 0, M, D, I, EPI_PARTIAL, st, GEMM_WEIGHT_MAJOR, e->ws, s));
             pending_splits = s;
         } else {

@@ -531,7 +531,12 @@ int gemm_init() {
     return g_init_status;
 }
 
+int gemm_sm_count() { return g_sm_count; }
+int make_tmap_2d(CUtensorMap* m, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows);
 static int make_tmap(CUtensorMap* m, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows) {
+    return make_tmap_2d(m, ptr, rows, cols, ld, box_rows);
+}
+int make_tmap_2d(CUtensorMap* m, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows) {
     cuuint64_t dims[2] = {cols, rows};
     cuuint64_t strides[1] = {ld * 2};
     cuuint32_t box[2] = {BK, box_rows};
