@@ -316,7 +316,7 @@ constexpr int kDecThreads = 256;
 constexpr int kDecStages = 6;                                           // 64-key blocks in flight per CTA (one CTA per SM)
 constexpr int kDecQBytes = 16 * 256;
 constexpr int kDecStageBytes = 2 * kTileKeys * 256;                    // K tile + V tile
-constexpr int kDecSmemBytes = kDecQBytes + kDecStages * kDecStageBytes;
+constexpr int kDecSmemBytes = 1024 + kDecQBytes + kDecStages * kDecStageBytes;   // + slack to align the TMA tiles to 1 KB
 constexpr int kDecMaxPages = 512;                                       // page-table row staged in shared memory
 constexpr int kDecMaxSplits = 8;                                        // split-K partials summed with all loads in flight
 constexpr int kDecRecvRows = 16;                                        // >= S * ceil(G / S) for G <= 8, S <= 8
@@ -335,14 +335,22 @@ __device__ __forceinline__ void st_cluster_f1(uint32_t addr, float v) {
     asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
 }
 
-__global__ void __launch_bounds__(kDecThreads, 1) attn_decode_kernel(DecodeAttnArgs a, float scale_log2) {
+// A K or V tile as TMA leaves it: two [64 slots x 64 columns] halves (8 KB each), rows of 128 B with the 128-byte swizzle.
+__device__ __forceinline__ uint32_t kv_off(int row, int chunk) {
+    return ((chunk >> 3) << 13) + row * 128 + ((((chunk & 7) ^ (row & 7))) << 4);
+}
+
+__global__ void __launch_bounds__(kDecThreads, 1)
+attn_decode_kernel(const __grid_constant__ CUtensorMap tmKV, DecodeAttnArgs a, float scale_log2) {
     constexpr int HD = 128;
     pdl_launch_dependents();
     trace_start(a.trace);
     cluster_arrive();                      // phase 1: "this CTA runs" (its shared memory may be written by peers later)
-    extern __shared__ __align__(128) uint8_t smem[];
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     uint8_t* sQ = smem;
     uint8_t* sKV = smem + kDecQBytes;
+    __shared__ uint64_t kvbar[kDecStages];
     __shared__ int s_pages[kDecMaxPages];
     __shared__ __align__(16) float recv_o[kDecRecvRows][HD];
     __shared__ float recv_m[kDecRecvRows], recv_l[kDecRecvRows];
@@ -361,6 +369,11 @@ __global__ void __launch_bounds__(kDecThreads, 1) attn_decode_kernel(DecodeAttnA
     const int ncols = (a.H + 2 * a.Hkv) * HD;
 
     // ---- constants (weights): before the dependency wait
+    if (tid == 0) {
+        tma_prefetch_desc(&tmKV);
+        for (int j = 0; j < kDecStages; ++j) mbar_init(&kvbar[j], 1);
+        fence_mbar_init();
+    }
     for (int i = tid; i < 16 * 16; i += kDecThreads) {                // padding rows of the Q tile
         const int r = i >> 4, ch = i & 15;
         if (r >= G) *reinterpret_cast<U4*>(sQ + tile_off<HD>(r, ch)) = U4{0, 0, 0, 0};
@@ -443,26 +456,23 @@ __global__ void __launch_bounds__(kDecThreads, 1) attn_decode_kernel(DecodeAttnA
     __syncthreads();                                                      // s_pages (and the Q padding) visible
     trace_dbg(a.trace, 0);
 
-    auto load_kv = [&](int kb, int stage) {
+    // ---- round trip 2: one thread asks TMA for up to kDecStages blocks (the CTA's whole range at B = 8, ctx <= 1.5k): four
+    // 8 KB boxes per block (K / V x column halves) completing on the slot's mbarrier.  The block that receives the new
+    // token is loaded like the others; its new row is patched in shared memory from the registers of the K/V warp.
+    auto issue_kv = [&](int kb, int stage) {
         const int page = s_pages[kb];
-        const bf16* kbase = a.pool.base + a.pool.tile_offset(page, a.layer, 0, kvh);
-        const bf16* vbase = a.pool.base + a.pool.tile_offset(page, a.layer, 1, kvh);
+        const int row_k = (int)(a.pool.tile_offset(page, a.layer, 0, kvh) / HD);
+        const int row_v = (int)(a.pool.tile_offset(page, a.layer, 1, kvh) / HD);
         uint8_t* dk = sKV + stage * kDecStageBytes;
-        uint8_t* dv = dk + kTileKeys * 256;
-        for (int i = tid; i < kTileKeys * 16; i += kDecThreads) {
-            const int r = i >> 4, ch = i & 15;
-            const bool ok = kb * kTileKeys + r < kvlen;
-            cp_async16(dk + tile_off<HD>(r, ch), kbase + (size_t)(ok ? r : 0) * HD + ch * 8, ok);
-            cp_async16(dv + tile_off<HD>(r, ch), vbase + (size_t)(ok ? r : 0) * HD + ch * 8, ok);
-        }
+        mbar_expect_tx(&kvbar[stage], kDecStageBytes);
+        tma_load_2d(dk, &tmKV, &kvbar[stage], 0, row_k, kEvictNormal);
+        tma_load_2d(dk + 8192, &tmKV, &kvbar[stage], 64, row_k, kEvictNormal);
+        tma_load_2d(dk + 16384, &tmKV, &kvbar[stage], 0, row_v, kEvictNormal);
+        tma_load_2d(dk + 24576, &tmKV, &kvbar[stage], 64, row_v, kEvictNormal);
     };
-    // ---- round trip 2: up to kDecStages blocks (the CTA's whole range at B = 8, ctx <= 1.5k) go out together, one commit
-    // group per ring slot.  The block that receives the new token is loaded like the others; its new row is patched in
-    // shared memory from the registers of the K/V warp once the tile has landed.
-#pragma unroll
-    for (int j = 0; j < kDecStages; ++j) {
-        if (kb_begin + j < kb_end) load_kv(kb_begin + j, j);
-        cp_async_commit();
+    if (tid == 0) {
+        for (int j = 0; j < kDecStages; ++j)
+            if (kb_begin + j < kb_end) issue_kv(kb_begin + j, j);
     }
 
     // ---- rows of this step: RMSNorm + RoPE of the query heads (-> sQ) and of the new K row, V row as is (-> page)
@@ -512,31 +522,32 @@ __global__ void __launch_bounds__(kDecThreads, 1) attn_decode_kernel(DecodeAttnA
 
     const int nblk = kb_end - kb_begin;
     for (int rd = 0; 2 * rd < nblk; ++rd) {
-        // commit groups, in order: kDecStages first-pass slots, then one refill group per finished round (two blocks).
-        // Round rd needs blocks 2rd, 2rd+1: first-pass groups <= 2rd+1 (rd < 3) or refill group rd-3.
-        if (rd == 0) cp_async_wait<kDecStages - 2>();
-        else if (rd == 1) cp_async_wait<kDecStages - 3>();
-        else cp_async_wait<kDecStages - 4>();
-        __syncthreads();
         const int j = 2 * rd + sub, kb = kb_begin + j, stage = j % kDecStages;
         if (owner && (last_block == kb_begin + 2 * rd || last_block == kb_begin + 2 * rd + 1)) {      // CTA-uniform
+            // the newest block: wait for its tile, clear the V rows of slots that do not exist yet (whatever the pool holds
+            // there is multiplied by probability 0), put the new K / V row in place
+            const int jl = last_block - kb_begin;
+            uint8_t* tk = sKV + (jl % kDecStages) * kDecStageBytes;
+            mbar_wait(&kvbar[jl % kDecStages], (jl / kDecStages) & 1);
+            for (int i = tid; i < (kTileKeys - 1 - new_slot) * 16; i += kDecThreads)
+                *reinterpret_cast<U4*>(tk + 16384 + kv_off(new_slot + 1 + (i >> 4), i & 15)) = U4{0, 0, 0, 0};
             if (is_kv) {
-                uint8_t* tk = sKV + ((last_block - kb_begin) % kDecStages) * kDecStageBytes;
-                *reinterpret_cast<uint2*>(tk + tile_off<HD>(new_slot, lane >> 1) + (lane & 1) * 8) = k_new;
-                *reinterpret_cast<uint2*>(tk + kTileKeys * 256 + tile_off<HD>(new_slot, lane >> 1) + (lane & 1) * 8) = v_new;
+                *reinterpret_cast<uint2*>(tk + kv_off(new_slot, lane >> 1) + (lane & 1) * 8) = k_new;
+                *reinterpret_cast<uint2*>(tk + 16384 + kv_off(new_slot, lane >> 1) + (lane & 1) * 8) = v_new;
             }
             __syncthreads();
         }
+        if (j < nblk) mbar_wait(&kvbar[stage], (j / kDecStages) & 1);
         if (rd < 3) trace_dbg(a.trace, 2 + rd);
         const uint8_t* cK = sKV + stage * kDecStageBytes;
-        const uint8_t* cV = cK + kTileKeys * 256;
+        const uint8_t* cV = cK + 16384;
         if (j < nblk) {
             float s0[4] = {0.f, 0.f, 0.f, 0.f}, s1[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
             for (int ks = 0; ks < 8; ++ks) {
                 uint32_t b0, b1, b2, b3;
                 ldmatrix_x4(b0, b1, b2, b3,
-                            smem_u32(cK + tile_off<HD>(quarter * 16 + (lane & 7) + ((lane >> 4) << 3), ks * 2 + ((lane >> 3) & 1))));
+                            smem_u32(cK + kv_off(quarter * 16 + (lane & 7) + ((lane >> 4) << 3), ks * 2 + ((lane >> 3) & 1))));
                 mma_bf16_16816(s0, qf[ks], b0, b1);
                 mma_bf16_16816(s1, qf[ks], b2, b3);
             }
@@ -562,7 +573,7 @@ __global__ void __launch_bounds__(kDecThreads, 1) attn_decode_kernel(DecodeAttnA
                 uint32_t b0, b1, b2, b3;
                 asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
                              : "=r"(b0), "=r"(b1), "=r"(b2), "=r"(b3)
-                             : "r"(smem_u32(cV + tile_off<HD>(quarter * 16 + (lane & 7) + (((lane >> 3) & 1) << 3), dp + (lane >> 4)))));
+                             : "r"(smem_u32(cV + kv_off(quarter * 16 + (lane & 7) + (((lane >> 3) & 1) << 3), dp + (lane >> 4)))));
                 float acc0[4] = {o[dp][0], o[dp][1], 0.f, 0.f}, acc1[4] = {o[dp + 1][0], o[dp + 1][1], 0.f, 0.f};
                 mma_bf16_16816(acc0, pf, b0, b1);
                 mma_bf16_16816(acc1, pf, b2, b3);
@@ -572,15 +583,16 @@ __global__ void __launch_bounds__(kDecThreads, 1) attn_decode_kernel(DecodeAttnA
         }
         if (2 * rd + kDecStages < nblk) {       // long contexts only: refill the two slots just consumed
             __syncthreads();
+            if (tid == 0) {
+                fence_proxy_async_smem();       // the generic-proxy reads of the slots are ordered before the TMA writes
 #pragma unroll
-            for (int u = 0; u < 2; ++u) {
-                const int jn = 2 * rd + u + kDecStages;
-                if (jn < nblk) load_kv(kb_begin + jn, jn % kDecStages);
+                for (int u = 0; u < 2; ++u) {
+                    const int jn = 2 * rd + u + kDecStages;
+                    if (jn < nblk) issue_kv(kb_begin + jn, jn % kDecStages);
+                }
             }
         }
-        cp_async_commit();
     }
-    cp_async_wait<0>();
     l_a += __shfl_xor_sync(0xffffffffu, l_a, 1);
     l_a += __shfl_xor_sync(0xffffffffu, l_a, 2);
 
@@ -667,9 +679,11 @@ int decode_attention(const DecodeAttnArgs& a, cudaStream_t s) {
     cfg.attrs = attr;
     cfg.numAttrs = g_pdl ? 2 : 1;
     const float scale_log2 = (1.0f / sqrtf(128.0f)) * 1.4426950408889634f;
+    UMV_REQUIRE(a.kv_tmap != nullptr, UMV_ERR_INVALID, "decode_attention: the KV pool tensor map is missing");
     DecodeAttnArgs at = a;
     at.trace = trace_next("attn_decode");
-    cudaError_t e = cudaLaunchKernelEx(&cfg, attn_decode_kernel, at, scale_log2);
+    at.kv_tmap = nullptr;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, attn_decode_kernel, *a.kv_tmap, at, scale_log2);
     ++g_launches;
     if (e == cudaSuccess) e = cudaGetLastError();
     if (e != cudaSuccess) {

@@ -206,6 +206,15 @@ static int build_runtime(umv_engine* e) {
     e->pool.head_dim = e->dh;
     const size_t page_elems = (size_t)d.layers * 2 * d.kv_heads * kPageTokens * e->dh;
     UMV_TRY(dev_alloc(e, &e->pool.base, page_elems * d.kv_pages));
+    // Zero the pool once: the decode kernel brings whole 64-slot tiles in by TMA and multiplies not-yet-written V rows by
+    // probability 0 -- they must never hold NaN / Inf bit patterns.
+    UMV_CUDA_OK(cudaMemset(e->pool.base, 0, page_elems * d.kv_pages * sizeof(bf16)));
+    e->kv_tmap_ok = false;
+    if (e->dh == 128 && gemm_init() == UMV_OK) {
+        // the pool as a 2-D tensor [slot rows, 128]: one 64 x 64 box = half (64 columns) of a K or V tile
+        e->kv_tmap_ok = make_tmap_2d(&e->kv_tmap, e->pool.base, (uint64_t)d.kv_pages * d.layers * 2 * d.kv_heads * kPageTokens, 128,
+                                     128, kPageTokens) == UMV_OK;
+    }
     e->page_ref.assign(d.kv_pages, 0);
     e->free_pages.clear();
     for (int p = d.kv_pages - 1; p >= 0; --p) e->free_pages.push_back(p);
@@ -377,21 +386,6 @@ static int llm_layers(umv_engine* e, const LlmRun& r, bf16* out, cudaStream_t st
     // decode-attention kernel (co-residency in shared memory) costs more streaming rate than the overlap returns -> 0 = full.
     static const int near_attn_stages = getenv("UMV_NEAR_ATTN_STAGES") ? atoi(getenv("UMV_NEAR_ATTN_STAGES")) : 0;
     static const int attn_cluster_max = getenv("UMV_ATTN_CLUSTER") ? atoi(getenv("UMV_ATTN_CLUSTER")) : 8;
-    // Decode with <= 8 rows: the two RMSNorm links of every layer are folded into the linears around them (gemm_decode.cu)
-    static const bool fuse_norm_on = !(getenv("UMV_FUSE_NORM") && atoi(getenv("UMV_FUSE_NORM")) == 0);
-    const bool fuse_norm = fuse_norm_on && partial && r.max_q_len == 1 && decode_linear_supported(M, D) && I % 64 == 0;
-    auto dec_norm_lin = [&](const bf16* w, const bf16* nw, int N, int epi, bf16* y, int ldy, int splits) {
-        DecodeLinear c;
-        c.w = w; c.N = N; c.K = D; c.M = M; c.epi = epi; c.y = y; c.ldy = ldy; c.ws = e->ws; c.splits = splits;
-        c.norm_h = e->h; c.norm_w = nw; c.eps = d.rms_eps;
-        return decode_linear(c, st);
-    };
-    auto dec_resid_lin = [&](const bf16* x, int K, const bf16* w) {      // h += x W^T, split-K over a 4-CTA cluster
-        DecodeLinear c;
-        c.x = x; c.ldx = K; c.w = w; c.N = D; c.K = K; c.M = M; c.epi = EPI_CLUSTER_RESID; c.y = e->h; c.ldy = D; c.splits = 4;
-        return decode_linear(c, st);
-    };
-
     auto norm = [&](const bf16* w0, const bf16* w1, bf16* y) {
         AddNormArgs a;
 
@@ -413,14 +407,10 @@ static int llm_layers(umv_engine* e, const LlmRun& r, bf16* out, cudaStream_t st
 
     for (int li = 0; li < d.layers; ++li) {
         const LayerW& L = e->layers[li];
-        if (!fuse_norm) UMV_TRY(norm(L.ln1[0], L.ln1[1], e->xn));
+        UMV_TRY(norm(L.ln1[0], L.ln1[1], e->xn));
         // ---- q/k/v projections
         RopeAppendArgs ra;
-        if (fuse_norm) {
-            const int s = pick_splits(QN, D, e->sm_count);
-            UMV_TRY(dec_norm_lin(L.wqkv[0], L.ln1[0], QN, EPI_PARTIAL, nullptr, 0, s));
-            ra.partial = e->ws; ra.splits = s; ra.bias = L.bqkv[0];
-        } else if (partial) {
+        if (partial) {
             const int s = pick_splits(QN, D, e->sm_count);
             UMV_TRY(lin(e, e->xn, D, L.wqkv[0], nullptr, nullptr, nullptr, 0, M, QN, D, EPI_PARTIAL, st, GEMM_WEIGHT_MAJOR, e->ws, s, near_attn_stages));
             ra.partial = e->ws; ra.splits = s; ra.bias = L.bqkv[0];
@@ -436,7 +426,7 @@ static int llm_layers(umv_engine* e, const LlmRun& r, bf16* out, cudaStream_t st
         // decode (one query token per sample, understanding expert): the whole rope -> append -> attention -> combine
         // chain is one cluster launch
         static const bool fused_attn = !(getenv("UMV_FUSED_ATTN") && atoi(getenv("UMV_FUSED_ATTN")) == 0);
-        const bool fuse = fused_attn && r.weight_major && r.max_q_len == 1 && !r.gen &&
+        const bool fuse = fused_attn && r.weight_major && r.max_q_len == 1 && !r.gen && e->kv_tmap_ok &&
                           decode_attention_supported(H, Hkv, dh, r.m.max_pages, ra.splits);
         if (fuse) {
             DecodeAttnArgs da;
@@ -444,7 +434,7 @@ static int llm_layers(umv_engine* e, const LlmRun& r, bf16* out, cudaStream_t st
             da.out = e->attn; da.ldo = D; da.positions = r.m.positions; da.kv_len = r.m.kv_len;
             da.page_table = r.m.page_table; da.max_pages = r.m.max_pages; da.inv_freq = e->inv_freq; da.rope_cs = r.m.rope_cs;
             da.qn = L.qn[0]; da.kn = L.kn[0]; da.pool = e->pool; da.layer = li; da.M = M; da.H = H; da.Hkv = Hkv;
-            da.eps = d.rms_eps;
+            da.eps = d.rms_eps; da.kv_tmap = e->kv_tmap_ok ? &e->kv_tmap : nullptr;
             const int blocks = (r.max_kv_len + kPageTokens - 1) / kPageTokens;
             // key ranges per (sample, kv head): as many as fit one wave of 2 CTAs per SM, at most one per 64-key block
             da.cluster = std::max(1, std::min(std::min(attn_cluster_max, blocks), e->sm_count / std::max(1, M * Hkv)));
@@ -467,9 +457,7 @@ static int llm_layers(umv_engine* e, const LlmRun& r, bf16* out, cudaStream_t st
         UMV_TRY(attention_forward(aa, st));
         }
         // ---- output projection + residual
-        if (fuse_norm) {
-            UMV_TRY(dec_resid_lin(e->attn, D, L.wo[0]));
-        } else if (partial) {
+        if (partial) {
             static const int force_s = getenv("UMV_SPLITS_RES") ? atoi(getenv("UMV_SPLITS_RES")) : 0;
             const int s = force_s ? force_s : pick_splits(D, D, e->sm_count);
             UMV_TRY(lin(e, e->attn, D, L.wo[0], nullptr, nullptr, nullptr, 0, M, D, D, EPI_PARTIAL, st, GEMM_WEIGHT_MAJOR, e->ws, s, near_attn_stages));
@@ -482,11 +470,6 @@ static int llm_layers(umv_engine* e, const LlmRun& r, bf16* out, cudaStream_t st
             }
             UMV_TRY(lin(e, e->attn, D, L.wo[E], nullptr, e->h, e->h, D, M, D, D, EPI_RESID, st));
             if (T > 0) UMV_TRY(copy_rows(e->yt, D, r.m.text_rows, e->h, D, T, D, 1, st));
-        }
-        if (fuse_norm) {
-            UMV_TRY(dec_norm_lin(L.wgu[0], L.ln2[0], 2 * I, EPI_SWIGLU, e->act, I, 1));
-            UMV_TRY(dec_resid_lin(e->act, I, L.wdown[0]));
-            continue;
         }
         UMV_TRY(norm(L.ln2[0], L.ln2[1], e->xn));
         // ---- SwiGLU MLP + residual

@@ -1,5 +1,6 @@
 // Engine state: weights in the engine layout, KV page pool + sequences, workspaces.
 #pragma once
+#include <cuda.h>
 #include <cstdint>
 #include <map>
 #include <string>
@@ -110,6 +111,8 @@ struct umv_engine {
 
     // KV
     umv::KVPool pool;
+    CUtensorMap kv_tmap;               // pool as [slot rows, head_dim] for the decode-attention TMA loads
+    bool kv_tmap_ok = false;
     std::vector<int> page_ref, free_pages;
     std::vector<umv::Seq> seqs;
 

@@ -13,7 +13,6 @@ enum Epilogue : int {
     EPI_SWIGLU = 2,    // weight rows interleaved [64 gate | 64 up]; y[:, j] = bf16(bf16(silu(g)) * u), g,u = bf16(acc)
     EPI_RESID = 3,     // y = bf16(bf16(acc + bias) + residual)
     EPI_PARTIAL = 4,   // fp32 split-K partials ws[split][token][feature] (weight-major only)
-    EPI_CLUSTER_RESID = 5,   // decode_linear only: split-K over a CTA cluster, y = bf16(y + bf16(sum)) in place
 };
 
 enum GemmImpl : int { GEMM_AUTO = 0, GEMM_TOKEN_MAJOR = 1, GEMM_WEIGHT_MAJOR = 2, GEMM_SIMPLE = 3 };
@@ -35,22 +34,7 @@ struct LinearCall {
     bool w_static = true;           // false: `w` is produced by the preceding kernel (activation x activation product)
 };
 
-// Decode linears with the neighbouring norm / residual links of the chain folded in (gemm_decode.cu), M <= 8 rows.
-struct DecodeLinear {
-    const bf16* x = nullptr; int ldx = 0;   // [M, K] activations (unused with a fused norm)
-    const bf16* w = nullptr;                // [N, K] weights
-    const bf16* bias = nullptr;
-    bf16* y = nullptr; int ldy = 0;         // output; for EPI_CLUSTER_RESID the residual stream, updated in place
-    float* ws = nullptr; int splits = 1;    // EPI_PARTIAL workspace / split count (EPI_CLUSTER_RESID: cluster size 2, 4 or 8)
-    int M = 0, N = 0, K = 0;
-    int epi = EPI_BF16;                     // EPI_BF16 | EPI_PARTIAL | EPI_SWIGLU (need norm_h), EPI_CLUSTER_RESID (needs x)
-    const bf16* norm_h = nullptr;           // fused RMSNorm: the activation operand is norm_w * rmsnorm(norm_h [M, K])
-    const bf16* norm_w = nullptr;
-    float eps = 1e-6f;
-};
-int decode_linear(const DecodeLinear& c, cudaStream_t stream);
-bool decode_linear_supported(int M, int D);   // M rows, hidden size D (K of the norm-fused linears)
-// shared with gemm.cu
+// shared TMA helpers
 int make_tmap_2d(CUtensorMap* m, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows);
 int gemm_sm_count();
 

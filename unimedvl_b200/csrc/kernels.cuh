@@ -1,6 +1,7 @@
 // Host-side interface of the HBM-bound glue kernels (kernels.cu) and attention (attention.cu).
 #pragma once
 #include <cstdint>
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include "common.cuh"
 
@@ -155,6 +156,7 @@ struct DecodeAttnArgs {
     const bf16* qn = nullptr; const bf16* kn = nullptr;
     KVPool pool; int layer = 0;
     int M = 0, H = 0, Hkv = 0;
+    const CUtensorMap* kv_tmap = nullptr;   // host pointer: the pool as a 2-D tensor [slot rows, 128], 64 x 64 boxes, 128 B swizzle
     int cluster = 8;                  // CTAs (key ranges) per (sample, kv head)
     float eps = 1e-6f;
     TraceSlot* trace = nullptr;
