@@ -1,1 +1,3 @@
-for c in "X=1" "UMV_SPLITS_RES=4"; do echo "== $c"; env $c timeout 200 python tools/decode_trace.py 2>&1 | grep -A12 "per kernel class" | tail -8; done
+mkdir -p gpurun_out
+timeout 600 ncu --set full --import-source on --clock-control none -k regex:"attn_fwd_kernel|rope_append_kernel|add_rmsnorm_kernel" --launch-skip 600 -c 4 -o gpurun_out/r1_t2i_attn -f python tools/t2i_trace.py > gpurun_out/ncu_t2i.log 2>&1
+tail -2 gpurun_out/ncu_t2i.log

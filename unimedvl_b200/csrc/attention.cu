@@ -10,6 +10,8 @@
 // Replaces flash_attn_varlen_func (flash-attn 2.x, external to the reference) at
 // qwen2_navit.py:605-614 (causal = bottom-right aligned, or full) and siglip_navit.py:232-241, and the
 // per-step full KV re-materialisation of qwen2_navit.py:589-600 (the cache is read in place).
+#include <cstdlib>
+
 #include "../../include/umv.h"
 #include "common.cuh"
 #include "gemm.cuh"
@@ -60,7 +62,8 @@ __global__ void __launch_bounds__(ROWS * 2) attn_fwd_kernel(AttnArgs a, float sc
     const int split = blockIdx.z;
     const int G = a.H / a.Hkv;
     const int qlen = a.q_len[b], kvlen = a.kv_len[b];
-    const int r0 = blockIdx.x * kTileRows;
+    // causal: the last row tiles see the most keys -- schedule them first so the grid does not end on its longest CTAs
+    const int r0 = (a.causal ? (int)(gridDim.x - 1 - blockIdx.x) : (int)blockIdx.x) * kTileRows;
     const int nrows = qlen * G;
     if (r0 >= nrows) return;
     const int qs = a.q_start[b];
@@ -744,6 +747,9 @@ int attention_forward(const AttnArgs& a, cudaStream_t s) {
     UMV_REQUIRE(a.H % a.Hkv == 0, UMV_ERR_INVALID, "attention: heads %d not a multiple of kv heads %d", a.H, a.Hkv);
     UMV_REQUIRE(a.splits == 1 || a.ws != nullptr, UMV_ERR_INVALID, "attention: split-KV needs a workspace");
     UMV_REQUIRE(a.ldq % 8 == 0 && a.ldo % 2 == 0, UMV_ERR_INVALID, "attention: q/out row strides must keep 16-byte rows");
+    const char* tc_env = getenv("UMV_ATTN_TC");            // read per call: tests switch paths inside one process
+    const bool tc_on = !(tc_env && atoi(tc_env) == 0);
+    if (tc_on && attention_tc_supported(a)) return attention_tc_forward(a, s);
     if (a.dh == 128) return launch_attn<128, 64>(a, s);
     if (a.dh == 72) return launch_attn<72, 64>(a, s);
     set_error("attention: head_dim %d is not built (128 and 72 are)", a.dh);

@@ -454,6 +454,7 @@ static int llm_layers(umv_engine* e, const LlmRun& r, bf16* out, cudaStream_t st
         aa.q_start = r.m.q_start; aa.q_len = r.m.q_len; aa.kv_len = r.m.kv_len;
         aa.n = r.n_seqs; aa.H = H; aa.Hkv = Hkv; aa.dh = dh; aa.causal = r.causal ? 1 : 0;
         aa.max_q_len = r.max_q_len; aa.max_kv_len = r.max_kv_len; aa.splits = attn_splits; aa.ws = e->attn_ws; aa.total_q = M;
+        aa.kv_tmap = e->kv_tmap_ok ? &e->kv_tmap : nullptr;
         UMV_TRY(attention_forward(aa, st));
         }
         // ---- output projection + residual

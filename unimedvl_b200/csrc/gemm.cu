@@ -552,6 +552,25 @@ int make_tmap_2d(CUtensorMap* m, const void* ptr, uint64_t rows, uint64_t cols, 
     return UMV_OK;
 }
 
+// 3-D bf16 map with 128-byte swizzle: dims (innermost first) {d0, d1, d2}, byte strides of d1 / d2, box {64, b1, b2}.
+int make_tmap_3d(CUtensorMap* m, const void* ptr, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t stride1_bytes,
+                 uint64_t stride2_bytes, uint32_t b1, uint32_t b2) {
+    cuuint64_t dims[3] = {d0, d1, d2};
+    cuuint64_t strides[2] = {stride1_bytes, stride2_bytes};
+    cuuint32_t box[3] = {BK, b1, b2};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), dims, strides, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled(3d) failed (%d) ptr=%p dims=%llu,%llu,%llu strides=%llu,%llu box=64,%u,%u", (int)r, ptr,
+                  (unsigned long long)d0, (unsigned long long)d1, (unsigned long long)d2, (unsigned long long)stride1_bytes,
+                  (unsigned long long)stride2_bytes, b1, b2);
+        return UMV_ERR_CUDA;
+    }
+    return UMV_OK;
+}
+
 int pick_splits(int N, int K, int sm_count) {
     const int a_tiles = (N + BM - 1) / BM;
     const int kb_total = (K + BK - 1) / BK;

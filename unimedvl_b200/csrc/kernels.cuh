@@ -86,7 +86,11 @@ struct AttnArgs {
     float* ws = nullptr;            // [splits][total_q*H][dh+1] fp32 partial outputs + lse
     int total_q = 0;
     TraceSlot* trace = nullptr; TraceSlot* trace_combine = nullptr;
+    const CUtensorMap* kv_tmap = nullptr;   // host pointer: the paged pool as [slot rows, 128] (64 x 64 boxes); enables attention_tc
 };
+// tcgen05 path (attention_tc.cu): head_dim 128, paged KV, at least one 128-row tile of (token, head) rows per sample
+bool attention_tc_supported(const AttnArgs& a);
+int attention_tc_forward(const AttnArgs& a, cudaStream_t s);
 int attention_forward(const AttnArgs& a, cudaStream_t s);
 int attention_init();   // once per process, before any capture
 
