@@ -99,3 +99,38 @@ def test_attention_varlen(ops, dh, H, Hkv, ql, kl, causal):
     s = ulp_stats(o, nm.attention_varlen(q, k, v, ql, kl, causal))
     # both sides round P to bf16 but the online softmax rescales per 64-key block: <= few ulp, tiny rel error
     assert not torch.isnan(o.float()).any() and s["rel_l2"] < 4e-3, s
+
+
+def test_attention_tcgen05_matches_mma_sync(monkeypatch):
+    """The tcgen05 prefill attention (attention_tc.cu) against the mma.sync kernel on the same paged cache: ragged
+    lengths, causal and full masks, a second chunk on top of an existing context (kv_len > q_len), tiles that end inside a
+    128-key block.  Both follow flash-attn's rounding points; they differ in fp32 accumulation order and in the key
+    granularity of the online softmax, i.e. bf16 ulp noise on the layer outputs."""
+    import os
+    from unimedvl_b200 import config as ucfg
+    from unimedvl_b200.engine import Engine
+    dims = ucfg.tiny(llm_layers=2)
+    eng = Engine(dims, max_tokens=1200, max_seqs=4, kv_pages=64, enable_vit=False, enable_gen=False)
+    eng.fill_synthetic(seed=5)
+    eng.finalize()
+    torch.manual_seed(11)
+    lens1, lens2 = [333, 130, 257], [40, 200, 19]
+    for causal in (True, False):
+        outs = {}
+        for tc in ("0", "1"):
+            monkeypatch.setenv("UMV_ATTN_TC", tc)
+            seqs = [eng.seq_new() for _ in lens1]
+            g = torch.Generator(device="cuda").manual_seed(3)
+            x1 = (torch.randn(sum(lens1), dims.llm.hidden, device="cuda", generator=g) * 0.5).bfloat16()
+            x2 = (torch.randn(sum(lens2), dims.llm.hidden, device="cuda", generator=g) * 0.5).bfloat16()
+            pos1 = [p for n in lens1 for p in range(n)]
+            pos2 = [lens1[i] + p for i, n in enumerate(lens2) for p in range(n)]
+            h1 = eng.llm_forward(x1, seqs, lens1, pos1, is_causal=causal, update_kv=True, want_hidden=True)
+            h2 = eng.llm_forward(x2, seqs, lens2, pos2, is_causal=causal, update_kv=True, want_hidden=True)
+            outs[tc] = (h1.float().cpu(), h2.float().cpu())
+            for s_ in seqs:
+                eng.seq_free(s_)
+        for a_, b_ in zip(outs["0"], outs["1"]):
+            assert torch.isfinite(b_).all()
+            rel = (a_ - b_).norm() / a_.norm()
+            assert rel < 5e-3, (causal, float(rel))
