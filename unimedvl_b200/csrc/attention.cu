@@ -473,10 +473,10 @@ attn_decode_kernel(const __grid_constant__ CUtensorMap tmKV, DecodeAttnArgs a, f
         tma_load_2d(dk + 16384, &tmKV, &kvbar[stage], 0, row_v, kEvictNormal);
         tma_load_2d(dk + 24576, &tmKV, &kvbar[stage], 64, row_v, kEvictNormal);
     };
-    if (tid == 0) {
-        for (int j = 0; j < kDecStages; ++j)
-            if (kb_begin + j < kb_end) issue_kv(kb_begin + j, j);
-    }
+    // one issuing lane per block (lane 0 of warp j takes ring slot j): the descriptor fetch + 4 requests of a block cost a
+    // few hundred cycles of a single thread, and every warp has to pass the barrier below before the key loop starts
+    static_assert(kDecStages <= kDecThreads / 32, "one warp per first-pass ring slot");
+    if (lane == 0 && warp < kDecStages && kb_begin + warp < kb_end) issue_kv(kb_begin + warp, warp);
 
     // ---- rows of this step: RMSNorm + RoPE of the query heads (-> sQ) and of the new K row, V row as is (-> page)
     uint2 k_new = make_uint2(0u, 0u), v_new = make_uint2(0u, 0u);

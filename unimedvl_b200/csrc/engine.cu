@@ -425,7 +425,8 @@ static int llm_layers(umv_engine* e, const LlmRun& r, bf16* out, cudaStream_t st
         }
         // decode (one query token per sample, understanding expert): the whole rope -> append -> attention -> combine
         // chain is one cluster launch
-        static const bool fused_attn = !(getenv("UMV_FUSED_ATTN") && atoi(getenv("UMV_FUSED_ATTN")) == 0);
+        const char* fa_env = getenv("UMV_FUSED_ATTN");        // read per call: tests switch paths inside one process
+        const bool fused_attn = !(fa_env && atoi(fa_env) == 0);
         const bool fuse = fused_attn && r.weight_major && r.max_q_len == 1 && !r.gen && e->kv_tmap_ok &&
                           decode_attention_supported(H, Hkv, dh, r.m.max_pages, ra.splits);
         if (fuse) {
