@@ -5,7 +5,7 @@ Public surface (mirrors the reference's objects): ``Engine``
 ``NaiveCache`` (codes/modeling/unimedvl/qwen2_navit.py), ``InterleaveInferencer`` (codes/inferencer.py),
 ``ImageTransform`` (codes/data/transforms.py).  Importing works without a GPU; creating an ``Engine`` does not.
 """
-from . import config  # noqa: F401
+from . import checkpoint, config  # noqa: F401
 from .autoencoder import AutoEncoder  # noqa: F401
 from .bagel import Bagel  # noqa: F401
 from .cache import NaiveCache  # noqa: F401
@@ -13,4 +13,4 @@ from .engine import Engine  # noqa: F401
 from .inferencer import InterleaveInferencer  # noqa: F401
 from .packing import ImageTransform  # noqa: F401
 
-__all__ = ["config", "Engine", "Bagel", "AutoEncoder", "NaiveCache", "InterleaveInferencer", "ImageTransform"]
+__all__ = ["checkpoint", "config", "Engine", "Bagel", "AutoEncoder", "NaiveCache", "InterleaveInferencer", "ImageTransform"]
