@@ -382,9 +382,6 @@ static int llm_layers(umv_engine* e, const LlmRun& r, bf16* out, cudaStream_t st
     const int T = r.gen ? r.m.n_text : 0;
     int pending_splits = 0;     // >0: e->ws holds split-K partials of the last residual-branch linear
 
-    // Tuning knobs (measured on B200, profiles/r1_decode_timeline.md): a shallower TMA ring for the linears next to the
-    // decode-attention kernel (co-residency in shared memory) costs more streaming rate than the overlap returns -> 0 = full.
-    static const int near_attn_stages = getenv("UMV_NEAR_ATTN_STAGES") ? atoi(getenv("UMV_NEAR_ATTN_STAGES")) : 0;
     static const int attn_cluster_max = getenv("UMV_ATTN_CLUSTER") ? atoi(getenv("UMV_ATTN_CLUSTER")) : 8;
     auto norm = [&](const bf16* w0, const bf16* w1, bf16* y) {
         AddNormArgs a;
@@ -412,7 +409,7 @@ static int llm_layers(umv_engine* e, const LlmRun& r, bf16* out, cudaStream_t st
         RopeAppendArgs ra;
         if (partial) {
             const int s = pick_splits(QN, D, e->sm_count);
-            UMV_TRY(lin(e, e->xn, D, L.wqkv[0], nullptr, nullptr, nullptr, 0, M, QN, D, EPI_PARTIAL, st, GEMM_WEIGHT_MAJOR, e->ws, s, near_attn_stages));
+            UMV_TRY(lin(e, e->xn, D, L.wqkv[0], nullptr, nullptr, nullptr, 0, M, QN, D, EPI_PARTIAL, st, GEMM_WEIGHT_MAJOR, e->ws, s));
             ra.partial = e->ws; ra.splits = s; ra.bias = L.bqkv[0];
         } else {
             UMV_TRY(lin(e, e->xn, D, L.wqkv[E], L.bqkv[E], nullptr, e->qkv, QN, M, QN, D, EPI_BF16, st));
@@ -460,9 +457,8 @@ static int llm_layers(umv_engine* e, const LlmRun& r, bf16* out, cudaStream_t st
         }
         // ---- output projection + residual
         if (partial) {
-            static const int force_s = getenv("UMV_SPLITS_RES") ? atoi(getenv("UMV_SPLITS_RES")) : 0;
-            const int s = force_s ? force_s : pick_splits(D, D, e->sm_count);
-            UMV_TRY(lin(e, e->attn, D, L.wo[0], nullptr, nullptr, nullptr, 0, M, D, D, EPI_PARTIAL, st, GEMM_WEIGHT_MAJOR, e->ws, s, near_attn_stages));
+            const int s = pick_splits(D, D, e->sm_count);
+            UMV_TRY(lin(e, e->attn, D, L.wo[0], nullptr, nullptr, nullptr, 0, M, D, D, EPI_PARTIAL, st, GEMM_WEIGHT_MAJOR, e->ws, s));
             pending_splits = s;
         } else {
             if (T > 0) {
@@ -483,8 +479,7 @@ static int llm_layers(umv_engine* e, const LlmRun& r, bf16* out, cudaStream_t st
         }
         UMV_TRY(lin(e, e->xn, D, L.wgu[E], nullptr, nullptr, e->act, I, M, 2 * I, D, EPI_SWIGLU, st));
         if (partial) {
-            static const int force_s = getenv("UMV_SPLITS_RES") ? atoi(getenv("UMV_SPLITS_RES")) : 0;
-            const int s = force_s ? force_s : pick_splits(D, I, e->sm_count);
+            const int s = pick_splits(D, I, e->sm_count);
             UMV_TRY(lin(e, e->act, I, L.wdown[0], nullptr, nullptr, nullptr, 0, M, D, I, EPI_PARTIAL, st, GEMM_WEIGHT_MAJOR, e->ws, s));
             pending_splits = s;
         } else {

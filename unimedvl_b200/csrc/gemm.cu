@@ -15,6 +15,7 @@
 // qwen2_navit.py:541-543,555-562,617-620; modeling_qwen2.py:234-235; bagel.py:1295;
 // siglip_navit.py:190,216-218,243,256-258; modeling_utils.py:108,120-122.
 #include <cuda.h>
+#include <algorithm>
 #include <cstdarg>
 #include <cstdlib>
 #include <cstring>
@@ -678,19 +679,38 @@ int linear_forward(const LinearCall& c, cudaStream_t stream) {
         return UMV_OK;
     }
     if (impl == GEMM_TOKEN_MAJOR) {
+        // Tile shape: single CTA (128 x BN) or CTA pair (256 x BN, gemm_2cta.cu), BN 256 or 128, by a cost model in units of
+        // one 128 x 256 single-CTA tile time: waves of the persistent grid x per-tile factor (measured on B200 at the 14B
+        // shapes, tools/gemm_bench.py: pair tiles 0.90; 128-wide tiles 0.54 single / 0.47 pair, plus up to 0.15 when the
+        // activation matrix no longer fits L2 and every extra column of tiles re-reads it from HBM).
+        const char* pair_env = getenv("UMV_2CTA");              // read per call: tests switch paths inside one process
+        const bool pair_ok = !(pair_env && atoi(pair_env) == 0) && linear_2cta_supported(c);
+        static const int force_bn = getenv("UMV_BN") ? atoi(getenv("UMV_BN")) : 0;
+        const long m1 = (c.M + BM - 1) / BM, m2 = (c.M + 2 * BM - 1) / (2 * BM);
+        const long n256 = (c.N + 255) / 256, n128 = (c.N + 127) / 128;
+        const long sms = g_sm_count, pairs = g_sm_count / 2;
+        auto waves = [](long tiles, long slots) { return (double)((tiles + slots - 1) / slots); };
+        const double spill = std::min(1.0, (double)c.M * c.K * 2 / 300e6) * 0.15;
         if (c.epi == EPI_SWIGLU) {
-            return (c.N % 256 == 0) ? launch_tc<256, 2, false>(c, stream) : launch_tc<128, 2, false>(c, stream);
+            const bool wide = c.N % 256 == 0;
+            if (pair_ok && wide && waves(m2 * n256, pairs) * 0.90 < waves(m1 * n256, sms)) return linear_2cta_forward(c, stream, 256);
+            return wide ? launch_tc<256, 2, false>(c, stream) : launch_tc<128, 2, false>(c, stream);
         }
         if (c.N > 128) {
-            // 128x256 tiles unless wave quantisation on the 148 persistent CTAs costs more than the narrower tile's
-            // lower efficiency (128x128: half the work per tile, B tile re-read twice as often: ~8 % slower per flop)
-            static const int force_bn = getenv("UMV_BN") ? atoi(getenv("UMV_BN")) : 0;
-            const long m_tiles = (c.M + BM - 1) / BM;
-            const long t256 = m_tiles * ((c.N + 255) / 256), t128 = m_tiles * ((c.N + 127) / 128);
-            const double cost256 = (double)((t256 + g_sm_count - 1) / g_sm_count);
-            const double cost128 = (double)((t128 + g_sm_count - 1) / g_sm_count) * 0.5 * 1.08;
-            const bool use128 = force_bn ? force_bn == 128 : cost128 < cost256;
-            return use128 ? launch_tc<128, 0, false>(c, stream) : launch_tc<256, 0, false>(c, stream);
+            double best = 1e30;
+            int best_pair = 0, best_bn = 256;
+            auto consider = [&](double cost, int pair, int bn) {
+                if (force_bn && bn != force_bn) return;
+                if (cost < best) { best = cost; best_pair = pair; best_bn = bn; }
+            };
+            consider(waves(m1 * n256, sms) * 1.0, 0, 256);
+            consider(waves(m1 * n128, sms) * (0.54 + spill), 0, 128);
+            if (pair_ok) {
+                consider(waves(m2 * n256, pairs) * 0.90, 1, 256);
+                consider(waves(m2 * n128, pairs) * (0.47 + spill), 1, 128);
+            }
+            if (best_pair) return linear_2cta_forward(c, stream, best_bn);
+            return best_bn == 128 ? launch_tc<128, 0, false>(c, stream) : launch_tc<256, 0, false>(c, stream);
         }
         if (c.N > 64) return launch_tc<128, 0, false>(c, stream);
         return launch_tc<64, 0, false>(c, stream);

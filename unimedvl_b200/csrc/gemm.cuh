@@ -40,6 +40,10 @@ int make_tmap_3d(CUtensorMap* m, const void* ptr, uint64_t d0, uint64_t d1, uint
                  uint64_t stride2_bytes, uint32_t b1, uint32_t b2);
 int gemm_sm_count();
 
+// Token-major linear on CTA pairs (gemm_2cta.cu, tcgen05 cta_group::2): 256-row tiles, each CTA stages half of the weight tile.
+bool linear_2cta_supported(const LinearCall& c);
+int linear_2cta_forward(const LinearCall& c, cudaStream_t stream, int bn);      // bn: 256 or 128 (SwiGLU: 256)
+
 // Returns 0 or a umv_status.  For EPI_PARTIAL the caller sums ws[0..splits) in a fixed order.
 int linear_forward(const LinearCall& c, cudaStream_t stream);
 // y = epilogue(sum of `splits` fp32 partials + bias) [+ residual] for epi in {EPI_BF16, EPI_GELU, EPI_RESID}.

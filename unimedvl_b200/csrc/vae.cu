@@ -500,36 +500,24 @@ int umv_vae_encode_moments(umv_engine* e, const void* x, int32_t n, int32_t Hh, 
     const size_t full = (size_t)Hh * Ww;
     UMV_TRY(vae_reserve(e, max_act_elems(h, w, false), full * 9 * 128 + 64, (size_t)h * w * h * w));
     const VaeHalf& H = V.enc;
-    const int dbg_stop = getenv("UMV_VAE_STOP") ? atoi(getenv("UMV_VAE_STOP")) : -1;   // development aid: dump a0 after N stages
-    int stage = 0;
-#define UMV_DBG_STAGE(CH)                                                                                          \
-    if (dbg_stop >= 0 && stage++ == dbg_stop) {                                                                    \
-        return cudaMemcpyAsync(out, V.a0, (size_t)im.H * im.W * (CH) * 2, cudaMemcpyDeviceToDevice, st) == cudaSuccess ? UMV_OK : UMV_ERR_CUDA; \
-    }
     for (int i = 0; i < n; ++i) {
         const bf16* xi = static_cast<const bf16*>(x) + (size_t)i * 3 * Hh * Ww;
         Img im{Hh, Ww};
         launch_k(nchw_to_nhwc_kernel, dim3((unsigned)((3 * full + 255) / 256)), dim3(256), 0, st, xi, V.a1, 3, (int)full, 1.f, 0.f, 0);
         UMV_LAUNCH_CHECK("nchw_to_nhwc_kernel");
         UMV_TRY(conv(e, H.conv_in, V.a1, im, V.a0, nullptr, 0, 1, nullptr, st));
-        UMV_DBG_STAGE(V.ch)
         for (int l = 0; l < V.nlev; ++l) {
             for (const VaeRes& r : H.levels[l].blocks) {
                 UMV_TRY(res_block(e, r, im, st));
-                UMV_DBG_STAGE(r.cout)
             }
             if (H.levels[l].has_resample) {
                 UMV_TRY(conv(e, H.levels[l].resample, V.a0, im, V.a1, &im, 0, 2, nullptr, st));
                 std::swap(V.a0, V.a1);
-                UMV_DBG_STAGE(H.levels[l].resample.cout)
             }
         }
         UMV_TRY(res_block(e, H.mid1, im, st));
-        UMV_DBG_STAGE(H.mid1.cout)
         UMV_TRY(attn_block(e, H.attn, im, st));
-        UMV_DBG_STAGE(H.attn.c)
         UMV_TRY(res_block(e, H.mid2, im, st));
-        UMV_DBG_STAGE(H.mid2.cout)
         UMV_TRY(gn(e, H.norm_out, V.a0, im, V.a1, 1, st));
         UMV_TRY(conv(e, H.conv_out, V.a1, im, V.a2, nullptr, 0, 1, nullptr, st));
         const int HW = im.H * im.W, C = 2 * V.z;
