@@ -52,7 +52,7 @@ for i in range(1, n):
 tot = sum(a[1] for a in agg.values())
 for k, (c, s) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:24]:
     out.append(f"| `{k}` | {c} | {s / c:.1f} | {s / 1e3:.3f} | {100 * s / tot:.1f}% |\n")
-ig = [i for i in range(n) if nm[i].startswith("gemm<256,2,0>")]
+ig = [i for i in range(n) if nm[i].startswith(("gemm<256,2,0>", "gemm2<256,2>"))]
 if ig:
     i0 = ig[len(ig) // 4]               # a gate/up launch of the image prefill
     out.append("\n## around one image-prefill layer (us; start/wait/end relative to the first row's start)\n\n"

@@ -274,8 +274,9 @@ int layernorm_bf16(const bf16* x, const bf16* w, const bf16* b, bf16* y, int M, 
 // One warp per (row, head-slot): slots [0,H) = q heads, [H,H+Hkv) = k heads, [H+Hkv,H+2Hkv) = v heads.
 // head_dim 128: lane l owns elements 4l..4l+3; the rotate_half partner (i +- 64) lives in lane l^16.
 // One CTA per row: the rope angles (and their bf16-rounded cos / sin), the row's norm-weight choice and its KV slot are
-// evaluated once and reused by the H + 2 Hkv head slots the CTA's 8 warps walk over (one warp per slot, lane = 4 columns).
-__global__ void __launch_bounds__(256, 4) rope_append_kernel(RopeAppendArgs a) {
+// evaluated once and reused by the H + 2 Hkv head slots the CTA's warps walk over (one warp per slot, lane = 4 columns).
+constexpr int kRopeWarps = 4;        // 128 threads per row: more rows resident per SM (the kernel is a latency chain per row)
+__global__ void __launch_bounds__(kRopeWarps * 32, 8) rope_append_kernel(RopeAppendArgs a) {
     pdl_launch_dependents();
     trace_start(a.trace);
     pdl_wait();
@@ -291,7 +292,7 @@ __global__ void __launch_bounds__(256, 4) rope_append_kernel(RopeAppendArgs a) {
     if (!a.partial) {
 #pragma unroll
         for (int i = 0; i < kBatch; ++i) {
-            const int slot = warp + 8 * i;
+            const int slot = warp + kRopeWarps * i;
             raw[i] = make_uint2(0u, 0u);
             if (slot < slots) raw[i] = *reinterpret_cast<const uint2*>(a.qkv + (size_t)row * ncols + slot * a.dh + lane * 4);
         }
@@ -346,7 +347,7 @@ __global__ void __launch_bounds__(256, 4) rope_append_kernel(RopeAppendArgs a) {
         }
     };
     if (a.partial) {
-        for (int slot = warp; slot < slots; slot += 8) {
+        for (int slot = warp; slot < slots; slot += kRopeWarps) {
             const int col = slot * a.dh + lane * 4;
             float acc[4] = {0.f, 0.f, 0.f, 0.f};
             for (int s = 0; s < a.splits; ++s) {
@@ -359,17 +360,17 @@ __global__ void __launch_bounds__(256, 4) rope_append_kernel(RopeAppendArgs a) {
             process(slot, x);
         }
     } else {
-        for (int s0 = warp; s0 < slots; s0 += 8 * kBatch) {
+        for (int s0 = warp; s0 < slots; s0 += kRopeWarps * kBatch) {
             if (s0 != warp) {
 #pragma unroll
                 for (int i = 0; i < kBatch; ++i) {
-                    const int slot = s0 + 8 * i;
+                    const int slot = s0 + kRopeWarps * i;
                     if (slot < slots) raw[i] = *reinterpret_cast<const uint2*>(a.qkv + (size_t)row * ncols + slot * a.dh + lane * 4);
                 }
             }
 #pragma unroll
             for (int i = 0; i < kBatch; ++i) {
-                const int slot = s0 + 8 * i;
+                const int slot = s0 + kRopeWarps * i;
                 if (slot < slots) {
                     const float2 f0 = unpack2(raw[i].x), f1 = unpack2(raw[i].y);
                     const float x[4] = {f0.x, f0.y, f1.x, f1.y};
@@ -407,7 +408,7 @@ int rope_append(const RopeAppendArgs& a0, cudaStream_t s) {
     UMV_REQUIRE(a.dh == 128, UMV_ERR_UNSUPPORTED, "rope_append: head_dim %d (only 128 is built)", a.dh);
     UMV_REQUIRE(a.rope_cs != nullptr, UMV_ERR_INVALID, "rope_append: the per-forward cos/sin table (rope_table) is required");
     const int blocks = a.M;
-    launch_k(rope_append_kernel, dim3(blocks), dim3(256), 0, s, a);
+    launch_k(rope_append_kernel, dim3(blocks), dim3(kRopeWarps * 32), 0, s, a);
     UMV_LAUNCH_CHECK("rope_append_kernel");
     return UMV_OK;
 }
