@@ -219,7 +219,7 @@ static int build_runtime(umv_engine* e) {
     e->free_pages.clear();
     for (int p = d.kv_pages - 1; p >= 0; --p) e->free_pages.push_back(p);
     // metadata staging
-    e->meta_bytes = (size_t)64 * 1024 + (size_t)20 * Mmax + (size_t)4 * d.max_seqs * 3 * (std::min(d.kv_pages, 8192) + 8);
+    e->meta_bytes = (size_t)64 * 1024 + (size_t)28 * Mmax + (size_t)4 * d.max_seqs * 3 * (std::min(d.kv_pages, 8192) + 8);
     for (int i = 0; i < umv_engine::kMetaRing; ++i) {
         if (cudaMallocHost(reinterpret_cast<void**>(&e->meta_host[i]), e->meta_bytes) != cudaSuccess) {
             set_error("cudaMallocHost(%zu) failed", e->meta_bytes);
@@ -349,7 +349,10 @@ struct LlmRun {
 };
 
 int lin(umv_engine* e, const bf16* x, int ldx, const bf16* w, const bf16* bias, const bf16* res, bf16* y, int ldy, int M,
-               int N, int K, int epi, cudaStream_t st, int impl, float* ws, int splits, int stages) {
+               int N, int K, int epi, cudaStream_t st, int impl, float* ws, int splits, int stages, const int* res_rows,
+               bf16* res_gather_tmp) {
+    // res_rows: the residual of row i is res[res_rows[i]] (row stride ldy).  The split-K finish kernel reads it in place;
+    // every other path gets the rows gathered into res_gather_tmp first.
     LinearCall c;
     c.stages = stages;
     c.x = x; c.ldx = ldx; c.w = w; c.bias = bias; c.residual = res; c.y = y; c.ldy = ldy;
@@ -368,8 +371,13 @@ int lin(umv_engine* e, const bf16* x, int ldx, const bf16* w, const bf16* bias, 
             c.impl = GEMM_WEIGHT_MAJOR; c.epi = EPI_PARTIAL; c.ws = e->ws; c.splits = s;
             c.bias = nullptr; c.residual = nullptr; c.y = nullptr;
             UMV_TRY(linear_forward(c, st));
-            return splitk_finish(e->ws, s, M, N, bias, res, y, ldy, epi, st);
+            return splitk_finish(e->ws, s, M, N, bias, res, y, ldy, epi, st, res_rows);
         }
+    }
+    if (res_rows) {
+        UMV_REQUIRE(res_gather_tmp != nullptr, UMV_ERR_INVALID, "lin: residual row map without a gather buffer");
+        UMV_TRY(copy_rows(res, ldy, res_rows, res_gather_tmp, ldy, M, N, 0, st));
+        c.residual = res_gather_tmp;
     }
     return linear_forward(c, st);
 }
@@ -389,6 +397,7 @@ static int llm_layers(umv_engine* e, const LlmRun& r, bf16* out, cudaStream_t st
         a.h = e->h; a.M = M; a.D = D; a.eps = d.rms_eps; a.w0 = w0; a.w1 = w1 ? w1 : w0;
         a.row_sel = r.gen ? r.m.row_sel : nullptr;
         a.y = y;
+        if (T > 0 && y == e->xn) { a.y2 = e->xt; a.row_slot = r.m.text_slot; }     // text rows also land gathered in xt
         if (pending_splits > 0) { a.partial = e->ws; a.splits = pending_splits; }
         pending_splits = 0;
         return add_rmsnorm(a, st);
@@ -413,8 +422,7 @@ static int llm_layers(umv_engine* e, const LlmRun& r, bf16* out, cudaStream_t st
             ra.partial = e->ws; ra.splits = s; ra.bias = L.bqkv[0];
         } else {
             UMV_TRY(lin(e, e->xn, D, L.wqkv[E], L.bqkv[E], nullptr, e->qkv, QN, M, QN, D, EPI_BF16, st));
-            if (T > 0) {
-                UMV_TRY(copy_rows(e->xn, D, r.m.text_rows, e->xt, D, T, D, 0, st));
+            if (T > 0) {      // xt = text rows of xn (written by the norm kernel)
                 UMV_TRY(lin(e, e->xt, D, L.wqkv[0], L.bqkv[0], nullptr, e->yt, QN, T, QN, D, EPI_BF16, st));
                 UMV_TRY(copy_rows(e->yt, QN, r.m.text_rows, e->qkv, QN, T, QN, 1, st));
             }
@@ -463,8 +471,7 @@ static int llm_layers(umv_engine* e, const LlmRun& r, bf16* out, cudaStream_t st
         } else {
             if (T > 0) {
                 UMV_TRY(copy_rows(e->attn, D, r.m.text_rows, e->xt, D, T, D, 0, st));
-                UMV_TRY(copy_rows(e->h, D, r.m.text_rows, e->ht, D, T, D, 0, st));
-                UMV_TRY(lin(e, e->xt, D, L.wo[0], nullptr, e->ht, e->yt, D, T, D, D, EPI_RESID, st));
+                UMV_TRY(lin(e, e->xt, D, L.wo[0], nullptr, e->h, e->yt, D, T, D, D, EPI_RESID, st, 0, nullptr, 1, 0, r.m.text_rows, e->ht));
             }
             UMV_TRY(lin(e, e->attn, D, L.wo[E], nullptr, e->h, e->h, D, M, D, D, EPI_RESID, st));
             if (T > 0) UMV_TRY(copy_rows(e->yt, D, r.m.text_rows, e->h, D, T, D, 1, st));
@@ -472,10 +479,8 @@ static int llm_layers(umv_engine* e, const LlmRun& r, bf16* out, cudaStream_t st
         UMV_TRY(norm(L.ln2[0], L.ln2[1], e->xn));
         // ---- SwiGLU MLP + residual
         if (T > 0) {
-            UMV_TRY(copy_rows(e->xn, D, r.m.text_rows, e->xt, D, T, D, 0, st));
             UMV_TRY(lin(e, e->xt, D, L.wgu[0], nullptr, nullptr, e->actt, I, T, 2 * I, D, EPI_SWIGLU, st));
-            UMV_TRY(copy_rows(e->h, D, r.m.text_rows, e->ht, D, T, D, 0, st));
-            UMV_TRY(lin(e, e->actt, I, L.wdown[0], nullptr, e->ht, e->yt, D, T, D, I, EPI_RESID, st));
+            UMV_TRY(lin(e, e->actt, I, L.wdown[0], nullptr, e->h, e->yt, D, T, D, I, EPI_RESID, st, 0, nullptr, 1, 0, r.m.text_rows, e->ht));
         }
         UMV_TRY(lin(e, e->xn, D, L.wgu[E], nullptr, nullptr, e->act, I, M, 2 * I, D, EPI_SWIGLU, st));
         if (partial) {
@@ -812,7 +817,7 @@ int llm_run(umv_engine* e, const bf16* x, int n_seqs, const int32_t* seqs, const
         r.max_kv_len = std::max(r.max_kv_len, sq[b]->len + q_lens[b]);
     }
     MetaBuilder mb;
-    UMV_TRY(meta_begin(e, &mb, (size_t)(n_seqs * 16 + 64) + (size_t)M * 20 + (size_t)n_seqs * max_pages * 4));
+    UMV_TRY(meta_begin(e, &mb, (size_t)(n_seqs * 16 + 64) + (size_t)M * 24 + (size_t)n_seqs * max_pages * 4));
     CallMeta& m = r.m;
     m.max_pages = max_pages;
     int* hq = mb.put<int>(nullptr, n_seqs + 1, &m.q_start);
@@ -843,6 +848,9 @@ int llm_run(umv_engine* e, const bf16* x, int n_seqs, const int32_t* seqs, const
         mb.put<uint8_t>(row_is_gen, M, &m.row_sel);
         mb.put<int>(text.data(), text.size(), &m.text_rows);
         m.n_text = (int)text.size();
+        std::vector<int> slot(M, -1);
+        for (size_t i = 0; i < text.size(); ++i) slot[text[i]] = (int)i;
+        mb.put<int>(slot.data(), M, &m.text_slot);
     }
     UMV_TRY(meta_commit(e, &mb, st));
     if (x) UMV_CUDA_OK(cudaMemcpy2DAsync(e->h, (size_t)D * 2, x, (size_t)D * 2, (size_t)D * 2, M, cudaMemcpyDeviceToDevice, st));

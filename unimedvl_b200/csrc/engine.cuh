@@ -50,6 +50,7 @@ struct CallMeta {
     int* row_kvpos = nullptr;   // [M]
     int* page_table = nullptr;  // [n][max_pages]
     int* text_rows = nullptr;   // [T] rows routed to the understanding expert (gen mode)
+    int* text_slot = nullptr;   // [M] inverse map: index into text_rows, or -1
     uint8_t* row_sel = nullptr; // [M]
     const float* rope_cs = nullptr;   // decode loop: per-step cos | sin table [n][dh]
     int max_pages = 0, n_text = 0;
@@ -82,7 +83,8 @@ int engine_alloc(umv_engine* e, void** out, size_t bytes);
 void engine_reg(umv_engine* e, const std::string& name, bf16* dst, int64_t rows, int64_t cols, int ndim, int conv_k, int conv_cin,
                 float bound, float mean);
 int lin(umv_engine* e, const bf16* x, int ldx, const bf16* w, const bf16* bias, const bf16* res, bf16* y, int ldy, int M, int N,
-        int K, int epi, cudaStream_t st, int impl = 0, float* ws = nullptr, int splits = 1, int stages = 0);
+        int K, int epi, cudaStream_t st, int impl = 0, float* ws = nullptr, int splits = 1, int stages = 0,
+        const int* res_rows = nullptr, bf16* res_gather_tmp = nullptr);
 int llm_run(umv_engine* e, const bf16* x, int n_seqs, const int32_t* seqs, const int32_t* q_lens, const int32_t* positions,
             const uint8_t* row_is_gen, int is_causal, int update_kv, bf16* out, cudaStream_t st);
 }  // namespace umv

@@ -422,7 +422,8 @@ __global__ void gemm_simple_kernel(const bf16* __restrict__ x, int ldx, const bf
 constexpr int kFinishMaxSplits = 16;
 __global__ void __launch_bounds__(256) splitk_finish_kernel(const float* __restrict__ ws, int splits, int M, int N,
                                                             const bf16* __restrict__ bias, const bf16* __restrict__ residual,
-                                                            bf16* __restrict__ y, int ldy, int epi, TraceSlot* trace) {
+                                                            bf16* __restrict__ y, int ldy, int epi, const int* __restrict__ res_rows,
+                                                            TraceSlot* trace) {
     pdl_launch_dependents();
     trace_start(trace);
     pdl_wait();
@@ -442,7 +443,7 @@ __global__ void __launch_bounds__(256) splitk_finish_kernel(const float* __restr
         }
         U4 bv = {0, 0, 0, 0}, rv = {0, 0, 0, 0};
         if (bias) bv = ldg16(bias + n);
-        if (epi == EPI_RESID) rv = ldg16(residual + (size_t)row * ldy + n);
+        if (epi == EPI_RESID) rv = ldg16(residual + (size_t)(res_rows ? res_rows[row] : row) * ldy + n);
         float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
 #pragma unroll
         for (int sp = 0; sp < kFinishMaxSplits; ++sp) {
@@ -471,13 +472,13 @@ __global__ void __launch_bounds__(256) splitk_finish_kernel(const float* __restr
 }
 
 int splitk_finish(const float* ws, int splits, int M, int N, const bf16* bias, const bf16* residual, bf16* y, int ldy, int epi,
-                  cudaStream_t stream) {
+                  cudaStream_t stream, const int* res_rows) {
     UMV_REQUIRE(splits >= 1 && splits <= kFinishMaxSplits && N % 8 == 0 && ldy % 8 == 0, UMV_ERR_INVALID,
                 "splitk_finish: splits=%d N=%d ldy=%d", splits, N, ldy);
     UMV_REQUIRE(epi == EPI_BF16 || epi == EPI_GELU || epi == EPI_RESID, UMV_ERR_INVALID, "splitk_finish: epilogue %d", epi);
     const int total = M * (N / 8);
     cudaError_t e = launch_k(splitk_finish_kernel, dim3((total + 255) / 256), dim3(256), 0, stream, ws, splits, M, N, bias, residual, y,
-                             ldy, epi, trace_next("splitk_finish"));
+                             ldy, epi, res_rows, trace_next("splitk_finish"));
     ++g_launches;
     if (e == cudaSuccess) e = cudaGetLastError();
     if (e != cudaSuccess) {

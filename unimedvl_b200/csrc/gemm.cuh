@@ -47,8 +47,9 @@ int linear_2cta_forward(const LinearCall& c, cudaStream_t stream, int bn);      
 // Returns 0 or a umv_status.  For EPI_PARTIAL the caller sums ws[0..splits) in a fixed order.
 int linear_forward(const LinearCall& c, cudaStream_t stream);
 // y = epilogue(sum of `splits` fp32 partials + bias) [+ residual] for epi in {EPI_BF16, EPI_GELU, EPI_RESID}.
+// res_rows (optional): the residual of output row i is residual[res_rows[i]] (rows gathered out of a larger matrix)
 int splitk_finish(const float* ws, int splits, int M, int N, const bf16* bias, const bf16* residual, bf16* y, int ldy, int epi,
-                  cudaStream_t stream);
+                  cudaStream_t stream, const int* res_rows = nullptr);
 // Heuristic split count for a weight-major (decode) GEMM: fills the 148 SMs without starving a split.
 int pick_splits(int N, int K, int sm_count);
 // Must be called once before the first tcgen05 launch (resolves cuTensorMapEncodeTiled, sets smem attrs).

@@ -94,6 +94,7 @@ __global__ void __launch_bounds__(kNormThreads) add_rmsnorm_kernel(AddNormArgs a
     ss = block_sum(ss, red);
     const float inv = 1.0f / sqrtf(ss / (float)a.D + a.eps);
     bf16* yrow = a.y + (size_t)row * a.D;
+    const int slot2 = (a.y2 && a.row_slot) ? a.row_slot[row] : -1;
 #pragma unroll
     for (int c = 0; c < NC; ++c) {
         const int ch = threadIdx.x + c * kNormThreads;
@@ -106,6 +107,7 @@ __global__ void __launch_bounds__(kNormThreads) add_rmsnorm_kernel(AddNormArgs a
                 o[j] = pack2(wf.x * rbf(v[c][2 * j] * inv), wf.y * rbf(v[c][2 * j + 1] * inv));   // R2
             }
             stg16(yrow + ch * 8, U4{o[0], o[1], o[2], o[3]});
+            if (slot2 >= 0) stg16(a.y2 + (size_t)slot2 * a.D + ch * 8, U4{o[0], o[1], o[2], o[3]});
         }
     }
     trace_end<false>(a.trace);
@@ -188,7 +190,7 @@ int add_rmsnorm(const AddNormArgs& a0, cudaStream_t s) {
     a.trace = trace_next("add_rmsnorm");
     UMV_REQUIRE(a.D % 8 == 0 && a.D <= 8 * kNormThreads * kNormMaxChunks, UMV_ERR_UNSUPPORTED,
                 "add_rmsnorm: D=%d must be a multiple of 8 and <= %d", a.D, 8 * kNormThreads * kNormMaxChunks);
-    if (a.partial && !a.delta && !a.row_sel && a.splits <= kNormDecMaxSplits && a.D <= 8 * kNormDecThreads && a.M <= 64) {
+    if (a.partial && !a.delta && !a.row_sel && !a.y2 && a.splits <= kNormDecMaxSplits && a.D <= 8 * kNormDecThreads && a.M <= 64) {
         launch_k(add_rmsnorm_splitk_kernel, dim3(a.M), dim3(kNormDecThreads), 0, s, a);
         UMV_LAUNCH_CHECK("add_rmsnorm_splitk_kernel");
         return UMV_OK;

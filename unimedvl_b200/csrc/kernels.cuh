@@ -29,6 +29,8 @@ struct AddNormArgs {
     const bf16* w1 = nullptr;       // norm weight for rows with row_sel == 1 (generation expert)
     const uint8_t* row_sel = nullptr;
     bf16* y = nullptr;              // [M, D] normalised output (null: only the residual add)
+    bf16* y2 = nullptr;             // optional compact copy: rows with row_slot[m] >= 0 are also written to y2[row_slot[m]]
+    const int* row_slot = nullptr;  //   (the understanding-expert rows of a gen-mode forward, gathered for their own linears)
     int M = 0, D = 0;
     float eps = 1e-6f;
     TraceSlot* trace = nullptr;
