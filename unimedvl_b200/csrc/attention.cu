@@ -303,17 +303,21 @@ __global__ void attn_combine_kernel(AttnArgs a) {
 // Fused decode attention: ONE launch per layer for the chain
 //   split-K reduce (+bias) of the q/k/v projection -> q/k RMSNorm -> RoPE -> KV append -> attention over the paged
 //   cache -> split-KV combine.
-// A thread-block cluster of `S` CTAs owns one (sample, kv head); CTA r covers a contiguous range of 64-key blocks.
-// The kernel is on the critical path of the decode chain and moves little data (18 MB per layer at B=8, ctx 1.1k), so
-// it is organised around the number of DEPENDENT memory round trips, not around bandwidth:
-//   1. after griddepcontrol.wait every load that does not depend on another load is issued at once: kv_len, position,
-//      the sample's page-table row (-> shared memory), all split-K partials of this CTA's q/k/v rows, bias, norm
-//      weights, inv_freq;
-//   2. as soon as the page row is known, the K/V tiles of up to three blocks (the CTA's whole range at ctx <= 1.5k) are
-//      in flight together (cp.async ring), while the warps normalise / rotate the G query rows and the new K/V row;
-//   3. inside a CTA the 4 compute warps split each 64-key block (only G <= 8 query rows exist); partial (m, l, O) are
+// A thread-block cluster of `S` CTAs (one CTA per SM) owns one (sample, kv head); CTA r covers a contiguous, balanced range
+// of 64-key blocks.  The kernel is on the critical path of the decode chain and moves little data (18 MB per layer at B=8,
+// ctx 1.1k), so it is organised around the number of DEPENDENT memory round trips, not around bandwidth:
+//   1. norm weights and bias (constants) are read before griddepcontrol.wait; after it every load that does not depend on
+//      another load is issued at once: kv_len, the sample's page-table row (-> shared memory), the per-step cos/sin table,
+//      all split-K partials of this CTA's q/k/v rows;
+//   2. as soon as the page row is known, up to six blocks (the CTA's whole range at ctx <= 1.5k) are requested from TMA
+//      -- 64 x 64 swizzled boxes straight out of the paged pool, one issuing lane and one mbarrier per ring slot -- while
+//      the warps normalise / rotate the G query rows and the new K/V row; the new row goes to the page in global memory and
+//      is patched into the staged tile in shared memory (no reload);
+//   3. the 8 warps take two blocks at a time (4 key quarters each; only G <= 7 query rows exist); partial (m, l, O) are
 //      merged across warps in shared memory and then PUSHED to the CTA that finishes the head through distributed
 //      shared memory (remote stores, no remote round trip), one cluster barrier, local combine, store.
+// In-graph timeline (us after the dependency wait, B200): loads landed 1.5, Q ready 2.6, first K/V block 4.3, key loop done
+// 5.5, merged 6.2, cluster barrier 8.2, stored 8.8 (profiles/r1_decode_timeline.md).
 // Numerics identical to rope_append_kernel + attn_fwd_kernel + attn_combine_kernel (und mode, R4-R6).
 constexpr int kDecThreads = 256;
 constexpr int kDecStages = 6;                                           // 64-key blocks in flight per CTA (one CTA per SM)
