@@ -170,3 +170,26 @@ def test_decode_attention_fused_matches_unfused(monkeypatch, n_seqs, ctx):
     rel = (outs["1"] - outs["0"]).norm() / outs["0"].norm()
     assert rel < 2e-2, float(rel)
     assert (outs["1"].argmax(-1) == outs["0"].argmax(-1)).float().mean() > 0.9
+
+
+def test_vit_padded_head_tcgen05_matches_mma_sync(monkeypatch):
+    """ViT tower with its q|k|v written into 128-column zero-padded heads and attended by the tcgen05 kernel (softmax scale
+    and output width of the real head_dim 72) against the head_dim-72 mma.sync path: ragged images, one of them shorter than
+    a 128-row tile boundary multiple."""
+    from unimedvl_b200 import config as ucfg
+    from unimedvl_b200.engine import Engine
+    dims = ucfg.tiny()
+    eng = Engine(dims, max_tokens=1024, max_seqs=2, kv_pages=8, enable_gen=False)
+    eng.fill_synthetic(seed=9)
+    eng.finalize()
+    lens = [400, 130, 256]
+    g = torch.Generator().manual_seed(2)
+    pixels = torch.randn(sum(lens), dims.vit.patch_dim, generator=g)
+    pos = torch.cat([torch.randperm(dims.vit.num_positions, generator=g)[:n] for n in lens])
+    outs = {}
+    for tc in ("0", "1"):
+        monkeypatch.setenv("UMV_ATTN_TC", tc)
+        outs[tc] = eng.vit_embed(pixels, pos, lens).float().cpu()
+    assert torch.isfinite(outs["1"]).all()
+    rel = (outs["1"] - outs["0"]).norm() / outs["0"].norm()
+    assert rel < 5e-3, float(rel)

@@ -1,4 +1,6 @@
-// Prefill / flow attention on the 5th-generation tensor cores (head_dim 128, paged KV).
+// Prefill / flow / ViT attention on the 5th-generation tensor cores (head_dim 128; paged KV, or packed K / V matrices whose
+// heads are zero-padded to 128 columns -- the ViT's 72-wide heads: the kernel is paced by the softmax pipe, not by the
+// MMAs, so the padded contraction is free).
 //
 // One CTA owns 128 query rows of ONE kv head -- rows are (token, head-in-group) pairs, 18 tokens x 7 heads at the 14B dims,
 // so a K/V block is fetched once for the whole GQA group -- and walks the visible keys in blocks of 128:
@@ -46,8 +48,8 @@ static_assert(kKeys % 32 == 0, "whole 32-column TMEM loads per thread");
 constexpr int kTcThreads = 64 + kSplit * 128;      // TMA warp, MMA warp, 4 * kSplit softmax warps
 
 __global__ void __launch_bounds__(kTcThreads, 1)
-attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV, AttnArgs a, int G, int TOK,
-               float scale_log2) {
+attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+               const __grid_constant__ CUtensorMap tmV, AttnArgs a, int G, int TOK, float scale_log2) {
     pdl_launch_dependents();
     trace_start(a.trace);
     extern __shared__ uint8_t smem_raw[];
@@ -81,7 +83,8 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmQ);
-        tma_prefetch_desc(&tmKV);
+        tma_prefetch_desc(&tmK);
+        tma_prefetch_desc(&tmV);
     }
     if (warp == 1) {
         if (lane == 0) {
@@ -123,12 +126,18 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
             for (int j = 0; j < nkb; ++j) {
                 const int stage = j & 1;
                 int row_k[2], row_v[2];
+                int col0 = 0;                      // column of the kv head's first element in the K / V matrices
 #pragma unroll
                 for (int pg = 0; pg < 2; ++pg) {
                     const int kb64 = 2 * j + pg;
-                    const int page = kb64 < a.max_pages ? a.page_table[(size_t)b * a.max_pages + kb64] : 0;
-                    row_k[pg] = (int)(a.pool.tile_offset(page, a.layer, 0, kvh) / HD);
-                    row_v[pg] = (int)(a.pool.tile_offset(page, a.layer, 1, kvh) / HD);
+                    if (a.paged) {
+                        const int page = kb64 < a.max_pages ? a.page_table[(size_t)b * a.max_pages + kb64] : 0;
+                        row_k[pg] = (int)(a.pool.tile_offset(page, a.layer, 0, kvh) / HD);
+                        row_v[pg] = (int)(a.pool.tile_offset(page, a.layer, 1, kvh) / HD);
+                    } else {                       // packed [Tk, Hkv * 128] matrices: rows past the sample's keys are masked
+                        row_k[pg] = row_v[pg] = a.k_start[b] + kb64 * 64;
+                        col0 = kvh * HD;
+                    }
                 }
                 mbar_wait(&k_empty[stage], ((j >> 1) & 1) ^ 1u);
                 mbar_expect_tx(&k_full[stage], kTile);
@@ -136,14 +145,14 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
                 for (int pg = 0; pg < 2; ++pg)
 #pragma unroll
                     for (int half = 0; half < 2; ++half)
-                        tma_load_2d(sK + stage * kTile + half * kHalf + pg * 8192, &tmKV, &k_full[stage], half * 64, row_k[pg], kEvictNormal);
+                        tma_load_2d(sK + stage * kTile + half * kHalf + pg * 8192, &tmK, &k_full[stage], col0 + half * 64, row_k[pg], kEvictNormal);
                 mbar_wait(&v_empty[stage], ((j >> 1) & 1) ^ 1u);
                 mbar_expect_tx(&v_full[stage], kTile);
 #pragma unroll
                 for (int pg = 0; pg < 2; ++pg)
 #pragma unroll
                     for (int half = 0; half < 2; ++half)
-                        tma_load_2d(sV + stage * kTile + half * kHalf + pg * 8192, &tmKV, &v_full[stage], half * 64, row_v[pg], kEvictNormal);
+                        tma_load_2d(sV + stage * kTile + half * kHalf + pg * 8192, &tmV, &v_full[stage], col0 + half * 64, row_v[pg], kEvictNormal);
             }
         }
     } else if (warp == 1) {
@@ -282,7 +291,8 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         mbar_wait(pv_done, (nkb - 1) & 1);
         tc_fence_after();
         const float inv = lt > 0.f ? 1.f / lt : 0.f;
-        bf16* dst = a.out + (size_t)(qs + t0 + (valid ? tok_l : 0)) * a.ldo + (kvh * G + (valid ? head_l : 0)) * HD + part * kKeys;
+        const int odh = a.out_dh ? a.out_dh : HD;             // real head width of the output (padded-head callers: < 128)
+        bf16* dst = a.out + (size_t)(qs + t0 + (valid ? tok_l : 0)) * a.ldo + (kvh * G + (valid ? head_l : 0)) * odh + part * kKeys;
 #pragma unroll
         for (int c = 0; c < kKeys / 32; ++c) tmem_ld32(lane_base + kColO + part * kKeys + c * 32, *reinterpret_cast<uint32_t(*)[32]>(&r[c * 32]));
         tmem_ld_wait();
@@ -293,7 +303,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
 #pragma unroll
                 for (int i = 0; i < 4; ++i)
                     o[i] = pack2(__uint_as_float(r[8 * q + 2 * i]) * inv, __uint_as_float(r[8 * q + 2 * i + 1]) * inv);
-                stg16(dst + q * 8, U4{o[0], o[1], o[2], o[3]});
+                if (part * kKeys + q * 8 < odh) stg16(dst + q * 8, U4{o[0], o[1], o[2], o[3]});
             }
         }
     }
@@ -306,10 +316,18 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
 }  // namespace
 
 bool attention_tc_supported(const AttnArgs& a) {
-    if (!(a.paged && a.dh == HD && a.kv_tmap && a.splits == 1 && a.Hkv > 0 && a.H % a.Hkv == 0)) return false;
+    if (!(a.dh == HD && a.splits == 1 && a.Hkv > 0 && a.H % a.Hkv == 0)) return false;
+    if (a.paged) {
+        if (!a.kv_tmap) return false;
+    } else {
+        if (!(a.k && a.v && a.k_start && a.total_k > 0 && a.ldk % 8 == 0 && a.ldv % 8 == 0 &&
+              ((reinterpret_cast<uintptr_t>(a.k) | reinterpret_cast<uintptr_t>(a.v)) & 15) == 0))
+            return false;
+    }
     const int G = a.H / a.Hkv;
     if (G > 16 || a.max_q_len * G < TQ) return false;            // at least one full tile of rows
-    return (a.ldq % 8 == 0) && (a.ldo % 8 == 0) && ((reinterpret_cast<uintptr_t>(a.q) & 15) == 0) &&
+    const int odh = a.out_dh ? a.out_dh : HD;
+    return (a.ldq % 8 == 0) && (a.ldo % 8 == 0) && (odh % 8 == 0) && odh <= HD && ((reinterpret_cast<uintptr_t>(a.q) & 15) == 0) &&
            ((reinterpret_cast<uintptr_t>(a.out) & 15) == 0);
 }
 
@@ -327,16 +345,21 @@ int attention_tc_forward(const AttnArgs& a0, cudaStream_t s) {
         }
         attr_set = true;
     }
-    CUtensorMap tmQ;
+    CUtensorMap tmQ, tmK, tmV;
     // q rows viewed as [tokens][heads][128]: a box of 64 columns x G heads x TOK tokens is the tile's [row][128 B] image
     rc = make_tmap_3d(&tmQ, a.q, HD, a.H, a.total_q, (uint64_t)HD * 2, (uint64_t)a.ldq * 2, G, TOK);
     if (rc) return rc;
+    if (a.paged) {
+        tmK = tmV = *a.kv_tmap;
+    } else {
+        if ((rc = make_tmap_2d(&tmK, a.k, a.total_k, (uint64_t)a.Hkv * HD, a.ldk, 64))) return rc;
+        if ((rc = make_tmap_2d(&tmV, a.v, a.total_k, (uint64_t)a.Hkv * HD, a.ldv, 64))) return rc;
+    }
     a.trace = trace_next("attn_tc");
-    const CUtensorMap tmKV = *a.kv_tmap;
     a.kv_tmap = nullptr;
-    const float scale_log2 = (1.0f / sqrtf((float)HD)) * 1.4426950408889634f;
+    const float scale_log2 = (a.scale > 0.f ? a.scale : 1.0f / sqrtf((float)HD)) * 1.4426950408889634f;
     dim3 grid((a.max_q_len + TOK - 1) / TOK, a.n * a.Hkv);
-    cudaError_t e = launch_k(attn_tc_kernel, grid, dim3(kTcThreads), kSmemBytes, s, tmQ, tmKV, a, G, TOK, scale_log2);
+    cudaError_t e = launch_k(attn_tc_kernel, grid, dim3(kTcThreads), kSmemBytes, s, tmQ, tmK, tmV, a, G, TOK, scale_log2);
     ++g_launches;
     if (e == cudaSuccess) e = cudaGetLastError();
     if (e != cudaSuccess) {

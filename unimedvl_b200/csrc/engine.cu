@@ -181,6 +181,14 @@ static int build_runtime(umv_engine* e) {
     UMV_TRY(dev_alloc(e, &e->qkv, (size_t)Mmax * e->w_qkv));
     UMV_TRY(dev_alloc(e, &e->attn, (size_t)Mmax * e->w_h));
     UMV_TRY(dev_alloc(e, &e->rope_tab, (size_t)Mmax * e->dh));
+    if (d.enable_vit && d.vit_heads > 0) {
+        const int dhv = d.vit_hidden / d.vit_heads;
+        if (dhv % 8 == 0 && dhv < 128) {           // pad columns are zeroed once and never written again
+            const size_t n = (size_t)Mmax * 3 * d.vit_heads * 128;
+            UMV_TRY(dev_alloc(e, &e->vit_qkvp, n));
+            UMV_CUDA_OK(cudaMemset(e->vit_qkvp, 0, n * sizeof(bf16)));
+        }
+    }
     UMV_TRY(dev_alloc(e, &e->act, (size_t)Mmax * e->w_act));
     UMV_TRY(dev_alloc(e, &e->logits, (size_t)64 * d.vocab));
     const int Tmax = std::min(Mmax, 8 * d.max_seqs);
@@ -901,16 +909,32 @@ int umv_vit_embed(umv_engine* e, const float* pixels, const int64_t* pos_ids, co
     UMV_TRY(f32_to_bf16_padded(pixels, xb, M, d.vit_patch_dim, Kp, st));
     UMV_TRY(lin(e, xb, Kp, e->vit_patch_w, e->vit_patch_b, nullptr, hv, Dv, M, Dv, Kp, EPI_BF16, st));
     UMV_TRY(gather_add_rows(hv, e->vit_pos, pos_ids, M, Dv, st));
+    const int dhv = Dv / d.vit_heads, ldp = 3 * d.vit_heads * 128;
+    const char* tc_env = getenv("UMV_ATTN_TC");
+    const bool tc_vit = !(tc_env && atoi(tc_env) == 0) && e->vit_qkvp && e->gemm_impl == 0 && M > 64 && max_len >= 128 && Dv % 8 == 0;
     for (int li = 0; li < d.vit_layers; ++li) {
         const VitLayerW& L = e->vit[li];
         UMV_TRY(layernorm_bf16(hv, L.ln1w, L.ln1b, e->xn, M, Dv, d.vit_eps, st));
-        UMV_TRY(lin(e, e->xn, Dv, L.wqkv, L.bqkv, nullptr, e->qkv, 3 * Dv, M, 3 * Dv, Dv, EPI_BF16, st));
         AttnArgs aa;
-        aa.q = e->qkv; aa.ldq = 3 * Dv; aa.k = e->qkv + Dv; aa.v = e->qkv + 2 * Dv; aa.ldk = aa.ldv = 3 * Dv;
         aa.out = e->attn; aa.ldo = Dv;
         aa.q_start = dq; aa.k_start = dq; aa.q_len = dl; aa.kv_len = dl;
-        aa.n = n_images; aa.H = d.vit_heads; aa.Hkv = d.vit_heads; aa.dh = Dv / d.vit_heads; aa.causal = 0;
+        aa.n = n_images; aa.H = d.vit_heads; aa.Hkv = d.vit_heads; aa.causal = 0;
         aa.max_q_len = max_len; aa.max_kv_len = max_len; aa.total_q = M;
+        if (tc_vit) {
+            // q|k|v written with every 72-wide head padded to 128 zero-filled columns: the tcgen05 attention kernel then runs
+            // as for head_dim 128 (its softmax pipe, not the contraction length, sets the pace) with the real softmax scale
+            LinearCall c;
+            c.x = e->xn; c.ldx = Dv; c.w = L.wqkv; c.bias = L.bqkv; c.y = e->vit_qkvp; c.ldy = ldp; c.M = M; c.N = 3 * Dv; c.K = Dv;
+            c.epi = EPI_BF16; c.impl = GEMM_TOKEN_MAJOR; c.out_head_dim = dhv; c.out_head_pad = 128;
+            UMV_TRY(linear_forward(c, st));
+            aa.q = e->vit_qkvp; aa.k = e->vit_qkvp + d.vit_heads * 128; aa.v = e->vit_qkvp + 2 * d.vit_heads * 128;
+            aa.ldq = aa.ldk = aa.ldv = ldp;
+            aa.dh = 128; aa.out_dh = dhv; aa.scale = 1.0f / sqrtf((float)dhv); aa.total_k = M;
+        } else {
+            UMV_TRY(lin(e, e->xn, Dv, L.wqkv, L.bqkv, nullptr, e->qkv, 3 * Dv, M, 3 * Dv, Dv, EPI_BF16, st));
+            aa.q = e->qkv; aa.ldq = 3 * Dv; aa.k = e->qkv + Dv; aa.v = e->qkv + 2 * Dv; aa.ldk = aa.ldv = 3 * Dv;
+            aa.dh = dhv;
+        }
         UMV_TRY(attention_forward(aa, st));
         UMV_TRY(lin(e, e->attn, Dv, L.wo, L.bo, hv, hv, Dv, M, Dv, Dv, EPI_RESID, st));
         UMV_TRY(layernorm_bf16(hv, L.ln2w, L.ln2b, e->xn, M, Dv, d.vit_eps, st));

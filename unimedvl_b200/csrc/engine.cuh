@@ -120,6 +120,7 @@ struct umv_engine {
 
     // workspaces
     umv::bf16 *h = nullptr, *xn = nullptr, *qkv = nullptr, *attn = nullptr, *act = nullptr, *logits = nullptr;
+    umv::bf16* vit_qkvp = nullptr;   // [max_tokens, 3 * vit_heads * 128]: ViT q|k|v with heads zero-padded to 128 columns (tcgen05 attention)
     umv::bf16 *xt = nullptr, *ht = nullptr, *yt = nullptr, *actt = nullptr;   // text-row (understanding expert) staging, gen mode
     float* ws = nullptr;          // split-K partials
     size_t ws_elems = 0;

@@ -81,6 +81,7 @@ struct GemmParams {
     int epi;
     int early_a;    // weight-major: A (weights) is constant data and may be fetched before griddepcontrol.wait
     TraceSlot* trace;
+    int hd, hp;     // output head padding (LinearCall::out_head_dim / out_head_pad), 0 = off
     int stages;     // ring depth of this launch (<= TcCfg::kStages); a shallow ring leaves shared memory for a neighbour CTA
 };
 
@@ -282,7 +283,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                                     }
                                     o[j] = pack2(v0, v1);
                                 }
-                                stg16(p.y + (size_t)row * p.ldy + n, U4{o[0], o[1], o[2], o[3]});
+                                const int nd = p.hd ? (n / p.hd) * p.hp + n % p.hd : n;
+                                stg16(p.y + (size_t)row * p.ldy + nd, U4{o[0], o[1], o[2], o[3]});
                             }
                         }
                     }
@@ -614,6 +616,11 @@ static int launch_tc(const LinearCall& c, cudaStream_t stream) {
     p.ws = c.ws;
     p.epi = c.epi;
     p.early_a = c.w_static ? 1 : 0;
+    p.hd = c.out_head_dim; p.hp = c.out_head_pad;
+    if (p.hd && (SWAP || MODE != 0 || c.epi != EPI_BF16 || p.hd % 8 != 0 || p.hp % 8 != 0)) {
+        set_error("linear: output head padding exists only on the token-major bf16 epilogue with 8-column aligned heads");
+        return UMV_ERR_UNSUPPORTED;
+    }
     {
         char nm[32];
         snprintf(nm, sizeof nm, "gemm<%d,%d,%d> N%d K%d", BN, MODE, (int)SWAP, c.N, c.K);
@@ -660,6 +667,10 @@ int linear_forward(const LinearCall& c, cudaStream_t stream) {
         }
         int rc = gemm_init();
         if (rc) return rc;
+    }
+    if (c.out_head_dim && impl != GEMM_TOKEN_MAJOR) {
+        set_error("linear: output head padding needs the token-major path (M=%d N=%d K=%d)", c.M, c.N, c.K);
+        return UMV_ERR_UNSUPPORTED;
     }
     if (c.epi == EPI_PARTIAL && impl != GEMM_WEIGHT_MAJOR) {
         set_error("linear: split-K partial epilogue exists only on the weight-major path");

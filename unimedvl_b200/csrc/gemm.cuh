@@ -30,6 +30,8 @@ struct LinearCall {
     int M = 0, N = 0, K = 0;
     int epi = EPI_BF16;
     int impl = GEMM_AUTO;
+    int out_head_dim = 0, out_head_pad = 0;   // token-major EPI_BF16 only: output column n lands at (n / dim) * pad + n % dim
+                                    //   (heads of `dim` columns padded to `pad`; the pad columns are never written)
     int stages = 0;                 // 0: deepest TMA ring that fits; else ring depth (shared memory left for a co-resident kernel)
     bool w_static = true;           // false: `w` is produced by the preceding kernel (activation x activation product)
 };

@@ -34,6 +34,7 @@ struct Gemm2Params {
     const bf16* bias;
     const bf16* residual;
     int epi;
+    int hd, hp;          // output head padding (LinearCall::out_head_dim / out_head_pad), 0 = off
     int stages;
     TraceSlot* trace;
 };
@@ -242,7 +243,8 @@ gemm_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                                     }
                                     o[j] = pack2(v0, v1);
                                 }
-                                stg16(p.y + (size_t)row * p.ldy + n, U4{o[0], o[1], o[2], o[3]});
+                                const int nd = p.hd ? (n / p.hd) * p.hp + n % p.hd : n;
+                                stg16(p.y + (size_t)row * p.ldy + nd, U4{o[0], o[1], o[2], o[3]});
                             }
                         }
                     }
@@ -298,6 +300,9 @@ int launch_2cta(const LinearCall& c, cudaStream_t stream) {
     p.n_tiles = (c.N + BN - 1) / BN;
     p.tokens = c.M; p.features = c.N;
     p.y = c.y; p.ldy = c.ldy; p.bias = c.bias; p.residual = c.residual; p.epi = c.epi;
+    p.hd = c.out_head_dim; p.hp = c.out_head_pad;
+    UMV_REQUIRE(!p.hd || (MODE == 0 && c.epi == EPI_BF16 && p.hd % 8 == 0 && p.hp % 8 == 0), UMV_ERR_UNSUPPORTED,
+                "linear: output head padding exists only on the bf16 epilogue with 8-column aligned heads");
     p.stages = C2::kStages;
     static bool attr_set = false;
     if (!attr_set) {

@@ -89,6 +89,11 @@ struct AttnArgs {
     int total_q = 0;
     TraceSlot* trace = nullptr; TraceSlot* trace_combine = nullptr;
     const CUtensorMap* kv_tmap = nullptr;   // host pointer: the paged pool as [slot rows, 128] (64 x 64 boxes); enables attention_tc
+    // head_dim-padded callers (ViT: 72 real columns in 128-wide, zero-padded heads): softmax scale and output width of the
+    // real head_dim; total_k = rows of the un-paged K / V matrices (tensor-map extent)
+    float scale = 0.f;              // 0: 1 / sqrt(dh)
+    int out_dh = 0;                 // 0: dh; else out holds heads of out_dh columns and only those are stored
+    int total_k = 0;
 };
 // tcgen05 path (attention_tc.cu): head_dim 128, paged KV, at least one 128-row tile of (token, head) rows per sample
 bool attention_tc_supported(const AttnArgs& a);
