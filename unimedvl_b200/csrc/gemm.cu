@@ -583,6 +583,9 @@ int pick_splits(int N, int K, int sm_count) {
     const int max_by_k = kb_total / 8 > 0 ? kb_total / 8 : 1;   // keep >= 8 k-blocks (128 KB of weights) per split
     if (s > max_by_k) s = max_by_k;
     if (s > 16) s = 16;
+    // 112 CTAs already stream at the full HBM rate (measured), and every extra split is another fp32 partial the consumer
+    // has to read on the critical path: do not go beyond 4 splits once 4 of them occupy three quarters of the SMs
+    if (s > 4 && 4 * a_tiles * 4 >= 3 * sm_count) s = 4;
     if (s < 1) s = 1;
     const int per = (kb_total + s - 1) / s;
     return (kb_total + per - 1) / per;        // effective count: no empty split
