@@ -249,11 +249,18 @@ class Bagel:
     @torch.no_grad()
     def generate_text(self, past_key_values, packed_key_value_indexes, key_values_lens, packed_start_tokens,
                       packed_query_position_ids, max_length: int, do_sample: bool = False, temperature: float = 1.0,
-                      end_token_id: Optional[int] = None, seed: int = 0, chunk: int = 32):
+                      end_token_id: Optional[int] = None, seed: int = 0, chunk: int = 32, stop: str = "first"):
         """bagel.py:1236-1317.  Returns LongTensor [steps, B] whose row 0 is the start tokens.  The loop runs
         on the device; with ``end_token_id`` set it proceeds in chunks and stops -- as the reference does --
         when SAMPLE 0 produces the end token (bagel.py:1313), trimming the cache to the steps the reference
-        would have executed."""
+        would have executed.
+
+        ``stop="each"`` (extension): every sample stops at its OWN end token.  The loop ends
+        when all samples have produced it (or at ``max_length``), each sequence's cache is trimmed to the steps that sample
+        executed, and rows of a finished sample are filled with ``end_token_id`` -- column b then equals what sample b
+        alone would return with the reference rule."""
+        if stop not in ("first", "each"):
+            raise ValueError(f"generate_text: stop={stop!r} (expected 'first' or 'each')")
         B = len(self._ints(key_values_lens))
         h = paged_handle(past_key_values, self.engine, B)
         self._check_kv(h, key_values_lens, packed_key_value_indexes, [0] * B, None, "generate_text")
@@ -262,6 +269,7 @@ class Bagel:
         pos = self._ints(packed_query_position_ids)
         temp = float(temperature) if do_sample else 0.0
         rows, done = [], 0
+        executed = [None] * B                   # steps executed by sample b up to and including the one that produced EOS
         while done < max_length:
             n = max_length - done if end_token_id is None else min(chunk, max_length - done)
             toks, nxt = self.engine.generate_text(h.seqs, tokens, pos, n, temperature=temp, seed=seed + done,
@@ -269,16 +277,28 @@ class Bagel:
             rows.append(toks)
             done += n
             if end_token_id is not None:
-                fed = torch.cat([toks[1:, 0], nxt[:1]]).tolist()      # token computed at each executed step, sample 0
-                if end_token_id in fed:
-                    executed = done - n + fed.index(end_token_id) + 1
-                    out = torch.cat(rows, dim=0)[:executed]
+                fed = torch.cat([toks[1:], nxt[None]], dim=0)          # token computed at each executed step, per sample
+                hit = (fed == end_token_id)
+                for b in range(B if stop == "each" else 1):
+                    if executed[b] is None and bool(hit[:, b].any()):
+                        executed[b] = done - n + int(torch.nonzero(hit[:, b])[0]) + 1
+                if stop == "first" and executed[0] is not None:
+                    out = torch.cat(rows, dim=0)[:executed[0]]
                     for s, l0 in zip(h.seqs, start_lens):
-                        self.engine.seq_truncate(s, l0 + executed)
+                        self.engine.seq_truncate(s, l0 + executed[0])
                     return out
+                if stop == "each" and all(e is not None for e in executed):
+                    break
             tokens = nxt.tolist()
             pos = [p + n for p in pos]
-        return torch.cat(rows, dim=0)
+        out = torch.cat(rows, dim=0)
+        if stop == "each" and end_token_id is not None:
+            steps = [e if e is not None else done for e in executed]
+            out = out[:max(steps)].clone()
+            for b, (s, l0) in enumerate(zip(h.seqs, start_lens)):
+                out[steps[b]:, b] = end_token_id
+                self.engine.seq_truncate(s, l0 + steps[b])
+        return out
 
     @torch.no_grad()
     def chat(self, tokenizer, new_token_ids, image_transform, images, prompt, max_length: int, do_sample: bool = False,
