@@ -7,9 +7,10 @@
 One step = one pass of the hot path over one batch per GPU:
   value : the 128-step greedy decode of 8 samples (ctx 1058 -> 1185) from a KV cache already
           resident in HBM -- Bagel.generate_text through the engine (device loop, CUDA-graph replay);
-  e2e   : the whole VQA job through the reference-facing call (Bagel.vqa_generate): pinned HOST
-          pixels / prompt ids -> H2D -> ViT + connector -> image prefill -> prompt prefill -> 128-step
-          decode -> D2H of the tokens; tokens/s counts the same 8 x 128 decoded tokens.
+  e2e   : the whole VQA job through the reference-facing call (Bagel.vqa_generate_images): pinned HOST
+          uint8 images / prompt ids -> H2D -> normalise + patchify on the device -> ViT + connector ->
+          image prefill -> prompt prefill -> 128-step decode -> D2H of the tokens; tokens/s counts the same
+          8 x 128 decoded tokens.
 N > 1: one process per GPU (torchrun), requests sharded data-parallel (weak scaling: 8 samples per
 GPU), one NCCL all_gather of the output tokens per step; time = max over ranks.
 --impl reference: the reference's CPU forward, restated by oracle/ (the reference itself cannot
@@ -88,17 +89,19 @@ def synthetic_job(rank: int):
     from PIL import Image
     from unimedvl_b200 import packing, synth
     tf = packing.ImageTransform(980, 378, 14, max_pixels=2_007_040)
-    toks, pos, lens, prompts = [], [], [], []
+    toks, pos, lens, prompts, images = [], [], [], [], []
     for i in range(B_PER_GPU):
         gid = rank * B_PER_GPU + i
-        t = tf(Image.fromarray(synth.synthetic_image(gid, IMG, IMG)))
+        raw = synth.synthetic_image(gid, IMG, IMG)
+        images.append(torch.from_numpy(raw.copy()).pin_memory())     # 448x448 passes the reference's resize rule unchanged
+        t = tf(Image.fromarray(raw))
         toks.append(packing.patchify(t, 14))
         pos.append(packing.flattened_position_ids(t.size(1), t.size(2), 14, 70))
         lens.append(toks[-1].shape[0])
         prompts.append(synth.synthetic_prompt_ids(gid, PROMPT_TOKENS))
     pixels = torch.cat(toks, 0).pin_memory()
     pos_ids = torch.cat(pos, 0).pin_memory()
-    return pixels, pos_ids, lens, prompts
+    return pixels, pos_ids, lens, prompts, images
 
 
 # ------------------------------------------------------------------------------------------------
@@ -262,7 +265,7 @@ def run_engine(args, rank: int, local_rank: int, world: int):
     eng.finalize()
     model = Bagel(eng, dims)
     tok = dict(ucfg.QWEN25_TOKEN_IDS)
-    pixels, pos_ids, lens, prompts = synthetic_job(rank)
+    pixels, pos_ids, lens, prompts, images = synthetic_job(rank)
 
     # ---- resident context for the device-timed decode: the same prefill the e2e path performs
     cache = NaiveCache(dims.llm.layers)
@@ -288,7 +291,7 @@ def run_engine(args, rank: int, local_rank: int, world: int):
         return dp.gather_tokens(t, world * B)       # one NCCL all_gather of the output tokens
 
     def e2e_step():
-        t = model.vqa_generate(pixels, pos_ids, lens, prompts, tok, DECODE_STEPS)
+        t = model.vqa_generate_images(images, prompts, tok, DECODE_STEPS)
         return dp.gather_tokens(t.cuda(), world * B) if world > 1 else t
 
     def barrier():
@@ -326,7 +329,7 @@ def run_engine(args, rank: int, local_rank: int, world: int):
     e2e_steps = max(1, min(args.steps, 5))
     ms_e2e = timed(e2e_step, e2e_steps)
     e2e_value = tokens_per_step * e2e_steps / (ms_e2e / 1e3)
-    h2d = pixels.numel() * 4 + pos_ids.numel() * 8 + sum(len(p) + 2 for p in prompts) * 8 + B * 2 * 8
+    h2d = sum(im.numel() for im in images) + sum(len(p) + 2 for p in prompts) * 8 + B * 2 * 8
     d2h = B * DECODE_STEPS * 8
 
     if rank != 0:
@@ -373,7 +376,8 @@ def run_engine(args, rank: int, local_rank: int, world: int):
         "ms_per_decode_forward": round(step_ms, 4),
         "e2e": {"value": round(e2e_value, 1), "unit": "tok/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                 "ms_per_step": round(ms_e2e / e2e_steps, 2), "steps": e2e_steps,
-                "path": "Bagel.vqa_generate: pinned host pixels/ids -> ViT -> image+prompt prefill -> 128-step decode -> host tokens"},
+                "path": "Bagel.vqa_generate_images: pinned host uint8 images + prompt ids -> H2D -> normalise/patchify on device -> ViT -> "
+                        "image+prompt prefill -> 128-step decode -> host tokens"},
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "kernel": "gemm_tc_kernel<16,2,true> (weight-major gate/up + SwiGLU, M=8)",
                      "achieved": round(achieved, 1), "peak": peak, "peak_source": peak_src, "unit": "GB/s",

@@ -96,6 +96,15 @@ int umv_pages_free(umv_engine* e, int32_t* n);
 int umv_vit_embed(umv_engine* e, const float* pixels, const int64_t* pos_ids, const int32_t* seqlens,
                   int32_t n_images, void* out, void* stream);
 
+/* ---- image pre-processing on the device: ToTensor + Normalize(0.5, 0.5) + patchify of
+ * uint8 HWC images, i.e. data/transforms.py:104-115 (`x / 255`, `(x - 0.5) / 0.5` in fp32) followed by
+ * data/data_utils.py:43-50 (patch vectors in (p_row, p_col, channel) order) and the flattened position ids of
+ * data_utils.py:53-58.  images: device uint8, image i is [h_i, w_i, 3] at byte offset offsets[i]; hw: host i32
+ * [n_images][2] (multiples of `patch`; resizing stays with the caller); out_pixels: f32 [sum_i h_i w_i / patch^2,
+ * 3 patch^2]; out_pos_ids: i64 [n_tokens] (row * max_per_side + col).  Bit-identical to the host transforms. */
+int umv_patchify_u8(const uint8_t* images, const int64_t* offsets, const int32_t* hw, int32_t n_images, int32_t patch,
+                    int32_t max_per_side, float* out_pixels, int64_t* out_pos_ids, void* stream);
+
 /* ---- embedding rows: language_model.model.embed_tokens (bagel.py:438,577,1264) ------------- */
 int umv_embed_tokens(umv_engine* e, const int64_t* ids, int32_t n, void* out, void* stream);
 

@@ -1,6 +1,7 @@
 """Host packing vs fixtures produced by the reference's Bagel.prepare_* (tests/golden/make_golden.py, G1).
 Integer / fp32 host work -> bit-exact."""
 import numpy as np
+import pytest
 import torch
 from PIL import Image
 
@@ -67,3 +68,28 @@ def test_empty_and_single():
     assert d["packed_text_ids"].tolist() == [TOK["bos_token_id"], TOK["eos_token_id"]] and lens == [2] and rope == [2]
     s = packing.prepare_start_tokens([], [], TOK)
     assert s["packed_start_tokens"].numel() == 0 and s["packed_key_value_indexes"].numel() == 0
+
+
+@pytest.mark.gpu
+def test_device_patchify_is_bit_identical_to_the_host_transforms():
+    """umv_patchify_u8 (ToTensor + Normalize + patchify + position ids on the device) vs ImageTransform + patchify +
+    flattened_position_ids on the host, ragged image sizes."""
+    import torch
+    from unimedvl_b200 import config as ucfg, packing, synth
+    from unimedvl_b200.engine import Engine
+    from PIL import Image
+    dims = ucfg.tiny()
+    eng = Engine(dims, max_tokens=64, max_seqs=1, kv_pages=4, enable_gen=False)
+    tf = packing.ImageTransform(980, 14, 14, max_pixels=2_007_040)
+    sizes = [(56, 84), (448, 448), (14, 14), (70, 28)]
+    imgs = [torch.from_numpy(synth.synthetic_image(i, h, w).copy()) for i, (h, w) in enumerate(sizes)]
+    pix, pos, lens = eng.patchify_u8([im.pin_memory() for im in imgs])
+    ref_pix, ref_pos = [], []
+    for im in imgs:
+        t = tf(Image.fromarray(im.numpy()))
+        assert tuple(t.shape[1:]) == tuple(im.shape[:2])             # these sizes pass the resize rule unchanged
+        ref_pix.append(packing.patchify(t, dims.vit.patch))
+        ref_pos.append(packing.flattened_position_ids(t.size(1), t.size(2), dims.vit.patch, dims.vit_max_num_patch_per_side))
+    assert lens == [p.shape[0] for p in ref_pix]
+    assert torch.equal(pix.cpu(), torch.cat(ref_pix, 0))
+    assert torch.equal(pos.cpu(), torch.cat(ref_pos, 0))

@@ -23,7 +23,7 @@ eng.fill_synthetic(0)
 eng.finalize()
 model = Bagel(eng, dims)
 tok = dict(ucfg.QWEN25_TOKEN_IDS)
-pixels, pos_ids, lens, prompts = bench.synthetic_job(0)
+pixels, pos_ids, lens, prompts, _ = bench.synthetic_job(0)
 model.vqa_generate(pixels, pos_ids, lens, prompts, tok, 3)
 torch.cuda.synchronize()
 CAP, NL = 8192, 32

@@ -319,6 +319,15 @@ class Bagel:
 
     # ------------------------------------------------------------------ batched VQA job (bench / serving)
     @torch.no_grad()
+    @torch.no_grad()
+    def vqa_generate_images(self, images: Sequence[torch.Tensor], prompt_ids: Sequence[Sequence[int]], new_token_ids: dict,
+                            max_length: int) -> torch.Tensor:
+        """vqa_generate from uint8 [H, W, 3] images (already at their ViT size: sides multiples of the patch) in pinned host
+        memory: the images go up as uint8 and are normalised / patchified on the device (Engine.patchify_u8)."""
+        pixels, pos, lens = self.engine.patchify_u8(images)
+        return self.vqa_generate(pixels, pos, lens, prompt_ids, new_token_ids, max_length)
+
+    @torch.no_grad()
     def vqa_generate(self, pixels: torch.Tensor, vit_pos_ids: torch.Tensor, vit_seqlens: Sequence[int],
                      prompt_ids: Sequence[Sequence[int]], new_token_ids: dict, max_length: int) -> torch.Tensor:
         """One packed VQA job for B samples (one image each): host (pinned) tensors in, host tokens out.

@@ -777,6 +777,24 @@ int umv_seq_export(umv_engine* e, int32_t seq, int32_t layer, void* k_dev, void*
 }
 
 // ------------------------------------------------------------------------------ forward passes
+int umv_patchify_u8(const uint8_t* images, const int64_t* offsets, const int32_t* hw, int32_t n_images, int32_t patch,
+                    int32_t max_per_side, float* out_pixels, int64_t* out_pos_ids, void* stream) {
+    UMV_REQUIRE(images && offsets && hw && out_pixels && out_pos_ids && n_images > 0 && patch > 0, UMV_ERR_INVALID,
+                "umv_patchify_u8: null/empty argument");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    size_t tok = 0;
+    for (int i = 0; i < n_images; ++i) {
+        const int H = hw[2 * i], W = hw[2 * i + 1];
+        UMV_REQUIRE(H > 0 && W > 0 && H % patch == 0 && W % patch == 0, UMV_ERR_INVALID,
+                    "umv_patchify_u8: image %d is %dx%d, not a multiple of the %d-pixel patch (resize first)", i, H, W, patch);
+        UMV_REQUIRE(H / patch <= max_per_side && W / patch <= max_per_side, UMV_ERR_INVALID,
+                    "umv_patchify_u8: image %d has more than %d patches per side", i, max_per_side);
+        UMV_TRY(patchify_u8(images + offsets[i], H, W, patch, max_per_side, out_pixels + tok * 3 * patch * patch, out_pos_ids + tok, st));
+        tok += (size_t)(H / patch) * (W / patch);
+    }
+    return UMV_OK;
+}
+
 int umv_embed_tokens(umv_engine* e, const int64_t* ids, int32_t n, void* out, void* stream) {
     UMV_REQUIRE(e && e->finalized, UMV_ERR_STATE, "engine not finalized");
     return embed_rows(e->embed, ids, n, e->d.hidden, e->d.vocab, static_cast<bf16*>(out), static_cast<cudaStream_t>(stream));

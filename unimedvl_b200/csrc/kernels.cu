@@ -461,6 +461,30 @@ int gather_add_rows(bf16* x, const bf16* table, const int64_t* ids, int M, int D
     return UMV_OK;
 }
 
+// ToTensor + Normalize(0.5, 0.5) + patchify (data/transforms.py:104-115, data_utils.py:43-58): the same fp32 operations in the
+// same order as torch (u / 255, - 0.5, / 0.5), so the patch vectors are bit-identical to the host path.
+__global__ void patchify_u8_kernel(const uint8_t* __restrict__ img, int W, int patch, int max_per_side, float* __restrict__ out,
+                                   int64_t* __restrict__ pos_ids) {
+    pdl_launch_dependents();
+    pdl_wait();
+    const int pr = blockIdx.y, pc = blockIdx.x, cols = gridDim.x;
+    const int token = pr * cols + pc;
+    const int n = patch * patch * 3;
+    float* dst = out + (size_t)token * n;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const int c = i % 3, q = (i / 3) % patch, p = i / (3 * patch);          // (p_row, p_col, channel)
+        const uint8_t u = img[((size_t)(pr * patch + p) * W + (pc * patch + q)) * 3 + c];
+        const float x = __fdiv_rn((float)u, 255.0f);
+        dst[i] = __fdiv_rn(__fsub_rn(x, 0.5f), 0.5f);
+    }
+    if (threadIdx.x == 0) pos_ids[token] = (int64_t)pr * max_per_side + pc;
+}
+int patchify_u8(const uint8_t* img, int H, int W, int patch, int max_per_side, float* out, int64_t* pos_ids, cudaStream_t s) {
+    launch_k(patchify_u8_kernel, dim3(W / patch, H / patch), dim3(128), 0, s, img, W, patch, max_per_side, out, pos_ids);
+    UMV_LAUNCH_CHECK("patchify_u8_kernel");
+    return UMV_OK;
+}
+
 __global__ void f32_to_bf16_padded_kernel(const float* __restrict__ x, bf16* __restrict__ y, int K, int Kpad) {
     pdl_launch_dependents();
     pdl_wait();

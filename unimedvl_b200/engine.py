@@ -150,6 +150,29 @@ class Engine:
         self._exit()
         return out
 
+    def patchify_u8(self, images: Sequence[torch.Tensor]):
+        """ToTensor + Normalize(0.5, 0.5) + patchify + flattened position ids on the device (data/transforms.py:104-115,
+        data/data_utils.py:43-58) for uint8 [H, W, 3] images whose sides are multiples of the ViT patch (resizing stays
+        with the caller's ImageTransform).  Host tensors are uploaded as uint8 (a twelfth of the fp32 patch matrix).
+        Returns (pixels f32 [n_tokens, patch_dim], pos_ids i64 [n_tokens], seqlens) on the device, bit-identical to the
+        host transforms."""
+        v = self.dims.vit
+        hw, offs, total = [], [], 0
+        for im in images:
+            assert im.dtype == torch.uint8 and im.dim() == 3 and im.shape[2] == v.channels, "uint8 [H, W, 3] images expected"
+            hw += [int(im.shape[0]), int(im.shape[1])]
+            offs.append(total)
+            total += im.numel()
+        flat = torch.empty(total, dtype=torch.uint8, device=self.device)
+        for im, o in zip(images, offs):
+            flat[o:o + im.numel()].copy_(im.reshape(-1), non_blocking=True)
+        lens = [(hw[2 * i] // v.patch) * (hw[2 * i + 1] // v.patch) for i in range(len(images))]
+        pixels = torch.empty((sum(lens), v.patch_dim), dtype=torch.float32, device=self.device)
+        pos = torch.empty((sum(lens),), dtype=torch.int64, device=self.device)
+        _lib.check(self.lib.umv_patchify_u8(_ptr(flat), _lib.i64_array(offs), _lib.i32_array(hw), len(images), v.patch,
+                                            self.dims.vit_max_num_patch_per_side, _ptr(pixels), _ptr(pos), _stream_ptr()))
+        return pixels, pos, lens
+
     def vit_embed(self, pixels: torch.Tensor, pos_ids: torch.Tensor, seqlens: Iterable[int]) -> torch.Tensor:
         pixels = pixels.to(self.device, torch.float32).contiguous()
         pos_ids = pos_ids.to(self.device, torch.int64).contiguous()
