@@ -105,3 +105,57 @@ def test_pool_exhaustion_is_reported(big):
             eng.llm_forward(x, [s], [64], list(range(64)), update_kv=True, want_hidden=False)
     eng.seq_free(s)
     assert eng.pages_free() == 256
+
+
+def test_flow_batch_invariance_and_determinism_fullsize():
+    """Text-to-image flow at the 14B dims (both experts resident): image 0 generated inside a batch of two equals image 0
+    generated alone, bit for bit -- although the two runs take different kernel schedules (198 vs 396 packed rows: single-CTA
+    vs CTA-pair linears, different tile widths, different tcgen05-attention tilings) -- and a repeat is bit-identical.
+    Per-image "global" CFG renorm (DESIGN.md batching rule), dual CFG active on every step."""
+    from unimedvl_b200 import config as ucfg, packing, synth
+    from unimedvl_b200.bagel import Bagel
+    from unimedvl_b200.cache import NaiveCache, paged_handle
+    from unimedvl_b200.engine import Engine
+    dims = ucfg.bagel_7b_mot()
+    eng = Engine(dims, max_tokens=3 * 2 * 66 + 64, max_seqs=8, kv_pages=32, enable_vit=False, enable_gen=True)
+    eng.fill_synthetic(seed=1)
+    eng.finalize()
+    model = Bagel(eng, dims)
+    tok = dict(ucfg.QWEN25_TOKEN_IDS)
+    H = W = 128
+
+    class _Ids:
+        def encode(self, i): return synth.synthetic_prompt_ids(200 + i, 12)
+
+    def generate(B):
+        g, lens, rope = packing.prepare_prompts([0] * B, [0] * B, list(range(B)), _Ids(), tok)
+        ctx = model.forward_cache_update_text(NaiveCache(dims.llm.layers), **g)
+        cfg_text = NaiveCache(dims.llm.layers)
+        paged_handle(cfg_text, eng, B)
+        cfg_img = model.forward_cache_update_text(NaiveCache(dims.llm.layers), **g)
+        torch.manual_seed(7)
+        gi = model.prepare_vae_latent(lens, rope, [(H, W)] * B, tok)
+        torch.manual_seed(7)
+        noise1 = model.prepare_vae_latent(lens[:1], rope[:1], [(H, W)], tok)["packed_init_noises"]
+        n1 = noise1.shape[0]
+        gi["packed_init_noises"] = torch.cat([noise1] * B, 0) if B > 1 else noise1       # same noise for image 0 in both runs
+        assert gi["packed_init_noises"].shape[0] == B * n1
+        ct = model.prepare_vae_latent_cfg([0] * B, [0] * B, [(H, W)] * B)
+        ci = model.prepare_vae_latent_cfg(lens, rope, [(H, W)] * B)
+        lat = model.generate_image(
+            past_key_values=ctx, cfg_text_past_key_values=cfg_text, cfg_img_past_key_values=cfg_img, num_timesteps=4,
+            timestep_shift=3.0, cfg_text_scale=4.0, cfg_img_scale=1.5, cfg_interval=(0.0, 1.0), cfg_renorm_min=0.0,
+            cfg_renorm_type="global", **gi,
+            cfg_text_packed_position_ids=ct["cfg_packed_position_ids"], cfg_text_packed_query_indexes=ct["cfg_packed_query_indexes"],
+            cfg_text_key_values_lens=ct["cfg_key_values_lens"], cfg_text_packed_key_value_indexes=ct["cfg_packed_key_value_indexes"],
+            cfg_img_packed_position_ids=ci["cfg_packed_position_ids"], cfg_img_packed_query_indexes=ci["cfg_packed_query_indexes"],
+            cfg_img_key_values_lens=ci["cfg_key_values_lens"], cfg_img_packed_key_value_indexes=ci["cfg_packed_key_value_indexes"])
+        return [x.cpu() for x in lat]
+
+    alone = generate(1)
+    both = generate(2)
+    again = generate(2)
+    assert all(torch.isfinite(x).all() for x in both)
+    assert torch.equal(both[0], again[0]) and torch.equal(both[1], again[1])
+    assert torch.equal(alone[0], both[0])
+    assert not torch.equal(both[0], both[1])           # different prompts -> different images
