@@ -2,7 +2,8 @@ import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from unimedvl_b200.engine import op_rmsnorm
-for M in (272, 1026, 3096, 8208, 16416):
+for warp, M in [(w, m) for w in ("0", "1") for m in (272, 1026, 3096, 8208, 16416)]:
+    os.environ["UMV_NORM_WARP"] = warp
     D = 3584
     x = torch.randn(M, D, device="cuda").bfloat16(); w = torch.ones(D, device="cuda").bfloat16()
     big = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
@@ -17,4 +18,4 @@ for M in (272, 1026, 3096, 8208, 16416):
     e0.record()
     for _ in range(10): y = op_rmsnorm(x, w)
     e1.record(); torch.cuda.synchronize()
-    print(f"M={M:6d}: cold {min(ts):7.1f} us  warm {e0.elapsed_time(e1) * 100:7.1f} us   ({M * D * 4 / min(ts) / 1e3:.0f} GB/s cold)")
+    print(f"warp={warp} M={M:6d}: cold {min(ts):7.1f} us  warm {e0.elapsed_time(e1) * 100:7.1f} us   ({M * D * 4 / min(ts) / 1e3:.0f} GB/s cold)")

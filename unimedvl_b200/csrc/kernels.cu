@@ -87,7 +87,7 @@ __global__ void __launch_bounds__(kNormThreads) add_rmsnorm_kernel(AddNormArgs a
                 stg16(hrow + ch * 8, U4{o[0], o[1], o[2], o[3]});
             }
 #pragma unroll
-            for (int j = 0; j < 8; ++j) ss += v[c][j] * v[c][j];
+            for (int j = 0; j < 8; ++j) ss = fmaf(v[c][j], v[c][j], ss);   // order shared with rmsnorm_rows_warp_kernel
         }
     }
     if (a.y == nullptr) return;
@@ -109,6 +109,81 @@ __global__ void __launch_bounds__(kNormThreads) add_rmsnorm_kernel(AddNormArgs a
             stg16(yrow + ch * 8, U4{o[0], o[1], o[2], o[3]});
             if (slot2 >= 0) stg16(a.y2 + (size_t)slot2 * a.D + ch * 8, U4{o[0], o[1], o[2], o[3]});
         }
+    }
+    trace_end<false>(a.trace);
+}
+
+// Many-row variant without residual input (prefill / flow: the residual add already happened in the linear's epilogue):
+// one WARP per row, the row held as packed bf16 in registers, warp shuffles only -- no block barrier, a quarter of the
+// registers per row of the block kernel, so several times more rows in flight per SM (M=8208: 43 -> 34 us, M=16416:
+// 77 -> 53 us; slower below ~4k rows, where the block kernel's 256 threads per row hide the load latency better).
+// The sum of squares is taken in EXACTLY the order of add_rmsnorm_kernel<NB> (lane l plays threads 32c+l, c = 0..7: per-thread
+// fma chain over its NB chunks, xor tree per "warp" c, then the xor tree over the eight warp sums), so which of the two
+// kernels runs -- a function of M -- never changes a bit of the result: batch invariance stays bit-exact.
+template <int NB>
+__global__ void __launch_bounds__(256, NB == 1 ? 4 : 2) rmsnorm_rows_warp_kernel(AddNormArgs a) {
+    pdl_launch_dependents();
+    trace_start(a.trace);
+    pdl_wait();
+    trace_wait(a.trace);
+    const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (row < a.M) {
+        const int nchunk = a.D / 8;
+        const bf16* hrow = a.h + (size_t)row * a.D;
+        const bf16* w = (a.row_sel && a.row_sel[row]) ? a.w1 : a.w0;
+        const int slot2 = (a.y2 && a.row_slot) ? a.row_slot[row] : -1;
+        U4 hv[NB][8];
+#pragma unroll
+        for (int n = 0; n < NB; ++n)
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                const int ch = n * kNormThreads + c * 32 + lane;
+                hv[n][c] = U4{0, 0, 0, 0};
+                if (ch < nchunk) hv[n][c] = ldg16(hrow + ch * 8);
+            }
+        float ws[8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            float ss = 0.f;
+#pragma unroll
+            for (int n = 0; n < NB; ++n) {           // zero-filled chunks past the row end add +0: same bits as skipping them
+                const uint32_t* hw = &hv[n][c].x;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float2 f = unpack2(hw[j]);
+                    ss = fmaf(f.x, f.x, ss);
+                    ss = fmaf(f.y, f.y, ss);
+                }
+            }
+            ws[c] = warp_sum(ss);
+        }
+#pragma unroll
+        for (int n = 0; n < NB; ++n)       // opaque to the optimiser: re-unpack below instead of keeping 8 fp32 per chunk live
+#pragma unroll
+            for (int c = 0; c < 8; ++c)
+                asm volatile("" : "+r"(hv[n][c].x), "+r"(hv[n][c].y), "+r"(hv[n][c].z), "+r"(hv[n][c].w));
+        const float ss = ((ws[0] + ws[4]) + (ws[2] + ws[6])) + ((ws[1] + ws[5]) + (ws[3] + ws[7]));   // block_sum's last tree
+        const float inv = 1.0f / sqrtf(ss / (float)a.D + a.eps);
+        bf16* yrow = a.y + (size_t)row * a.D;
+#pragma unroll
+        for (int n = 0; n < NB; ++n)
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                const int ch = n * kNormThreads + c * 32 + lane;
+                if (ch < nchunk) {
+                    const U4 wv = ldg16(w + ch * 8);
+                    const uint32_t* hw = &hv[n][c].x;
+                    const uint32_t* ww = &wv.x;
+                    uint32_t o[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const float2 f = unpack2(hw[j]), wf = unpack2(ww[j]);
+                        o[j] = pack2(wf.x * rbf(f.x * inv), wf.y * rbf(f.y * inv));   // R2
+                    }
+                    stg16(yrow + ch * 8, U4{o[0], o[1], o[2], o[3]});
+                    if (slot2 >= 0) stg16(a.y2 + (size_t)slot2 * a.D + ch * 8, U4{o[0], o[1], o[2], o[3]});
+                }
+            }
     }
     trace_end<false>(a.trace);
 }
@@ -193,6 +268,15 @@ int add_rmsnorm(const AddNormArgs& a0, cudaStream_t s) {
     if (a.partial && !a.delta && !a.row_sel && !a.y2 && a.splits <= kNormDecMaxSplits && a.D <= 8 * kNormDecThreads && a.M <= 64) {
         launch_k(add_rmsnorm_splitk_kernel, dim3(a.M), dim3(kNormDecThreads), 0, s, a);
         UMV_LAUNCH_CHECK("add_rmsnorm_splitk_kernel");
+        return UMV_OK;
+    }
+    const char* warp_env = getenv("UMV_NORM_WARP");        // read per call: tests switch paths inside one process
+    const int warp_min_rows = warp_env ? (atoi(warp_env) ? 1 : 0x7fffffff) : 4096;
+    if (!a.delta && !a.partial && a.y && a.M >= warp_min_rows && a.D / 8 <= 2 * kNormThreads) {   // plain RMSNorm of many rows
+        const dim3 grid((a.M + 7) / 8);
+        if (a.D / 8 <= kNormThreads) launch_k(rmsnorm_rows_warp_kernel<1>, grid, dim3(256), 0, s, a);
+        else launch_k(rmsnorm_rows_warp_kernel<2>, grid, dim3(256), 0, s, a);
+        UMV_LAUNCH_CHECK("rmsnorm_rows_warp_kernel");
         return UMV_OK;
     }
     const int nc = (a.D / 8 + kNormThreads - 1) / kNormThreads;
