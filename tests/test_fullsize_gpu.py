@@ -96,6 +96,24 @@ def test_batch_invariance_and_fork_idempotence(big):
     assert eng.pages_free() == free0
 
 
+def test_rope_append_kernels_bit_identical(big, monkeypatch):
+    """The many-row q/k-norm + RoPE + KV-append kernel (16-byte lanes, packed-bf16 rounding chain) against the warp-per-head
+    kernel the few-row / split-K path keeps: same hidden states and same KV, bit for bit (understanding mode)."""
+    eng, dims = big
+    torch.manual_seed(5)
+    ids = torch.randint(0, 151643, (B, CTX))
+    outs = []
+    for flag in ("0", "1"):
+        monkeypatch.setenv("UMV_ROPE_ROWS", flag)
+        seqs = [eng.seq_new() for _ in range(B)]
+        h = _prefill(eng, dims, seqs, ids).clone()
+        toks = eng.generate_text(seqs, [151644] * B, [CTX] * B, 4).cpu()       # reads the KV the kernel appended
+        outs.append((h, toks))
+        for s in seqs:
+            eng.seq_free(s)
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
+
+
 def test_pool_exhaustion_is_reported(big):
     eng, dims = big
     s = eng.seq_new()
@@ -107,7 +125,7 @@ def test_pool_exhaustion_is_reported(big):
     assert eng.pages_free() == 256
 
 
-def test_flow_batch_invariance_and_determinism_fullsize():
+def test_flow_batch_invariance_and_determinism_fullsize(monkeypatch):
     """Text-to-image flow at the 14B dims (both experts resident): image 0 generated inside a batch of two equals image 0
     generated alone, bit for bit -- although the two runs take different kernel schedules (198 vs 396 packed rows: single-CTA
     vs CTA-pair linears, different tile widths, different tcgen05-attention tilings) -- and a repeat is bit-identical.
@@ -159,3 +177,7 @@ def test_flow_batch_invariance_and_determinism_fullsize():
     assert torch.equal(both[0], again[0]) and torch.equal(both[1], again[1])
     assert torch.equal(alone[0], both[0])
     assert not torch.equal(both[0], both[1])           # different prompts -> different images
+    monkeypatch.setenv("UMV_ROPE_ROWS", "0")           # generation mode (fp32 q/k norm + RoPE): both row kernels, same bits
+    monkeypatch.setenv("UMV_NORM_WARP", "0")
+    other = generate(2)
+    assert torch.equal(both[0], other[0]) and torch.equal(both[1], other[1])

@@ -468,6 +468,129 @@ __global__ void __launch_bounds__(kRopeWarps * 32, 8) rope_append_kernel(RopeApp
     trace_end<false>(a.trace);
 }
 
+// Many-row variant (prefill / flow; input = the q|k|v linear's bf16 output): ncu showed rope_append_kernel issue-bound at
+// 8208 rows (73 % issue slots, 185 warp instructions per head slot), so this one spends a quarter of the instructions: a lane
+// owns 8 columns (16-byte loads / stores), a warp works on TWO head slots at once (16 lanes each; the rotate_half partner is
+// lane ^ 8), and the understanding-mode rounding chain (R4, R5) runs on packed bf16x2: for bf16 operands
+// mul.rn.bf16x2 == bf16(fp32 product) and add.rn.bf16x2 == bf16(fp32 sum) (both fp32 results are exact before the
+// rounding).  The sum of squares follows rope_append_kernel's order (old lane 2j | 2j+1 = the two halves of new lane j, then
+// the same xor tree), so both kernels -- and the fused decode attention -- produce the same bits.
+__device__ __forceinline__ uint32_t bmul2(uint32_t a, uint32_t b) {
+    uint32_t d;
+    asm("mul.rn.bf16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
+    return d;
+}
+__device__ __forceinline__ uint32_t badd2(uint32_t a, uint32_t b) {
+    uint32_t d;
+    asm("add.rn.bf16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
+    return d;
+}
+constexpr int kRopePairs = 5;        // slot pairs per warp kept in flight (4 warps x 5 pairs x 2 = 40 >= H + 2 Hkv = 36)
+template <bool GEN>
+__global__ void __launch_bounds__(kRopeWarps * 32, 8) rope_append_rows_kernel(RopeAppendArgs a) {
+    pdl_launch_dependents();
+    trace_start(a.trace);
+    pdl_wait();
+    trace_wait(a.trace);
+    const int row = blockIdx.x;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, sub = lane & 15, hsel = lane >> 4;
+    const int slots = a.H + 2 * a.Hkv;
+    const int ncols = slots * 128;
+    const bf16* qrow = a.qkv + (size_t)row * ncols + sub * 8;
+    for (int p0 = warp; 2 * p0 < slots; p0 += kRopeWarps * kRopePairs) {
+        U4 raw[kRopePairs];
+#pragma unroll
+        for (int i = 0; i < kRopePairs; ++i) {
+            const int slot = 2 * (p0 + kRopeWarps * i) + hsel;
+            raw[i] = U4{0, 0, 0, 0};
+            if (slot < slots) raw[i] = ldg16(qrow + slot * 128);
+        }
+        const bool gen_row = a.row_sel && a.row_sel[row];
+        const int pos_kv = a.row_kvpos[row];
+        const int seq = a.row_seq[row];
+        const float* csrow = a.rope_cs + (size_t)row * 128 + (sub & 7) * 8;
+        const float4 c0 = *reinterpret_cast<const float4*>(csrow), c1 = *reinterpret_cast<const float4*>(csrow + 4);
+        const float4 s0 = *reinterpret_cast<const float4*>(csrow + 64), s1 = *reinterpret_cast<const float4*>(csrow + 68);
+        const U4 wq = ldg16((gen_row ? a.qn1 : a.qn0) + sub * 8);
+        const U4 wk = ldg16((gen_row ? a.kn1 : a.kn0) + sub * 8);
+        const int page = a.page_table[(size_t)seq * a.max_pages + pos_kv / kPageTokens];
+        const float c[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
+        const float sn[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+        uint32_t c2[4], s2[4];                          // the table holds bf16-rounded values: packing is exact
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            c2[k] = pack2(c[2 * k], c[2 * k + 1]);
+            s2[k] = pack2(sn[2 * k], sn[2 * k + 1]);
+        }
+        const uint32_t sign = (sub < 8) ? 0x80008000u : 0u;        // rotate_half: -x[i + 64] for i < 64, +x[i - 64] above
+#pragma unroll
+        for (int i = 0; i < kRopePairs; ++i) {
+            const int slot = 2 * (p0 + kRopeWarps * i) + hsel;
+            if (2 * (p0 + kRopeWarps * i) >= slots) break;          // warp-uniform
+            const bool valid = slot < slots;
+            const bool is_q = slot < a.H;
+            const bool is_v = slot >= a.H + a.Hkv;
+            const uint32_t* rw = &raw[i].x;
+            float x[8];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const float2 f = unpack2(rw[k]);
+                x[2 * k] = f.x;
+                x[2 * k + 1] = f.y;
+            }
+            float sa = fmaf(x[3], x[3], fmaf(x[2], x[2], fmaf(x[1], x[1], __fmul_rn(x[0], x[0]))));
+            float sb = fmaf(x[7], x[7], fmaf(x[6], x[6], fmaf(x[5], x[5], __fmul_rn(x[4], x[4]))));
+#pragma unroll
+            for (int o = 8; o > 0; o >>= 1) {
+                sa += __shfl_xor_sync(0xffffffffu, sa, o);
+                sb += __shfl_xor_sync(0xffffffffu, sb, o);
+            }
+            const float inv = 1.0f / sqrtf((sa + sb) * (1.0f / 128.0f) + a.eps);
+            const U4 wv = is_q ? wq : wk;
+            const uint32_t* ww = &wv.x;
+            uint32_t o2[4];
+            if constexpr (GEN) {                                                         // fp32 throughout, one rounding
+                float n[8];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const float2 wf = unpack2(ww[k]);
+                    n[2 * k] = __fmul_rn(wf.x, __fmul_rn(x[2 * k], inv));
+                    n[2 * k + 1] = __fmul_rn(wf.y, __fmul_rn(x[2 * k + 1], inv));
+                }
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    float r[2];
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        const float partner = __shfl_xor_sync(0xffffffffu, n[2 * k + e], 8);
+                        const float rot = (sub < 8) ? -partner : partner;
+                        r[e] = __fadd_rn(__fmul_rn(n[2 * k + e], c[2 * k + e]), __fmul_rn(rot, sn[2 * k + e]));
+                    }
+                    o2[k] = pack2(r[0], r[1]);
+                }
+            } else {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const uint32_t t2 = pack2(__fmul_rn(x[2 * k], inv), __fmul_rn(x[2 * k + 1], inv));   // R4: bf16(x * inv)
+                    const uint32_t n2 = bmul2(ww[k], t2);                                               //     bf16(w * .)
+                    const uint32_t rot2 = __shfl_xor_sync(0xffffffffu, n2, 8) ^ sign;
+                    o2[k] = badd2(bmul2(n2, c2[k]), bmul2(rot2, s2[k]));                                // R5: three roundings
+                }
+            }
+            if (!valid) continue;
+            const U4 outv = is_v ? raw[i] : U4{o2[0], o2[1], o2[2], o2[3]};
+            if (is_q) {
+                stg16(a.q_out + (size_t)row * a.ldq + slot * 128 + sub * 8, outv);
+            } else {
+                const int kv = is_v ? 1 : 0;
+                const int head = slot - a.H - (is_v ? a.Hkv : 0);
+                stg16(a.pool.base + a.pool.tile_offset(page, a.layer, kv, head) + (size_t)(pos_kv % kPageTokens) * 128 + sub * 8, outv);
+            }
+        }
+    }
+    trace_end<false>(a.trace);
+}
+
 __global__ void rope_table_kernel(const int* __restrict__ positions, const float* __restrict__ inv_freq, int M, int dh,
                                   float* __restrict__ cs) {
     pdl_launch_dependents();
@@ -494,6 +617,13 @@ int rope_append(const RopeAppendArgs& a0, cudaStream_t s) {
     UMV_REQUIRE(a.dh == 128, UMV_ERR_UNSUPPORTED, "rope_append: head_dim %d (only 128 is built)", a.dh);
     UMV_REQUIRE(a.rope_cs != nullptr, UMV_ERR_INVALID, "rope_append: the per-forward cos/sin table (rope_table) is required");
     const int blocks = a.M;
+    const char* rows_env = getenv("UMV_ROPE_ROWS");        // read per call: tests switch paths inside one process
+    if (!a.partial && !(rows_env && atoi(rows_env) == 0)) {
+        if (a.gen_mode) launch_k(rope_append_rows_kernel<true>, dim3(blocks), dim3(kRopeWarps * 32), 0, s, a);
+        else launch_k(rope_append_rows_kernel<false>, dim3(blocks), dim3(kRopeWarps * 32), 0, s, a);
+        UMV_LAUNCH_CHECK("rope_append_rows_kernel");
+        return UMV_OK;
+    }
     launch_k(rope_append_kernel, dim3(blocks), dim3(kRopeWarps * 32), 0, s, a);
     UMV_LAUNCH_CHECK("rope_append_kernel");
     return UMV_OK;
