@@ -348,8 +348,92 @@ __global__ void __launch_bounds__(kNormThreads) layernorm_kernel(const bf16* __r
     }
 }
 
+// Rows up to 4096 wide (the ViT's 1152): one WARP per row, the row as packed bf16 in registers, shuffle-only statistics.  The
+// block kernel above keeps 64 fp32 per thread for its widest case (107 registers -> 2 rows in flight per SM, two block
+// barriers each): ~100 us for the ViT's 8192 x 1152 rows where the traffic is worth 8.  Chosen by D only, never by M.
+template <int WC>
+__global__ void __launch_bounds__(256) layernorm_rows_warp_kernel(const bf16* __restrict__ x, const bf16* __restrict__ w,
+                                                                   const bf16* __restrict__ b, bf16* __restrict__ y, int M, int D,
+                                                                   float eps, TraceSlot* trace) {
+    pdl_launch_dependents();
+    trace_start(trace);
+    pdl_wait();
+    trace_wait(trace);
+    const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (row < M) {
+        const int nchunk = D / 8;
+        const bf16* xrow = x + (size_t)row * D;
+        U4 hv[WC];
+#pragma unroll
+        for (int c = 0; c < WC; ++c) {
+            const int ch = lane + c * 32;
+            hv[c] = U4{0, 0, 0, 0};
+            if (ch < nchunk) hv[c] = ldg16(xrow + ch * 8);
+        }
+        float sum = 0.f;
+#pragma unroll
+        for (int c = 0; c < WC; ++c) {
+            const uint32_t* hw = &hv[c].x;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float2 f = unpack2(hw[j]);
+                sum += f.x + f.y;
+            }
+        }
+        const float mean = warp_sum(sum) / (float)D;
+#pragma unroll
+        for (int c = 0; c < WC; ++c) asm volatile("" : "+r"(hv[c].x), "+r"(hv[c].y), "+r"(hv[c].z), "+r"(hv[c].w));   // stay packed
+        float sq = 0.f;
+#pragma unroll
+        for (int c = 0; c < WC; ++c) {
+            if (lane + c * 32 < nchunk) {
+                const uint32_t* hw = &hv[c].x;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float2 f = unpack2(hw[j]);
+                    const float d0 = f.x - mean, d1 = f.y - mean;
+                    sq += d0 * d0;
+                    sq += d1 * d1;
+                }
+            }
+        }
+        const float var = warp_sum(sq) / (float)D;
+        const float inv = 1.0f / sqrtf(var + eps);
+#pragma unroll
+        for (int c = 0; c < WC; ++c) asm volatile("" : "+r"(hv[c].x), "+r"(hv[c].y), "+r"(hv[c].z), "+r"(hv[c].w));
+#pragma unroll
+        for (int c = 0; c < WC; ++c) {
+            const int ch = lane + c * 32;
+            if (ch < nchunk) {
+                const U4 wv = ldg16(w + ch * 8), bv = ldg16(b + ch * 8);
+                const uint32_t* hw = &hv[c].x;
+                const uint32_t* ww = &wv.x;
+                const uint32_t* bw = &bv.x;
+                uint32_t o[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float2 f = unpack2(hw[j]), wf = unpack2(ww[j]), bf = unpack2(bw[j]);
+                    o[j] = pack2((f.x - mean) * inv * wf.x + bf.x, (f.y - mean) * inv * wf.y + bf.y);
+                }
+                stg16(y + (size_t)row * D + ch * 8, U4{o[0], o[1], o[2], o[3]});
+            }
+        }
+    }
+    trace_end<false>(trace);
+}
+
 int layernorm_bf16(const bf16* x, const bf16* w, const bf16* b, bf16* y, int M, int D, float eps, cudaStream_t s) {
     if (M <= 0) return UMV_OK;
+    if (D % 8 == 0 && D / 8 <= 32 * 16) {
+        const int wc = (D / 8 + 31) / 32;
+        const dim3 grid((M + 7) / 8);
+        TraceSlot* tr = trace_next("layernorm");
+        if (wc <= 4) launch_k(layernorm_rows_warp_kernel<4>, grid, dim3(256), 0, s, x, w, b, y, M, D, eps, tr);
+        else if (wc <= 8) launch_k(layernorm_rows_warp_kernel<8>, grid, dim3(256), 0, s, x, w, b, y, M, D, eps, tr);
+        else launch_k(layernorm_rows_warp_kernel<16>, grid, dim3(256), 0, s, x, w, b, y, M, D, eps, tr);
+        UMV_LAUNCH_CHECK("layernorm_rows_warp_kernel");
+        return UMV_OK;
+    }
     UMV_REQUIRE(D % 8 == 0 && D <= 8 * kNormThreads * kNormMaxChunks, UMV_ERR_UNSUPPORTED, "layernorm: bad D=%d", D);
     launch_k(layernorm_kernel, dim3(M), dim3(kNormThreads), 0, s, x, w, b, y, D, eps);
     UMV_LAUNCH_CHECK("layernorm_kernel");
