@@ -114,6 +114,25 @@ def test_rope_append_kernels_bit_identical(big, monkeypatch):
     assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
 
 
+def test_decode_graph_cache_replays_on_new_sequences(big, monkeypatch):
+    """The instantiated decode-step graph is kept across generate_text calls (same batch size / page stride / block count):
+    a replay on DIFFERENT sequences of the same shape must give what a freshly captured graph gives."""
+    eng, dims = big
+    torch.manual_seed(11)
+    want, got = [], []
+    for cache in ("0", "1"):
+        monkeypatch.setenv("UMV_GRAPH_CACHE", cache)
+        for k in range(2):
+            ids = torch.randint(0, 151643, (3, CTX), generator=torch.Generator().manual_seed(100 + k))
+            seqs = [eng.seq_new() for _ in range(3)]
+            _prefill(eng, dims, seqs, ids)
+            (want if cache == "0" else got).append(eng.generate_text(seqs, [151644] * 3, [CTX] * 3, 9).cpu())
+            for s in seqs:
+                eng.seq_free(s)
+    assert torch.equal(want[0], got[0]) and torch.equal(want[1], got[1])
+    assert not torch.equal(got[0], got[1])
+
+
 def test_pool_exhaustion_is_reported(big):
     eng, dims = big
     s = eng.seq_new()

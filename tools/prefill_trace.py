@@ -68,6 +68,13 @@ if iv:
     for i in range(i0 - 5, i0 + 4):
         out.append(f"| {i} | `{nm[i]}` | {(t[i, 0] - t[i0 - 5, 0]) / 1e3:.1f} | {(t[i, 1] - t[i0 - 5, 0]) / 1e3:.1f} | "
                    f"{(t[i, 3] - t[i0 - 5, 0]) / 1e3:.1f} | {(t[i, 3] - t[i - 1, 3]) / 1e3:.1f} |\n")
+gaps = sorted(((t[i, 0] - t[i - 1, 3]) / 1e3, i) for i in range(1, n))[::-1][:12]
+out.append("\n## largest idle gaps (first CTA start minus the previous traced kernel's last CTA end: host work, untraced kernels, copies)\n\n"
+           "| # | kernel | after | gap us | at ms |\n|---|---|---|---:|---:|\n")
+for g, i in gaps:
+    out.append(f"| {i} | `{nm[i]}` | `{nm[i - 1]}` | {g:.1f} | {(t[i, 0] - t[0, 0]) / 1e6:.2f} |\n")
+out.append(f"\nsum of all positive gaps: {sum(max(0, (t[i, 0] - t[i - 1, 3])) for i in range(1, n)) / 1e6:.2f} ms of "
+           f"{(t[n - 1, 3] - t[0, 0]) / 1e6:.2f} ms first start -> last end\n")
 text = "".join(out)
 print(text)
 if len(sys.argv) > 1:

@@ -102,6 +102,7 @@ struct TraceSlot {
     unsigned long long t_start, t_wait, t_end_first, t_end_last;
     unsigned long long dbg[8];      // kernel-specific intermediate stamps of the first CTA
 };
+bool trace_active();                               // host: a trace is being recorded (slot pointers get baked into launches)
 TraceSlot* trace_next(const char* kernel_name);     // host: next slot of the active trace, or nullptr (tracing off)
 #ifdef __CUDACC__
 __device__ __forceinline__ unsigned long long gtime() {

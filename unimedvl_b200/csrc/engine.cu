@@ -570,6 +570,8 @@ int umv_destroy(umv_engine* e) {
     if (!e) return UMV_OK;
     cudaDeviceSynchronize();
     for (void* p : e->allocs) cudaFree(p);
+    for (auto& g : e->dec_graphs) cudaGraphExecDestroy(g.exec);
+    if (e->dec_out) cudaFree(e->dec_out);
     delete e->vae;
     for (int i = 0; i < umv_engine::kMetaRing; ++i) {
         if (e->meta_host[i]) cudaFreeHost(e->meta_host[i]);
@@ -1023,7 +1025,70 @@ int umv_generate_text(umv_engine* e, int32_t n_seqs, const int32_t* seqs, const 
     };
 
     const bool graph_ok = e->use_graph && logits_out == nullptr && st != nullptr && n_steps > 1;
-    if (graph_ok) {
+    // A captured step depends on the batch size, the page-table stride, the 64-key block count the attention split was sized
+    // for, the sampling parameters and the per-call kernel switches -- not on the sequences themselves (lengths, pages and
+    // tokens live in device arrays the graph only points to).  Same key -> replay the instantiated graph of an earlier call.
+    const bool cache_ok = graph_ok && forced_tokens == nullptr && !trace_active() && !(getenv("UMV_GRAPH_CACHE") && atoi(getenv("UMV_GRAPH_CACHE")) == 0);
+    if (cache_ok) {
+        auto flag = [](const char* name, int bit) { const char* v = getenv(name); return (v && atoi(v) == 0) ? (1u << bit) : 0u; };
+        const unsigned flags = flag("UMV_FUSED_ATTN", 0) | flag("UMV_ATTN_TC", 1) | flag("UMV_ROPE_ROWS", 2) | flag("UMV_NORM_WARP", 3);
+        const int blocks = (r.max_kv_len + kPageTokens - 1) / kPageTokens;
+        const size_t need = (size_t)n_steps * B;
+        if (need > e->dec_out_cap) {                   // grown rarely; graphs captured against the old buffer are dropped
+            for (auto& g : e->dec_graphs) cudaGraphExecDestroy(g.exec);
+            e->dec_graphs.clear();
+            if (e->dec_out) cudaFree(e->dec_out);
+            e->dec_out = nullptr; e->dec_out_cap = 0;
+            UMV_CUDA_OK(cudaMalloc(&e->dec_out, std::max(need, (size_t)4096) * sizeof(int64_t)));
+            e->dec_out_cap = std::max(need, (size_t)4096);
+        }
+        umv_engine::DecodeGraph* hit = nullptr;
+        for (auto& g : e->dec_graphs)
+            if (g.B == B && g.max_pages == max_pages && g.blocks == blocks && g.temperature == temperature &&
+                (temperature <= 0.f || g.seed == seed) && g.flags == flags) hit = &g;
+        if (!hit) {
+            cudaGraph_t graph = nullptr;
+            umv_engine::DecodeGraph g;
+            g.B = B; g.max_pages = max_pages; g.blocks = blocks; g.temperature = temperature; g.seed = seed; g.flags = flags;
+            UMV_CUDA_OK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+            const long long launches_before = g_launches;
+            auto cstep = [&]() -> int {
+                UMV_TRY(decode_begin_step(e->embed, D, V, ds, nullptr, e->dec_out, B, e->h, st));
+                UMV_TRY(llm_layers(e, r, e->xn, st));
+                UMV_TRY(lin(e, e->xn, D, e->lm_head, nullptr, nullptr, e->logits, V, B, V, D, EPI_BF16, st));
+                if (temperature > 0.f) UMV_TRY(sample_rows(e->logits, B, V, temperature, seed, e->dec_step, e->dec_tokens, st));
+                else UMV_TRY(argmax_rows(e->logits, B, V, e->dec_tokens, st));
+                return decode_end_step(ds, B, st);
+            };
+            int rc = cstep();
+            g.launches = g_launches - launches_before;
+            g_launches = launches_before;
+            cudaError_t ce = cudaStreamEndCapture(st, &graph);
+            if (rc != UMV_OK) { if (graph) cudaGraphDestroy(graph); return rc; }
+            UMV_CUDA_OK(ce);
+            ce = cudaGraphInstantiate(&g.exec, graph, 0);
+            cudaGraphDestroy(graph);
+            UMV_CUDA_OK(ce);
+            if (e->dec_graphs.size() >= 8) {           // evict the least recently used
+                size_t lru = 0;
+                for (size_t i = 1; i < e->dec_graphs.size(); ++i) if (e->dec_graphs[i].used < e->dec_graphs[lru].used) lru = i;
+                cudaGraphExecDestroy(e->dec_graphs[lru].exec);
+                e->dec_graphs.erase(e->dec_graphs.begin() + lru);
+            }
+            e->dec_graphs.push_back(g);
+            hit = &e->dec_graphs.back();
+        }
+        hit->used = ++e->dec_graph_clock;
+        for (int i = 0; i < n_steps; ++i) {
+            cudaError_t le = cudaGraphLaunch(hit->exec, st);
+            if (le != cudaSuccess) {
+                set_error("cudaGraphLaunch failed at step %d: %s", i, cudaGetErrorString(le));
+                return UMV_ERR_CUDA;
+            }
+        }
+        g_launches += hit->launches * n_steps;
+        UMV_CUDA_OK(cudaMemcpyAsync(tokens_out, e->dec_out, need * sizeof(int64_t), cudaMemcpyDeviceToDevice, st));
+    } else if (graph_ok) {
         cudaGraph_t graph = nullptr;
         cudaGraphExec_t exec = nullptr;
         UMV_CUDA_OK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));

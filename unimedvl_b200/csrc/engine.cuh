@@ -147,4 +147,18 @@ struct umv_engine {
     float* rope_tab = nullptr;         // [max_tokens][dh] per-forward rope cos | sin
     float* dec_rope = nullptr;         // [64][dh] per-step rope cos | sin
     int dec_pages_cap = 0;
+    // decode-step CUDA graphs kept across umv_generate_text calls (capture + instantiate of the 201-launch step costs ~7 ms)
+    struct DecodeGraph {
+        int B = 0, max_pages = 0, blocks = 0;
+        float temperature = 0.f;
+        uint64_t seed = 0;
+        unsigned flags = 0;
+        cudaGraphExec_t exec = nullptr;
+        long long launches = 0;      // kernels per replay
+        uint64_t used = 0;           // LRU stamp
+    };
+    std::vector<DecodeGraph> dec_graphs;
+    uint64_t dec_graph_clock = 0;
+    int64_t* dec_out = nullptr;      // [steps, B] tokens of a cached-graph run (copied to the caller's tokens_out afterwards)
+    size_t dec_out_cap = 0;
 };

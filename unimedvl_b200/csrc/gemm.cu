@@ -37,6 +37,7 @@ bool g_pdl = true;
 static TraceSlot* g_trace_dev = nullptr;
 static int g_trace_cap = 0, g_trace_n = 0;
 static std::vector<std::string> g_trace_names;
+bool trace_active() { return g_trace_dev != nullptr; }
 TraceSlot* trace_next(const char* kernel_name) {
     if (!g_trace_dev || g_trace_n >= g_trace_cap) return nullptr;
     g_trace_names.emplace_back(kernel_name);
