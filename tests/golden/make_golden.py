@@ -2,7 +2,7 @@
 
 Run in the build container only (needs /root/reference; the GPU box has no copy):
 
-    python tests/golden/make_golden.py
+    python tests/golden/make_golden.py [packing|vqa|t2i|edit|e2e|recon ...]
 
 The reference ships no tests or golden vectors, so parity is pinned on the
 outputs of the unmodified reference modules imported from /root/reference/codes, executed on CPU
@@ -300,6 +300,38 @@ def golden_e2e(model, vae, out):
         out["e2e.edit_image"] = np.asarray(r["image"])
 
 
+def golden_recon(model, vae, out):
+    """G7: the VQA + reconstruction workflows (inferencer.py:282-549) through the reference's own methods; `__call__` with
+    inference_ver=1 for ver1.  On CPU the VAE posterior noise (autoencoder.py:270) and the initial latent noise
+    (bagel.py:835-837) both come from the default CPU generator, so a seed pins the whole run."""
+    tok = FakeTokenizer()
+    inf = InterleaveInferencer(model, vae, tok, ImageTransform(1024, 32, 16), ImageTransform(980, 28, 14), TOK)
+    imgs = make_images([(70, 98), (64, 64)], base=30)
+    sizes = [(98, 70), (64, 64), (2000, 1500), (3000, 500), (20, 400), (1024, 1024), (17, 17), (1500, 1499), (4096, 4096)]
+    out["recon.sizes_in"] = np.asarray(sizes)
+    out["recon.sizes_out"] = np.asarray([inf._calculate_target_size_with_aspect_ratio(w, h) for w, h in sizes])
+    kw = dict(reconstruct_image=True, max_think_token_n=7, do_sample=False, num_timesteps=3, cfg_interval=[0.0, 1.0])
+    with torch.no_grad(), torch.autocast("cpu", dtype=torch.bfloat16):
+        torch.manual_seed(51)
+        r = inf(image=imgs, text="Describe the findings.", inference_ver=1, **kw)
+        out["recon.ver1_text"] = np.asarray(r["text"])
+        for i, im in enumerate(r["image"]):
+            out[f"recon.ver1_image{i}"] = np.asarray(im)
+        torch.manual_seed(52)
+        r = inf.interleave_inference_for_vqa_reconstruction_ver0_1(imgs + ["Describe the findings."], **kw)
+        out["recon.ver0_1_text"] = np.asarray(r[0])
+        for i, im in enumerate(r[1:]):
+            out[f"recon.ver0_1_image{i}"] = np.asarray(im)
+        torch.manual_seed(52)          # same draws as ver0_1 up to its first image
+        r = inf.interleave_inference_for_vqa_reconstruction_ver0(imgs + ["Describe the findings."], **kw)
+        out["recon.ver0_text"] = np.asarray(r[0])
+        assert len(r) == 2
+        out["recon.ver0_image0"] = np.asarray(r[1])
+        r = inf(image=imgs[0], text="Describe the findings.", inference_ver=1, max_think_token_n=7, do_sample=False)
+        assert r["image"] is None
+        out["recon.ver1_noimage_text"] = np.asarray(r["text"])
+
+
 def main():
     torch.manual_seed(0)
     torch.set_num_threads(8)
@@ -309,7 +341,10 @@ def main():
                      ("vqa", lambda o: golden_vqa(model, o)),
                      ("t2i", lambda o: golden_t2i(model, vae, o)),
                      ("edit", lambda o: golden_edit(model, vae, o)),
-                     ("e2e", lambda o: golden_e2e(model, vae, o))):
+                     ("e2e", lambda o: golden_e2e(model, vae, o)),
+                     ("recon", lambda o: golden_recon(model, vae, o))):
+        if len(sys.argv) > 1 and name not in sys.argv[1:]:
+            continue
         out = {}
         fn(out)
         path = os.path.join(HERE, f"{name}.npz")

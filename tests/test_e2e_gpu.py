@@ -84,6 +84,58 @@ def test_image_edit(inferencer):
     assert abs(float(got.mean()) - float(gold.mean())) < 25.0
 
 
+def _recon_images():
+    return [Image.fromarray(synth.synthetic_image(30 + i, h, w)) for i, (h, w) in enumerate([(70, 98), (64, 64)])]
+
+
+_RECON_KW = dict(reconstruct_image=True, max_think_token_n=7, do_sample=False, num_timesteps=3, cfg_interval=[0.0, 1.0])
+
+
+@pytest.mark.parametrize("variant", ["ver1", "ver0_1", "ver0"])
+def test_vqa_reconstruction_workflows(inferencer, variant):
+    """answer the question, then regenerate the input image(s) from [image, answer]
+    (inferencer.py:282-549) vs the reference's own methods run on CPU.  With the VAE posterior noise drawn from the CPU
+    generator (as the CPU reference run does) one seed pins every draw: same answer text, images to bf16 noise."""
+    inf, eng = inferencer
+    gold = Golden("recon").z
+    imgs = _recon_images()
+    inf.vae_model.noise_device = "cpu"
+    try:
+        if variant == "ver1":
+            torch.manual_seed(51)
+            r = inf(image=imgs, text="Describe the findings.", inference_ver=1, **_RECON_KW)
+            text, images = r["text"], r["image"]
+        elif variant == "ver0_1":
+            torch.manual_seed(52)
+            r = inf.interleave_inference_for_vqa_reconstruction_ver0_1(imgs + ["Describe the findings."], **_RECON_KW)
+            text, images = r[0], r[1:]
+        else:
+            torch.manual_seed(52)          # same draws as ver0_1 up to its first image
+            r = inf.interleave_inference_for_vqa_reconstruction_ver0(imgs + ["Describe the findings."], **_RECON_KW)
+            text, images = r[0], r[1:]
+    finally:
+        inf.vae_model.noise_device = "cuda"
+    assert text == str(gold[f"recon.{variant}_text"])
+    assert len(images) == (1 if variant == "ver0" else 2)
+    for i, im in enumerate(images):
+        g = gold[f"recon.{variant}_image{i}"]
+        assert np.asarray(im).shape == g.shape
+        mean, far = _diff(im, g)
+        assert mean < 8.0 and far < 0.03, (variant, i, mean, far)
+
+
+def test_vqa_reconstruction_without_reconstruction(inferencer):
+    inf, eng = inferencer
+    free0 = eng.pages_free()
+    r = inf(image=_recon_images()[0], text="Describe the findings.", inference_ver=1, max_think_token_n=7, do_sample=False)
+    assert r["image"] is None and r["text"] == str(Golden("recon").z["recon.ver1_noimage_text"])
+    with pytest.raises(ValueError):
+        inf(text="x", inference_ver=2)
+    import gc
+    gc.collect()
+    assert eng.pages_free() == free0
+
+
 def test_unsupported_input_raises(inferencer):
     inf, _ = inferencer
     with pytest.raises(ValueError):

@@ -93,3 +93,13 @@ def test_device_patchify_is_bit_identical_to_the_host_transforms():
     assert lens == [p.shape[0] for p in ref_pix]
     assert torch.equal(pix.cpu(), torch.cat(ref_pix, 0))
     assert torch.equal(pos.cpu(), torch.cat(ref_pos, 0))
+
+
+def test_reconstruction_target_size_matches_reference():
+    """InterleaveInferencer._calculate_target_size_with_aspect_ratio (inferencer.py:42-71) vs the reference's own values."""
+    from unimedvl_b200.inferencer import InterleaveInferencer
+    from unimedvl_b200.packing import ImageTransform
+    z = Golden("recon").z
+    inf = InterleaveInferencer(None, None, None, ImageTransform(1024, 32, 16), ImageTransform(980, 28, 14), {})
+    got = [inf._calculate_target_size_with_aspect_ratio(int(w), int(h)) for w, h in z["recon.sizes_in"]]
+    assert got == [tuple(int(v) for v in r) for r in z["recon.sizes_out"]]

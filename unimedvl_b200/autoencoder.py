@@ -16,6 +16,7 @@ class AutoEncoder:
         self._probe = torch.empty(0, dtype=torch.bfloat16, device=engine.device)
         self.sample = True                  # DiagonalGaussian(sample=True), autoencoder.py:260-272
         self.generator: torch.Generator | None = None
+        self.noise_device = "cuda"          # "cpu": draw like a CPU run of the reference (torch.randn_like on the CPU generator)
 
     def parameters(self):
         yield self._probe
@@ -44,7 +45,8 @@ class AutoEncoder:
         mean, logvar = torch.chunk(m, 2, dim=1)
         if self.sample:
             if noise is None:
-                noise = torch.randn(mean.shape, dtype=mean.dtype, device=mean.device, generator=self.generator)
+                dev = mean.device if self.noise_device == "cuda" else torch.device("cpu")
+                noise = torch.randn(mean.shape, dtype=mean.dtype, device=dev, generator=self.generator)
             z = mean + torch.exp(0.5 * logvar) * noise.to(mean.device, mean.dtype)
         else:
             z = mean

@@ -159,6 +159,116 @@ class InterleaveInferencer:
                                           cfg_renorm_type=cfg_renorm_type))
         return output_list
 
+    # ------------------------------------------------------------------ VQA + reconstruction workflows
+    def _calculate_target_size_with_aspect_ratio(self, original_width: int, original_height: int):
+        """inferencer.py:42-71: the (H, W) a reconstruction is generated at -- the input's aspect ratio under the VAE
+        transform's max_size / min_size / stride / max_pixels rules."""
+        rt = self.vae_transform.resize_transform
+        stride = rt.stride
+
+        def snap(width, height, scale):
+            return tuple(max(stride, int(round(round(v * scale) / stride) * stride)) for v in (width, height))
+
+        scale = max(min(rt.max_size / max(original_width, original_height), 1.0), rt.min_size / min(original_width, original_height))
+        w, h = snap(original_width, original_height, scale)
+        if w * h > rt.max_pixels:
+            w, h = snap(w, h, rt.max_pixels / (w * h))
+        if max(w, h) > rt.max_size:
+            w, h = snap(w, h, rt.max_size / max(w, h))
+        return h, w
+
+    def _vqa_answer(self, input_lists, need_text_only_context: bool, max_think_token_n, do_sample, text_temperature):
+        """Common first half of the three variants (inferencer.py:303-323, 392-416, 488-507): every image enters the VQA
+        context through BOTH encoders (VAE latent tokens + ViT tokens), then one answer is decoded.  The text-only context the
+        reference prefills alongside is read by ver1's reconstruction only, so it is built only when that will run."""
+        vqa_context = self.init_gen_context()
+        text_only = deepcopy(vqa_context) if need_text_only_context else None
+        for term in input_lists:
+            if isinstance(term, str):
+                vqa_context = self.update_context_text(term, vqa_context)
+                if text_only is not None:
+                    text_only = self.update_context_text(term, text_only)
+            elif isinstance(term, Image.Image):
+                vqa_context = self.update_context_image(self.vae_transform.resize_transform(pil_img2rgb(term)), vqa_context,
+                                                        vae=True, vit=True)
+            else:
+                raise ValueError(f"Unsupported input type: {type(term)}")
+        answer = self.gen_text(vqa_context, do_sample=do_sample, temperature=text_temperature, max_length=max_think_token_n)
+        return answer, vqa_context, text_only
+
+    @torch.no_grad()
+    def interleave_inference_for_vqa_reconstruction_ver1(
+            self, input_lists, reconstruct_image=False, think=False, understanding_output=True, max_think_token_n=1000,
+            do_sample=False, text_temperature=0.3, cfg_text_scale=3.0, cfg_img_scale=1.5, cfg_interval=(0.4, 1.0),
+            timestep_shift=3.0, num_timesteps=50, cfg_renorm_min=0.0, cfg_renorm_type="global", image_shapes=(1024, 1024)):
+        """inferencer.py:282-362: answer the question, then regenerate every input image conditioned on
+        [inputs, answer]; each generated image joins the context (VAE tokens only) before the next one.
+        CFG contexts: text = the VQA context without the answer, img = the text-only context plus the answer."""
+        images = [t for t in input_lists if isinstance(t, Image.Image)]
+        answer, vqa_context, text_only = self._vqa_answer(input_lists, reconstruct_image and bool(images), max_think_token_n,
+                                                          do_sample, text_temperature)
+        out: List[Union[str, Image.Image]] = [answer]
+        if not reconstruct_image or not answer or not answer.strip() or not images:
+            return out
+        cfg_text = deepcopy(vqa_context)
+        cfg_img = self.update_context_text(answer, text_only)
+        full = self.update_context_text(answer, deepcopy(vqa_context))
+        for original in images:
+            shape = self._calculate_target_size_with_aspect_ratio(*original.size)
+            generated = self.gen_image(shape, full, cfg_text_precontext=cfg_text, cfg_img_precontext=cfg_img,
+                                       cfg_text_scale=cfg_text_scale, cfg_img_scale=cfg_img_scale, cfg_interval=cfg_interval,
+                                       timestep_shift=timestep_shift, num_timesteps=num_timesteps, cfg_renorm_min=cfg_renorm_min,
+                                       cfg_renorm_type=cfg_renorm_type)
+            out.append(generated)
+            again = self.vae_transform.resize_transform(pil_img2rgb(generated))
+            full = self.update_context_image(again, full, vae=True, vit=False)
+            cfg_text = self.update_context_image(again, cfg_text, vae=True, vit=False)
+        return out
+
+    def _reconstruct_from_scratch(self, originals, answer, cfg_interval, timestep_shift, num_timesteps, cfg_renorm_min,
+                                  cfg_renorm_type):
+        """Second half of ver0 / ver0_1 (inferencer.py:427-462, 521-547): per image a FRESH context [image (VAE + ViT), answer];
+        CFG text context = the image alone, CFG img context = the answer alone; both scales fixed at 7.0."""
+        out = []
+        for original in originals:
+            shape = self._calculate_target_size_with_aspect_ratio(*original.size)
+            processed = self.vae_transform.resize_transform(pil_img2rgb(original))
+            cfg_text = self.update_context_image(processed, self.init_gen_context(), vae=True, vit=True)
+            full = self.update_context_text(answer, deepcopy(cfg_text))
+            cfg_img = self.update_context_text(answer, self.init_gen_context())
+            out.append(self.gen_image(shape, full, cfg_text_precontext=cfg_text, cfg_img_precontext=cfg_img, cfg_text_scale=7.0,
+                                      cfg_img_scale=7.0, cfg_interval=cfg_interval, timestep_shift=timestep_shift,
+                                      num_timesteps=num_timesteps, cfg_renorm_min=cfg_renorm_min, cfg_renorm_type=cfg_renorm_type))
+        return out
+
+    @torch.no_grad()
+    def interleave_inference_for_vqa_reconstruction_ver0_1(
+            self, input_lists, reconstruct_image=False, think=False, understanding_output=True, max_think_token_n=1000,
+            do_sample=False, text_temperature=0.3, cfg_text_scale=3.0, cfg_img_scale=1.5, cfg_interval=(0.4, 1.0),
+            timestep_shift=3.0, num_timesteps=50, cfg_renorm_min=0.0, cfg_renorm_type="global", image_shapes=(1024, 1024)):
+        """inferencer.py:365-462: answer, then reconstruct EVERY input image from a fresh [image, answer] context."""
+        answer, _, _ = self._vqa_answer(input_lists, False, max_think_token_n, do_sample, text_temperature)
+        out: List[Union[str, Image.Image]] = [answer]
+        images = [t for t in input_lists if isinstance(t, Image.Image)]
+        if reconstruct_image and answer and answer.strip() and images:
+            out += self._reconstruct_from_scratch(images, answer, cfg_interval, timestep_shift, num_timesteps, cfg_renorm_min,
+                                                  cfg_renorm_type)
+        return out
+
+    @torch.no_grad()
+    def interleave_inference_for_vqa_reconstruction_ver0(
+            self, input_lists, reconstruct_image=False, think=False, understanding_output=True, max_think_token_n=1000,
+            do_sample=False, text_temperature=0.3, cfg_text_scale=3.0, cfg_img_scale=1.5, cfg_interval=(0.4, 1.0),
+            timestep_shift=3.0, num_timesteps=50, cfg_renorm_min=0.0, cfg_renorm_type="global", image_shapes=(1024, 1024)):
+        """inferencer.py:465-549: as ver0_1 but only the FIRST input image is reconstructed."""
+        answer, _, _ = self._vqa_answer(input_lists, False, max_think_token_n, do_sample, text_temperature)
+        out: List[Union[str, Image.Image]] = [answer]
+        images = [t for t in input_lists if isinstance(t, Image.Image)][:1]
+        if reconstruct_image and answer and answer.strip() and images:
+            out += self._reconstruct_from_scratch(images, answer, cfg_interval, timestep_shift, num_timesteps, cfg_renorm_min,
+                                                  cfg_renorm_type)
+        return out
+
     def __call__(self, image: Optional[Union[Image.Image, List[Image.Image]]] = None, text: Optional[str] = None,
                  inference_ver=0, **kargs) -> Dict[str, Any]:
         """inferencer.py:640-680."""
@@ -170,9 +280,13 @@ class InterleaveInferencer:
             inputs.extend(image if isinstance(image, list) else [image])
         if text is not None:
             inputs.append(text)
-        if inference_ver != 0:
-            raise ValueError(f"Unsupported inference_ver: {inference_ver}")   # VQA-reconstruction variants: SURVEY.md section 8f rank 4
-        for item in self.interleave_inference(inputs, **kargs):
+        if inference_ver == 0:
+            items = self.interleave_inference(inputs, **kargs)
+        elif inference_ver == 1:
+            items = self.interleave_inference_for_vqa_reconstruction_ver1(inputs, **kargs)
+        else:
+            raise ValueError(f"Unsupported inference_ver: {inference_ver}")
+        for item in items:
             if isinstance(item, Image.Image):
                 out["image"] = (out["image"] or []) + [item]
             elif isinstance(item, str):
