@@ -1,0 +1,210 @@
+"""Continuous batching over the paged KV cache.
+
+The reference decodes one packed batch until SAMPLE 0 emits the end token (bagel.py:1313) and has no scheduler:
+a finished sample keeps burning decode steps and a waiting request cannot start until the whole batch ends.  Here
+every request owns one engine sequence (a page list), so the set of sequences a decode call runs over can change
+between calls:
+
+  * admission  -- waiting requests are prefilled TOGETHER (one packed ViT + image-block forward, one packed prompt
+    forward: the same ``prepare_* / forward_cache_update_*`` calls ``Bagel.chat`` makes, bagel.py:1321-1392) as soon as
+    a batch slot and their worst-case KV pages are free;
+  * decode     -- all running requests advance ``chunk`` steps in one device-resident loop (``umv_generate_text``);
+  * retirement -- a request ends at ITS OWN end token or length budget; its pages return to the pool and its slot is
+    re-used by the next admission;
+  * shared prefixes -- requests naming the same ``prefix`` (e.g. the think-mode system prompt, inferencer.py:574-577)
+    fork one prefilled sequence (ref-counted pages, copy-on-write tail) instead of prefilling it again.
+
+Samples are independent (SURVEY.md section 8a "Batching semantics verified"), so every request returns exactly the
+tokens ``Bagel.chat`` / ``generate_text`` would return for it alone (tests/test_scheduler_gpu.py).
+"""
+from __future__ import annotations
+
+from collections import deque
+from dataclasses import dataclass, field
+from typing import Any, Deque, Dict, List, Optional, Sequence
+
+import torch
+
+from .cache import NaiveCache, PagedKV
+
+_PAGE = 64      # tokens per KV page (include/umv.h: UMV_PAGE_TOKENS)
+
+
+@dataclass
+class Request:
+    """One VQA / text request: optional image (PIL, goes through the ViT transform), prompt text, length budget as
+    ``generate_text(max_length=...)`` counts it (rows of the returned column, the start token included)."""
+    prompt: str
+    image: Any = None
+    max_length: int = 128
+    prefix: Optional[str] = None
+    rid: int = -1
+    # running state
+    seq: int = -1
+    kv_len: int = 0
+    rope: int = 0
+    next_token: int = 0
+    inputs: List[int] = field(default_factory=list)
+    pages: int = 0
+
+
+class _Borrowed:
+    """A NaiveCache view over sequences the scheduler owns (not freed when the view dies)."""
+
+    def __init__(self, engine, layers: int, seqs: Sequence[int]):
+        self.cache = NaiveCache(layers)
+        self.cache._umv = PagedKV(engine, seqs=list(seqs))
+
+    def __enter__(self):
+        return self.cache
+
+    def __exit__(self, *exc):
+        self.cache._umv.seqs = []
+        return False
+
+
+class ContinuousBatcher:
+    def __init__(self, model, tokenizer, new_token_ids: Dict[str, int], vit_transform, max_batch: int = 8, chunk: int = 16,
+                 end_token_id: Optional[int] = None, max_prefill_tokens: Optional[int] = None):
+        self.model, self.engine = model, model.engine
+        self.tokenizer, self.tok, self.vit_transform = tokenizer, new_token_ids, vit_transform
+        self.max_batch = min(max_batch, self.engine.max_seqs, 64)
+        self.chunk = chunk
+        self.eos = new_token_ids["eos_token_id"] if end_token_id is None else end_token_id
+        self.max_prefill_tokens = max_prefill_tokens or self.engine.max_tokens
+        self.layers = model.config.llm_config.num_hidden_layers
+        self.waiting: Deque[Request] = deque()
+        self.running: List[Request] = []
+        self.finished: Dict[int, torch.Tensor] = {}
+        self._prefixes: Dict[str, tuple] = {}           # text -> (seq, kv_len, rope)
+        self._next_id = 0
+        self.capacity = self.engine.pages_free()
+        self.stats = {"prefill_calls": 0, "decode_calls": 0, "decode_steps": 0, "slot_steps_used": 0, "admitted": 0}
+
+    # ------------------------------------------------------------------ public
+    def submit(self, prompt: str, image=None, max_length: int = 128, prefix: Optional[str] = None) -> int:
+        if max_length < 1:
+            raise ValueError("max_length must be >= 1")
+        r = Request(prompt=prompt, image=image, max_length=max_length, prefix=prefix, rid=self._next_id)
+        self._next_id += 1
+        self.waiting.append(r)
+        return r.rid
+
+    def run(self) -> Dict[int, torch.Tensor]:
+        """Drain the queue.  Returns {request id: i64 tokens} -- for each request the column ``generate_text`` returns for it
+        alone: the start token, then the generated tokens up to (not including) its end token."""
+        while self.waiting or self.running:
+            self.step()
+        out, self.finished = self.finished, {}
+        return out
+
+    def close(self):
+        for seq, _, _ in self._prefixes.values():
+            self.engine.seq_free(seq)
+        self._prefixes.clear()
+
+    # ------------------------------------------------------------------ one scheduling iteration
+    @torch.no_grad()
+    def step(self) -> List[int]:
+        self._admit()
+        return self._decode_chunk()
+
+    def _rows_and_pages(self, r: Request, prefix_len: int):
+        """Worst-case geometry of a request before it is tokenised for real: prefill rows and KV pages."""
+        n_txt = len(self.tokenizer.encode(r.prompt)) + 2
+        n_img = 0
+        if r.image is not None:
+            w, h = r.image.size
+            tw, th = self.vit_transform.resize_transform.target_size(w, h)
+            p = self.model.vit_patch_size
+            n_img = (tw // p) * (th // p) + 2
+        total = prefix_len + n_img + n_txt + r.max_length
+        return max(n_img, n_txt), (total + _PAGE - 1) // _PAGE + 1       # +1: copy-on-write tail of a forked prefix
+
+    def _prefix(self, text: str):
+        if text not in self._prefixes:
+            seq = self.engine.seq_new()
+            g, lens, rope = self.model.prepare_prompts([0], [0], [text], self.tokenizer, self.tok)
+            with _Borrowed(self.engine, self.layers, [seq]) as c:
+                self.model.forward_cache_update_text(c, **g)
+            self._prefixes[text] = (seq, lens[0], rope[0])
+            self.capacity = min(self.capacity, self.engine.pages_free())
+        return self._prefixes[text]
+
+    def _admit(self):
+        group: List[Request] = []
+        rows = 0
+        committed = sum(r.pages for r in self.running)
+        while self.waiting and len(self.running) + len(group) < self.max_batch:
+            r = self.waiting[0]
+            plen = self._prefix(r.prefix)[1] if r.prefix else 0
+            need_rows, need_pages = self._rows_and_pages(r, plen)
+            if need_pages > self.capacity:
+                raise MemoryError(f"request {r.rid} needs {need_pages} KV pages, the pool has {self.capacity}")
+            if committed + need_pages > self.capacity or (group and rows + need_rows > self.max_prefill_tokens):
+                break
+            self.waiting.popleft()
+            r.pages = need_pages
+            committed += need_pages
+            rows += need_rows
+            group.append(r)
+        if not group:
+            return
+        m = self.model
+        for r in group:
+            if r.prefix:
+                seq, r.kv_len, r.rope = self._prefix(r.prefix)
+                r.seq = self.engine.seq_fork(seq)
+            else:
+                r.seq, r.kv_len, r.rope = self.engine.seq_new(), 0, 0
+        with_img = [r for r in group if r.image is not None]
+        if with_img:
+            g, lens, ropes = m.prepare_vit_images([r.kv_len for r in with_img], [r.rope for r in with_img],
+                                                  [r.image for r in with_img], self.vit_transform, self.tok)
+            with _Borrowed(self.engine, self.layers, [r.seq for r in with_img]) as c:
+                m.forward_cache_update_vit(c, **g)
+            for r, l, p in zip(with_img, lens, ropes):
+                r.kv_len, r.rope = l, p
+            self.stats["prefill_calls"] += 1
+        g, lens, ropes = m.prepare_prompts([r.kv_len for r in group], [r.rope for r in group], [r.prompt for r in group],
+                                           self.tokenizer, self.tok)
+        with _Borrowed(self.engine, self.layers, [r.seq for r in group]) as c:
+            m.forward_cache_update_text(c, **g)
+        self.stats["prefill_calls"] += 1
+        for r, l, p in zip(group, lens, ropes):
+            r.kv_len, r.rope = l, p
+            r.next_token = self.tok["bos_token_id"]             # prepare_start_tokens (bagel.py:1213-1233)
+            r.inputs = []
+        self.running.extend(group)
+        self.stats["admitted"] += len(group)
+
+    def _decode_chunk(self) -> List[int]:
+        if not self.running:
+            return []
+        run = self.running
+        n = min(self.chunk, max(r.max_length - len(r.inputs) for r in run))
+        toks, nxt = self.engine.generate_text([r.seq for r in run], [r.next_token for r in run], [r.rope for r in run], n,
+                                              return_next=True)
+        toks, nxt = toks.cpu(), nxt.cpu()
+        computed = torch.cat([toks[1:], nxt[None]], dim=0)          # token computed by each executed step, per sample
+        self.stats["decode_calls"] += 1
+        self.stats["decode_steps"] += n * len(run)
+        done: List[int] = []
+        still: List[Request] = []
+        for b, r in enumerate(run):
+            budget = min(n, r.max_length - len(r.inputs))
+            hit = torch.nonzero(computed[:budget, b] == self.eos)
+            used = int(hit[0]) + 1 if hit.numel() else budget
+            r.inputs.extend(toks[:used, b].tolist())
+            self.stats["slot_steps_used"] += used
+            if hit.numel() or len(r.inputs) >= r.max_length:
+                self.finished[r.rid] = torch.tensor(r.inputs, dtype=torch.int64)
+                self.engine.seq_free(r.seq)
+                done.append(r.rid)
+            else:
+                r.next_token = int(nxt[b])
+                r.kv_len += n
+                r.rope += n
+                still.append(r)
+        self.running = still
+        return done
