@@ -105,6 +105,18 @@ int umv_vit_embed(umv_engine* e, const float* pixels, const int64_t* pos_ids, co
 int umv_patchify_u8(const uint8_t* images, const int64_t* offsets, const int32_t* hw, int32_t n_images, int32_t patch,
                     int32_t max_per_side, float* out_pixels, int64_t* out_pos_ids, void* stream);
 
+/* Bicubic, antialiased resize of 8-bit HWC images on the device: PIL.Image.resize((out_w, out_h), BICUBIC) as
+ * MaxLongEdgeMinShortEdgeResize.forward performs it through torchvision F.resize (data/transforms.py:60-87).  Pillow's
+ * 8-bit resampler restated (weights in double precision on the host, 22-bit fixed point, horizontal pass into an 8-bit
+ * intermediate, vertical pass): bit-identical to Pillow.  src: u8 [in_h, in_w, 3] device; dst: u8 [out_h, out_w, 3]
+ * device; workspace: device scratch of umv_resize_workspace_bytes(...) bytes (weight tables + intermediate image).
+ * umv_resize_coefficients exposes one axis' table (host only: bounds i32 [out][2] = first tap, tap count; kk i32
+ * [out][*ksize]); pass NULL tables to query ksize. */
+int umv_resize_bicubic_u8(const uint8_t* src, int32_t in_h, int32_t in_w, uint8_t* dst, int32_t out_h, int32_t out_w,
+                          void* workspace, int64_t workspace_bytes, void* stream);
+int64_t umv_resize_workspace_bytes(int32_t in_h, int32_t in_w, int32_t out_h, int32_t out_w);
+int umv_resize_coefficients(int32_t in_size, int32_t out_size, int32_t* bounds, int32_t* kk, int32_t* ksize);
+
 /* ---- embedding rows: language_model.model.embed_tokens (bagel.py:438,577,1264) ------------- */
 int umv_embed_tokens(umv_engine* e, const int64_t* ids, int32_t n, void* out, void* stream);
 

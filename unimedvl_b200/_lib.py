@@ -62,6 +62,9 @@ SIGNATURES = {
     "umv_pages_free": (C.c_int, [_P, _IP]),
     "umv_vit_embed": (C.c_int, [_P, _P, _P, _IP, _I, _P, _P]),
     "umv_patchify_u8": (C.c_int, [_P, _LP, _IP, _I, _I, _I, _P, _P, _P]),
+    "umv_resize_bicubic_u8": (C.c_int, [_P, _I, _I, _P, _I, _I, _P, C.c_int64, _P]),
+    "umv_resize_workspace_bytes": (C.c_int64, [_I, _I, _I, _I]),
+    "umv_resize_coefficients": (C.c_int, [_I, _I, _IP, _IP, _IP]),
     "umv_embed_tokens": (C.c_int, [_P, _P, _I, _P, _P]),
     "umv_llm_forward": (C.c_int, [_P, _P, _I, _IP, _IP, _IP, C.POINTER(C.c_uint8), _I, _I, _P, _P]),
     "umv_lm_head": (C.c_int, [_P, _P, _I, _P, _P]),

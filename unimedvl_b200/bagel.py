@@ -321,9 +321,17 @@ class Bagel:
     @torch.no_grad()
     @torch.no_grad()
     def vqa_generate_images(self, images: Sequence[torch.Tensor], prompt_ids: Sequence[Sequence[int]], new_token_ids: dict,
-                            max_length: int) -> torch.Tensor:
-        """vqa_generate from uint8 [H, W, 3] images (already at their ViT size: sides multiples of the patch) in pinned host
-        memory: the images go up as uint8 and are normalised / patchified on the device (Engine.patchify_u8)."""
+                            max_length: int, resize_transform=None) -> torch.Tensor:
+        """vqa_generate from uint8 [H, W, 3] images in pinned host memory: the images go up as uint8 and are normalised /
+        patchified on the device (Engine.patchify_u8).  Without `resize_transform` they must already be at their ViT size
+        (sides multiples of the patch); with it (``vit_transform.resize_transform``, data/transforms.py:15-87) each image is
+        first resized on the device to the size that rule gives (Engine.resize_u8)."""
+        if resize_transform is not None:          # the ViT transform's resize rule, applied on the device (bit-identical to PIL)
+            sized = []
+            for im in images:
+                w, h = resize_transform.target_size(int(im.shape[1]), int(im.shape[0]))
+                sized.append(im if (h, w) == tuple(im.shape[:2]) else self.engine.resize_u8(im, h, w))
+            images = sized
         pixels, pos, lens = self.engine.patchify_u8(images)
         return self.vqa_generate(pixels, pos, lens, prompt_ids, new_token_ids, max_length)
 

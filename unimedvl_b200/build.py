@@ -17,7 +17,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "libumv.so")
-SOURCES = ["gemm.cu", "gemm_2cta.cu", "kernels.cu", "attention.cu", "attention_tc.cu", "engine.cu", "flow.cu", "vae.cu"]
+SOURCES = ["gemm.cu", "gemm_2cta.cu", "kernels.cu", "attention.cu", "attention_tc.cu", "engine.cu", "flow.cu", "vae.cu", "resize.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
          "-Xcompiler", "-fPIC", "-Xptxas", "-v", "--expt-relaxed-constexpr"]

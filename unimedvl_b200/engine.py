@@ -173,6 +173,18 @@ class Engine:
                                             self.dims.vit_max_num_patch_per_side, _ptr(pixels), _ptr(pos), _stream_ptr()))
         return pixels, pos, lens
 
+    def resize_u8(self, image: torch.Tensor, out_h: int, out_w: int) -> torch.Tensor:
+        """PIL.Image.resize((out_w, out_h), BICUBIC) -- the resize of MaxLongEdgeMinShortEdgeResize (data/transforms.py:60-87)
+        -- on the device, bit-identical to Pillow: uint8 [H, W, 3] (host or device) -> device uint8 [out_h, out_w, 3]."""
+        assert image.dtype == torch.uint8 and image.dim() == 3 and image.shape[2] == 3, "uint8 [H, W, 3] image expected"
+        src = image.to(self.device, non_blocking=True).contiguous()
+        H, W = int(src.shape[0]), int(src.shape[1])
+        dst = torch.empty((out_h, out_w, 3), dtype=torch.uint8, device=self.device)
+        nbytes = int(self.lib.umv_resize_workspace_bytes(H, W, out_h, out_w))
+        ws = torch.empty(max(nbytes, 1), dtype=torch.uint8, device=self.device)
+        _lib.check(self.lib.umv_resize_bicubic_u8(_ptr(src), H, W, _ptr(dst), out_h, out_w, _ptr(ws), nbytes, _stream_ptr()))
+        return dst
+
     def vit_embed(self, pixels: torch.Tensor, pos_ids: torch.Tensor, seqlens: Iterable[int]) -> torch.Tensor:
         pixels = pixels.to(self.device, torch.float32).contiguous()
         pos_ids = pos_ids.to(self.device, torch.int64).contiguous()
