@@ -1,6 +1,8 @@
 """In-stream timeline of the VQA prefill at the 14B dims (8 samples of 448x448 + 32-token prompt per GPU): ViT + connector,
 image prefill, prompt prefill, then 2 decode steps.  Per-kernel-class share of the critical path.
-    python tools/prefill_trace.py [out.md]"""
+    python tools/prefill_trace.py [out.md]
+    UMV_NCU=1 ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none --csv --log-file l.csv \\
+        python tools/prefill_trace.py     # launch list of exactly one job"""
 import ctypes as C
 import os
 import sys
@@ -29,9 +31,14 @@ torch.cuda.synchronize()
 CAP, NL = 8192, 32
 _lib.check(eng.lib.umv_trace_begin(CAP))
 ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+if os.environ.get("UMV_NCU"):           # ncu --profile-from-start off: only this job is profiled
+    torch.cuda.profiler.start()
 ev0.record()
 model.vqa_generate(pixels, pos_ids, lens, prompts, tok, 3)
 ev1.record()
+if os.environ.get("UMV_NCU"):
+    torch.cuda.synchronize()
+    torch.cuda.profiler.stop()
 torch.cuda.synchronize()
 stamps = np.zeros((CAP, 12), dtype=np.uint64)
 names = C.create_string_buffer(CAP * NL)
