@@ -39,6 +39,10 @@ PROMPT_TOKENS = 30
 IMG = 448
 
 
+WORKLOAD = ("VQA batch=8 per GPU, 448x448 (1024 ViT tokens + 2 markers), 32-token prompt, 14B MoT bf16 "
+            "(both experts resident), 128-token greedy decode, ctx 1058->1185")      # BASELINE.json configs[1], both arms
+
+
 def _peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -181,8 +185,8 @@ def run_reference(args, rank: int, world: int):
     line = {"impl": "reference", "metric": "VQA decode tok/s @14B (B=8/GPU, 448x448, 128-token greedy)", "value": base["value"],
             "unit": "tok/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": base["ms_per_step_extrapolated"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "bf16", "data": "synthetic", "config": {"workload": "VQA batch=8, 448x448, 14B bf16, 128-token greedy decode",
-                                                             "arm": "CPU forward of the reference algorithm (oracle port)"},
+            "dtype": "bf16", "data": "synthetic", "config": {"workload": WORKLOAD,
+                                                             "arm": "CPU forward of the reference algorithm (oracle port), rank 0 only"},
             "cpu_baseline": base, "e2e": {"value": base["value"], "unit": "tok/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0, "wall_s": round(time.perf_counter() - t0, 1)}
     print(json.dumps(line), flush=True)
@@ -369,8 +373,7 @@ def run_engine(args, rank: int, local_rank: int, world: int):
         "metric": "VQA decode tok/s @14B (B=8/GPU, 448x448, 128-token greedy)", "value": round(value, 1), "unit": "tok/s",
         "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": round(ms / args.steps, 3),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": "VQA batch=8 per GPU, 448x448 (1024 ViT tokens + 2 markers), 32-token prompt, 14B MoT bf16 "
-                               "(both experts resident), 128-token greedy decode, ctx 1058->1185",
+        "config": {"workload": WORKLOAD,
                    "parallelism": f"dp{world}", "l2": "weights streamed per decode forward (14.1 GB) exceed the 126 MB L2",
                    "weights": "random-init, generated on device", "step": "generate_text(max_length=128) for the batch"},
         "ms_per_decode_forward": round(step_ms, 4),

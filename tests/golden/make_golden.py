@@ -2,7 +2,7 @@
 
 Run in the build container only (needs /root/reference; the GPU box has no copy):
 
-    python tests/golden/make_golden.py [packing|vqa|t2i|edit|e2e|recon ...]
+    python tests/golden/make_golden.py [packing|vqa|t2i|edit|e2e|recon|think ...]
 
 The reference ships no tests or golden vectors, so parity is pinned on the
 outputs of the unmodified reference modules imported from /root/reference/codes, executed on CPU
@@ -332,6 +332,23 @@ def golden_recon(model, vae, out):
         out["recon.ver1_noimage_text"] = np.asarray(r["text"])
 
 
+def golden_think(model, vae, out):
+    """G8: think mode of interleave_inference (inferencer.py:574-577,612-620): the system prompt is prefilled first; for
+    generation the model first writes its plan (gen_text), the plan joins the context, then the image is generated."""
+    tok = FakeTokenizer()
+    inf = InterleaveInferencer(model, vae, tok, ImageTransform(1024, 32, 16), ImageTransform(980, 28, 14), TOK)
+    img = make_images([(70, 98)], base=30)[0]
+    with torch.no_grad(), torch.autocast("cpu", dtype=torch.bfloat16):
+        r = inf(image=img, text="What is shown in this image?", think=True, understanding_output=True, max_think_token_n=8,
+                do_sample=False)
+        out["think.i2t_text"] = np.asarray(r["text"])
+        torch.manual_seed(61)
+        r = inf(text="a chest x-ray with cardiomegaly", think=True, understanding_output=False, max_think_token_n=6, do_sample=False,
+                num_timesteps=3, image_shapes=(64, 64), cfg_text_scale=4.0, cfg_img_scale=1.5, cfg_interval=[0.0, 1.0])
+        out["think.t2i_text"] = np.asarray(r["text"])
+        out["think.t2i_image"] = np.asarray(r["image"])
+
+
 def main():
     torch.manual_seed(0)
     torch.set_num_threads(8)
@@ -342,7 +359,8 @@ def main():
                      ("t2i", lambda o: golden_t2i(model, vae, o)),
                      ("edit", lambda o: golden_edit(model, vae, o)),
                      ("e2e", lambda o: golden_e2e(model, vae, o)),
-                     ("recon", lambda o: golden_recon(model, vae, o))):
+                     ("recon", lambda o: golden_recon(model, vae, o)),
+                     ("think", lambda o: golden_think(model, vae, o))):
         if len(sys.argv) > 1 and name not in sys.argv[1:]:
             continue
         out = {}

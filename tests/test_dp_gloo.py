@@ -25,7 +25,8 @@ def _worker(rank, world, port, n_items, q):
     ids = torch.arange(lo, hi)
     toks = torch.stack([ids * 1000 + s for s in range(5)], 0)
     full = dp.gather_tokens(toks, n_items)
-    q.put((rank, full))
+    imgs = (ids.view(-1, 1, 1, 1) * 3 + torch.arange(3).view(1, 1, 1, 3)).expand(-1, 4, 6, 3).to(torch.uint8)
+    q.put((rank, full, dp.gather_images(imgs.contiguous(), n_items)))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -47,10 +48,14 @@ def test_gather_tokens_world2_ragged():
     procs = [ctx.Process(target=_worker, args=(r, world, port, n_items, q)) for r in range(world)]
     for p in procs:
         p.start()
-    got = dict(q.get(timeout=120) for _ in range(world))
+    res = [q.get(timeout=120) for _ in range(world)]
+    got = {r: t for r, t, _ in res}
+    got_img = {r: i for r, _, i in res}
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
     want = torch.stack([torch.arange(n_items) * 1000 + s for s in range(5)], 0)
+    want_img = (torch.arange(n_items).view(-1, 1, 1, 1) * 3 + torch.arange(3).view(1, 1, 1, 3)).expand(-1, 4, 6, 3).to(torch.uint8)
     for r in range(world):
         assert torch.equal(got[r], want)
+        assert torch.equal(got_img[r], want_img)

@@ -84,6 +84,22 @@ def test_image_edit(inferencer):
     assert abs(float(got.mean()) - float(gold.mean())) < 25.0
 
 
+def test_think_mode(inferencer):
+    """think=True (inferencer.py:574-577,612-620): system prompt first; for generation the plan is decoded, appended to
+    the context and returned next to the image."""
+    inf, eng = inferencer
+    gold = Golden("think").z
+    r = inf(image=_img(), text="What is shown in this image?", think=True, understanding_output=True, max_think_token_n=8,
+            do_sample=False)
+    assert r["image"] is None and r["text"] == str(gold["think.i2t_text"])
+    torch.manual_seed(61)
+    r = inf(text="a chest x-ray with cardiomegaly", think=True, understanding_output=False, max_think_token_n=6, do_sample=False,
+            num_timesteps=3, image_shapes=(64, 64), cfg_text_scale=4.0, cfg_img_scale=1.5, cfg_interval=[0.0, 1.0])
+    assert r["text"] == str(gold["think.t2i_text"])
+    mean, far = _diff(r["image"], gold["think.t2i_image"])
+    assert mean < 8.0 and far < 0.03, (mean, far)
+
+
 def _recon_images():
     return [Image.fromarray(synth.synthetic_image(30 + i, h, w)) for i, (h, w) in enumerate([(70, 98), (64, 64)])]
 

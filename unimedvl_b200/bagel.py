@@ -319,7 +319,6 @@ class Bagel:
 
     # ------------------------------------------------------------------ batched VQA job (bench / serving)
     @torch.no_grad()
-    @torch.no_grad()
     def vqa_generate_images(self, images: Sequence[torch.Tensor], prompt_ids: Sequence[Sequence[int]], new_token_ids: dict,
                             max_length: int, resize_transform=None) -> torch.Tensor:
         """vqa_generate from uint8 [H, W, 3] images in pinned host memory: the images go up as uint8 and are normalised /

@@ -35,3 +35,19 @@ def gather_tokens(tokens: torch.Tensor, n_items: int) -> torch.Tensor:
     out = [torch.empty_like(pad) for _ in range(world)]
     dist.all_gather(out, pad.contiguous())          # the path's only collective
     return torch.cat([out[r][:, :hi - lo] for r, (lo, hi) in enumerate(sizes)], dim=1)
+
+
+def gather_images(images: torch.Tensor, n_items: int) -> torch.Tensor:
+    """images: uint8 [B_local, H, W, 3] (one size per job, as BASELINE.json's text-to-image configs) on every rank ->
+    [n_items, H, W, 3] on every rank in batch order; the text-to-image counterpart of gather_tokens (SURVEY.md section 8e:
+    768 KB per rank at 4 x 256 x 256)."""
+    if not dist.is_initialized() or dist.get_world_size() == 1:
+        return images
+    world = dist.get_world_size()
+    sizes = [shard_bounds(n_items, r, world) for r in range(world)]
+    bmax = max(hi - lo for lo, hi in sizes)
+    pad = torch.zeros((bmax,) + tuple(images.shape[1:]), dtype=images.dtype, device=images.device)
+    pad[:images.shape[0]] = images
+    out = [torch.empty_like(pad) for _ in range(world)]
+    dist.all_gather(out, pad.contiguous())
+    return torch.cat([out[r][:hi - lo] for r, (lo, hi) in enumerate(sizes)], dim=0)
