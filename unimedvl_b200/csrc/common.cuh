@@ -45,6 +45,20 @@ __device__ __forceinline__ float2 unpack2(uint32_t u) {
     return __bfloat1622float2(v);
 }
 
+// Packed bf16 arithmetic with ONE rounding per lane.  For bf16 operands the fp32 product (16 significant bits) and the fp32 sum
+// relevant here are exact before rounding, so mul.rn.bf16x2 == bf16(float(a) * float(b)) and add.rn.bf16x2 == bf16(float(a) + float(b)):
+// the reference's "compute in fp32, store bf16" steps on bf16 inputs at half the instructions (no unpack, no separate convert).
+__device__ __forceinline__ uint32_t bmul2(uint32_t a, uint32_t b) {
+    uint32_t d;
+    asm("mul.rn.bf16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
+    return d;
+}
+__device__ __forceinline__ uint32_t badd2(uint32_t a, uint32_t b) {
+    uint32_t d;
+    asm("add.rn.bf16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
+    return d;
+}
+
 // torch's silu on a bf16 tensor: fp32 x / (1 + exp(-x)), one rounding.
 __device__ __forceinline__ float silu_f(float x) { return x / (1.0f + expf(-x)); }
 // torch gelu(approximate="tanh") opmath: 0.5 x (1 + tanh(sqrt(2/pi) (x + 0.044715 x^3)))

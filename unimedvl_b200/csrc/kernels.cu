@@ -102,10 +102,8 @@ __global__ void __launch_bounds__(kNormThreads) add_rmsnorm_kernel(AddNormArgs a
             const uint32_t* ww = &wv[c].x;
             uint32_t o[4];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const float2 wf = unpack2(ww[j]);
-                o[j] = pack2(wf.x * rbf(v[c][2 * j] * inv), wf.y * rbf(v[c][2 * j + 1] * inv));   // R2
-            }
+            for (int j = 0; j < 4; ++j)      // R2: bf16(w * bf16(h * inv)); the outer product of two bf16 values is one mul.rn.bf16x2
+                o[j] = bmul2(ww[j], pack2(__fmul_rn(v[c][2 * j], inv), __fmul_rn(v[c][2 * j + 1], inv)));
             stg16(yrow + ch * 8, U4{o[0], o[1], o[2], o[3]});
             if (slot2 >= 0) stg16(a.y2 + (size_t)slot2 * a.D + ch * 8, U4{o[0], o[1], o[2], o[3]});
         }
@@ -177,8 +175,8 @@ __global__ void __launch_bounds__(256, NB == 1 ? 4 : 2) rmsnorm_rows_warp_kernel
                     uint32_t o[4];
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
-                        const float2 f = unpack2(hw[j]), wf = unpack2(ww[j]);
-                        o[j] = pack2(wf.x * rbf(f.x * inv), wf.y * rbf(f.y * inv));   // R2
+                        const float2 f = unpack2(hw[j]);
+                        o[j] = bmul2(ww[j], pack2(__fmul_rn(f.x, inv), __fmul_rn(f.y, inv)));   // R2 (see add_rmsnorm_kernel)
                     }
                     stg16(yrow + ch * 8, U4{o[0], o[1], o[2], o[3]});
                     if (slot2 >= 0) stg16(a.y2 + (size_t)slot2 * a.D + ch * 8, U4{o[0], o[1], o[2], o[3]});
@@ -559,16 +557,6 @@ __global__ void __launch_bounds__(kRopeWarps * 32, 8) rope_append_kernel(RopeApp
 // mul.rn.bf16x2 == bf16(fp32 product) and add.rn.bf16x2 == bf16(fp32 sum) (both fp32 results are exact before the
 // rounding).  The sum of squares follows rope_append_kernel's order (old lane 2j | 2j+1 = the two halves of new lane j, then
 // the same xor tree), so both kernels -- and the fused decode attention -- produce the same bits.
-__device__ __forceinline__ uint32_t bmul2(uint32_t a, uint32_t b) {
-    uint32_t d;
-    asm("mul.rn.bf16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
-    return d;
-}
-__device__ __forceinline__ uint32_t badd2(uint32_t a, uint32_t b) {
-    uint32_t d;
-    asm("add.rn.bf16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
-    return d;
-}
 constexpr int kRopePairs = 5;        // slot pairs per warp kept in flight (4 warps x 5 pairs x 2 = 40 >= H + 2 Hkv = 36)
 template <bool GEN>
 __global__ void __launch_bounds__(kRopeWarps * 32, 8) rope_append_rows_kernel(RopeAppendArgs a) {
