@@ -78,8 +78,8 @@ def test_norms(ops, M, D):
 
 @pytest.mark.parametrize("M,D", [(4100, 3584), (300, 2048), (1027, 1152), (515, 4096)])
 def test_rmsnorm_row_kernels_bit_identical(ops, M, D, monkeypatch):
-    """The warp-per-row kernel (picked for >= 4096 rows) sums the squares in the block kernel's order: whichever runs, the
-    bits are the same -- batch invariance (tests/test_fullsize_gpu.py) rests on it."""
+    """The warp-per-row kernel (>= 4096 rows) and the 128-threads-per-row kernel (256 .. 4095 rows) sum the squares in the block
+    kernel's order: whichever runs, the bits are the same -- batch invariance (tests/test_fullsize_gpu.py) rests on it."""
     torch.manual_seed(M)
     x = (torch.randn(M, D) * torch.rand(M, 1) * 8).bfloat16().cuda()
     w = (1 + 0.1 * torch.randn(D)).bfloat16().cuda()
@@ -87,7 +87,9 @@ def test_rmsnorm_row_kernels_bit_identical(ops, M, D, monkeypatch):
     y_block = ops.op_rmsnorm(x, w)
     monkeypatch.setenv("UMV_NORM_WARP", "1")
     y_warp = ops.op_rmsnorm(x, w)
-    assert torch.equal(y_block, y_warp)
+    monkeypatch.setenv("UMV_NORM_WARP", "2")
+    y_half = ops.op_rmsnorm(x, w)
+    assert torch.equal(y_block, y_warp) and torch.equal(y_block, y_half)
     s = ulp_stats(y_warp, nm.rmsnorm(x.cpu(), w.cpu(), 1e-6))
     assert s["max_ulp"] <= 1 and s["frac"] < 1e-3, s
 

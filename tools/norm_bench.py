@@ -2,7 +2,7 @@ import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from unimedvl_b200.engine import op_rmsnorm
-for warp, M in [(w, m) for w in ("0", "1") for m in (272, 1026, 3096, 8208, 16416)]:
+for warp, M in [(w, m) for w in ("0", "2", "1") for m in (272, 1026, 3096, 8208, 16416)]:
     os.environ["UMV_NORM_WARP"] = warp
     D = 3584
     x = torch.randn(M, D, device="cuda").bfloat16(); w = torch.ones(D, device="cuda").bfloat16()

@@ -186,6 +186,78 @@ __global__ void __launch_bounds__(256, NB == 1 ? 4 : 2) rmsnorm_rows_warp_kernel
     trace_end<false>(a.trace);
 }
 
+// Mid-size variant (256 .. 4095 rows, e.g. the 3096 rows of a text-to-image flow step): one CTA of 128 threads per row, packed
+// registers.  add_rmsnorm_kernel keeps 62 registers x 256 threads per row -> 4 rows in flight per SM (ncu: occupancy limited by
+// registers), 5.2 rounds for 21 rows per SM; here a row costs 128 x ~40 registers, so 12 fit.  Same summation order again: thread u
+// plays the block kernel's threads u and u + 128 (virtual warps w and w + 4), then the fixed tree over the eight warp sums.
+template <int NB>
+__global__ void __launch_bounds__(128, 8) rmsnorm_rows_half_kernel(AddNormArgs a) {
+    pdl_launch_dependents();
+    trace_start(a.trace);
+    pdl_wait();
+    trace_wait(a.trace);
+    __shared__ float red[8];
+    const int row = blockIdx.x, u = threadIdx.x, warp = u >> 5, lane = u & 31;
+    const int nchunk = a.D / 8;
+    const bf16* hrow = a.h + (size_t)row * a.D;
+    const bf16* w = (a.row_sel && a.row_sel[row]) ? a.w1 : a.w0;
+    const int slot2 = (a.y2 && a.row_slot) ? a.row_slot[row] : -1;
+    U4 hv[2][NB];
+#pragma unroll
+    for (int v = 0; v < 2; ++v)
+#pragma unroll
+        for (int n = 0; n < NB; ++n) {
+            const int ch = n * kNormThreads + v * 128 + u;
+            hv[v][n] = U4{0, 0, 0, 0};
+            if (ch < nchunk) hv[v][n] = ldg16(hrow + ch * 8);
+        }
+#pragma unroll
+    for (int v = 0; v < 2; ++v) {
+        float ss = 0.f;
+#pragma unroll
+        for (int n = 0; n < NB; ++n) {
+            const uint32_t* hw = &hv[v][n].x;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float2 f = unpack2(hw[j]);
+                ss = fmaf(f.x, f.x, ss);
+                ss = fmaf(f.y, f.y, ss);
+            }
+        }
+        ss = warp_sum(ss);
+        if (lane == 0) red[warp + 4 * v] = ss;
+    }
+    __syncthreads();
+    const float ss = ((red[0] + red[4]) + (red[2] + red[6])) + ((red[1] + red[5]) + (red[3] + red[7]));   // block_sum's last tree
+    const float inv = 1.0f / sqrtf(ss / (float)a.D + a.eps);
+#pragma unroll
+    for (int v = 0; v < 2; ++v)
+#pragma unroll
+        for (int n = 0; n < NB; ++n)
+            asm volatile("" : "+r"(hv[v][n].x), "+r"(hv[v][n].y), "+r"(hv[v][n].z), "+r"(hv[v][n].w));   // stay packed
+    bf16* yrow = a.y + (size_t)row * a.D;
+#pragma unroll
+    for (int v = 0; v < 2; ++v)
+#pragma unroll
+        for (int n = 0; n < NB; ++n) {
+            const int ch = n * kNormThreads + v * 128 + u;
+            if (ch < nchunk) {
+                const U4 wv = ldg16(w + ch * 8);
+                const uint32_t* hw = &hv[v][n].x;
+                const uint32_t* ww = &wv.x;
+                uint32_t o[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float2 f = unpack2(hw[j]);
+                    o[j] = bmul2(ww[j], pack2(__fmul_rn(f.x, inv), __fmul_rn(f.y, inv)));   // R2 (see add_rmsnorm_kernel)
+                }
+                stg16(yrow + ch * 8, U4{o[0], o[1], o[2], o[3]});
+                if (slot2 >= 0) stg16(a.y2 + (size_t)slot2 * a.D + ch * 8, U4{o[0], o[1], o[2], o[3]});
+            }
+        }
+    trace_end<false>(a.trace);
+}
+
 // Decode variant (split-K partials of the preceding weight-major linear, a handful of rows): the kernel sits on the
 // critical path of the decode chain and is pure latency, so one thread owns one 8-element chunk and EVERY global load
 // (norm weight before griddepcontrol.wait -- it is constant --, residual row and all split partials right after it) is
@@ -268,14 +340,24 @@ int add_rmsnorm(const AddNormArgs& a0, cudaStream_t s) {
         UMV_LAUNCH_CHECK("add_rmsnorm_splitk_kernel");
         return UMV_OK;
     }
-    const char* warp_env = getenv("UMV_NORM_WARP");        // read per call: tests switch paths inside one process
-    const int warp_min_rows = warp_env ? (atoi(warp_env) ? 1 : 0x7fffffff) : 4096;
-    if (!a.delta && !a.partial && a.y && a.M >= warp_min_rows && a.D / 8 <= 2 * kNormThreads) {   // plain RMSNorm of many rows
-        const dim3 grid((a.M + 7) / 8);
-        if (a.D / 8 <= kNormThreads) launch_k(rmsnorm_rows_warp_kernel<1>, grid, dim3(256), 0, s, a);
-        else launch_k(rmsnorm_rows_warp_kernel<2>, grid, dim3(256), 0, s, a);
-        UMV_LAUNCH_CHECK("rmsnorm_rows_warp_kernel");
-        return UMV_OK;
+    // plain RMSNorm of many rows: kernel by row count (0 = block, 1 = warp per row, 2 = 128 threads per row); all three sum in the
+    // same order, so the choice never changes a bit.  UMV_NORM_WARP forces one (read per call: tests switch inside one process).
+    const char* warp_env = getenv("UMV_NORM_WARP");
+    if (!a.delta && !a.partial && a.y && a.D / 8 <= 2 * kNormThreads) {
+        const int kind = warp_env ? atoi(warp_env) : (a.M >= 4096 ? 1 : (a.M >= 256 ? 2 : 0));
+        if (kind == 1) {
+            const dim3 grid((a.M + 7) / 8);
+            if (a.D / 8 <= kNormThreads) launch_k(rmsnorm_rows_warp_kernel<1>, grid, dim3(256), 0, s, a);
+            else launch_k(rmsnorm_rows_warp_kernel<2>, grid, dim3(256), 0, s, a);
+            UMV_LAUNCH_CHECK("rmsnorm_rows_warp_kernel");
+            return UMV_OK;
+        }
+        if (kind == 2) {
+            if (a.D / 8 <= kNormThreads) launch_k(rmsnorm_rows_half_kernel<1>, dim3(a.M), dim3(128), 0, s, a);
+            else launch_k(rmsnorm_rows_half_kernel<2>, dim3(a.M), dim3(128), 0, s, a);
+            UMV_LAUNCH_CHECK("rmsnorm_rows_half_kernel");
+            return UMV_OK;
+        }
     }
     const int nc = (a.D / 8 + kNormThreads - 1) / kNormThreads;
     if (nc <= 1) launch_k(add_rmsnorm_kernel<1>, dim3(a.M), dim3(kNormThreads), 0, s, a);
