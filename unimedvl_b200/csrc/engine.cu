@@ -1020,7 +1020,7 @@ int umv_generate_text(umv_engine* e, int32_t n_seqs, const int32_t* seqs, const 
         UMV_TRY(llm_layers(e, r, e->xn, s));
         UMV_TRY(lin(e, e->xn, D, e->lm_head, nullptr, nullptr, logits, V, B, V, D, EPI_BF16, s));
         if (temperature > 0.f) UMV_TRY(sample_rows(logits, B, V, temperature, seed, e->dec_step, e->dec_tokens, s));
-        else UMV_TRY(argmax_rows(logits, B, V, e->dec_tokens, s));
+        else return argmax_rows(logits, B, V, e->dec_tokens, s, &ds);        // greedy: the argmax launch also ends the step
         return decode_end_step(ds, B, s);
     };
 
@@ -1057,7 +1057,7 @@ int umv_generate_text(umv_engine* e, int32_t n_seqs, const int32_t* seqs, const 
                 UMV_TRY(llm_layers(e, r, e->xn, st));
                 UMV_TRY(lin(e, e->xn, D, e->lm_head, nullptr, nullptr, e->logits, V, B, V, D, EPI_BF16, st));
                 if (temperature > 0.f) UMV_TRY(sample_rows(e->logits, B, V, temperature, seed, e->dec_step, e->dec_tokens, st));
-                else UMV_TRY(argmax_rows(e->logits, B, V, e->dec_tokens, st));
+                else return argmax_rows(e->logits, B, V, e->dec_tokens, st, &ds);
                 return decode_end_step(ds, B, st);
             };
             int rc = cstep();

@@ -890,7 +890,10 @@ int copy_rows(const bf16* src, int lds, const int* rows, bf16* dst, int ldd, int
 
 // ------------------------------------------------------------------------------------------
 // torch.argmax over bf16 logits: maximum value, ties -> lowest index (R8).  One CTA per row.
-__global__ void __launch_bounds__(1024) argmax_kernel(const bf16* __restrict__ logits, int vocab, int64_t* __restrict__ out) {
+// `end` (decode loop only): the row's CTA also advances that sample's loop state -- what decode_end_kernel does -- saving a
+// launch on the per-step critical path (nothing later in the step reads positions / kv_len / step).
+__global__ void __launch_bounds__(1024) argmax_kernel(const bf16* __restrict__ logits, int vocab, int64_t* __restrict__ out,
+                                                       DecodeState end, int advance) {
     pdl_launch_dependents();
     pdl_wait();
     __shared__ float sval[32];
@@ -899,15 +902,27 @@ __global__ void __launch_bounds__(1024) argmax_kernel(const bf16* __restrict__ l
     float best = -INFINITY;
     int bi = 0x7fffffff;
     const int nchunk = vocab / 8;
-    for (int c = threadIdx.x; c < nchunk; c += blockDim.x) {
-        const U4 v = ldg16_stream(row + c * 8);
-        const uint32_t* w = &v.x;
+    constexpr int kAhead = 5;                       // a thread's loads of 5 strides in flight together (19 chunks per thread at 152k)
+    for (int c0 = threadIdx.x; c0 < nchunk; c0 += kAhead * blockDim.x) {
+        U4 v[kAhead];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const float2 f = unpack2(w[j]);
-            const int i0 = c * 8 + 2 * j;
-            if (f.x > best || (f.x == best && i0 < bi)) { best = f.x; bi = i0; }
-            if (f.y > best || (f.y == best && i0 + 1 < bi)) { best = f.y; bi = i0 + 1; }
+        for (int u = 0; u < kAhead; ++u) {
+            const int c = c0 + u * blockDim.x;
+            if (c < nchunk) v[u] = ldg16_stream(row + c * 8);
+        }
+#pragma unroll
+        for (int u = 0; u < kAhead; ++u) {
+            const int c = c0 + u * blockDim.x;
+            if (c < nchunk) {
+                const uint32_t* w = &v[u].x;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float2 f = unpack2(w[j]);
+                    const int i0 = c * 8 + 2 * j;
+                    if (f.x > best || (f.x == best && i0 < bi)) { best = f.x; bi = i0; }
+                    if (f.y > best || (f.y == best && i0 + 1 < bi)) { best = f.y; bi = i0 + 1; }
+                }
+            }
         }
     }
     for (int i = nchunk * 8 + threadIdx.x; i < vocab; i += blockDim.x) {
@@ -933,14 +948,23 @@ __global__ void __launch_bounds__(1024) argmax_kernel(const bf16* __restrict__ l
             const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
             if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
         }
-        if (lane == 0) out[blockIdx.x] = (bi == 0x7fffffff) ? 0 : bi;   // all-NaN row -> 0
+        if (lane == 0) {
+            out[blockIdx.x] = (bi == 0x7fffffff) ? 0 : bi;   // all-NaN row -> 0
+            if (advance) {
+                const int b = blockIdx.x;
+                end.positions[b] += 1;     // packed_query_position_ids + 1 (bagel.py:1310)
+                end.kv_len[b] += 1;        // key_values_lens + 1 (bagel.py:1309)
+                end.row_kvpos[b] += 1;
+                if (b == 0) *end.step += 1;
+            }
+        }
     }
 }
-int argmax_rows(const bf16* logits, int rows, int vocab, int64_t* out, cudaStream_t s) {
+int argmax_rows(const bf16* logits, int rows, int vocab, int64_t* out, cudaStream_t s, const DecodeState* end) {
     if (rows <= 0) return UMV_OK;
     UMV_REQUIRE((reinterpret_cast<uintptr_t>(logits) & 15) == 0 && vocab % 8 == 0, UMV_ERR_INVALID,
                 "argmax: logits must be 16-byte aligned with vocab %% 8 == 0 (vocab=%d)", vocab);
-    launch_k(argmax_kernel, dim3(rows), dim3(1024), 0, s, logits, vocab, out);
+    launch_k(argmax_kernel, dim3(rows), dim3(1024), 0, s, logits, vocab, out, end ? *end : DecodeState{}, end ? 1 : 0);
     UMV_LAUNCH_CHECK("argmax_kernel");
     return UMV_OK;
 }

@@ -107,7 +107,9 @@ int gather_add_rows(bf16* x, const bf16* table, const int64_t* ids, int M, int D
 // uint8 HWC image -> normalised fp32 patch vectors + position ids (one CTA per patch)
 int patchify_u8(const uint8_t* img, int H, int W, int patch, int max_per_side, float* out, int64_t* pos_ids, cudaStream_t s);
 int f32_to_bf16_padded(const float* x, bf16* y, int M, int K, int Kpad, cudaStream_t s);
-int argmax_rows(const bf16* logits, int rows, int vocab, int64_t* out, cudaStream_t s);
+struct DecodeState;
+// `end` != null (decode loop): each row's CTA also advances that sample's loop state (replaces decode_end_step)
+int argmax_rows(const bf16* logits, int rows, int vocab, int64_t* out, cudaStream_t s, const DecodeState* end = nullptr);
 int copy_rows(const bf16* src, int lds, const int* rows, bf16* dst, int ldd, int n, int D, int scatter, cudaStream_t s);
 int fill_uniform_bf16(bf16* p, size_t n, uint64_t seed, float bound, float mean, cudaStream_t s);
 
