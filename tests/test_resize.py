@@ -77,3 +77,25 @@ def test_device_resize_then_patchify_equals_host_transform(eng):
         pixels, pos, lens = eng.patchify_u8([sized])
         assert lens == [want.shape[0]] and torch.equal(pixels.cpu(), want)
         assert torch.equal(pos.cpu(), packing.flattened_position_ids(t.size(1), t.size(2), dims.vit.patch, dims.vit_max_num_patch_per_side))
+
+
+def test_random_geometries_property():
+    """Property over random geometries (seeded): oracle == Pillow and library weight tables == oracle, including extreme
+    aspect ratios, 1-pixel sides and up/down scaling mixed per axis."""
+    from unimedvl_b200 import _lib
+    lib = _lib.load()
+    rng = np.random.default_rng(2024)
+    for _ in range(40):
+        H, W, h, w = (int(v) for v in rng.integers(1, 160, 4))
+        a = rng.integers(0, 256, (H, W, 3), dtype=np.uint8)
+        ref = np.asarray(Image.fromarray(a).resize((w, h), Image.BICUBIC))
+        assert np.array_equal(oresize.resize_bicubic_u8(a, h, w), ref), (H, W, h, w)
+        for n_in, n_out in ((W, w), (H, h)):
+            ks = C.c_int32()
+            _lib.check(lib.umv_resize_coefficients(n_in, n_out, None, None, C.byref(ks)))
+            bounds = np.zeros((n_out, 2), dtype=np.int32)
+            kk = np.zeros((n_out, ks.value), dtype=np.int32)
+            _lib.check(lib.umv_resize_coefficients(n_in, n_out, bounds.ctypes.data_as(C.POINTER(C.c_int32)),
+                                                   kk.ctypes.data_as(C.POINTER(C.c_int32)), C.byref(ks)))
+            ob, ok = oresize.coefficients(n_in, n_out)
+            assert np.array_equal(bounds, ob) and np.array_equal(kk, ok), (n_in, n_out)
