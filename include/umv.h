@@ -201,7 +201,23 @@ int umv_op_layernorm(const void* x, const void* w, const void* b, void* y, int32
 int umv_op_attention(const void* q, const void* k, const void* v, void* out, int32_t n, const int32_t* q_lens,
                      const int32_t* k_lens, int32_t heads, int32_t kv_heads, int32_t head_dim, int32_t causal,
                      void* stream);
-int umv_op_argmax(const void* logits, int32_t rows, int32_t vocab, int64_t* out, void* stream);
+/* The attention block of decoder layer `layer` ALONE, exactly as the model path runs it (PackedAttentionMoT.forward_inference after
+ * the q/k/v projections, qwen2_navit.py:544-614): per-head q/k RMSNorm (the layer's q_norm / k_norm weights, *_moe_gen for rows with
+ * row_is_gen) + RoPE at `positions` + append of the new K/V rows to the sequences' pages + varlen attention over past + new keys.
+ * Projection outputs come either as bf16 rows `qkv` [M, (heads + 2 kv_heads) * head_dim] (bias applied) or -- as the decode step
+ * produces them -- as `n_partials` fp32 split-K partials `qkv_partial` [n_partials][M][..] plus `bias` (bf16).  out: bf16
+ * [M, heads * head_dim].  *path_out: kernel family that ran (1 mma.sync flash kernel, 2 tcgen05 flash kernel, 3 fused decode cluster
+ * kernel); chosen as in the model (query rows per sample, UMV_ATTN_TC / UMV_FUSED_ATTN switches).  With update_kv the sequences
+ * keep the appended rows.  Parity hook: lets a test compare attn_tc_kernel / attn_decode_kernel with the oracle directly. */
+int umv_op_attention_block(umv_engine* e, int32_t layer, const void* qkv, const float* qkv_partial, int32_t n_partials,
+                           const void* bias, int32_t n_seqs, const int32_t* seqs, const int32_t* q_lens, const int32_t* positions,
+                           const uint8_t* row_is_gen, int32_t is_causal, int32_t update_kv, void* out, int32_t* path_out,
+                           void* stream);
+/* The sampling branch of generate_text (bagel.py:1297-1301: softmax(pred_logits / temperature) in fp32 + multinomial) as the
+ * decode loop runs it: row r draws from softmax(bf16(logits[r] * (1/T))) by inverse CDF with u from the engine's counter-based
+ * hash of (seed, step 0, r).  u_force >= 0 replaces u (test hook for the u * total == total rounding edge). */
+int umv_op_sample(const void* logits, int32_t rows, int32_t vocab, float temperature, uint64_t seed, float u_force, int64_t* out,
+                  void* stream);
 
 /* Measurement hook (bench.py roofline): launch ONE weight-major decode linear of layer `layer` exactly
  * as the decode step does, on m rows of the engine's activation workspace.  which: 0 qkv (split-K

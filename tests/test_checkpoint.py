@@ -43,14 +43,16 @@ def test_load_checkpoint_matches_direct_load(tmp_path):
     _write_configs(str(tmp_path), d)
     fp32 = {k: v.float().contiguous() for k, v in sd.items()}           # an fp32 checkpoint: rounded to bf16 on ingest
     fp32["training_only.step"] = torch.zeros(1)                          # a tensor the engine has no slot for
+    fp32["training_only.counter"] = torch.zeros(1, dtype=torch.int64)   # a non-float buffer: skipped, not an error
     save_file(fp32, str(tmp_path / "ema.safetensors"))
-    save_file({k: v.contiguous() for k, v in vsd.items()}, str(tmp_path / "ae.safetensors"))
+    # the FLUX autoencoder file ships in fp32 and may carry a DataParallel "module." prefix (load_ae, autoencoder.py:352-361)
+    save_file({"module." + k: v.float().contiguous() for k, v in vsd.items()}, str(tmp_path / "ae.safetensors"))
 
     dims = checkpoint.dims_from_checkpoint(str(tmp_path))
     a = Engine(dims, max_tokens=256, max_seqs=2, kv_pages=16, enable_vae=True)
     stats = checkpoint.load_checkpoint(a, str(tmp_path))
     a.finalize()
-    assert stats["skipped"] == 1 and stats["tensors"] == len(sd) + len(vsd)
+    assert stats["skipped"] == 2 and stats["tensors"] == len(sd) + len(vsd)
     b = Engine(d, max_tokens=256, max_seqs=2, kv_pages=16, enable_vae=True)
     b.load_state_dict(sd)
     b.load_state_dict({"vae_model." + k: v for k, v in vsd.items()})

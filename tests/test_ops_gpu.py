@@ -211,3 +211,113 @@ def test_vit_padded_head_tcgen05_matches_mma_sync(monkeypatch):
     assert torch.isfinite(outs["1"]).all()
     rel = (outs["1"] - outs["0"]).norm() / outs["0"].norm()
     assert rel < 5e-3, float(rel)
+
+
+# ------------------------------------------------------------------------------------------------ sampling (bagel.py:1297-1301)
+def _ref_probs(logits, T):
+    """softmax(pred_logits / temperature) as the reference computes it on CUDA: the division of the bf16 logits by the Python
+    scalar is x * (1.0f / T) in fp32 rounded to bf16 (ATen's div-by-CPU-scalar), the softmax is an fp32-policy autocast op."""
+    scaled = (logits.float() * (torch.tensor(1.0, dtype=torch.float32) / torch.tensor(T, dtype=torch.float32))).bfloat16()
+    return torch.softmax(scaled.float(), dim=-1)
+
+
+@pytest.mark.parametrize("T", [0.1, 1.0])
+def test_sampling_distribution_chi2(ops, T):
+    """>= 10k draws from one row of logits (every CTA row hashes (seed, row) to its own u): chi-square of the counts against the fp32
+    softmax of the reference -- T = 0.1 is the shipped default of the VQA script (interactive_vqa_inferencer.py:66)."""
+    V, N = 64, 40000
+    torch.manual_seed(5)
+    row = (torch.randn(V) * (0.25 if T < 1 else 1.5)).bfloat16()
+    logits = row[None].repeat(N, 1).cuda()
+    draws = ops.op_sample(logits, T, seed=1234).cpu()
+    assert draws.min() >= 0 and draws.max() < V
+    p = _ref_probs(row[None], T)[0].double()
+    counts = torch.bincount(draws, minlength=V).double()
+    keep = p * N >= 5                                    # pool the rare cells (standard chi-square validity rule)
+    exp = torch.cat([p[keep] * N, (p[~keep].sum() * N)[None]])
+    obs = torch.cat([counts[keep], counts[~keep].sum()[None]])
+    ok = exp > 0
+    chi2 = float((((obs - exp) ** 2)[ok] / exp[ok]).sum())
+    dof = int(ok.sum()) - 1
+    # 99.99 % quantile of chi-square(dof) by Wilson-Hilferty; a wrong CDF (off-by-one span, missing temperature) gives thousands
+    z = 3.72
+    bound = dof * (1 - 2 / (9 * dof) + z * (2 / (9 * dof)) ** 0.5) ** 3
+    assert chi2 < bound, (T, chi2, bound, dof)
+    # and the most likely token is drawn most often
+    assert int(counts.argmax()) == int(p.argmax())
+
+
+def test_sampling_seed_determinism_and_step_variation(ops):
+    V = 152064
+    torch.manual_seed(6)
+    logits = torch.randn(8, V).bfloat16().cuda()
+    a = ops.op_sample(logits, 1.0, seed=77)
+    b = ops.op_sample(logits, 1.0, seed=77)
+    c = ops.op_sample(logits, 1.0, seed=78)
+    assert torch.equal(a, b)                              # same (seed, step, row) -> same draw
+    assert not torch.equal(a, c)
+    assert len(set(a.tolist())) > 1                       # rows draw independently from (nearly) the same flat distribution
+
+
+def test_sampling_full_vocab_edges(ops):
+    """V = 152064 with 1024 threads: span 149 -> the last three threads own nothing.  u * total rounding up to total (u_force = 1)
+    must land on the last token with mass, never leave out[] unwritten; u = 0 lands on the first token with mass."""
+    V = 152064
+    logits = torch.full((4, V), -30.0).bfloat16()
+    logits[0, 5] = logits[0, V - 1] = 10.0
+    logits[1, 100] = 10.0                                  # all mass far from the end: the tail spans hold ~0 probability
+    logits[2, V - 1] = 10.0
+    logits[3, 0] = logits[3, V - 2] = 10.0
+    lg = logits.cuda()
+    sentinel = torch.full((4,), -7, dtype=torch.int64, device="cuda")
+    from unimedvl_b200 import _lib
+    import ctypes as C
+    lib = _lib.load()
+    for u, name in ((1.0, "u=1"), (0.99999994, "u=1-2^-24"), (0.0, "u=0")):
+        out = sentinel.clone()
+        _lib.check(lib.umv_op_sample(C.c_void_p(lg.data_ptr()), 4, V, C.c_float(1.0), C.c_uint64(0), C.c_float(u),
+                                     C.c_void_p(out.data_ptr()), C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+        got = out.cpu().tolist()
+        assert all(0 <= t < V for t in got), (name, got)               # every row written
+        if u == 0.0:
+            assert got[0] in (0, 5) and got[3] == 0 and got[2] in range(0, V), (name, got)
+        else:
+            assert got[0] == V - 1 and got[2] == V - 1 and got[3] in (V - 2, V - 1), (name, got)
+            assert got[1] >= 100, (name, got)
+    # temperature -> 0 limit reproduces argmax
+    torch.manual_seed(8)
+    rnd = torch.randn(8, V).bfloat16()
+    rnd[torch.arange(8), torch.arange(8) * 1000 + 17] = 20.0          # a unique maximum per row (bf16 ties would be a coin flip)
+    rnd = rnd.cuda()
+    assert torch.equal(ops.op_sample(rnd, 1e-3, seed=3), ops.op_argmax(rnd))
+
+
+def test_generate_text_sampling_branch(ops):
+    """do_sample=True through Bagel.generate_text: same seed -> same tokens, the draws follow the step counter (different tokens per
+    step)."""
+    from unimedvl_b200 import config as ucfg
+    from unimedvl_b200.bagel import Bagel
+    from unimedvl_b200.cache import NaiveCache
+    from unimedvl_b200.engine import Engine
+    from unimedvl_b200 import packing
+    dims = ucfg.tiny()
+    eng = Engine(dims, max_tokens=256, max_seqs=4, kv_pages=32, enable_vit=False, enable_gen=False)
+    eng.fill_synthetic(seed=3)
+    eng.finalize()
+    model = Bagel(eng, dims)
+    tok = dict(bos_token_id=2040, eos_token_id=2041, start_of_image=2042, end_of_image=2043)
+
+    class _Ids:
+        def encode(self, i): return [(7 * i + j * 13) % 2000 for j in range(9 + i)]
+
+    def run(**kw):
+        g, lens, rope = packing.prepare_prompts([0, 0], [0, 0], [0, 1], _Ids(), tok)
+        cache = model.forward_cache_update_text(NaiveCache(dims.llm.layers), **g)
+        st = packing.prepare_start_tokens(lens, rope, tok)
+        return model.generate_text(past_key_values=cache, max_length=12, end_token_id=None, **st, **kw).cpu()
+    greedy = run()
+    a = run(do_sample=True, temperature=1.0, seed=5)
+    b = run(do_sample=True, temperature=1.0, seed=5)
+    c = run(do_sample=True, temperature=1.0, seed=6)
+    assert torch.equal(a, b) and not torch.equal(a, c) and not torch.equal(a, greedy)
+    assert a.shape == (12, 2) and int(a.max()) < dims.llm.vocab

@@ -1,0 +1,527 @@
+"""Parity against the UNMODIFIED reference running on the same B200 ("the primary parity oracle").
+
+The reference's own modules (`baseline/_ref/codes`, placed by tools/install_ref.py; real `flash_attn_varlen_func`, CUDA
+autocast, shims S1+S2 only -- tests/refharness.py) hold the same synthetic state dict as the engine.  Three groups:
+
+  wide   engine vs reference at the 14B WIDTH (D=3584, 28/4 heads x 128, I=18944, V=152064, ViT 1152 / 16 x 72) with 3 LLM
+         and 2 ViT layers: ViT + connector, prefill KV, lm_head as a single contraction, teacher-forced logits + argmax,
+         free-running greedy tokens, one guided flow velocity at 4 x 258 x 3 rows (pair-linear path), VAE decode / encode;
+  pin    the oracle's `Semantics.cuda` (what the engine is compared with everywhere else) vs the reference on CUDA, tiny
+         dims and the wide dims: KV, logits, tokens, the three CFG renorm variants, VAE -- this pins the oracle's CUDA
+         semantics, which the CPU-generated fixtures cannot;
+  drop   the reference's OWN `InterleaveInferencer` class driving `unimedvl_b200.Bagel` / `AutoEncoder` (the drop-in claim of
+         INTEGRATION.md): image->text, text->image, image edit vs the fixtures and vs the same class over the reference model.
+
+Tolerances (north_star: 1e-3 relative for bf16 logits per contraction, argmax bit-exact under a fixed seed):
+  * single contraction on identical inputs (lm_head): rel-L2 < 1e-3;
+  * layer-0 V of a text prefill (embedding -> RMSNorm -> one contraction): differences <= 2 ulp, on < 0.5 % of the elements beyond
+    1 ulp; K adds q/k-norm + RoPE (four more roundings): same ulp bound;
+  * whole-model quantities (KV of later layers, logits): rel-L2 < 1e-2 -- one bf16 ulp is 3.9e-3 relative and every flip is
+    re-normalised into all channels by the next norm (two runs of cuBLAS with different split-K already differ by that);
+  * argmax equal wherever the reference's top-2 margin exceeds 2 bf16 ulp; free-running tokens equal for as long as every earlier
+    step of that sample had such a margin.
+Every measured statistic is also written to gpurun_out/parity_reference.json (copied to profiles/ by hand).
+"""
+import copy
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+from PIL import Image
+
+import refharness as rh
+from util import Golden, Semantics, TOK, oracle_dims, tiny_weights, ulp_stats
+
+pytestmark = [pytest.mark.gpu, pytest.mark.skipif(rh.ref_path() is None, reason="no reference copy: run tools/install_ref.py")]
+
+_STATS = {}
+_ULP2 = 2 * 2.0 ** -7
+
+
+def _note(name, **kw):
+    _STATS[name] = {k: (round(v, 6) if isinstance(v, float) else v) for k, v in kw.items()}
+    out = os.path.join(rh.ROOT, "gpurun_out")
+    os.makedirs(out, exist_ok=True)
+    with open(os.path.join(out, "parity_reference.json"), "w") as f:
+        json.dump(_STATS, f, indent=1, sort_keys=True)
+
+
+def _rel(a, b):
+    a, b = a.float().cpu(), b.float().cpu()
+    return ((a - b).norm() / b.norm().clamp(min=1e-30)).item()
+
+
+def _safe_argmax_equal(got, ref):
+    """argmax equality on rows whose reference top-2 margin exceeds 2 bf16 ulp; returns (n_safe, n_rows, n_equal_all)."""
+    got, ref = got.float().cpu(), ref.float().cpu()
+    top2 = ref.topk(2, -1).values
+    safe = (top2[:, 0] - top2[:, 1]) > _ULP2 * top2[:, 0].abs().clamp(min=1.0)
+    ga, ra = got.argmax(-1), ref.argmax(-1)
+    assert torch.equal(ga[safe], ra[safe]), (ga.tolist(), ra.tolist(), safe.tolist())
+    return int(safe.sum()), int(safe.numel()), int((ga == ra).sum()), safe
+
+
+def _prefix_tokens_equal(got, ref, safe_steps):
+    """got/ref [T, B]; safe_steps [T-1, B] bool (margin of the step that produced row t+1).  Column b must agree up to and
+    including the first row produced by an unsafe step (after that the runs legitimately diverge)."""
+    T, B = ref.shape
+    agreed = 0
+    for b in range(B):
+        for t in range(T):
+            if t > 0 and not bool(safe_steps[t - 1, b]):
+                break
+            assert int(got[t, b]) == int(ref[t, b]), (b, t, got[:, b].tolist(), ref[:, b].tolist())
+            agreed += 1
+    return agreed
+
+
+def _cfg_kwargs(ct, ci):
+    return dict(
+        cfg_text_packed_position_ids=ct["cfg_packed_position_ids"], cfg_text_packed_query_indexes=ct["cfg_packed_query_indexes"],
+        cfg_text_key_values_lens=ct["cfg_key_values_lens"], cfg_text_packed_key_value_indexes=ct["cfg_packed_key_value_indexes"],
+        cfg_img_packed_position_ids=ci["cfg_packed_position_ids"], cfg_img_packed_query_indexes=ci["cfg_packed_query_indexes"],
+        cfg_img_key_values_lens=ci["cfg_key_values_lens"], cfg_img_packed_key_value_indexes=ci["cfg_packed_key_value_indexes"])
+
+
+def _to(d, dev):
+    # always a copy: the reference shifts packed_key_value_indexes IN PLACE while decoding (bagel.py:1272-1274)
+    return {k: (v.to(dev).clone() if torch.is_tensor(v) else v) for k, v in d.items()}
+
+
+class _IdTokenizer:
+    """prompts are given as id lists (no vocab files offline)."""
+
+    def encode(self, ids):
+        return list(ids)
+
+
+def _spy_flow(model):
+    """Record every velocity `_forward_flow` returns (the guided v_t of bagel.py:1209)."""
+    trace, orig = [], model._forward_flow
+
+    def spy(*a, **k):
+        v = orig(*a, **k)
+        trace.append(v.detach().float().clone())
+        return v
+    model._forward_flow = spy
+    return trace, lambda: setattr(model, "_forward_flow", orig)
+
+
+# =================================================================================================== wide (14B width)
+WIDE_TOK = dict(bos_token_id=151644, eos_token_id=151645, start_of_image=151652, end_of_image=151653)
+
+
+@pytest.fixture(scope="module")
+def wide():
+    from unimedvl_b200 import config as ucfg, synth
+    from unimedvl_b200.autoencoder import AutoEncoder
+    from unimedvl_b200.bagel import Bagel
+    from unimedvl_b200.engine import Engine
+    dims = ucfg.BagelDims(llm=ucfg.LLMDims(layers=3), vit=ucfg.ViTDims(layers=2))
+    with synth.on_device("cuda"):
+        sd = synth.bagel_state_dict(dims, seed=5)
+        vsd = synth.vae_state_dict(dims.vae, seed=5)
+    ref, rvae = rh.build_reference(dims, sd, vsd, "cuda")
+    eng = Engine(dims, max_tokens=3200, max_seqs=12, kv_pages=320, enable_vae=True)
+    eng.load_state_dict(sd)
+    vae = AutoEncoder(eng)
+    vae.load_state_dict(vsd)
+    eng.finalize()
+    yield dict(dims=dims, sd=sd, vsd=vsd, ref=ref, rvae=rvae, eng=eng, model=Bagel(eng, dims), vae=vae)
+    eng.close()
+
+
+def _wide_vqa_inputs(model):
+    from unimedvl_b200 import synth
+    from unimedvl_b200.packing import ImageTransform
+    tf = ImageTransform(980, 378, 14, max_pixels=2_007_040)
+    imgs = [Image.fromarray(synth.synthetic_image(0, 448, 448)), Image.fromarray(synth.synthetic_image(1, 392, 504))]
+    gv, lens, rope = model.prepare_vit_images([0, 0], [0, 0], imgs, tf, WIDE_TOK)
+    prompts = [synth.synthetic_prompt_ids(0, 30), synth.synthetic_prompt_ids(1, 11)]
+    gt, lens, rope = model.prepare_prompts(lens, rope, prompts, _IdTokenizer(), WIDE_TOK)
+    gs = model.prepare_start_tokens(lens, rope, WIDE_TOK)
+    return gv, gt, gs
+
+
+def test_wide_vit_connector(wide):
+    """siglip_navit.py:389-402 + connector + vit_pos_embed (bagel.py:581-594) on the real FA2 hdim-72 path."""
+    ref, eng, model = wide["ref"], wide["eng"], wide["model"]
+    gv, _, _ = _wide_vqa_inputs(model)
+    lens = gv["vit_token_seqlens"]
+    cu = torch.nn.functional.pad(torch.cumsum(lens, 0), (1, 0)).to(torch.int32).cuda()
+    with torch.no_grad(), rh.autocast("cuda"):
+        x = ref.vit_model(packed_pixel_values=gv["packed_vit_tokens"].cuda(), packed_flattened_position_ids=gv["packed_vit_position_ids"].cuda(),
+                          cu_seqlens=cu, max_seqlen=int(lens.max()))
+        x = ref.connector(x)
+        want = x + ref.vit_pos_embed(gv["packed_vit_position_ids"].cuda())
+    got = eng.vit_embed(gv["packed_vit_tokens"], gv["packed_vit_position_ids"], lens.tolist())
+    s = ulp_stats(got, want)
+    _note("wide.vit_connector", **s)
+    assert s["rel_l2"] < 8e-3, s
+
+
+def test_wide_vqa_prefill_logits_tokens(wide):
+    from unimedvl_b200.cache import NaiveCache
+    ref, eng, model, dims = wide["ref"], wide["eng"], wide["model"], wide["dims"]
+    R = rh.load()
+    gv, gt, gs = _wide_vqa_inputs(model)
+    L, T = dims.llm.layers, 9
+    logits, hidden = [], []
+    h1 = ref.language_model.lm_head.register_forward_hook(lambda m, i, o: (hidden.append(i[0].detach().clone()), logits.append(o.detach().clone())))
+    with torch.no_grad(), rh.autocast("cuda"):
+        rc = R.NaiveCache(L)
+        rc = ref.forward_cache_update_vit(rc, **_to(gv, "cuda"))
+        kv_img = [(rc.key_cache[i].clone(), rc.value_cache[i].clone()) for i in range(L)]
+        rc = ref.forward_cache_update_text(rc, **_to(gt, "cuda"))
+        kv_all = [(rc.key_cache[i].clone(), rc.value_cache[i].clone()) for i in range(L)]
+        rtoks = ref.generate_text(past_key_values=copy.deepcopy(rc), max_length=T, do_sample=False, end_token_id=None, **_to(gs, "cuda"))
+    h1.remove()
+    rlogits = torch.stack(logits, 0)                               # [T, B, V]
+
+    cache = model.forward_cache_update_vit(NaiveCache(L), **gv)
+    for li in range(L):
+        for w, name in ((0, "k"), (1, "v")):
+            got = (cache.key_cache if w == 0 else cache.value_cache)[li]
+            s = ulp_stats(got, kv_img[li][w])
+            _note(f"wide.kv_after_image.{name}{li}", **s)
+            assert s["rel_l2"] < 1e-2, (li, name, s)
+    cache = model.forward_cache_update_text(cache, **gt)
+    # rows of the text prefill inside the packed cache (per sample: image block, then prompt)
+    kvl = gt["key_values_lens"].tolist()
+    tl = gt["text_token_lens"].tolist()
+    rows, base = [], 0
+    for a, b in zip(kvl, tl):
+        rows += list(range(base + a, base + a + b))
+        base += a + b
+    rows = torch.tensor(rows)
+    for li in range(L):
+        for w, name in ((0, "k"), (1, "v")):
+            got = (cache.key_cache if w == 0 else cache.value_cache)[li].cpu()
+            s = ulp_stats(got, kv_all[li][w])
+            _note(f"wide.kv_after_text.{name}{li}", **s)
+            assert s["rel_l2"] < 1e-2, (li, name, s)
+            if li == 0:          # text rows of layer 0 see no history of roundings: embedding -> norm -> one contraction (-> norm, RoPE)
+                s = ulp_stats(got[rows], kv_all[0][w].cpu()[rows])
+                _note(f"wide.layer0_text_rows.{name}", **s)
+                assert s["max_ulp"] <= 2 and s["frac_gt1"] < 5e-3, (name, s)
+
+    # lm_head as a single contraction on the reference's own final hidden states
+    hcat = torch.cat(hidden, 0)
+    s = ulp_stats(eng.lm_head(hcat), torch.cat(logits, 0))
+    _note("wide.lm_head_single_contraction", **s)
+    assert s["rel_l2"] < 1e-3 and s["frac_gt1"] < 1e-3, s
+
+    # teacher-forced logits on a fork (the reference's tokens are fed back)
+    fork = copy.deepcopy(cache)
+    toks, lg = eng.generate_text(fork._umv.seqs, gs["packed_start_tokens"].tolist(), gs["packed_query_position_ids"].tolist(), T,
+                                 forced_tokens=rtoks, return_logits=True)
+    assert torch.equal(toks.cpu(), rtoks.cpu())
+    safe_steps = []
+    worst = 0.0
+    n_safe = n_rows = n_eq = 0
+    for s_ in range(T):
+        r = _rel(lg[s_], rlogits[s_])
+        worst = max(worst, r)
+        assert r < 1e-2, (s_, r)
+        a, b, c, safe = _safe_argmax_equal(lg[s_], rlogits[s_])
+        n_safe, n_rows, n_eq = n_safe + a, n_rows + b, n_eq + c
+        safe_steps.append(safe)
+    _note("wide.teacher_forced_logits", worst_rel_l2=worst, rows=n_rows, rows_margin_gt_2ulp=n_safe, argmax_equal_rows=n_eq)
+    # free-running greedy tokens through the reference-shaped call
+    out = model.generate_text(past_key_values=copy.deepcopy(cache), max_length=T, end_token_id=None, **gs).cpu()
+    agreed = _prefix_tokens_equal(out, rtoks.cpu(), torch.stack(safe_steps, 0))
+    _note("wide.free_running_tokens", agreed_positions=agreed, total=int(out.numel()), identical=bool(torch.equal(out, rtoks.cpu())))
+    wide["vqa"] = dict(gv=gv, gt=gt, gs=gs, kv_all=[(k.cpu(), v.cpu()) for k, v in kv_all], rlogits=rlogits.cpu(), rtoks=rtoks.cpu())
+
+
+def test_wide_oracle_cuda_semantics_pinned(wide):
+    """The CPU oracle (`Semantics.cuda`) vs the reference on CUDA at the 14B width: same bars as the engine."""
+    from oracle import model as omodel
+    if "vqa" not in wide:
+        pytest.skip("needs test_wide_vqa_prefill_logits_tokens")
+    v, dims = wide["vqa"], wide["dims"]
+    sd = {k: t.cpu() for k, t in wide["sd"].items()}
+    o = omodel.BagelOracle(sd, oracle_dims(dims), Semantics.cuda, True, None)
+    torch.set_num_threads(os.cpu_count() or 8)
+    oc = o.forward_cache_update_vit(o.new_cache(), **v["gv"])
+    oc = o.forward_cache_update_text(oc, **v["gt"])
+    for li in range(dims.llm.layers):
+        for w, name in ((0, "k"), (1, "v")):
+            s = ulp_stats((oc.key if w == 0 else oc.value)[li], v["kv_all"][li][w])
+            _note(f"pin.wide.kv.{name}{li}", **s)
+            assert s["rel_l2"] < 1e-2, (li, name, s)
+    gs, T = v["gs"], v["rtoks"].shape[0]
+    lg = []
+    o.generate_text(oc, gs["packed_key_value_indexes"], gs["key_values_lens"], gs["packed_start_tokens"], gs["packed_query_position_ids"], T,
+                    forced_tokens=v["rtoks"], logits_out=lg)
+    worst = 0.0
+    for s_ in range(T):
+        worst = max(worst, _rel(lg[s_], v["rlogits"][s_]))
+        _safe_argmax_equal(lg[s_], v["rlogits"][s_])
+    _note("pin.wide.teacher_forced_logits", worst_rel_l2=worst)
+    assert worst < 1e-2
+
+
+def _t2i_contexts(fwd_text, new_cache, prep, B, shapes, seed=42):
+    """main context: one 30-token prompt per image; cfg_text: empty; cfg_img: the prompt (no image) -- what
+    interleave_inference builds for a pure T2I request (inferencer.py:552-638)."""
+    from unimedvl_b200 import synth
+    prompts = [synth.synthetic_prompt_ids(100 + i, 30) for i in range(B)]
+    g, lens, rope = prep.prepare_prompts([0] * B, [0] * B, prompts, _IdTokenizer(), WIDE_TOK)
+    ctx = fwd_text(new_cache(), g)
+    torch.manual_seed(seed)
+    gi = prep.prepare_vae_latent(lens, rope, shapes, WIDE_TOK)
+    ct = prep.prepare_vae_latent_cfg([0] * B, [0] * B, shapes)
+    ci = prep.prepare_vae_latent_cfg(lens, rope, shapes)
+    return ctx, gi, ct, ci
+
+
+def test_wide_flow_velocity_and_latents(wide):
+    """generate_image, 4 x 256^2 images, dual CFG (3 branches -> 3,096 packed rows: the CTA-pair linears), text_channel renorm (batch
+    independent, so B=4 compares with the reference exactly), 3 timesteps."""
+    from unimedvl_b200.cache import NaiveCache, paged_handle
+    ref, eng, model, dims = wide["ref"], wide["eng"], wide["model"], wide["dims"]
+    R = rh.load()
+    B, shapes, L = 4, [(256, 256)] * 4, dims.llm.layers
+    kw = dict(num_timesteps=4, timestep_shift=3.0, cfg_text_scale=4.0, cfg_img_scale=1.5, cfg_interval=(0.4, 1.0), cfg_renorm_min=0.0,
+              cfg_renorm_type="text_channel")
+    with torch.no_grad(), rh.autocast("cuda"):
+        rctx, gi, ct, ci = _t2i_contexts(lambda c, g: ref.forward_cache_update_text(c, **_to(g, "cuda")), lambda: R.NaiveCache(L), ref, B, shapes)
+        trace, undo = _spy_flow(ref)
+        rlat = ref.generate_image(past_key_values=rctx, cfg_text_past_key_values=R.NaiveCache(L), cfg_img_past_key_values=rctx,
+                                  **_to(gi, "cuda"), **_to(_cfg_kwargs(ct, ci), "cuda"), **kw)
+        undo()
+    ctx, gi2, ct2, ci2 = _t2i_contexts(lambda c, g: model.forward_cache_update_text(c, **g), lambda: NaiveCache(L), model, B, shapes)
+    assert torch.equal(gi2["packed_init_noises"], gi["packed_init_noises"])
+    empty = NaiveCache(L)
+    paged_handle(empty, eng, B)
+    # the first velocity (x_t = the initial noise, t = 1): one _forward_flow call against one umv_flow_velocity call
+    lens, lat_lens, pos = model._flow_geometry(gi["packed_seqlens"], gi["packed_position_ids"])
+    _, _, pos_t = model._flow_geometry(gi["packed_seqlens"], ct["cfg_packed_position_ids"])
+    _, _, pos_i = model._flow_geometry(gi["packed_seqlens"], ci["cfg_packed_position_ids"])
+    x0 = gi["packed_init_noises"].cuda().float().contiguous()
+    ctx_img = copy.deepcopy(ctx)                 # its own pages: a branch may not share sequences with the main context
+    v0 = eng.flow_velocity(x0, gi["packed_vae_position_ids"], lat_lens, ctx._umv.seqs, pos, gi["packed_text_ids"][:2].tolist(), 1.0,
+                           (empty._umv.seqs, pos_t), (ctx_img._umv.seqs, pos_i), 4.0, 1.5, 0.0, 2)
+    del ctx_img
+    r0 = _rel(v0, trace[0])
+    _note("wide.flow.first_velocity", rel_l2=r0, rows=3 * sum(lens))
+    assert r0 < 2e-2, r0
+    lat = model.generate_image(past_key_values=ctx, cfg_text_past_key_values=empty, cfg_img_past_key_values=ctx, **gi, **_cfg_kwargs(ct, ci), **kw)
+    worst = max(_rel(a, b) for a, b in zip(lat, rlat))
+    _note("wide.flow.latents_after_3_steps", worst_rel_l2=worst)
+    assert worst < 3e-2, worst
+
+
+def test_wide_vae_decode_encode(wide):
+    """AutoEncoder.decode / Encoder (autoencoder.py:169-257) vs the reference's cuDNN convolutions, 256 x 256."""
+    rvae, vae = wide["rvae"], wide["vae"]
+    torch.manual_seed(9)
+    z = torch.randn(1, 16, 32, 32).bfloat16().cuda()
+    x = (torch.rand(1, 3, 256, 256) * 2 - 1).bfloat16().cuda()
+    with torch.no_grad(), rh.autocast("cuda"):
+        want = rvae.decode(z)
+        mom = rvae.encoder(x)
+    got = vae.decode(z)
+    s = ulp_stats(got, want)
+    u8 = lambda im: ((im.float() * 0.5 + 0.5).clamp(0, 1) * 255).to(torch.uint8).int()
+    d = (u8(got) - u8(want)).abs()
+    _note("wide.vae_decode", grey_mean=d.float().mean().item(), grey_max=int(d.max()), **s)
+    assert s["rel_l2"] < 5e-2 and d.float().mean().item() < 2.0, s
+    s = ulp_stats(vae.encode_moments(x), mom)
+    _note("wide.vae_encode_moments", **s)
+    assert s["rel_l2"] < 5e-2, s
+
+
+# =================================================================================================== pin (tiny dims)
+@pytest.fixture(scope="module")
+def tiny():
+    from unimedvl_b200.autoencoder import AutoEncoder
+    from unimedvl_b200.bagel import Bagel
+    from unimedvl_b200.engine import Engine
+    from util import make_oracle
+    dims, sd, vsd = tiny_weights(vae=True)
+    ref, rvae = rh.build_reference(dims, sd, vsd, "cuda")
+    eng = Engine(dims, max_tokens=1024, max_seqs=4, kv_pages=128, enable_vae=True)
+    eng.load_state_dict(sd)
+    vae = AutoEncoder(eng)
+    vae.load_state_dict(vsd)
+    eng.finalize()
+    yield dict(dims=dims, ref=ref, rvae=rvae, eng=eng, model=Bagel(eng, dims), vae=vae, oracle=make_oracle(Semantics.cuda, vae=True))
+    eng.close()
+
+
+def test_pin_vqa_reference_cuda_vs_oracle_vs_engine(tiny):
+    """The VQA fixture inputs through the reference ON CUDA: the oracle (Semantics.cuda) and the engine must both sit within bf16
+    summation-order noise of it, and all three must produce the fixture's tokens."""
+    from unimedvl_b200.cache import NaiveCache
+    ref, model, o, dims = tiny["ref"], tiny["model"], tiny["oracle"], tiny["dims"]
+    R, g, L = rh.load(), Golden("vqa"), tiny["dims"].llm.layers
+    gv, gt, gs = g.group("vqa.vit_in"), g.group("vqa.text_in"), g.group("vqa.start")
+    logits = []
+    h = ref.language_model.lm_head.register_forward_hook(lambda m, i, out: logits.append(out.detach().float().cpu()))
+    with torch.no_grad(), rh.autocast("cuda"):
+        rc = ref.forward_cache_update_vit(R.NaiveCache(L), **_to(gv, "cuda"))
+        rc = ref.forward_cache_update_text(rc, **_to(gt, "cuda"))
+        rkv = [(rc.key_cache[i].cpu(), rc.value_cache[i].cpu()) for i in range(L)]
+        rtoks = ref.generate_text(past_key_values=rc, max_length=9, do_sample=False, end_token_id=None, **_to(gs, "cuda")).cpu()
+    h.remove()
+    assert torch.equal(rtoks, g.t("vqa.tokens")), "reference on CUDA and on CPU (fixture) decode different tokens"
+    oc = o.forward_cache_update_text(o.forward_cache_update_vit(o.new_cache(), **gv), **gt)
+    cache = model.forward_cache_update_text(model.forward_cache_update_vit(NaiveCache(L), **gv), **gt)
+    for li in range(L):
+        for w, name in ((0, "k"), (1, "v")):
+            so = ulp_stats((oc.key if w == 0 else oc.value)[li], rkv[li][w])
+            se = ulp_stats((cache.key_cache if w == 0 else cache.value_cache)[li], rkv[li][w])
+            _note(f"pin.tiny.kv.{name}{li}", oracle_rel_l2=so["rel_l2"], engine_rel_l2=se["rel_l2"])
+            assert so["rel_l2"] < 1e-2 and se["rel_l2"] < 1e-2, (li, name, so, se)
+    lg = []
+    o.generate_text(oc, gs["packed_key_value_indexes"], gs["key_values_lens"], gs["packed_start_tokens"], gs["packed_query_position_ids"], 9,
+                    forced_tokens=rtoks, logits_out=lg)
+    _, elg = tiny["eng"].generate_text(cache._umv.seqs, gs["packed_start_tokens"].tolist(), gs["packed_query_position_ids"].tolist(), 9,
+                                       forced_tokens=rtoks, return_logits=True)
+    wo = max(_rel(lg[s], logits[s]) for s in range(9))
+    we = max(_rel(elg[s], logits[s]) for s in range(9))
+    _note("pin.tiny.teacher_forced_logits", oracle_worst_rel_l2=wo, engine_worst_rel_l2=we)
+    assert wo < 1e-2 and we < 1e-2
+    for s in range(9):
+        _safe_argmax_equal(lg[s], logits[s])
+        _safe_argmax_equal(elg[s], logits[s])
+
+
+@pytest.mark.parametrize("renorm", ["global", "channel", "text_channel"])
+def test_pin_flow_reference_cuda_vs_oracle_vs_engine(tiny, renorm):
+    """generate_image on CUDA (fp32 torch.norm, fp32 v*scale for the per-token renorms -- the points where CUDA and CPU autocast differ):
+    B=2 for the per-token renorms; `global` at batch 1, the only batch size for which the reference's whole-pack norm and the engine's
+    per-image norm are the same computation (bagel.py:1196-1198)."""
+    from unimedvl_b200.cache import NaiveCache
+    ref, model, o, dims = tiny["ref"], tiny["model"], tiny["oracle"], tiny["dims"]
+    R, g, L = rh.load(), Golden("t2i"), tiny["dims"].llm.layers
+    tok = rh.FakeTokenizer()
+    prompts = ["a chest x-ray with cardiomegaly", "retina"]
+    shapes = [(64, 64), (64, 96)]
+    if renorm == "global":
+        prompts, shapes = prompts[:1], shapes[:1]
+    B = len(prompts)
+    kw = dict(num_timesteps=5, timestep_shift=3.0, cfg_text_scale=4.0, cfg_img_scale=1.5, cfg_interval=(0.4, 1.0), cfg_renorm_min=0.0,
+              cfg_renorm_type=renorm)
+    gtext, lens, rope = model.prepare_prompts([0] * B, [0] * B, prompts, tok, TOK)
+    gcfg, lens_c, rope_c = model.prepare_prompts([0] * B, [0] * B, ["x", "yy"][:B], tok, TOK)
+    torch.manual_seed(42)
+    gi = model.prepare_vae_latent(lens, rope, shapes, TOK)
+    ct = model.prepare_vae_latent_cfg(lens_c, rope_c, shapes)
+    ci = model.prepare_vae_latent_cfg(lens, rope, shapes)
+    with torch.no_grad(), rh.autocast("cuda"):
+        rctx = ref.forward_cache_update_text(R.NaiveCache(L), **_to(gtext, "cuda"))
+        rcfg = ref.forward_cache_update_text(R.NaiveCache(L), **_to(gcfg, "cuda"))
+        trace, undo = _spy_flow(ref)
+        rlat = ref.generate_image(past_key_values=rctx, cfg_text_past_key_values=rcfg, cfg_img_past_key_values=rctx, **_to(gi, "cuda"),
+                                  **_to(_cfg_kwargs(ct, ci), "cuda"), **kw)
+        undo()
+    octx = o.forward_cache_update_text(o.new_cache(), **gtext)
+    ocfg = o.forward_cache_update_text(o.new_cache(), **gcfg)
+    otrace = []
+    olat = o.generate_image(gi, octx, dict(ct, cache=ocfg), dict(ci, cache=octx), per_image_global=False, trace=otrace, **kw)
+    ctx = model.forward_cache_update_text(NaiveCache(L), **gtext)
+    cfg = model.forward_cache_update_text(NaiveCache(L), **gcfg)
+    lat = model.generate_image(past_key_values=ctx, cfg_text_past_key_values=cfg, cfg_img_past_key_values=ctx, **gi, **_cfg_kwargs(ct, ci), **kw)
+    # dtype of the guided velocity is part of the CUDA semantics: fp32 after a per-token norm, bf16-valued otherwise
+    v0 = trace[0]
+    is_bf16_valued = bool(torch.equal(v0, v0.bfloat16().float()))
+    assert is_bf16_valued == (renorm == "global"), (renorm, is_bf16_valued)
+    wo = max(_rel(a, b) for a, b in zip(olat, rlat))
+    we = max(_rel(a, b) for a, b in zip(lat, rlat))
+    wv = max(_rel(a, b) for a, b in zip(otrace, trace))
+    _note(f"pin.tiny.flow.{renorm}", oracle_latent_rel_l2=wo, engine_latent_rel_l2=we, oracle_worst_velocity_rel_l2=wv, batch=B)
+    assert wo < 3e-2 and we < 3e-2, (renorm, wo, we)
+
+
+def test_pin_vae_reference_cuda_vs_oracle_vs_engine(tiny):
+    """GroupNorm returns fp32 under CUDA autocast and swish then runs in fp32 (autoencoder.py:84-90) -- the oracle's Semantics.cuda."""
+    from oracle import vae as ovae
+    rvae, vae, o = tiny["rvae"], tiny["vae"], tiny["oracle"]
+    z = Golden("t2i").t("vae.decode_in")
+    torch.manual_seed(0)
+    x = (torch.rand(1, 3, 32, 48) * 2 - 1).bfloat16()
+    with torch.no_grad(), rh.autocast("cuda"):
+        want = rvae.decode(z.cuda()).cpu()
+        mom = rvae.encoder(x.cuda()).cpu()
+    so = ulp_stats(ovae.decode(o.vae_sd, z, o.dims.vae, Semantics.cuda), want)
+    se = ulp_stats(vae.decode(z.cuda()), want)
+    sc = ulp_stats(ovae.decode(o.vae_sd, z, o.dims.vae, Semantics.cpu), want)
+    _note("pin.tiny.vae_decode", oracle_cuda_rel_l2=so["rel_l2"], engine_rel_l2=se["rel_l2"], oracle_cpu_semantics_rel_l2=sc["rel_l2"])
+    assert so["rel_l2"] < 3e-2 and se["rel_l2"] < 3e-2, (so, se)
+    so = ulp_stats(ovae.encoder(o.vae_sd, x, o.dims.vae, Semantics.cuda), mom)
+    se = ulp_stats(vae.encode_moments(x.cuda()), mom)
+    _note("pin.tiny.vae_encode", oracle_cuda_rel_l2=so["rel_l2"], engine_rel_l2=se["rel_l2"])
+    assert so["rel_l2"] < 3e-2 and se["rel_l2"] < 3e-2, (so, se)
+
+
+# =================================================================================================== drop-in
+def _diff(a, b):
+    d = np.abs(np.asarray(a).astype(np.int32) - np.asarray(b).astype(np.int32))
+    return float(d.mean()), float((d > 32).mean())
+
+
+def test_dropin_reference_inferencer_over_engine(tiny):
+    """The reference's own InterleaveInferencer class (inferencer.py:31-680), unmodified, holding unimedvl_b200.Bagel / AutoEncoder
+    instead of the torch modules -- and the same class over the reference model on CUDA next to it."""
+    R = rh.load()
+    tok = rh.FakeTokenizer()
+    vae_tf, vit_tf = R.ImageTransform(1024, 32, 16), R.ImageTransform(980, 28, 14)
+    ours = R.InterleaveInferencer(tiny["model"], tiny["vae"], tok, vae_tf, vit_tf, TOK)
+    theirs = R.InterleaveInferencer(tiny["ref"], tiny["rvae"], tok, vae_tf, vit_tf, TOK)
+    from unimedvl_b200 import synth
+    img = Image.fromarray(synth.synthetic_image(30, 70, 98))
+    gold = Golden("e2e").z
+    eng = tiny["eng"]
+    free0 = eng.pages_free()
+
+    def both(**kw):
+        seed = kw.pop("seed", None)
+        if seed is not None:
+            torch.manual_seed(seed)
+        a = ours(**kw)
+        if seed is not None:
+            torch.manual_seed(seed)
+        with rh.autocast("cuda"):
+            b = theirs(**kw)
+        return a, b
+    a, b = both(image=img, text="What is shown in this image?", understanding_output=True, max_think_token_n=9, do_sample=False)
+    assert a["image"] is None and a["text"] == b["text"] == str(gold["e2e.i2t_text"])
+    a, b = both(seed=42, text="a chest x-ray with cardiomegaly", understanding_output=False, num_timesteps=5, image_shapes=(64, 64),
+                cfg_text_scale=4.0, cfg_img_scale=1.5)
+    m_ref, f_ref = _diff(a["image"], b["image"])
+    m_fix, f_fix = _diff(a["image"], gold["e2e.t2i_image"])
+    _note("drop.t2i", vs_reference_cuda_mean_grey=m_ref, vs_reference_cuda_frac_gt32=f_ref, vs_cpu_fixture_mean_grey=m_fix)
+    assert a["text"] is None and m_ref < 6.0 and f_ref < 0.02 and m_fix < 6.0, (m_ref, f_ref, m_fix)
+    # image edit: VAE-encode context; the posterior noise comes from the device RNG in both (same generator state -> same draw)
+    a, b = both(seed=43, image=img, text="make it brighter", understanding_output=False, num_timesteps=4, image_shapes=(64, 80),
+                cfg_text_scale=4.0, cfg_img_scale=2.0, cfg_interval=[0, 1.0], cfg_renorm_type="text_channel")
+    ga, gb = np.asarray(a["image"]), np.asarray(b["image"])
+    assert ga.shape == gb.shape == (64, 80, 3) and ga.dtype == np.uint8
+    m_ref, f_ref = _diff(ga, gb)
+    _note("drop.edit", vs_reference_cuda_mean_grey=m_ref, vs_reference_cuda_frac_gt32=f_ref)
+    assert abs(float(ga.mean()) - float(gb.mean())) < 25.0
+    # think mode through the reference's driver
+    a, b = both(image=img, text="What is shown in this image?", think=True, understanding_output=True, max_think_token_n=8, do_sample=False)
+    assert a["text"] == b["text"] == str(Golden("think").z["think.i2t_text"])
+    del a, b
+    import gc
+    gc.collect()
+    assert eng.pages_free() == free0, "KV pages leaked through the reference's deepcopy forks"
+
+
+def test_dropin_bagel_chat(tiny):
+    """Bagel.chat (bagel.py:1321-1392, the call VQAInferencer.infer_single makes) on the façade == the reference's own chat on CUDA."""
+    R = rh.load()
+    from unimedvl_b200 import synth
+    tok, tf = rh.FakeTokenizer(), R.ImageTransform(980, 28, 14)
+    imgs = [Image.fromarray(synth.synthetic_image(30, 70, 98)), Image.fromarray(synth.synthetic_image(31, 56, 84))]
+    for images in (imgs[:1], imgs):
+        with torch.no_grad(), rh.autocast("cuda"):
+            want = tiny["ref"].chat(tok, TOK, tf, images, "Describe the findings.", max_length=10, do_sample=False)
+        got = tiny["model"].chat(tok, TOK, tf, images, "Describe the findings.", max_length=10, do_sample=False)
+        assert got == want and len(got.split()) >= 1, (got, want)

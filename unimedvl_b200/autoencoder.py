@@ -26,7 +26,8 @@ class AutoEncoder:
 
     def load_state_dict(self, sd: dict) -> None:
         """Keys as AutoEncoder.state_dict() (encoder.* / decoder.*)."""
-        self.engine.load_state_dict({"vae_model." + k: v for k, v in sd.items()})
+        strip = lambda k: k[len("module."):] if k.startswith("module.") else k       # as load_ae does (autoencoder.py:352-361)
+        self.engine.load_state_dict({"vae_model." + strip(k): v for k, v in sd.items()})
 
     @torch.no_grad()
     def decode(self, z: torch.Tensor) -> torch.Tensor:

@@ -157,7 +157,11 @@ class Bagel:
             z = z[:, :hh * p, :ww * p].reshape(C, hh, p, ww, p)
             rows.append(z.permute(1, 3, 2, 4, 0).reshape(-1, p * p * C))
         packed_latent = torch.cat(rows, dim=0)
-        t = float(self._ints(packed_timesteps)[0]) if torch.is_tensor(packed_timesteps) else float(packed_timesteps[0])
+        # the reference hands the float tensor to time_embedder (bagel.py:777): no integer truncation of e.g. timestep=0.5
+        ts = packed_timesteps.reshape(-1).float().tolist() if torch.is_tensor(packed_timesteps) else [float(v) for v in packed_timesteps]
+        if any(v != ts[0] for v in ts):
+            raise NotImplementedError("forward_cache_update_vae: one timestep per call (prepare_vae_images emits a constant)")
+        t = ts[0]
         seq = torch.zeros((sum(lens), self.hidden_size), dtype=torch.bfloat16, device=dev)
         seq[packed_text_indexes.to(dev)] = self.engine.embed_tokens(packed_text_ids)
         seq[packed_vae_token_indexes.to(dev)] = self.engine.latent_embed(packed_latent.float(), packed_vae_position_ids, t)
@@ -233,11 +237,15 @@ class Bagel:
             on = bool(t > cfg_interval[0] and t <= cfg_interval[1])
             ts_, is_ = (cfg_text_scale, cfg_img_scale) if on else (1.0, 1.0)
             use_text = cfg_text if ts_ > 1.0 else None
-            use_img = cfg_img if is_ > 1.0 else None
+            # the reference evaluates the cfg_img branch only inside `if cfg_text_scale > 1.0` (bagel.py:1173-1207): without
+            # text guidance it is computed and discarded -- skip the forward
             if ts_ > 1.0 and use_text is None:
                 raise ValueError("cfg_text_scale > 1 needs cfg_text_past_key_values")
-            if is_ > 1.0 and use_img is None:
+            if is_ > 1.0 and cfg_img is None:
                 raise ValueError("cfg_img_scale > 1 needs cfg_img_past_key_values")
+            if ts_ <= 1.0:
+                is_ = 1.0
+            use_img = cfg_img if is_ > 1.0 else None
             self.engine.flow_velocity(x_t, pos_ids, lat_lens, h.seqs, pos, ids[:2], float(t), use_text, use_img, ts_, is_,
                                       cfg_renorm_min, renorm, out=v)
             # velocity dtype in the reference: bf16 unless a per-token (fp32) norm scaled it

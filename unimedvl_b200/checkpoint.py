@@ -68,6 +68,11 @@ def load_checkpoint(engine, model_path: str, use_model_checkpoint: bool = False,
     def put(name: str, t: torch.Tensor):
         if t.dtype in (torch.float16, torch.float64):
             t = t.to(torch.float32)
+        if t.dtype not in (torch.bfloat16, torch.float32):      # integer buffers (step counters, position ids): not weights
+            if strict:
+                raise ValueError(f"{name}: dtype {t.dtype} (bf16 or fp32 expected)")
+            stats["skipped"] += 1
+            return
         try:
             engine.load_state_dict({name: t}, strict=True)
             stats["tensors"] += 1
@@ -85,6 +90,6 @@ def load_checkpoint(engine, model_path: str, use_model_checkpoint: bool = False,
     if want_vae:
         if not os.path.exists(ae):
             raise FileNotFoundError(f"VAE checkpoint not found: {ae}")
-        for name, t in _stream(ae):
-            put("vae_model." + name, t)
+        for name, t in _stream(ae):          # load_ae strips a DataParallel "module." prefix (autoencoder.py:352-361)
+            put("vae_model." + (name[len("module."):] if name.startswith("module.") else name), t)
     return stats

@@ -354,6 +354,7 @@ struct LlmRun {
     int M = 0, n_seqs = 0, max_q_len = 0, max_kv_len = 0;
     bool causal = true, gen = false, weight_major = false;
     CallMeta m;
+    AttnProbe* probe = nullptr;
 };
 
 int lin(umv_engine* e, const bf16* x, int ldx, const bf16* w, const bf16* bias, const bf16* res, bf16* y, int ldy, int M,
@@ -419,6 +420,64 @@ static int llm_layers(umv_engine* e, const LlmRun& r, bf16* out, cudaStream_t st
         attn_splits = std::max(1, std::min(std::min(max_splits, blocks), (waves * e->sm_count + r.n_seqs * Hkv - 1) / (r.n_seqs * Hkv)));
     }
 
+    // q/k RMSNorm + RoPE + KV append + attention over the paged cache (past + the rows just appended) of layer li; `ra` names the
+    // projection outputs (bf16 rows or split-K partials + bias).  Returns through *path which kernel family ran.
+    auto attention_block = [&](int li, RopeAppendArgs& ra, int* path) -> int {
+        const LayerW& L = e->layers[li];
+        // decode (one query token per sample, understanding expert): the whole rope -> append -> attention -> combine
+        // chain is one cluster launch
+        const char* fa_env = getenv("UMV_FUSED_ATTN");        // read per call: tests switch paths inside one process
+        const bool fused_attn = !(fa_env && atoi(fa_env) == 0);
+        const bool fuse = fused_attn && r.weight_major && r.max_q_len == 1 && !r.gen && e->kv_tmap_ok &&
+                          decode_attention_supported(H, Hkv, dh, r.m.max_pages, ra.splits);
+        if (fuse) {
+            DecodeAttnArgs da;
+            da.qkv = ra.qkv; da.partial = ra.partial; da.ksplits = ra.splits; da.bias = ra.bias;
+            da.out = e->attn; da.ldo = D; da.positions = r.m.positions; da.kv_len = r.m.kv_len;
+            da.page_table = r.m.page_table; da.max_pages = r.m.max_pages; da.inv_freq = e->inv_freq; da.rope_cs = r.m.rope_cs;
+            da.qn = L.qn[0]; da.kn = L.kn[0]; da.pool = e->pool; da.layer = li; da.M = M; da.H = H; da.Hkv = Hkv;
+            da.eps = d.rms_eps; da.kv_tmap = e->kv_tmap_ok ? &e->kv_tmap : nullptr;
+            const int blocks = (r.max_kv_len + kPageTokens - 1) / kPageTokens;
+            // key ranges per (sample, kv head): as many as fit one wave of 2 CTAs per SM, at most one per 64-key block
+            da.cluster = std::max(1, std::min(std::min(attn_cluster_max, blocks), e->sm_count / std::max(1, M * Hkv)));
+            if (path) *path = 3;
+            return decode_attention(da, st);
+        }
+        ra.q_out = e->qkv; ra.ldq = QN;
+        ra.positions = r.m.positions; ra.row_seq = r.m.row_seq; ra.row_kvpos = r.m.row_kvpos;
+        ra.page_table = r.m.page_table; ra.max_pages = r.m.max_pages; ra.inv_freq = e->inv_freq; ra.rope_cs = r.m.rope_cs;
+        ra.qn0 = L.qn[0]; ra.kn0 = L.kn[0]; ra.qn1 = L.qn[E]; ra.kn1 = L.kn[E];
+        ra.row_sel = r.gen ? r.m.row_sel : nullptr; ra.gen_mode = r.gen ? 1 : 0;
+        ra.pool = e->pool; ra.layer = li; ra.M = M; ra.H = H; ra.Hkv = Hkv; ra.dh = dh; ra.eps = d.rms_eps;
+        UMV_TRY(rope_append(ra, st));
+        AttnArgs aa;
+        aa.q = e->qkv; aa.ldq = QN; aa.out = e->attn; aa.ldo = D;
+        aa.paged = 1; aa.pool = e->pool; aa.layer = li; aa.page_table = r.m.page_table; aa.max_pages = r.m.max_pages;
+        aa.q_start = r.m.q_start; aa.q_len = r.m.q_len; aa.kv_len = r.m.kv_len;
+        aa.n = r.n_seqs; aa.H = H; aa.Hkv = Hkv; aa.dh = dh; aa.causal = r.causal ? 1 : 0;
+        aa.max_q_len = r.max_q_len; aa.max_kv_len = r.max_kv_len; aa.splits = attn_splits; aa.ws = e->attn_ws; aa.total_q = M;
+        aa.kv_tmap = e->kv_tmap_ok ? &e->kv_tmap : nullptr;
+        if (path) {
+            const char* tc_env = getenv("UMV_ATTN_TC");
+            *path = (!(tc_env && atoi(tc_env) == 0) && attention_tc_supported(aa)) ? 2 : 1;
+        }
+        return attention_forward(aa, st);
+    };
+
+    if (r.probe) {      // umv_op_attention_block: this layer's attention block alone, on the caller's projection outputs
+        AttnProbe& p = *r.probe;
+        RopeAppendArgs ra;
+        if (p.partial) {
+            ra.partial = p.partial; ra.splits = p.splits; ra.bias = p.bias;
+        } else {
+            UMV_CUDA_OK(cudaMemcpyAsync(e->qkv, p.qkv, (size_t)M * QN * sizeof(bf16), cudaMemcpyDeviceToDevice, st));
+            ra.qkv = e->qkv;
+        }
+        UMV_TRY(attention_block(p.layer, ra, &p.path));
+        UMV_CUDA_OK(cudaMemcpyAsync(p.out, e->attn, (size_t)M * D * sizeof(bf16), cudaMemcpyDeviceToDevice, st));
+        return UMV_OK;
+    }
+
     for (int li = 0; li < d.layers; ++li) {
         const LayerW& L = e->layers[li];
         UMV_TRY(norm(L.ln1[0], L.ln1[1], e->xn));
@@ -436,41 +495,7 @@ static int llm_layers(umv_engine* e, const LlmRun& r, bf16* out, cudaStream_t st
             }
             ra.qkv = e->qkv;
         }
-        // decode (one query token per sample, understanding expert): the whole rope -> append -> attention -> combine
-        // chain is one cluster launch
-        const char* fa_env = getenv("UMV_FUSED_ATTN");        // read per call: tests switch paths inside one process
-        const bool fused_attn = !(fa_env && atoi(fa_env) == 0);
-        const bool fuse = fused_attn && r.weight_major && r.max_q_len == 1 && !r.gen && e->kv_tmap_ok &&
-                          decode_attention_supported(H, Hkv, dh, r.m.max_pages, ra.splits);
-        if (fuse) {
-            DecodeAttnArgs da;
-            da.qkv = ra.qkv; da.partial = ra.partial; da.ksplits = ra.splits; da.bias = ra.bias;
-            da.out = e->attn; da.ldo = D; da.positions = r.m.positions; da.kv_len = r.m.kv_len;
-            da.page_table = r.m.page_table; da.max_pages = r.m.max_pages; da.inv_freq = e->inv_freq; da.rope_cs = r.m.rope_cs;
-            da.qn = L.qn[0]; da.kn = L.kn[0]; da.pool = e->pool; da.layer = li; da.M = M; da.H = H; da.Hkv = Hkv;
-            da.eps = d.rms_eps; da.kv_tmap = e->kv_tmap_ok ? &e->kv_tmap : nullptr;
-            const int blocks = (r.max_kv_len + kPageTokens - 1) / kPageTokens;
-            // key ranges per (sample, kv head): as many as fit one wave of 2 CTAs per SM, at most one per 64-key block
-            da.cluster = std::max(1, std::min(std::min(attn_cluster_max, blocks), e->sm_count / std::max(1, M * Hkv)));
-            UMV_TRY(decode_attention(da, st));
-        } else {
-        ra.q_out = e->qkv; ra.ldq = QN;
-        ra.positions = r.m.positions; ra.row_seq = r.m.row_seq; ra.row_kvpos = r.m.row_kvpos;
-        ra.page_table = r.m.page_table; ra.max_pages = r.m.max_pages; ra.inv_freq = e->inv_freq; ra.rope_cs = r.m.rope_cs;
-        ra.qn0 = L.qn[0]; ra.kn0 = L.kn[0]; ra.qn1 = L.qn[E]; ra.kn1 = L.kn[E];
-        ra.row_sel = r.gen ? r.m.row_sel : nullptr; ra.gen_mode = r.gen ? 1 : 0;
-        ra.pool = e->pool; ra.layer = li; ra.M = M; ra.H = H; ra.Hkv = Hkv; ra.dh = dh; ra.eps = d.rms_eps;
-        UMV_TRY(rope_append(ra, st));
-        // ---- attention over the paged cache (past + the rows just appended)
-        AttnArgs aa;
-        aa.q = e->qkv; aa.ldq = QN; aa.out = e->attn; aa.ldo = D;
-        aa.paged = 1; aa.pool = e->pool; aa.layer = li; aa.page_table = r.m.page_table; aa.max_pages = r.m.max_pages;
-        aa.q_start = r.m.q_start; aa.q_len = r.m.q_len; aa.kv_len = r.m.kv_len;
-        aa.n = r.n_seqs; aa.H = H; aa.Hkv = Hkv; aa.dh = dh; aa.causal = r.causal ? 1 : 0;
-        aa.max_q_len = r.max_q_len; aa.max_kv_len = r.max_kv_len; aa.splits = attn_splits; aa.ws = e->attn_ws; aa.total_q = M;
-        aa.kv_tmap = e->kv_tmap_ok ? &e->kv_tmap : nullptr;
-        UMV_TRY(attention_forward(aa, st));
-        }
+        UMV_TRY(attention_block(li, ra, nullptr));
         // ---- output projection + residual
         if (partial) {
             const int s = pick_splits(D, D, e->sm_count);
@@ -610,10 +635,16 @@ int umv_load_tensor(umv_engine* e, const char* name, const void* data, int dtype
         UMV_REQUIRE(ndim == 4 && shape[0] == s.rows && shape[1] == s.conv_cin && shape[2] == s.conv_k && shape[3] == s.conv_k,
                     UMV_ERR_INVALID, "umv_load_tensor: '%s' expects a conv weight [%lld,%d,%d,%d]", name, (long long)s.rows,
                     s.conv_cin, s.conv_k, s.conv_k);
-        UMV_REQUIRE(dtype == UMV_BF16, UMV_ERR_UNSUPPORTED, "conv weights must be bf16");
+        UMV_REQUIRE(dtype == UMV_BF16 || (dtype == UMV_F32 && !data_on_device), UMV_ERR_UNSUPPORTED,
+                    "umv_load_tensor: dtype must be bf16 (or host fp32)");
         const size_t n = (size_t)s.rows * s.cols;
         std::vector<bf16> src(n), dst(n);
-        UMV_CUDA_OK(cudaMemcpy(src.data(), data, n * 2, cudaMemcpyDefault));
+        if (dtype == UMV_F32) {      // an fp32 ae.safetensors: round to bf16 on the way, as `.to(torch.bfloat16)` after load_ae does
+            const float* f = static_cast<const float*>(data);
+            for (size_t i = 0; i < n; ++i) src[i] = __float2bfloat16_rn(f[i]);
+        } else {
+            UMV_CUDA_OK(cudaMemcpy(src.data(), data, n * 2, cudaMemcpyDefault));
+        }
         const int kk = s.conv_k * s.conv_k, cin = s.conv_cin;
         for (int64_t o = 0; o < s.rows; ++o)
             for (int c = 0; c < cin; ++c)
@@ -816,12 +847,13 @@ int umv_llm_forward(umv_engine* e, const void* x, int32_t n_seqs, const int32_t*
 namespace umv {
 // Packed forward over n_seqs sequences; x == nullptr means the packed query sequence is already in e->h.
 int llm_run(umv_engine* e, const bf16* x, int n_seqs, const int32_t* seqs, const int32_t* q_lens, const int32_t* positions,
-            const uint8_t* row_is_gen, int is_causal, int update_kv, bf16* out, cudaStream_t st) {
+            const uint8_t* row_is_gen, int is_causal, int update_kv, bf16* out, cudaStream_t st, AttnProbe* probe) {
     UMV_REQUIRE(seqs && q_lens && positions && n_seqs > 0, UMV_ERR_INVALID, "umv_llm_forward: null/empty argument");
     UMV_REQUIRE(n_seqs <= 3 * e->d.max_seqs, UMV_ERR_INVALID, "umv_llm_forward: %d sequences > 3*max_seqs", n_seqs);
     UMV_REQUIRE(!row_is_gen || e->d.enable_gen, UMV_ERR_STATE, "generation expert weights were not enabled");
     const int D = e->d.hidden;
     LlmRun r;
+    r.probe = probe;
     r.n_seqs = n_seqs;
     r.causal = is_causal != 0;
     r.gen = row_is_gen != nullptr;
@@ -1319,8 +1351,33 @@ int umv_op_attention(const void* q, const void* k, const void* v, void* out, int
     cudaFree(dmeta);
     return rc;
 }
+int umv_op_attention_block(umv_engine* e, int32_t layer, const void* qkv, const float* qkv_partial, int32_t n_partials,
+                           const void* bias, int32_t n_seqs, const int32_t* seqs, const int32_t* q_lens, const int32_t* positions,
+                           const uint8_t* row_is_gen, int32_t is_causal, int32_t update_kv, void* out, int32_t* path_out,
+                           void* stream) {
+    UMV_REQUIRE(e && e->finalized, UMV_ERR_STATE, "engine not finalized");
+    UMV_REQUIRE(layer >= 0 && layer < e->d.layers && out && (qkv || (qkv_partial && bias && n_partials > 0)), UMV_ERR_INVALID,
+                "umv_op_attention_block: bad argument");
+    int M = 0;
+    for (int b = 0; b < n_seqs; ++b) M += q_lens[b];
+    UMV_REQUIRE(!qkv_partial || (size_t)n_partials * M * e->qkvn <= e->ws_elems, UMV_ERR_NOMEM,
+                "umv_op_attention_block: partials exceed the split-K workspace");
+    AttnProbe p;
+    p.layer = layer; p.qkv = static_cast<const bf16*>(qkv); p.partial = qkv_partial; p.splits = qkv_partial ? n_partials : 0;
+    p.bias = static_cast<const bf16*>(bias); p.out = static_cast<bf16*>(out);
+    int rc = umv::llm_run(e, nullptr, n_seqs, seqs, q_lens, positions, row_is_gen, is_causal, update_kv, nullptr,
+                          static_cast<cudaStream_t>(stream), &p);
+    if (path_out) *path_out = p.path;
+    return rc;
+}
 int umv_op_argmax(const void* logits, int32_t rows, int32_t vocab, int64_t* out, void* stream) {
     return argmax_rows(static_cast<const bf16*>(logits), rows, vocab, out, static_cast<cudaStream_t>(stream));
+}
+int umv_op_sample(const void* logits, int32_t rows, int32_t vocab, float temperature, uint64_t seed, float u_force, int64_t* out,
+                  void* stream) {
+    UMV_REQUIRE(logits && out && rows > 0 && vocab > 0 && temperature > 0.f, UMV_ERR_INVALID, "umv_op_sample: bad argument");
+    return sample_rows(static_cast<const bf16*>(logits), rows, vocab, temperature, seed, nullptr, out, static_cast<cudaStream_t>(stream),
+                       u_force);
 }
 
 }  // extern "C"

@@ -85,8 +85,18 @@ void engine_reg(umv_engine* e, const std::string& name, bf16* dst, int64_t rows,
 int lin(umv_engine* e, const bf16* x, int ldx, const bf16* w, const bf16* bias, const bf16* res, bf16* y, int ldy, int M, int N,
         int K, int epi, cudaStream_t st, int impl = 0, float* ws = nullptr, int splits = 1, int stages = 0,
         const int* res_rows = nullptr, bf16* res_gather_tmp = nullptr);
+// Parity hook (umv_op_attention_block): run only the attention block of one layer on caller-provided projection outputs.
+struct AttnProbe {
+    int layer = 0;
+    const bf16* qkv = nullptr;        // [M, (H+2Hkv)*dh] bf16 (bias applied), or
+    const float* partial = nullptr;   // [splits][M][(H+2Hkv)*dh] fp32 split-K partials + bias
+    int splits = 0;
+    const bf16* bias = nullptr;
+    bf16* out = nullptr;              // [M, H*dh]
+    int path = 0;                     // out: 1 mma.sync, 2 tcgen05, 3 fused decode cluster kernel
+};
 int llm_run(umv_engine* e, const bf16* x, int n_seqs, const int32_t* seqs, const int32_t* q_lens, const int32_t* positions,
-            const uint8_t* row_is_gen, int is_causal, int update_kv, bf16* out, cudaStream_t st);
+            const uint8_t* row_is_gen, int is_causal, int update_kv, bf16* out, cudaStream_t st, AttnProbe* probe = nullptr);
 }  // namespace umv
 
 struct umv_engine {

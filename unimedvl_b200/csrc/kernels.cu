@@ -977,8 +977,9 @@ __device__ __forceinline__ uint64_t splitmix64(uint64_t x) {
     x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
     return x ^ (x >> 31);
 }
+// `u_force` < 0: draw u from the hash; otherwise use it as u (test hook for the u*total == total rounding edge).
 __global__ void __launch_bounds__(1024) sample_kernel(const bf16* __restrict__ logits, int vocab, float inv_t, uint64_t seed,
-                                                       const int* __restrict__ step, int64_t* __restrict__ out) {
+                                                       const int* __restrict__ step, int64_t* __restrict__ out, float u_force) {
     pdl_launch_dependents();
     pdl_wait();
     __shared__ float red[32];
@@ -1007,9 +1008,13 @@ __global__ void __launch_bounds__(1024) sample_kernel(const bf16* __restrict__ l
     __syncthreads();
     const float total = red[0];
     const uint64_t h = splitmix64(seed ^ splitmix64(((uint64_t)(step ? *step : 0) << 32) | blockIdx.x));
-    const float target = (float)((h >> 40) * (1.0 / 16777216.0)) * total;
+    const float u = u_force >= 0.f ? u_force : (float)((h >> 40) * (1.0 / 16777216.0));
+    const float target = u * total;
     const float before = s_prefix[threadIdx.x];
-    if (target >= before && (target < before + local || threadIdx.x == blockDim.x - 1) && i0 < i1) {
+    // u < 1, but u * total may round UP to total in fp32: then no span satisfies target < before + local and the LAST NON-EMPTY
+    // span must take it (with span = ceil(vocab / 1024) the trailing threads own nothing: 149 x 1021 >= 152064)
+    const int last = (vocab - 1) / span;
+    if (target >= before && (target < before + local || threadIdx.x == last) && i0 < i1) {
         float run = before;
         int pick = i1 - 1;
         for (int i = i0; i < i1; ++i) {
@@ -1020,9 +1025,10 @@ __global__ void __launch_bounds__(1024) sample_kernel(const bf16* __restrict__ l
     }
 }
 int sample_rows(const bf16* logits, int rows, int vocab, float temperature, uint64_t seed, const int* step, int64_t* out,
-                cudaStream_t s) {
+                cudaStream_t s, float u_force) {
     if (rows <= 0) return UMV_OK;
-    launch_k(sample_kernel, dim3(rows), dim3(1024), 0, s, logits, vocab, 1.0f / temperature, seed, step, out);
+    // logits / T on a bf16 CUDA tensor with a Python scalar is x * (1.0f / T) in fp32, rounded to bf16 (ATen's div-by-scalar)
+    launch_k(sample_kernel, dim3(rows), dim3(1024), 0, s, logits, vocab, 1.0f / temperature, seed, step, out, u_force);
     UMV_LAUNCH_CHECK("sample_kernel");
     return UMV_OK;
 }

@@ -128,7 +128,7 @@ int decode_begin_step(const bf16* table, int D, int64_t vocab, DecodeState st, c
                       int B, bf16* x, cudaStream_t s);
 int decode_end_step(DecodeState st, int B, cudaStream_t s);
 int sample_rows(const bf16* logits, int rows, int vocab, float temperature, uint64_t seed, const int* step, int64_t* out,
-                cudaStream_t s);
+                cudaStream_t s, float u_force = -1.f);
 int export_kv(KVPool pool, int layer, const int* pages, int len, bf16* k_out, bf16* v_out, cudaStream_t s);
 int copy_page(KVPool pool, int src_page, int dst_page, cudaStream_t s);
 

@@ -67,6 +67,8 @@ class Engine:
         for name, t in sd.items():
             t = t.detach()
             if t.dtype not in (torch.bfloat16, torch.float32):
+                if not strict:          # e.g. an int64 step counter / position_ids buffer in the shard: nothing the engine holds
+                    continue
                 raise ValueError(f"{name}: dtype {t.dtype} (bf16 or fp32 expected)")
             if t.dtype == torch.float32 and t.is_cuda:
                 t = t.to(torch.bfloat16)
@@ -212,6 +214,28 @@ class Engine:
         self._exit()
         return out
 
+    def attention_block(self, layer: int, seqs: Sequence[int], q_lens: Sequence[int], positions: Sequence[int], qkv=None,
+                        partial=None, bias=None, row_is_gen=None, is_causal: bool = True, update_kv: bool = True):
+        """umv_op_attention_block: q/k-norm + RoPE + KV append + attention of one layer on given projection outputs.
+        Returns (out bf16 [M, heads*head_dim], path) with path 1 mma.sync / 2 tcgen05 / 3 fused decode kernel."""
+        M = sum(int(q) for q in q_lens)
+        l = self.dims.llm
+        out = torch.empty((M, l.heads * l.head_dim), dtype=torch.bfloat16, device=self.device)
+        if qkv is not None:
+            qkv = qkv.to(self.device, torch.bfloat16).contiguous()
+        if partial is not None:
+            partial = partial.to(self.device, torch.float32).contiguous()
+            bias = bias.to(self.device, torch.bfloat16).contiguous()
+        sel = (C.c_uint8 * M)(*[int(b) for b in row_is_gen]) if row_is_gen is not None else None
+        path = C.c_int32()
+        self._enter()
+        _lib.check(self.lib.umv_op_attention_block(
+            self.h, layer, _ptr(qkv), None if partial is None else C.c_void_p(partial.data_ptr()),
+            0 if partial is None else partial.shape[0], _ptr(bias), len(seqs), _lib.i32_array(seqs), _lib.i32_array(q_lens),
+            _lib.i32_array(positions), sel, int(is_causal), int(update_kv), _ptr(out), C.byref(path), _stream_ptr(self.stream)))
+        self._exit()
+        return out, path.value
+
     def lm_head(self, hidden: torch.Tensor) -> torch.Tensor:
         hidden = hidden.to(self.device, torch.bfloat16).contiguous()
         out = torch.empty((hidden.shape[0], self.dims.llm.vocab), dtype=torch.bfloat16, device=self.device)
@@ -343,4 +367,12 @@ def op_argmax(logits) -> torch.Tensor:
     lib = _lib.load()
     out = torch.empty((logits.shape[0],), dtype=torch.int64, device=logits.device)
     _lib.check(lib.umv_op_argmax(_ptr(logits), logits.shape[0], logits.shape[1], _ptr(out), _stream_ptr()))
+    return out
+
+
+def op_sample(logits, temperature: float, seed: int = 0, u_force: float = -1.0) -> torch.Tensor:
+    lib = _lib.load()
+    out = torch.empty((logits.shape[0],), dtype=torch.int64, device=logits.device)
+    _lib.check(lib.umv_op_sample(_ptr(logits), logits.shape[0], logits.shape[1], C.c_float(temperature), C.c_uint64(seed),
+                                 C.c_float(u_force), _ptr(out), _stream_ptr()))
     return out

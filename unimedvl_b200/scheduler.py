@@ -118,8 +118,10 @@ class ContinuousBatcher:
             tw, th = self.vit_transform.resize_transform.target_size(w, h)
             p = self.model.vit_patch_size
             n_img = (tw // p) * (th // p) + 2
-        total = prefix_len + n_img + n_txt + r.max_length
-        return max(n_img, n_txt), (total + _PAGE - 1) // _PAGE + 1       # +1: copy-on-write tail of a forked prefix
+        # a chunk runs min(chunk, longest remaining budget) steps for EVERY running sequence, so a request may grow up to
+        # chunk - 1 tokens past its own budget before it is retired; +1: copy-on-write tail of a forked prefix
+        total = prefix_len + n_img + n_txt + r.max_length + self.chunk
+        return max(n_img, n_txt), (total + _PAGE - 1) // _PAGE + 1
 
     def _prefix(self, text: str):
         if text not in self._prefixes:
@@ -128,20 +130,25 @@ class ContinuousBatcher:
             with _Borrowed(self.engine, self.layers, [seq]) as c:
                 self.model.forward_cache_update_text(c, **g)
             self._prefixes[text] = (seq, lens[0], rope[0])
-            self.capacity = min(self.capacity, self.engine.pages_free())
         return self._prefixes[text]
 
     def _admit(self):
         group: List[Request] = []
         rows = 0
-        committed = sum(r.pages for r in self.running)
+        # pages the running requests may still claim (reserved, not yet held); the pool is re-read at every admission so
+        # pages held by other caches on the same engine count (back-pressure instead of a mid-decode "pool exhausted")
+        held = lambda r: (r.kv_len + _PAGE - 1) // _PAGE
+        committed = sum(max(r.pages - held(r), 0) for r in self.running)
         while self.waiting and len(self.running) + len(group) < self.max_batch:
             r = self.waiting[0]
             plen = self._prefix(r.prefix)[1] if r.prefix else 0
+            avail = self.engine.pages_free()
             need_rows, need_pages = self._rows_and_pages(r, plen)
             if need_pages > self.capacity:
                 raise MemoryError(f"request {r.rid} needs {need_pages} KV pages, the pool has {self.capacity}")
-            if committed + need_pages > self.capacity or (group and rows + need_rows > self.max_prefill_tokens):
+            if committed + need_pages > avail or (group and rows + need_rows > self.max_prefill_tokens):
+                if not self.running and not group:
+                    raise MemoryError(f"request {r.rid} needs {need_pages} KV pages, only {avail} are free and nothing is running")
                 break
             self.waiting.popleft()
             r.pages = need_pages

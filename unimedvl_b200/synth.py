@@ -22,16 +22,53 @@ import torch
 from .config import BagelDims, LLMDims, ViTDims, VAEDims
 
 
+def _key(name: str, seed: int) -> int:
+    return (zlib.crc32(name.encode()) ^ (seed * 0x9E3779B1)) & 0xFFFFFFFF
+
+
 def _rng(name: str, seed: int) -> np.random.Generator:
-    return np.random.Generator(np.random.PCG64((zlib.crc32(name.encode()) ^ (seed * 0x9E3779B1)) & 0xFFFFFFFF))
+    return np.random.Generator(np.random.PCG64(_key(name, seed)))
+
+
+_DEVICE = None      # set by on_device(): draw with torch's generator on that device instead of numpy on the host
+
+
+class on_device:
+    """``with synth.on_device("cuda"): sd = synth.bagel_state_dict(dims)`` draws every tensor with torch's Philox
+    generator on the device (seeded per tensor name as on the host path).  For full-width (14B-dims) parity runs, where
+    2e9 host-side normals would take minutes; the values differ from the host stream, so fixtures stay on the host path."""
+
+    def __init__(self, device):
+        self.device = torch.device(device)
+
+    def __enter__(self):
+        global _DEVICE
+        self._prev, _DEVICE = _DEVICE, self.device
+        return self
+
+    def __exit__(self, *exc):
+        global _DEVICE
+        _DEVICE = self._prev
+
+
+def _device_gen(name, seed):
+    g = torch.Generator(device=_DEVICE)
+    g.manual_seed(_key(name, seed))
+    return g
 
 
 def _normal(name, shape, std, seed, mean=0.0, dtype=torch.bfloat16):
+    if _DEVICE is not None:
+        a = torch.randn(tuple(shape), generator=_device_gen(name, seed), device=_DEVICE, dtype=torch.float32)
+        return a.mul_(std).add_(mean).to(dtype)
     a = _rng(name, seed).standard_normal(size=shape, dtype=np.float32) * np.float32(std) + np.float32(mean)
     return torch.from_numpy(a).to(dtype)
 
 
 def _uniform(name, shape, bound, seed, dtype=torch.bfloat16):
+    if _DEVICE is not None:
+        a = torch.rand(tuple(shape), generator=_device_gen(name, seed), device=_DEVICE, dtype=torch.float32)
+        return a.mul_(2 * bound).sub_(bound).to(dtype)
     a = _rng(name, seed).random(size=shape, dtype=np.float32) * np.float32(2 * bound) - np.float32(bound)
     return torch.from_numpy(a).to(dtype)
 
@@ -105,8 +142,8 @@ def glue_state_dict(d: BagelDims, seed: int = 0, std: float = 0.02) -> dict:
     sd["connector.fc1.bias"] = _normal("c.fc1b", (D,), std, seed)
     sd["connector.fc2.weight"] = _normal("c.fc2w", (D, D), 1.0 / math.sqrt(D), seed)
     sd["connector.fc2.bias"] = _normal("c.fc2b", (D,), std, seed)
-    sd["vit_pos_embed.pos_embed"] = sincos_2d_table(D, d.vit_max_num_patch_per_side).to(torch.bfloat16)
-    sd["latent_pos_embed.pos_embed"] = sincos_2d_table(D, d.max_latent_size).to(torch.bfloat16)
+    sd["vit_pos_embed.pos_embed"] = sincos_2d_table(D, d.vit_max_num_patch_per_side).to(torch.bfloat16).to(_DEVICE or "cpu")
+    sd["latent_pos_embed.pos_embed"] = sincos_2d_table(D, d.max_latent_size).to(torch.bfloat16).to(_DEVICE or "cpu")
     sd["time_embedder.mlp.0.weight"] = _normal("t.0w", (D, 256), 1.0 / 16.0, seed)
     sd["time_embedder.mlp.0.bias"] = _normal("t.0b", (D,), std, seed)
     sd["time_embedder.mlp.2.weight"] = _normal("t.2w", (D, D), 1.0 / math.sqrt(D), seed)
