@@ -186,6 +186,61 @@ int umv_latent_embed(umv_engine* e, const float* x, const int64_t* pos_ids, int3
 int umv_vae_decode(umv_engine* e, const void* z, int32_t n, int32_t h, int32_t w, void* out, void* stream);
 int umv_vae_encode_moments(umv_engine* e, const void* x, int32_t n, int32_t H, int32_t W, void* out, void* stream);
 
+/* ---- the reference's prefill drivers, one call each: the packed query sequence (marker / text embeddings, ViT or latent
+ * embeddings scattered to their packed rows) is composed inside the engine and run through the LLM with the cache update.
+ * Index arguments are the `generation_input` tensors of the matching Bagel.prepare_* method, as HOST arrays:
+ *   text:  Bagel.forward_cache_update_text (bagel.py:412-458): text_lens [n_seqs], text_ids [sum] (packed_text_ids), positions [sum]
+ *          (packed_text_position_ids); causal.
+ *   vit:   Bagel.forward_cache_update_vit (bagel.py:523-615): seq_lens = packed_seqlens, text_ids / text_rows = packed_text_ids /
+ *          packed_text_indexes (the <vision_start> / <vision_end> markers), pixels / vit_pos_ids (DEVICE) / vit_seqlens as umv_vit_embed,
+ *          vit_rows = packed_vit_token_indexes, positions = packed_position_ids; full attention inside the block.
+ *   vae:   Bagel.forward_cache_update_vae (bagel.py:697-806) after vae_model.encode: latent = the encoded, padded batch bf16
+ *          [n_images, latent_dim / patch^2, Hl, Wl] (DEVICE); latent_hw = patchified_vae_latent_shapes [n_images][2]; lat_pos_ids =
+ *          packed_vae_position_ids (DEVICE); lat_rows = packed_vae_token_indexes; timestep = packed_timesteps (one value);
+ *          generation-expert routing for the latent rows, full attention.
+ * text_rows and the block rows must tile [0, sum(seq_lens)) exactly (UMV_ERR_INVALID otherwise). */
+int umv_forward_cache_update_text(umv_engine* e, int32_t n_seqs, const int32_t* seqs, const int32_t* text_lens,
+                                  const int64_t* text_ids, const int32_t* positions, void* stream);
+int umv_forward_cache_update_vit(umv_engine* e, int32_t n_seqs, const int32_t* seqs, const int32_t* seq_lens, int32_t n_text,
+                                 const int64_t* text_ids, const int32_t* text_rows, const float* pixels, const int64_t* vit_pos_ids,
+                                 int32_t n_images, const int32_t* vit_seqlens, const int32_t* vit_rows, const int32_t* positions,
+                                 void* stream);
+int umv_forward_cache_update_vae(umv_engine* e, int32_t n_seqs, const int32_t* seqs, const int32_t* seq_lens, int32_t n_text,
+                                 const int64_t* text_ids, const int32_t* text_rows, const void* latent, int32_t n_images, int32_t Hl,
+                                 int32_t Wl, const int32_t* latent_hw, int32_t patch, const int64_t* lat_pos_ids, const int32_t* lat_rows,
+                                 float timestep, const int32_t* positions, void* stream);
+
+/* ---- the inner module boundary, for layer-level parity against the reference's own sub-modules:
+ *   umv_vit_model     vit_model(packed_pixel_values, packed_flattened_position_ids, cu_seqlens, max_seqlen) (siglip_navit.py:389-402)
+ *                     -> bf16 [n_tokens, vit_hidden]: the post-layernorm rows as the next Linear sees them (the reference's LayerNorm
+ *                     returns fp32 under CUDA autocast and the connector's first Linear rounds it to exactly this bf16 value)
+ *   umv_connector     connector(x) (modeling_utils.py:119-123): bf16 [n, vit_hidden] -> bf16 [n, hidden]
+ *   umv_pos_embed     vit_pos_embed(ids) (which = 0) / latent_pos_embed(ids) (which = 1) (modeling_utils.py:142-143): rows of the frozen table
+ *   umv_vae2llm       vae2llm(x) (bagel.py:114): fp32 [n, latent_dim] (cast to bf16 by autocast) -> bf16 [n, hidden]
+ *   umv_llm2vae       llm2vae(h) (bagel.py:115): bf16 [n, hidden] -> bf16 [n, latent_dim]
+ *   umv_time_embedder time_embedder(t) (modeling_utils.py:73-109): HOST fp32 [n] -> bf16 [n, hidden]
+ * language_model.forward_inference is umv_llm_forward, lm_head umv_lm_head, embed_tokens umv_embed_tokens, vae_model.encode / decode
+ * umv_vae_encode_moments (+ umv_vae_sample) / umv_vae_decode. */
+int umv_vit_model(umv_engine* e, const float* pixels, const int64_t* pos_ids, const int32_t* seqlens, int32_t n_images, void* out,
+                  void* stream);
+int umv_connector(umv_engine* e, const void* x, int32_t n, void* out, void* stream);
+int umv_pos_embed(umv_engine* e, int32_t which, const int64_t* pos_ids, int32_t n, void* out, void* stream);
+int umv_vae2llm(umv_engine* e, const float* x, int32_t n, void* out, void* stream);
+int umv_llm2vae(umv_engine* e, const void* h, int32_t n, void* out, void* stream);
+int umv_time_embedder(umv_engine* e, const float* timesteps, int32_t n, void* out, void* stream);
+
+/* DiagonalGaussian sampling + AutoEncoder.encode's affine (autoencoder.py:266-272,300-303), op by op on bf16 as torch does:
+ * out = scale * ((mean + exp(0.5 * logvar) * noise) - shift).  moments bf16 [n, 2z, h, w] (umv_vae_encode_moments), noise bf16
+ * [n, z, h, w] drawn by the caller (the reference uses torch.randn_like) or NULL for sample=False; out bf16 [n, z, h, w]. */
+int umv_vae_sample(umv_engine* e, const void* moments, const void* noise, int32_t n, int32_t h, int32_t w, void* out, void* stream);
+
+/* InterleaveInferencer.decode_image (inferencer.py:234-256) on the device: packed latent tokens fp32 [n][h*w][patch^2 * z] (what
+ * generate_image returns per image) -> unpatchify "nhwpqc->nchpwq" -> AutoEncoder.decode -> (x * 0.5 + 0.5).clamp(0, 1) * 255 -> uint8
+ * with torch's bf16 rounding after every op and the truncating cast; out uint8 [n][8 h patch][8 w patch][3] (HWC, what Image.fromarray
+ * takes).  n images of one size per call. */
+int umv_decode_image_u8(umv_engine* e, const float* latent_tokens, int32_t n, int32_t h, int32_t w, int32_t patch, uint8_t* out,
+                        void* stream);
+
 /* ---- op-level entry points (parity tests; each is the kernel the model path uses) ---------- */
 /* y[M,N] = x[M,K] @ w[N,K]^T (+bias) with epilogue `epi`: 0 bf16, 1 gelu_tanh, 2 swiglu (w rows
  * interleaved 64 gate | 64 up, y is [M, N/2]), 3 +residual (y = bf16(bf16(acc+bias) + res)).
@@ -213,6 +268,7 @@ int umv_op_attention_block(umv_engine* e, int32_t layer, const void* qkv, const 
                            const void* bias, int32_t n_seqs, const int32_t* seqs, const int32_t* q_lens, const int32_t* positions,
                            const uint8_t* row_is_gen, int32_t is_causal, int32_t update_kv, void* out, int32_t* path_out,
                            void* stream);
+int umv_op_argmax(const void* logits, int32_t rows, int32_t vocab, int64_t* out, void* stream);
 /* The sampling branch of generate_text (bagel.py:1297-1301: softmax(pred_logits / temperature) in fp32 + multinomial) as the
  * decode loop runs it: row r draws from softmax(bf16(logits[r] * (1/T))) by inverse CDF with u from the engine's counter-based
  * hash of (seed, step 0, r).  u_force >= 0 replaces u (test hook for the u * total == total rounding edge). */

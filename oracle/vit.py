@@ -39,6 +39,8 @@ def vit_forward(sd, dims: ViTDims, packed_pixel_values, packed_flattened_positio
     lin = lambda name, t: nm.linear(t, sd[P + name + ".weight"], sd[P + name + ".bias"], exact)
     x = lin("embeddings.patch_embedding", packed_pixel_values)                      # :190 (linearised conv)
     x = x + sd[P + "embeddings.position_embedding.weight"][packed_flattened_position_ids]   # :192 bf16+bf16
+    if taps is not None:
+        taps["vit_embed"] = x.clone()
     lens = [int(t) for t in seqlens]
     H, dh = dims.heads, dims.head_dim
     for li in range(dims.layers):
@@ -49,6 +51,8 @@ def vit_forward(sd, dims: ViTDims, packed_pixel_values, packed_flattened_positio
         v = lin(L + "self_attn.v_proj", h).view(-1, H, dh)
         a = nm.attention_varlen(q, k, v, lens, lens, causal=False, p_bf16=sem is Semantics.cuda).reshape(-1, dims.hidden)   # :232-241
         x = x + lin(L + "self_attn.out_proj", a)
+        if taps is not None:
+            taps[f"vit_attn{li}"] = x.clone()
         h = nm.layernorm(x, sd[P + L + "layer_norm2.weight"], sd[P + L + "layer_norm2.bias"], dims.eps, sem)
         h = lin(L + "mlp.fc1", h)
         h = nm.gelu_tanh(h)

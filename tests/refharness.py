@@ -142,6 +142,18 @@ class FakeTokenizer:
         return " ".join(self.m.get(int(i), str(int(i))) for i in ids)
 
 
+def exact_reductions(on: bool = True):
+    """`torch.backends.cuda.matmul.allow_bf16_reduced_precision_reduction = not on`.  PyTorch's default (True) lets cuBLASLt reduce
+    split-K partial sums in bf16; whether it does depends on the GEMM shape and the GPU, not on the model.  Measured on the B200
+    (tools/exp/redprec.py, profiles/r2_reference_parity.md): with the default, 43 % of the reference's own tiny-dims patch-embedding
+    outputs (one Linear, K = 588) sit >= 1 bf16 ulp away from the fp32-accumulated value; with fp32 reductions that drops to 1e-4 (1 ulp).
+    The parity tests therefore run the reference with fp32 reductions (a global torch switch, no reference code touched) and record the
+    default-switch figures next to them.  Returns the previous setting."""
+    prev = torch.backends.cuda.matmul.allow_bf16_reduced_precision_reduction
+    torch.backends.cuda.matmul.allow_bf16_reduced_precision_reduction = not on
+    return not prev
+
+
 def autocast(device):
     """The context the reference's entry points run under: CUDA autocast bf16 (interactive_vqa_inferencer.py:311,
     inferencer.py:651); on CPU the equivalent CPU autocast."""

@@ -74,6 +74,17 @@ SIGNATURES = {
     "umv_latent_embed": (C.c_int, [_P, _P, _P, _I, _F, _P, _P]),
     "umv_vae_decode": (C.c_int, [_P, _P, _I, _I, _I, _P, _P]),
     "umv_vae_encode_moments": (C.c_int, [_P, _P, _I, _I, _I, _P, _P]),
+    "umv_forward_cache_update_text": (C.c_int, [_P, _I, _IP, _IP, _LP, _IP, _P]),
+    "umv_forward_cache_update_vit": (C.c_int, [_P, _I, _IP, _IP, _I, _LP, _IP, _P, _P, _I, _IP, _IP, _IP, _P]),
+    "umv_forward_cache_update_vae": (C.c_int, [_P, _I, _IP, _IP, _I, _LP, _IP, _P, _I, _I, _I, _IP, _I, _P, _IP, _F, _IP, _P]),
+    "umv_vit_model": (C.c_int, [_P, _P, _P, _IP, _I, _P, _P]),
+    "umv_connector": (C.c_int, [_P, _P, _I, _P, _P]),
+    "umv_pos_embed": (C.c_int, [_P, _I, _P, _I, _P, _P]),
+    "umv_vae2llm": (C.c_int, [_P, _P, _I, _P, _P]),
+    "umv_llm2vae": (C.c_int, [_P, _P, _I, _P, _P]),
+    "umv_time_embedder": (C.c_int, [_P, C.POINTER(C.c_float), _I, _P, _P]),
+    "umv_vae_sample": (C.c_int, [_P, _P, _P, _I, _I, _I, _P, _P]),
+    "umv_decode_image_u8": (C.c_int, [_P, _P, _I, _I, _I, _I, _P, _P]),
     "umv_op_linear": (C.c_int, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P]),
     "umv_op_rmsnorm": (C.c_int, [_P, _P, _P, _I, _I, _F, _P]),
     "umv_op_layernorm": (C.c_int, [_P, _P, _P, _P, _I, _I, _F, _P]),

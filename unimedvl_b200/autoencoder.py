@@ -43,12 +43,8 @@ class AutoEncoder:
         """autoencoder.py:300-303: z = mean + exp(0.5 logvar) * randn (device RNG -- not reproducible across
         implementations, so `noise` may be injected), then scale * (z - shift); bf16 tensor ops as in the reference."""
         m = self.encode_moments(x)
-        mean, logvar = torch.chunk(m, 2, dim=1)
-        if self.sample:
-            if noise is None:
-                dev = mean.device if self.noise_device == "cuda" else torch.device("cpu")
-                noise = torch.randn(mean.shape, dtype=mean.dtype, device=dev, generator=self.generator)
-            z = mean + torch.exp(0.5 * logvar) * noise.to(mean.device, mean.dtype)
-        else:
-            z = mean
-        return self.scale_factor * (z - self.shift_factor)
+        if self.sample and noise is None:           # the draw itself is torch's generator, as in the reference (torch.randn_like)
+            shape = (m.shape[0], m.shape[1] // 2, m.shape[2], m.shape[3])
+            dev = m.device if self.noise_device == "cuda" else torch.device("cpu")
+            noise = torch.randn(shape, dtype=m.dtype, device=dev, generator=self.generator)
+        return self.engine.vae_sample(m, noise if self.sample else None)

@@ -18,17 +18,6 @@ from .config import BagelDims
 from .engine import Engine
 
 
-class _DeviceProbe:
-    """``next(model.language_model.model.embed_tokens.parameters()).device`` (inferencer.py:99-101,
-    bagel.py:422,538) must resolve to the engine's device."""
-
-    def __init__(self, device):
-        self._t = torch.empty(0, device=device)
-
-    def parameters(self):
-        yield self._t
-
-
 def _canonical(indexes: torch.Tensor, expected: torch.Tensor, what: str):
     """The engine addresses the cache by (sample, position); it accepts exactly the packed index layout
     the reference's prepare_* methods emit and refuses anything else instead of mis-addressing."""
@@ -36,6 +25,83 @@ def _canonical(indexes: torch.Tensor, expected: torch.Tensor, what: str):
         return
     if indexes.numel() != expected.numel() or not torch.equal(indexes.to("cpu", torch.int64), expected):
         raise NotImplementedError(f"{what}: only the index layout produced by Bagel.prepare_* is supported")
+
+
+class BaseNavitOutputWithPast:
+    """qwen2_navit.py:224-227."""
+
+    def __init__(self, packed_query_sequence=None, past_key_values=None):
+        self.packed_query_sequence, self.past_key_values = packed_query_sequence, past_key_values
+
+    def __iter__(self):
+        return iter((self.packed_query_sequence, self.past_key_values))
+
+
+class _Module:
+    """A sub-module of the reference's Bagel as a callable over the engine (SURVEY.md section 8b "inner module boundary"):
+    `module(x)`, `.parameters()` for device discovery, `.eval()`."""
+
+    def __init__(self, engine: Engine, fn, dtype=torch.bfloat16):
+        self._engine, self._fn = engine, fn
+        self._probe = torch.empty(0, dtype=dtype, device=engine.device)
+
+    def __call__(self, *a, **k):
+        return self._fn(*a, **k)
+
+    forward = __call__
+
+    def parameters(self):
+        yield self._probe
+
+    def eval(self):
+        return self
+
+
+class _QwenBody:
+    """language_model.model: only `embed_tokens` is reached from outside (bagel.py:438,577,1264; inferencer.py:99-101)."""
+
+    def __init__(self, engine: Engine):
+        self.embed_tokens = _Module(engine, lambda ids: engine.embed_tokens(ids.reshape(-1)).reshape(*ids.shape, -1))
+
+
+class _LanguageModel:
+    """Qwen2ForCausalLM as the reference's Bagel uses it: `.model.embed_tokens`, `.lm_head`, `.forward_inference(...)`
+    (qwen2_navit.py:1243-1274) over umv_embed_tokens / umv_lm_head / umv_llm_forward."""
+
+    def __init__(self, bagel: "Bagel"):
+        self._b = bagel
+        eng = bagel.engine
+        self.model = _QwenBody(eng)
+        self.lm_head = _Module(eng, lambda h: eng.lm_head(h.reshape(-1, h.shape[-1])).reshape(*h.shape[:-1], -1))
+
+    def eval(self):
+        return self
+
+    @torch.no_grad()
+    def forward_inference(self, packed_query_sequence, query_lens, packed_query_position_ids, packed_query_indexes,
+                          past_key_values=None, key_values_lens=None, packed_key_value_indexes=None, update_past_key_values=True,
+                          is_causal=True, mode="und", packed_vae_token_indexes=None, packed_text_indexes=None):
+        """Same arguments and return shape as the reference.  The cache is addressed by (sample, position), so the index tensors
+        must be the canonical layout Bagel.prepare_* emits (checked); `past_key_values` None runs against empty contexts."""
+        b, eng = self._b, self._b.engine
+        lens = b._ints(query_lens)
+        if mode not in ("und", "gen"):
+            raise ValueError(f"forward_inference: mode {mode!r}")
+        cache = past_key_values if past_key_values is not None else NaiveCache(b.config.llm_config.num_hidden_layers)
+        h = paged_handle(cache, eng, len(lens))
+        kv = b._ints(key_values_lens) if key_values_lens is not None else [0] * len(lens)
+        b._check_kv(h, kv, packed_key_value_indexes, lens, packed_query_indexes, "forward_inference")
+        M = sum(lens)
+        is_gen = None
+        if mode == "gen":
+            is_gen = [0] * M
+            for i in b._ints(packed_vae_token_indexes):
+                is_gen[i] = 1
+            if packed_text_indexes is not None and sorted(b._ints(packed_text_indexes) + b._ints(packed_vae_token_indexes)) != list(range(M)):
+                raise ValueError("forward_inference: packed_text_indexes + packed_vae_token_indexes must cover every packed row once")
+        out = eng.llm_forward(packed_query_sequence, h.seqs, lens, b._ints(packed_query_position_ids), row_is_gen=is_gen,
+                              is_causal=bool(is_causal), update_kv=bool(update_past_key_values), want_hidden=True)
+        return BaseNavitOutputWithPast(packed_query_sequence=out, past_key_values=cache if update_past_key_values else past_key_values)
 
 
 class Bagel:
@@ -60,9 +126,21 @@ class Bagel:
         self.vit_patch_size = dims.vit.patch
         self.vit_max_num_patch_per_side = dims.vit_max_num_patch_per_side
         self.vit_hidden_size = dims.vit.hidden
-        probe = _DeviceProbe(engine.device)
-        self.language_model = SimpleNamespace(model=SimpleNamespace(embed_tokens=probe))
         self.device = engine.device
+        # inner module boundary: the reference's sub-modules as callables over the C ABI
+        self.language_model = _LanguageModel(self)
+        e = engine
+
+        def _vit(packed_pixel_values, packed_flattened_position_ids, cu_seqlens, max_seqlen=None):
+            cu = self._ints(cu_seqlens)
+            return e.vit_model(packed_pixel_values, packed_flattened_position_ids, [b - a for a, b in zip(cu[:-1], cu[1:])])
+        self.vit_model = _Module(e, _vit)                                  # siglip_navit.py:389-402
+        self.connector = _Module(e, lambda x: e.connector(x))                           # modeling_utils.py:119-123
+        self.vit_pos_embed = _Module(e, lambda ids: e.pos_embed(0, ids))   # modeling_utils.py:142-143
+        self.latent_pos_embed = _Module(e, lambda ids: e.pos_embed(1, ids))
+        self.vae2llm = _Module(e, lambda x: e.vae2llm(x))                               # bagel.py:114
+        self.llm2vae = _Module(e, lambda h: e.llm2vae(h))                               # bagel.py:115
+        self.time_embedder = _Module(e, lambda t: e.time_embedder(t))                   # modeling_utils.py:73-109
 
     def eval(self):
         return self
@@ -110,6 +188,8 @@ class Bagel:
             _canonical(packed_indexes, torch.as_tensor(exp_q), what + ".packed_indexes")
 
     # ------------------------------------------------------------------ prefill
+    # Each driver is ONE C-ABI call: the engine composes the packed query sequence itself (marker / text embeddings and the ViT /
+    # latent embeddings written at their packed rows) -- no torch index_put / permute / cat on the path.
     @torch.no_grad()
     def forward_cache_update_text(self, past_key_values, packed_text_ids, packed_text_position_ids, text_token_lens,
                                   packed_text_indexes, packed_key_value_indexes, key_values_lens):
@@ -117,9 +197,7 @@ class Bagel:
         lens = self._ints(text_token_lens)
         h = paged_handle(past_key_values, self.engine, len(lens))
         self._check_kv(h, key_values_lens, packed_key_value_indexes, lens, packed_text_indexes, "forward_cache_update_text")
-        x = self.engine.embed_tokens(packed_text_ids)
-        self.engine.llm_forward(x, h.seqs, lens, self._ints(packed_text_position_ids), is_causal=True, update_kv=True,
-                                want_hidden=False)
+        self.engine.forward_cache_update_text(h.seqs, lens, self._ints(packed_text_ids), self._ints(packed_text_position_ids))
         return past_key_values
 
     @torch.no_grad()
@@ -130,13 +208,9 @@ class Bagel:
         lens = self._ints(packed_seqlens)
         h = paged_handle(past_key_values, self.engine, len(lens))
         self._check_kv(h, key_values_lens, packed_key_value_indexes, lens, packed_indexes, "forward_cache_update_vit")
-        dev = self.device
-        seq = torch.zeros((sum(lens), self.hidden_size), dtype=torch.bfloat16, device=dev)
-        seq[packed_text_indexes.to(dev)] = self.engine.embed_tokens(packed_text_ids)
-        seq[packed_vit_token_indexes.to(dev)] = self.engine.vit_embed(packed_vit_tokens, packed_vit_position_ids,
-                                                                      self._ints(vit_token_seqlens))
-        self.engine.llm_forward(seq, h.seqs, lens, self._ints(packed_position_ids), is_causal=False, update_kv=True,
-                                want_hidden=False)
+        self.engine.forward_cache_update_vit(h.seqs, lens, self._ints(packed_text_ids), self._ints(packed_text_indexes),
+                                             packed_vit_tokens, packed_vit_position_ids, self._ints(vit_token_seqlens),
+                                             self._ints(packed_vit_token_indexes), self._ints(packed_position_ids))
         return past_key_values
 
     @torch.no_grad()
@@ -149,26 +223,15 @@ class Bagel:
         lens = self._ints(packed_seqlens)
         h = paged_handle(past_key_values, self.engine, len(lens))
         self._check_kv(h, key_values_lens, packed_key_value_indexes, lens, packed_indexes, "forward_cache_update_vae")
-        dev = self.device
-        p, C = self.latent_patch_size, self.latent_channel
-        latent = vae_model.encode(padded_images.to(dev))                         # [B, C, Hp/8, Wp/8] bf16
-        rows = []
-        for z, (hh, ww) in zip(latent, patchified_vae_latent_shapes):
-            z = z[:, :hh * p, :ww * p].reshape(C, hh, p, ww, p)
-            rows.append(z.permute(1, 3, 2, 4, 0).reshape(-1, p * p * C))
-        packed_latent = torch.cat(rows, dim=0)
+        latent = vae_model.encode(padded_images.to(self.device))                 # [B, C, Hp/8, Wp/8] bf16
         # the reference hands the float tensor to time_embedder (bagel.py:777): no integer truncation of e.g. timestep=0.5
         ts = packed_timesteps.reshape(-1).float().tolist() if torch.is_tensor(packed_timesteps) else [float(v) for v in packed_timesteps]
         if any(v != ts[0] for v in ts):
             raise NotImplementedError("forward_cache_update_vae: one timestep per call (prepare_vae_images emits a constant)")
-        t = ts[0]
-        seq = torch.zeros((sum(lens), self.hidden_size), dtype=torch.bfloat16, device=dev)
-        seq[packed_text_indexes.to(dev)] = self.engine.embed_tokens(packed_text_ids)
-        seq[packed_vae_token_indexes.to(dev)] = self.engine.latent_embed(packed_latent.float(), packed_vae_position_ids, t)
-        is_gen = torch.zeros(sum(lens), dtype=torch.uint8)
-        is_gen[packed_vae_token_indexes.cpu()] = 1
-        self.engine.llm_forward(seq, h.seqs, lens, self._ints(packed_position_ids), row_is_gen=is_gen.tolist(), is_causal=False,
-                                update_kv=True, want_hidden=False)
+        self.engine.forward_cache_update_vae(h.seqs, lens, self._ints(packed_text_ids), self._ints(packed_text_indexes), latent,
+                                             [(int(a), int(b)) for a, b in patchified_vae_latent_shapes], self.latent_patch_size,
+                                             packed_vae_position_ids, self._ints(packed_vae_token_indexes), ts[0],
+                                             self._ints(packed_position_ids))
         return past_key_values
 
     # ------------------------------------------------------------------ image generation (rectified flow)

@@ -932,14 +932,17 @@ int umv_lm_head(umv_engine* e, const void* hidden, int32_t m, void* logits, void
                e->d.vocab, m, e->d.vocab, e->d.hidden, EPI_BF16, static_cast<cudaStream_t>(stream));
 }
 
-int umv_vit_embed(umv_engine* e, const float* pixels, const int64_t* pos_ids, const int32_t* seqlens, int32_t n_images,
-                  void* out, void* stream) {
+}  // extern "C"
+
+// SiglipVisionTransformer.forward (siglip_navit.py:345-371): leaves the post-layernorm rows (bf16: the value the consumer Linear
+// sees after its autocast cast) in e->xn [M, vit_hidden]; *M_out = number of patch tokens.
+static int vit_tower(umv_engine* e, const float* pixels, const int64_t* pos_ids, const int32_t* seqlens, int32_t n_images,
+                     cudaStream_t st, int* M_out) {
     UMV_REQUIRE(e && e->finalized, UMV_ERR_STATE, "engine not finalized");
     UMV_REQUIRE(e->d.enable_vit, UMV_ERR_STATE, "ViT weights were not enabled");
-    UMV_REQUIRE(pixels && pos_ids && seqlens && out && n_images > 0, UMV_ERR_INVALID, "umv_vit_embed: null/empty argument");
-    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    UMV_REQUIRE(pixels && pos_ids && seqlens && n_images > 0, UMV_ERR_INVALID, "vit: null/empty argument");
     const umv_dims& d = e->d;
-    const int Dv = d.vit_hidden, Iv = d.vit_inter, D = d.hidden, Kp = e->vit_kpad;
+    const int Dv = d.vit_hidden, Iv = d.vit_inter, Kp = e->vit_kpad;
     int M = 0, max_len = 0;
     for (int i = 0; i < n_images; ++i) {
         UMV_REQUIRE(seqlens[i] > 0, UMV_ERR_INVALID, "umv_vit_embed: empty image %d", i);
@@ -993,11 +996,82 @@ int umv_vit_embed(umv_engine* e, const float* pixels, const int64_t* pos_ids, co
         UMV_TRY(lin(e, e->xn, Dv, L.w1, L.b1, nullptr, e->act, Iv, M, Iv, Dv, EPI_GELU, st));
         UMV_TRY(lin(e, e->act, Iv, L.w2, L.b2, hv, hv, Dv, M, Dv, Iv, EPI_RESID, st));
     }
-    UMV_TRY(layernorm_bf16(hv, e->vit_post_w, e->vit_post_b, e->xn, M, Dv, d.vit_eps, st));
-    // connector (modeling_utils.py:119-123) + vit_pos_embed (bagel.py:590-594)
-    UMV_TRY(lin(e, e->xn, Dv, e->conn_w1, e->conn_b1, nullptr, e->act, D, M, D, Dv, EPI_GELU, st));
-    UMV_TRY(lin(e, e->act, D, e->conn_w2, e->conn_b2, nullptr, static_cast<bf16*>(out), D, M, D, D, EPI_BF16, st));
-    return gather_add_rows(static_cast<bf16*>(out), e->vit_pos_embed, pos_ids, M, D, st);
+    *M_out = M;
+    return layernorm_bf16(hv, e->vit_post_w, e->vit_post_b, e->xn, M, Dv, d.vit_eps, st);
+}
+// MLPconnector.forward (modeling_utils.py:119-123): x [M, vit_hidden] -> out [M, hidden]; e->act is the fc1 scratch.
+static int connector_rows(umv_engine* e, const bf16* x, int M, bf16* out, cudaStream_t st) {
+    const int Dv = e->d.vit_hidden, D = e->d.hidden;
+    UMV_TRY(lin(e, x, Dv, e->conn_w1, e->conn_b1, nullptr, e->act, D, M, D, Dv, EPI_GELU, st));
+    return lin(e, e->act, D, e->conn_w2, e->conn_b2, nullptr, out, D, M, D, D, EPI_BF16, st);
+}
+// host index array -> checked against [0, M) and that text rows + block rows tile the packed sequence exactly once
+static int check_row_cover(const int32_t* a, int na, const int32_t* b, int nb, int M, const char* what) {
+    std::vector<uint8_t> seen((size_t)M, 0);
+    for (int pass = 0; pass < 2; ++pass) {
+        const int32_t* r = pass ? b : a;
+        const int n = pass ? nb : na;
+        for (int i = 0; i < n; ++i) {
+            UMV_REQUIRE(r[i] >= 0 && r[i] < M && !seen[r[i]], UMV_ERR_INVALID, "%s: packed row index %d out of range or repeated", what, r[i]);
+            seen[r[i]] = 1;
+        }
+    }
+    UMV_REQUIRE(na + nb == M, UMV_ERR_INVALID, "%s: %d text + %d block rows do not tile the %d packed rows", what, na, nb, M);
+    return UMV_OK;
+}
+
+extern "C" {
+
+int umv_vit_embed(umv_engine* e, const float* pixels, const int64_t* pos_ids, const int32_t* seqlens, int32_t n_images,
+                  void* out, void* stream) {
+    UMV_REQUIRE(out, UMV_ERR_INVALID, "umv_vit_embed: null out");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    int M = 0;
+    UMV_TRY(vit_tower(e, pixels, pos_ids, seqlens, n_images, st, &M));
+    UMV_TRY(connector_rows(e, e->xn, M, static_cast<bf16*>(out), st));      // + vit_pos_embed (bagel.py:590-594)
+    return gather_add_rows(static_cast<bf16*>(out), e->vit_pos_embed, pos_ids, M, e->d.hidden, st);
+}
+
+// ---- the inner module boundary: each sub-module of the reference's Bagel as its own call
+int umv_vit_model(umv_engine* e, const float* pixels, const int64_t* pos_ids, const int32_t* seqlens, int32_t n_images, void* out,
+                  void* stream) {
+    UMV_REQUIRE(out, UMV_ERR_INVALID, "umv_vit_model: null out");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    int M = 0;
+    UMV_TRY(vit_tower(e, pixels, pos_ids, seqlens, n_images, st, &M));
+    UMV_CUDA_OK(cudaMemcpyAsync(out, e->xn, (size_t)M * e->d.vit_hidden * sizeof(bf16), cudaMemcpyDeviceToDevice, st));
+    return UMV_OK;
+}
+int umv_connector(umv_engine* e, const void* x, int32_t n, void* out, void* stream) {
+    UMV_REQUIRE(e && e->finalized, UMV_ERR_STATE, "engine not finalized");
+    UMV_REQUIRE(e->d.enable_vit, UMV_ERR_STATE, "ViT weights were not enabled");
+    UMV_REQUIRE(x && out && n > 0 && n <= e->d.max_tokens, UMV_ERR_INVALID, "umv_connector: bad argument");
+    return connector_rows(e, static_cast<const bf16*>(x), n, static_cast<bf16*>(out), static_cast<cudaStream_t>(stream));
+}
+int umv_pos_embed(umv_engine* e, int32_t which, const int64_t* pos_ids, int32_t n, void* out, void* stream) {
+    UMV_REQUIRE(e && e->finalized, UMV_ERR_STATE, "engine not finalized");
+    UMV_REQUIRE(pos_ids && out && n > 0 && (which == 0 || which == 1), UMV_ERR_INVALID, "umv_pos_embed: bad argument");
+    const bf16* table = which == 0 ? e->vit_pos_embed : e->latent_pos;
+    UMV_REQUIRE(table, UMV_ERR_STATE, "umv_pos_embed: that sub-model was not enabled");
+    return embed_rows(table, pos_ids, n, e->d.hidden, which == 0 ? e->d.vit_pos_table : e->d.latent_pos_table, static_cast<bf16*>(out),
+                      static_cast<cudaStream_t>(stream));
+}
+int umv_vae2llm(umv_engine* e, const float* x, int32_t n, void* out, void* stream) {
+    UMV_REQUIRE(e && e->finalized, UMV_ERR_STATE, "engine not finalized");
+    UMV_REQUIRE(e->d.enable_gen, UMV_ERR_STATE, "generation expert weights were not enabled");
+    UMV_REQUIRE(x && out && n > 0 && n <= e->d.max_tokens, UMV_ERR_INVALID, "umv_vae2llm: bad argument");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int C = e->d.latent_dim;
+    UMV_TRY(f32_to_bf16_padded(x, e->attn, n, C, C, st));          // the autocast Linear casts its fp32 input to bf16
+    return lin(e, e->attn, C, e->vae2llm_w, e->vae2llm_b, nullptr, static_cast<bf16*>(out), e->d.hidden, n, e->d.hidden, C, EPI_BF16, st);
+}
+int umv_llm2vae(umv_engine* e, const void* h, int32_t n, void* out, void* stream) {
+    UMV_REQUIRE(e && e->finalized, UMV_ERR_STATE, "engine not finalized");
+    UMV_REQUIRE(e->d.enable_gen, UMV_ERR_STATE, "generation expert weights were not enabled");
+    UMV_REQUIRE(h && out && n > 0, UMV_ERR_INVALID, "umv_llm2vae: bad argument");
+    const int C = e->d.latent_dim, D = e->d.hidden;
+    return lin(e, static_cast<const bf16*>(h), D, e->llm2vae_w, e->llm2vae_b, nullptr, static_cast<bf16*>(out), C, n, C, D, EPI_BF16,
+               static_cast<cudaStream_t>(stream));
 }
 
 int umv_generate_text(umv_engine* e, int32_t n_seqs, const int32_t* seqs, const int64_t* start_tokens,
@@ -1237,6 +1311,136 @@ int umv_flow_velocity(umv_engine* e, const umv_flow_args* a, const float* x_t, f
     c.text_scale = a->cfg_text_scale; c.img_scale = a->cfg_img_scale; c.renorm_min = a->cfg_renorm_min;
     c.renorm_type = a->renorm_type; c.img_row0 = d_row0; c.img_lat0 = d_lat0; c.img_n = d_n; c.out = v_out;
     return cfg_combine(c, B, st);
+}
+
+}  // extern "C"
+// TimestepEmbedder.forward (modeling_utils.py:106-109) for one timestep: fp32 sinusoid -> Linear -> SiLU (bf16) -> Linear -> temb [hidden]
+static int time_embed_one(umv_engine* e, float t, bf16* temb, cudaStream_t st) {
+    const int D = e->d.hidden;
+    bf16* tf = e->flow_small;
+    bf16* th = e->flow_small + std::max(D, 256);
+    UMV_TRY(timestep_freq(t, e->t_freqs, 128, tf, st));
+    UMV_TRY(lin(e, tf, 256, e->t_w0, e->t_b0, nullptr, th, D, 1, D, 256, EPI_BF16, st));
+    UMV_TRY(silu_inplace(th, D, st));
+    return lin(e, th, D, e->t_w2, e->t_b2, nullptr, temb, D, 1, D, D, EPI_BF16, st);
+}
+extern "C" {
+int umv_time_embedder(umv_engine* e, const float* timesteps, int32_t n, void* out, void* stream) {
+    UMV_REQUIRE(e && e->finalized, UMV_ERR_STATE, "engine not finalized");
+    UMV_REQUIRE(e->d.enable_gen, UMV_ERR_STATE, "generation expert weights were not enabled");
+    UMV_REQUIRE(timesteps && out && n > 0, UMV_ERR_INVALID, "umv_time_embedder: bad argument");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int D = e->d.hidden;
+    bf16* temb = e->flow_small + 2 * std::max(D, 256);
+    for (int i = 0; i < n; ++i) {        // a row per DISTINCT value would do; callers pass a handful of timesteps
+        if (i > 0 && timesteps[i] == timesteps[i - 1]) {
+            UMV_CUDA_OK(cudaMemcpyAsync(static_cast<bf16*>(out) + (size_t)i * D, static_cast<bf16*>(out) + (size_t)(i - 1) * D,
+                                        (size_t)D * sizeof(bf16), cudaMemcpyDeviceToDevice, st));
+            continue;
+        }
+        UMV_TRY(time_embed_one(e, timesteps[i], temb, st));
+        UMV_CUDA_OK(cudaMemcpyAsync(static_cast<bf16*>(out) + (size_t)i * D, temb, (size_t)D * sizeof(bf16), cudaMemcpyDeviceToDevice, st));
+    }
+    return UMV_OK;
+}
+
+// ---- prefill drivers: one call per reference method, the packed query sequence is composed inside the engine
+int umv_forward_cache_update_text(umv_engine* e, int32_t n_seqs, const int32_t* seqs, const int32_t* text_lens,
+                                  const int64_t* text_ids, const int32_t* positions, void* stream) {
+    UMV_REQUIRE(e && e->finalized, UMV_ERR_STATE, "engine not finalized");
+    UMV_REQUIRE(seqs && text_lens && text_ids && positions && n_seqs > 0, UMV_ERR_INVALID, "umv_forward_cache_update_text: null/empty argument");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    int M = 0;
+    for (int b = 0; b < n_seqs; ++b) M += text_lens[b];
+    UMV_REQUIRE(M > 0 && M <= e->d.max_tokens, UMV_ERR_NOMEM, "umv_forward_cache_update_text: %d tokens > max_tokens %d", M, e->d.max_tokens);
+    for (int i = 0; i < M; ++i)
+        UMV_REQUIRE(text_ids[i] >= 0 && text_ids[i] < e->d.vocab, UMV_ERR_INVALID, "token id %lld out of range", (long long)text_ids[i]);
+    MetaBuilder mb;
+    UMV_TRY(meta_begin(e, &mb, (size_t)M * 8 + 64));
+    int64_t* d_ids;
+    mb.put<int64_t>(text_ids, M, &d_ids);
+    UMV_TRY(meta_commit(e, &mb, st));
+    UMV_TRY(embed_rows(e->embed, d_ids, M, e->d.hidden, e->d.vocab, e->h, st));
+    return umv::llm_run(e, nullptr, n_seqs, seqs, text_lens, positions, nullptr, 1, 1, nullptr, st);
+}
+
+int umv_forward_cache_update_vit(umv_engine* e, int32_t n_seqs, const int32_t* seqs, const int32_t* seq_lens, int32_t n_text,
+                                 const int64_t* text_ids, const int32_t* text_rows, const float* pixels, const int64_t* vit_pos_ids,
+                                 int32_t n_images, const int32_t* vit_seqlens, const int32_t* vit_rows, const int32_t* positions,
+                                 void* stream) {
+    UMV_REQUIRE(e && e->finalized, UMV_ERR_STATE, "engine not finalized");
+    UMV_REQUIRE(seqs && seq_lens && text_ids && text_rows && vit_rows && positions && n_seqs > 0 && n_text >= 0, UMV_ERR_INVALID,
+                "umv_forward_cache_update_vit: null/empty argument");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int D = e->d.hidden;
+    int M = 0, N = 0;
+    for (int b = 0; b < n_seqs; ++b) M += seq_lens[b];
+    for (int i = 0; i < n_images; ++i) N += vit_seqlens[i];
+    UMV_REQUIRE(M <= e->d.max_tokens, UMV_ERR_NOMEM, "umv_forward_cache_update_vit: %d tokens > max_tokens %d", M, e->d.max_tokens);
+    UMV_TRY(check_row_cover(text_rows, n_text, vit_rows, N, M, "umv_forward_cache_update_vit"));
+    for (int i = 0; i < n_text; ++i)
+        UMV_REQUIRE(text_ids[i] >= 0 && text_ids[i] < e->d.vocab, UMV_ERR_INVALID, "token id %lld out of range", (long long)text_ids[i]);
+    int Mv = 0;
+    UMV_TRY(vit_tower(e, pixels, vit_pos_ids, vit_seqlens, n_images, st, &Mv));
+    UMV_TRY(connector_rows(e, e->xn, Mv, e->attn, st));            // e->h (the tower's residual stream) is free from here on
+    MetaBuilder mb;
+    UMV_TRY(meta_begin(e, &mb, (size_t)n_text * 12 + (size_t)N * 4 + 64));
+    int64_t* d_ids; int *d_trows, *d_vrows;
+    mb.put<int64_t>(text_ids, n_text, &d_ids);
+    mb.put<int>(text_rows, n_text, &d_trows);
+    mb.put<int>(vit_rows, N, &d_vrows);
+    UMV_TRY(meta_commit(e, &mb, st));
+    UMV_TRY(scatter_add_rows(e->attn, e->vit_pos_embed, vit_pos_ids, d_vrows, e->h, N, D, st));      // + vit_pos_embed, to its rows
+    UMV_TRY(embed_rows_scatter(e->embed, d_ids, d_trows, n_text, D, e->d.vocab, e->h, st));          // marker embeddings
+    return umv::llm_run(e, nullptr, n_seqs, seqs, seq_lens, positions, nullptr, 0, 1, nullptr, st);
+}
+
+int umv_forward_cache_update_vae(umv_engine* e, int32_t n_seqs, const int32_t* seqs, const int32_t* seq_lens, int32_t n_text,
+                                 const int64_t* text_ids, const int32_t* text_rows, const void* latent, int32_t n_images, int32_t Hl,
+                                 int32_t Wl, const int32_t* latent_hw, int32_t patch, const int64_t* lat_pos_ids, const int32_t* lat_rows,
+                                 float timestep, const int32_t* positions, void* stream) {
+    UMV_REQUIRE(e && e->finalized, UMV_ERR_STATE, "engine not finalized");
+    UMV_REQUIRE(e->d.enable_gen, UMV_ERR_STATE, "generation expert weights were not enabled");
+    UMV_REQUIRE(seqs && seq_lens && text_ids && text_rows && latent && latent_hw && lat_pos_ids && lat_rows && positions && n_seqs > 0 &&
+                n_images > 0 && patch > 0 && n_text == 2 * n_images, UMV_ERR_INVALID, "umv_forward_cache_update_vae: bad argument");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int D = e->d.hidden, C = e->d.latent_dim, Cz = C / (patch * patch);
+    UMV_REQUIRE(Cz * patch * patch == C, UMV_ERR_INVALID, "latent patch %d does not divide latent_dim %d", patch, C);
+    int M = 0, N = 0;
+    for (int b = 0; b < n_seqs; ++b) M += seq_lens[b];
+    for (int i = 0; i < n_images; ++i) {
+        UMV_REQUIRE(latent_hw[2 * i] > 0 && latent_hw[2 * i + 1] > 0 && latent_hw[2 * i] * patch <= Hl && latent_hw[2 * i + 1] * patch <= Wl,
+                    UMV_ERR_INVALID, "latent shape of image %d exceeds the padded plane", i);
+        N += latent_hw[2 * i] * latent_hw[2 * i + 1];
+    }
+    UMV_REQUIRE(M <= e->d.max_tokens, UMV_ERR_NOMEM, "umv_forward_cache_update_vae: %d tokens > max_tokens %d", M, e->d.max_tokens);
+    UMV_TRY(check_row_cover(text_rows, n_text, lat_rows, N, M, "umv_forward_cache_update_vae"));
+    for (int i = 0; i < n_text; ++i)
+        UMV_REQUIRE(text_ids[i] == text_ids[i % 2] && text_ids[i] >= 0 && text_ids[i] < e->d.vocab, UMV_ERR_UNSUPPORTED,
+                    "every image must use the same start / end marker ids");
+    // latent patchify "chpwq->hwpqc" (bagel.py:760-765) -> bf16 rows; vae2llm; + time embedding + latent_pos_embed; markers
+    bf16* xtb = e->attn;
+    bf16* lat = e->act;
+    int off = 0;
+    for (int i = 0; i < n_images; ++i) {
+        const int h = latent_hw[2 * i], w = latent_hw[2 * i + 1];
+        UMV_TRY(latent_patchify(static_cast<const bf16*>(latent) + (size_t)i * Cz * Hl * Wl, xtb + (size_t)off * C, Cz, Hl, Wl, h, w, patch, st));
+        off += h * w;
+    }
+    UMV_TRY(lin(e, xtb, C, e->vae2llm_w, e->vae2llm_b, nullptr, lat, D, N, D, C, EPI_BF16, st));
+    bf16* temb = e->flow_small + 2 * std::max(D, 256);
+    UMV_TRY(time_embed_one(e, timestep, temb, st));
+    std::vector<int> src((size_t)M, 0);
+    std::vector<uint8_t> is_gen((size_t)M, 0);
+    for (int i = 0; i < n_text; ++i) src[text_rows[i]] = (i % 2 == 0) ? -1 : -2;
+    for (int i = 0; i < N; ++i) { src[lat_rows[i]] = i; is_gen[lat_rows[i]] = 1; }
+    MetaBuilder mb;
+    UMV_TRY(meta_begin(e, &mb, (size_t)M * 4 + 64));
+    int* d_src;
+    mb.put<int>(src.data(), M, &d_src);
+    UMV_TRY(meta_commit(e, &mb, st));
+    UMV_TRY(flow_compose(lat, temb, e->latent_pos, lat_pos_ids, e->embed, text_ids[0], text_ids[1], d_src, M, 1, D, e->h, st));
+    return umv::llm_run(e, nullptr, n_seqs, seqs, seq_lens, positions, is_gen.data(), 0, 1, nullptr, st);
 }
 
 int umv_latent_embed(umv_engine* e, const float* x, const int64_t* pos_ids, int32_t n, float timestep, void* out, void* stream) {

@@ -78,6 +78,7 @@ struct VaeState {
     size_t act_elems = 0, col_elems = 0, s_elems = 0;
 };
 int vae_build(umv_engine* e);
+int latent_patchify(const bf16* z, bf16* rows, int C, int Hl, int Wl, int h, int w, int p, cudaStream_t st);
 // engine.cu internals shared with flow.cu / vae.cu
 int engine_alloc(umv_engine* e, void** out, size_t bytes);
 void engine_reg(umv_engine* e, const std::string& name, bf16* dst, int64_t rows, int64_t cols, int ndim, int conv_k, int conv_cin,

@@ -802,6 +802,56 @@ int embed_rows(const bf16* table, const int64_t* ids, int n, int D, int64_t voca
     return UMV_OK;
 }
 
+// dst[dst_rows[i]] = table[ids[i]]: marker / text-token embeddings written straight into the packed query sequence
+// (packed_sequence[packed_text_indexes] = embed_tokens(packed_text_ids), bagel.py:577-579).
+__global__ void embed_rows_scatter_kernel(const bf16* __restrict__ table, const int64_t* __restrict__ ids, const int* __restrict__ dst_rows,
+                                          int D, int64_t vocab, bf16* __restrict__ out) {
+    pdl_launch_dependents();
+    pdl_wait();
+    int64_t id = ids[blockIdx.x];
+    if (id < 0 || id >= vocab) id = 0;
+    const U4* src = reinterpret_cast<const U4*>(table + (size_t)id * D);
+    U4* dst = reinterpret_cast<U4*>(out + (size_t)dst_rows[blockIdx.x] * D);
+    for (int c = threadIdx.x; c < D / 8; c += blockDim.x) dst[c] = src[c];
+}
+int embed_rows_scatter(const bf16* table, const int64_t* ids, const int* dst_rows, int n, int D, int64_t vocab, bf16* out, cudaStream_t s) {
+    if (n <= 0) return UMV_OK;
+    launch_k(embed_rows_scatter_kernel, dim3(n), dim3(128), 0, s, table, ids, dst_rows, D, vocab, out);
+    UMV_LAUNCH_CHECK("embed_rows_scatter_kernel");
+    return UMV_OK;
+}
+
+// dst[dst_rows[m]] = bf16(src[m] + table[ids[m]]): the frozen 2-D position embedding added to the connector output and the
+// result scattered to its rows of the packed query sequence in one pass (bagel.py:590-595).
+__global__ void scatter_add_rows_kernel(const bf16* __restrict__ src, const bf16* __restrict__ table, const int64_t* __restrict__ ids,
+                                        const int* __restrict__ dst_rows, bf16* __restrict__ dst, int D) {
+    pdl_launch_dependents();
+    pdl_wait();
+    const int row = blockIdx.x;
+    const bf16* t = table + (size_t)ids[row] * D;
+    const bf16* xr = src + (size_t)row * D;
+    bf16* yr = dst + (size_t)dst_rows[row] * D;
+    for (int c = threadIdx.x; c < D / 8; c += blockDim.x) {
+        const U4 a = ldg16(xr + c * 8), b = ldg16(t + c * 8);
+        const uint32_t* aw = &a.x;
+        const uint32_t* bw = &b.x;
+        uint32_t o[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float2 fa = unpack2(aw[j]), fb = unpack2(bw[j]);
+            o[j] = pack2(fa.x + fb.x, fa.y + fb.y);
+        }
+        stg16(yr + c * 8, U4{o[0], o[1], o[2], o[3]});
+    }
+}
+int scatter_add_rows(const bf16* src, const bf16* table, const int64_t* ids, const int* dst_rows, bf16* dst, int M, int D,
+                     cudaStream_t s) {
+    if (M <= 0) return UMV_OK;
+    launch_k(scatter_add_rows_kernel, dim3(M), dim3(128), 0, s, src, table, ids, dst_rows, dst, D);
+    UMV_LAUNCH_CHECK("scatter_add_rows_kernel");
+    return UMV_OK;
+}
+
 __global__ void gather_add_rows_kernel(bf16* __restrict__ x, const bf16* __restrict__ table, const int64_t* __restrict__ ids,
                                        int D) {
     pdl_launch_dependents();

@@ -104,6 +104,8 @@ int attention_init();   // once per process, before any capture
 // ---- misc
 int embed_rows(const bf16* table, const int64_t* ids, int n, int D, int64_t vocab, bf16* out, cudaStream_t s);
 int gather_add_rows(bf16* x, const bf16* table, const int64_t* ids, int M, int D, cudaStream_t s);  // x[m] = bf16(x[m] + table[ids[m]])
+int embed_rows_scatter(const bf16* table, const int64_t* ids, const int* dst_rows, int n, int D, int64_t vocab, bf16* out, cudaStream_t s);
+int scatter_add_rows(const bf16* src, const bf16* table, const int64_t* ids, const int* dst_rows, bf16* dst, int M, int D, cudaStream_t s);
 // uint8 HWC image -> normalised fp32 patch vectors + position ids (one CTA per patch)
 int patchify_u8(const uint8_t* img, int H, int W, int patch, int max_per_side, float* out, int64_t* pos_ids, cudaStream_t s);
 int f32_to_bf16_padded(const float* x, bf16* y, int M, int K, int Kpad, cudaStream_t s);

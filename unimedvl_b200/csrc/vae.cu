@@ -53,6 +53,62 @@ __global__ void nhwc_to_nchw_kernel(const bf16* __restrict__ x, bf16* __restrict
     y[i] = x[(size_t)p * C + c];
 }
 
+// Packed latent tokens (fp32 [h*w, p*p*C], token = latent patch, channel-minor "hw pqc") -> the NHWC latent image the decoder reads,
+// i.e. InterleaveInferencer.decode_image's reshape + einsum("nhwpqc->nchpwq") + .to(bf16) (inferencer.py:239-249) followed by
+// AutoEncoder.decode's z / scale + shift (two bf16 roundings).
+__global__ void tokens_to_nhwc_kernel(const float* __restrict__ tok, bf16* __restrict__ y, int h, int w, int p, int C, float scale,
+                                      float shift) {
+    pdl_launch_dependents();
+    pdl_wait();
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int Wl = w * p;
+    if (i >= h * p * Wl * C) return;
+    const int c = i % C, px = (i / C) % Wl, py = i / (C * Wl);
+    const int hh = py / p, pp = py % p, ww = px / p, q = px % p;
+    float v = rbf(tok[((size_t)(hh * w + ww) * p * p + (pp * p + q)) * C + c]);
+    y[i] = f2b(rbf(rbf(v / scale) + shift));
+}
+// (image * 0.5 + 0.5).clamp(0, 1) * 255 -> uint8 (inferencer.py:253-254) on the decoder's NHWC bf16 output: every torch op on the bf16
+// tensor rounds to bf16 (x * 0.5 is exact), the cast to uint8 truncates.  HWC uint8 out -- the layout Image.fromarray takes.
+__global__ void image_to_u8_kernel(const bf16* __restrict__ x, uint8_t* __restrict__ y, int n) {
+    pdl_launch_dependents();
+    pdl_wait();
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float v = rbf(b2f(x[i]) * 0.5f);
+    v = rbf(v + 0.5f);
+    v = fminf(fmaxf(v, 0.f), 1.f);
+    v = rbf(v * 255.f);
+    y[i] = (uint8_t)v;
+}
+// DiagonalGaussian.forward + AutoEncoder.encode's affine (autoencoder.py:266-272,300-303) on bf16 tensors, op by op:
+// std = exp(0.5 * logvar); z = mean + std * noise; out = scale * (z - shift).  moments [2C, HW] (mean | logvar), noise / out [C, HW].
+__global__ void vae_sample_kernel(const bf16* __restrict__ mom, const bf16* __restrict__ noise, bf16* __restrict__ out, int CHW,
+                                  float scale, float shift) {
+    pdl_launch_dependents();
+    pdl_wait();
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= CHW) return;
+    float z = b2f(mom[i]);
+    if (noise) {
+        const float sd = rbf(expf(rbf(0.5f * b2f(mom[CHW + i]))));
+        z = rbf(z + rbf(sd * b2f(noise[i])));
+    }
+    out[i] = f2b(rbf(scale * rbf(z - shift)));
+}
+// Patchify the encoded latent for the LLM (bagel.py:760-765: latent[:, :h*p, :w*p].reshape(C, h, p, w, p) -> "chpwq->hwpqc"):
+// z bf16 [C, Hl, Wl] (padded batch plane) -> rows [h*w, p*p*C].
+__global__ void latent_patchify_kernel(const bf16* __restrict__ z, bf16* __restrict__ rows, int C, int Hl, int Wl, int h, int w, int p) {
+    pdl_launch_dependents();
+    pdl_wait();
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int per = p * p * C;
+    if (i >= h * w * per) return;
+    const int c = i % C, q = (i / C) % p, pp = (i / (C * p)) % p, t = i / per;
+    const int hh = t / w, ww = t % w;
+    rows[i] = z[((size_t)c * Hl + (hh * p + pp)) * Wl + (ww * p + q)];
+}
+
 // im2col for a 3x3 conv on NHWC: out[(y*Wo+x), (ky*3+kx)*C + c].  up: source is the nearest-2x upsampled input
 // (Upsample, autoencoder.py:116-119); stride 2: Downsample's pad (0,1,0,1) + stride-2 valid conv (:104-108).
 __global__ void im2col3x3_kernel(const bf16* __restrict__ x, bf16* __restrict__ col, int H, int W, int C, int Ho, int Wo,
@@ -447,6 +503,36 @@ static size_t max_act_elems(int H8, int W8, bool decode) {
     return std::max(full * (decode ? 256 : 128), (size_t)3 * H8 * W8 * 512) + 64;
 }
 
+// Decoder.forward (autoencoder.py:240-257) on the NHWC latent in V.a1 (already z / scale + shift); leaves conv_out's NHWC
+// [H*W, 3] bf16 image in V.a2 and the output geometry in *im.
+static int decode_body(umv_engine* e, Img* im_io, cudaStream_t st) {
+    VaeState& V = *e->vae;
+    const VaeHalf& H = V.dec;
+    Img im = *im_io;
+    UMV_TRY(conv(e, H.conv_in, V.a1, im, V.a0, nullptr, 0, 1, nullptr, st));
+    UMV_TRY(res_block(e, H.mid1, im, st));
+    UMV_TRY(attn_block(e, H.attn, im, st));
+    UMV_TRY(res_block(e, H.mid2, im, st));
+    for (int l = V.nlev - 1; l >= 0; --l) {
+        for (const VaeRes& r : H.levels[l].blocks) UMV_TRY(res_block(e, r, im, st));
+        if (H.levels[l].has_resample) {
+            UMV_TRY(conv(e, H.levels[l].resample, V.a0, im, V.a1, &im, 1, 1, nullptr, st));   // nearest x2 folded into the gather
+            std::swap(V.a0, V.a1);
+        }
+    }
+    UMV_TRY(gn(e, H.norm_out, V.a0, im, V.a1, 1, st));
+    UMV_TRY(conv(e, H.conv_out, V.a1, im, V.a2, nullptr, 0, 1, nullptr, st));
+    *im_io = im;
+    return UMV_OK;
+}
+
+int latent_patchify(const bf16* z, bf16* rows, int C, int Hl, int Wl, int h, int w, int p, cudaStream_t st) {
+    const int n = h * w * p * p * C;
+    launch_k(latent_patchify_kernel, dim3((n + 255) / 256), dim3(256), 0, st, z, rows, C, Hl, Wl, h, w, p);
+    UMV_LAUNCH_CHECK("latent_patchify_kernel");
+    return UMV_OK;
+}
+
 }  // namespace umv
 
 using namespace umv;
@@ -461,30 +547,58 @@ int umv_vae_decode(umv_engine* e, const void* z, int32_t n, int32_t h, int32_t w
     VaeState& V = *e->vae;
     const size_t full = (size_t)h * 8 * w * 8;
     UMV_TRY(vae_reserve(e, max_act_elems(h, w, true), full * 9 * 256 + 64, (size_t)h * w * h * w));
-    const VaeHalf& H = V.dec;
     for (int i = 0; i < n; ++i) {
         const bf16* zi = static_cast<const bf16*>(z) + (size_t)i * V.z * h * w;
-        Img im{h, w};
         const int nel = V.z * h * w;
         launch_k(nchw_to_nhwc_kernel, dim3((nel + 255) / 256), dim3(256), 0, st, zi, V.a1, V.z, h * w, V.scale, V.shift, 1);
         UMV_LAUNCH_CHECK("nchw_to_nhwc_kernel");
-        UMV_TRY(conv(e, H.conv_in, V.a1, im, V.a0, nullptr, 0, 1, nullptr, st));
-        UMV_TRY(res_block(e, H.mid1, im, st));
-        UMV_TRY(attn_block(e, H.attn, im, st));
-        UMV_TRY(res_block(e, H.mid2, im, st));
-        for (int l = V.nlev - 1; l >= 0; --l) {
-            for (const VaeRes& r : H.levels[l].blocks) UMV_TRY(res_block(e, r, im, st));
-            if (H.levels[l].has_resample) {
-                UMV_TRY(conv(e, H.levels[l].resample, V.a0, im, V.a1, &im, 1, 1, nullptr, st));   // nearest x2 folded into the gather
-                std::swap(V.a0, V.a1);
-            }
-        }
-        UMV_TRY(gn(e, H.norm_out, V.a0, im, V.a1, 1, st));
-        UMV_TRY(conv(e, H.conv_out, V.a1, im, V.a2, nullptr, 0, 1, nullptr, st));
+        Img im{h, w};
+        UMV_TRY(decode_body(e, &im, st));
         const int HW = im.H * im.W;
         launch_k(nhwc_to_nchw_kernel, dim3((3 * HW + 255) / 256), dim3(256), 0, st, (const bf16*)V.a2,
                  static_cast<bf16*>(out) + (size_t)i * 3 * HW, 3, HW);
         UMV_LAUNCH_CHECK("nhwc_to_nchw_kernel");
+    }
+    return UMV_OK;
+}
+
+int umv_decode_image_u8(umv_engine* e, const float* latent_tokens, int32_t n, int32_t h, int32_t w, int32_t p, uint8_t* out,
+                        void* stream) {
+    UMV_REQUIRE(e && e->finalized, UMV_ERR_STATE, "engine not finalized");
+    UMV_REQUIRE(e->vae, UMV_ERR_STATE, "VAE weights were not enabled");
+    UMV_REQUIRE(latent_tokens && out && n > 0 && h > 0 && w > 0 && p > 0, UMV_ERR_INVALID, "umv_decode_image_u8: null/empty argument");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    VaeState& V = *e->vae;
+    UMV_REQUIRE(p * p * V.z == e->d.latent_dim, UMV_ERR_INVALID, "umv_decode_image_u8: latent patch %d does not match latent_dim %d", p,
+                e->d.latent_dim);
+    const int hl = h * p, wl = w * p;
+    const size_t full = (size_t)hl * 8 * wl * 8;
+    UMV_TRY(vae_reserve(e, max_act_elems(hl, wl, true), full * 9 * 256 + 64, (size_t)hl * wl * hl * wl));
+    for (int i = 0; i < n; ++i) {
+        const int nel = V.z * hl * wl;
+        launch_k(tokens_to_nhwc_kernel, dim3((nel + 255) / 256), dim3(256), 0, st, latent_tokens + (size_t)i * nel, V.a1, h, w, p, V.z,
+                 V.scale, V.shift);
+        UMV_LAUNCH_CHECK("tokens_to_nhwc_kernel");
+        Img im{hl, wl};
+        UMV_TRY(decode_body(e, &im, st));
+        const int npx = 3 * im.H * im.W;
+        launch_k(image_to_u8_kernel, dim3((npx + 255) / 256), dim3(256), 0, st, (const bf16*)V.a2, out + (size_t)i * npx, npx);
+        UMV_LAUNCH_CHECK("image_to_u8_kernel");
+    }
+    return UMV_OK;
+}
+
+int umv_vae_sample(umv_engine* e, const void* moments, const void* noise, int32_t n, int32_t h, int32_t w, void* out, void* stream) {
+    UMV_REQUIRE(e && e->vae, UMV_ERR_STATE, "VAE weights were not enabled");
+    UMV_REQUIRE(moments && out && n > 0 && h > 0 && w > 0, UMV_ERR_INVALID, "umv_vae_sample: null/empty argument");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    VaeState& V = *e->vae;
+    const int chw = V.z * h * w;
+    for (int i = 0; i < n; ++i) {
+        launch_k(vae_sample_kernel, dim3((chw + 255) / 256), dim3(256), 0, st, static_cast<const bf16*>(moments) + (size_t)i * 2 * chw,
+                 noise ? static_cast<const bf16*>(noise) + (size_t)i * chw : nullptr, static_cast<bf16*>(out) + (size_t)i * chw, chw,
+                 V.scale, V.shift);
+        UMV_LAUNCH_CHECK("vae_sample_kernel");
     }
     return UMV_OK;
 }

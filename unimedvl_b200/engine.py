@@ -301,6 +301,104 @@ class Engine:
         self._exit()
         return out
 
+    # ------------------------------------------------------------------ prefill drivers (one C call per reference method)
+    def forward_cache_update_text(self, seqs, text_lens, text_ids, positions) -> None:
+        """umv_forward_cache_update_text: host index lists in, KV pages updated."""
+        self._enter()
+        _lib.check(self.lib.umv_forward_cache_update_text(self.h, len(seqs), _lib.i32_array(seqs), _lib.i32_array(text_lens),
+                                                          _lib.i64_array(text_ids), _lib.i32_array(positions), _stream_ptr(self.stream)))
+        self._exit()
+
+    def forward_cache_update_vit(self, seqs, seq_lens, text_ids, text_rows, pixels, vit_pos_ids, vit_seqlens, vit_rows, positions) -> None:
+        pixels = pixels.to(self.device, torch.float32, non_blocking=True).contiguous()
+        vit_pos_ids = vit_pos_ids.to(self.device, torch.int64, non_blocking=True).contiguous()
+        self._enter()
+        _lib.check(self.lib.umv_forward_cache_update_vit(
+            self.h, len(seqs), _lib.i32_array(seqs), _lib.i32_array(seq_lens), len(text_ids), _lib.i64_array(text_ids),
+            _lib.i32_array(text_rows), _ptr(pixels), _ptr(vit_pos_ids), len(vit_seqlens), _lib.i32_array(vit_seqlens),
+            _lib.i32_array(vit_rows), _lib.i32_array(positions), _stream_ptr(self.stream)))
+        self._exit()
+
+    def forward_cache_update_vae(self, seqs, seq_lens, text_ids, text_rows, latent, latent_hw, patch, lat_pos_ids, lat_rows, timestep,
+                                 positions) -> None:
+        latent = latent.to(self.device, torch.bfloat16).contiguous()
+        lat_pos_ids = lat_pos_ids.to(self.device, torch.int64).contiguous()
+        n, _, Hl, Wl = latent.shape
+        hw = [int(v) for pair in latent_hw for v in pair]
+        self._enter()
+        _lib.check(self.lib.umv_forward_cache_update_vae(
+            self.h, len(seqs), _lib.i32_array(seqs), _lib.i32_array(seq_lens), len(text_ids), _lib.i64_array(text_ids),
+            _lib.i32_array(text_rows), _ptr(latent), n, Hl, Wl, _lib.i32_array(hw), int(patch), _ptr(lat_pos_ids),
+            _lib.i32_array(lat_rows), C.c_float(timestep), _lib.i32_array(positions), _stream_ptr(self.stream)))
+        self._exit()
+
+    # ------------------------------------------------------------------ inner modules (SURVEY.md section 8b)
+    def vit_model(self, pixels: torch.Tensor, pos_ids: torch.Tensor, seqlens: Iterable[int]) -> torch.Tensor:
+        pixels = pixels.to(self.device, torch.float32).contiguous()
+        pos_ids = pos_ids.to(self.device, torch.int64).contiguous()
+        lens = [int(x) for x in seqlens]
+        out = torch.empty((pixels.shape[0], self.dims.vit.hidden), dtype=torch.bfloat16, device=self.device)
+        self._enter()
+        _lib.check(self.lib.umv_vit_model(self.h, _ptr(pixels), _ptr(pos_ids), _lib.i32_array(lens), len(lens), _ptr(out),
+                                          _stream_ptr(self.stream)))
+        self._exit()
+        return out
+
+    def _rows(self, fn, x: torch.Tensor, dtype, cols: int, *extra) -> torch.Tensor:
+        x = x.to(self.device, dtype).contiguous()
+        out = torch.empty((x.shape[0], cols), dtype=torch.bfloat16, device=self.device)
+        self._enter()
+        _lib.check(fn(self.h, *extra, _ptr(x), x.shape[0], _ptr(out), _stream_ptr(self.stream)))
+        self._exit()
+        return out
+
+    def connector(self, x: torch.Tensor) -> torch.Tensor:
+        return self._rows(self.lib.umv_connector, x, torch.bfloat16, self.dims.llm.hidden)
+
+    def pos_embed(self, which: int, pos_ids: torch.Tensor) -> torch.Tensor:
+        return self._rows(self.lib.umv_pos_embed, pos_ids.reshape(-1), torch.int64, self.dims.llm.hidden, which)
+
+    def vae2llm(self, x: torch.Tensor) -> torch.Tensor:
+        return self._rows(self.lib.umv_vae2llm, x, torch.float32, self.dims.llm.hidden)
+
+    def llm2vae(self, h: torch.Tensor) -> torch.Tensor:
+        return self._rows(self.lib.umv_llm2vae, h, torch.bfloat16, self.dims.patch_latent_dim)
+
+    def time_embedder(self, t) -> torch.Tensor:
+        ts = [float(v) for v in (t.reshape(-1).tolist() if torch.is_tensor(t) else t)]
+        out = torch.empty((len(ts), self.dims.llm.hidden), dtype=torch.bfloat16, device=self.device)
+        self._enter()
+        _lib.check(self.lib.umv_time_embedder(self.h, (C.c_float * len(ts))(*ts), len(ts), _ptr(out), _stream_ptr(self.stream)))
+        self._exit()
+        return out
+
+    def vae_sample(self, moments: torch.Tensor, noise: torch.Tensor | None) -> torch.Tensor:
+        """umv_vae_sample: scale * ((mean + exp(0.5 logvar) * noise) - shift) with torch's bf16 rounding after every op."""
+        moments = moments.to(self.device, torch.bfloat16).contiguous()
+        n, c2, h, w = moments.shape
+        if noise is not None:
+            noise = noise.to(self.device, torch.bfloat16).contiguous()
+        out = torch.empty((n, c2 // 2, h, w), dtype=torch.bfloat16, device=self.device)
+        self._enter()
+        _lib.check(self.lib.umv_vae_sample(self.h, _ptr(moments), _ptr(noise), n, h, w, _ptr(out), _stream_ptr(self.stream)))
+        self._exit()
+        return out
+
+    def decode_image_u8(self, latent_tokens: torch.Tensor, h: int, w: int, out: torch.Tensor | None = None) -> torch.Tensor:
+        """umv_decode_image_u8: fp32 latent tokens [n, h*w, patch_latent_dim] (or [h*w, ..]) -> device uint8 [n, 16h, 16w, 3]."""
+        x = latent_tokens.to(self.device, torch.float32).contiguous()
+        if x.dim() == 2:
+            x = x[None]
+        p = self.dims.latent_patch_size
+        n = x.shape[0]
+        assert x.shape[1] == h * w and x.shape[2] == self.dims.patch_latent_dim
+        if out is None:
+            out = torch.empty((n, 8 * p * h, 8 * p * w, 3), dtype=torch.uint8, device=self.device)
+        self._enter()
+        _lib.check(self.lib.umv_decode_image_u8(self.h, _ptr(x), n, h, w, p, _ptr(out), _stream_ptr(self.stream)))
+        self._exit()
+        return out
+
     def vae_decode(self, z: torch.Tensor) -> torch.Tensor:
         """AutoEncoder.decode: bf16 [n, 16, h, w] -> bf16 [n, 3, 8h, 8w]."""
         z = z.to(self.device, torch.bfloat16).contiguous()

@@ -91,16 +91,32 @@ class InterleaveInferencer:
 
     def decode_image(self, latent: torch.Tensor, image_shape) -> Image.Image:
         """inferencer.py:234-256: un-patchify (nhwpqc -> nchpwq), VAE decode, (x*0.5+0.5).clamp(0,1)*255 -> uint8 PIL."""
+        return self.decode_images([latent], image_shape)[0]
+
+    def decode_images(self, latents, image_shape) -> List[Image.Image]:
+        """decode_image for a batch of same-sized latents: one umv_decode_image_u8 call (un-patchify, VAE decode and the uint8
+        conversion run on the device with the reference's bf16 rounding after every op), one asynchronous D2H of the uint8
+        HWC images into pinned memory.  A vae_model that is not the engine's AutoEncoder falls back to its own decode()."""
         H, W = image_shape
         m = self.model
         h, w = H // m.latent_downsample, W // m.latent_downsample
-        p, c = m.latent_patch_size, m.latent_channel
-        z = latent.reshape(1, h, w, p, p, c).permute(0, 5, 1, 3, 2, 4).reshape(1, c, h * p, w * p)
-        probe = next(self.vae_model.parameters())
-        z = z.to(device=probe.device, dtype=probe.dtype)
-        image = self.vae_model.decode(z)
-        image = (image * 0.5 + 0.5).clamp(0, 1)[0].permute(1, 2, 0) * 255
-        return Image.fromarray(image.to(torch.uint8).cpu().numpy())
+        eng = getattr(self.vae_model, "engine", None)
+        if eng is None or not hasattr(eng, "decode_image_u8"):
+            p, c = m.latent_patch_size, m.latent_channel
+            out = []
+            for latent in latents:
+                z = latent.reshape(1, h, w, p, p, c).permute(0, 5, 1, 3, 2, 4).reshape(1, c, h * p, w * p)
+                probe = next(self.vae_model.parameters())
+                image = self.vae_model.decode(z.to(device=probe.device, dtype=probe.dtype))
+                image = (image * 0.5 + 0.5).clamp(0, 1)[0].permute(1, 2, 0) * 255
+                out.append(Image.fromarray(image.to(torch.uint8).cpu().numpy()))
+            return out
+        x = torch.stack([l.reshape(h * w, -1) for l in latents], 0)
+        u8 = eng.decode_image_u8(x, h, w)
+        host = torch.empty(u8.shape, dtype=torch.uint8, pin_memory=True)
+        host.copy_(u8, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return [Image.fromarray(host[i].numpy()) for i in range(host.shape[0])]
 
     @torch.no_grad()
     def gen_text(self, gen_context, max_length: int = 500, do_sample: bool = True, temperature: float = 1.0) -> str:

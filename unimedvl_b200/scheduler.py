@@ -142,7 +142,8 @@ class ContinuousBatcher:
         while self.waiting and len(self.running) + len(group) < self.max_batch:
             r = self.waiting[0]
             plen = self._prefix(r.prefix)[1] if r.prefix else 0
-            avail = self.engine.pages_free()
+            # free pages right now, capped by this scheduler's own budget (`capacity` minus what its running requests hold)
+            avail = min(self.engine.pages_free(), self.capacity - sum(held(q) for q in self.running))
             need_rows, need_pages = self._rows_and_pages(r, plen)
             if need_pages > self.capacity:
                 raise MemoryError(f"request {r.rid} needs {need_pages} KV pages, the pool has {self.capacity}")
