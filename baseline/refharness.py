@@ -1,7 +1,6 @@
 """Harness that runs the UNMODIFIED reference (uni-medical/UniMedVL `codes/`) as the parity oracle.
 
-Test / measurement infrastructure only (tests/, bench.py's reference legs, tests/golden/make_golden.py);
-the product never imports it.  The reference tree is looked up at, in order, $UMV_REFERENCE,
+Test / measurement infrastructure only (tests/, bench.py's reference legs); the product never imports it.  The reference tree is looked up at, in order, $UMV_REFERENCE,
 `baseline/_ref/codes` (the git-ignored copy tools/install_ref.py makes, which travels to the GPU box) and
 `/root/reference/codes` (build container only).
 
@@ -84,9 +83,36 @@ def load():
     return _MODS
 
 
-def build_reference(dims, sd: dict, vsd: dict | None, device="cpu"):
+def random_fill(device, seed: int = 0):
+    """A filler for build_reference(sd=None): random-init weights of the reference architecture without a host-side RNG pass over
+    14.6e9 parameters.  CUDA: torch.randn on the device.  CPU: one 32 Mi-element normal block tiled into every tensor (distinct
+    memory per tensor, so a timed CPU forward streams the real number of bytes; the values repeat, which timing does not see).
+    Norm weights are 1, everything else N(0, 0.02) -- activations stay O(1) (no denormals on the CPU path)."""
+    device = torch.device(device)
+    state = {"base": None, "g": None}
+
+    def fill(name: str, shape):
+        n = 1
+        for d in shape:
+            n *= int(d)
+        if name.endswith("norm.weight") or "layernorm" in name or "layer_norm" in name or ".norm" in name and name.endswith("weight") and len(shape) == 1:
+            return torch.ones(tuple(shape), dtype=torch.bfloat16, device=device)
+        if device.type == "cuda":
+            if state["g"] is None:
+                state["g"] = torch.Generator(device=device).manual_seed(seed)
+            return (torch.randn(tuple(shape), device=device, generator=state["g"], dtype=torch.float32) * 0.02).to(torch.bfloat16)
+        if state["base"] is None:
+            state["base"] = (torch.randn(1 << 25, generator=torch.Generator().manual_seed(seed)) * 0.02).to(torch.bfloat16)
+        base = state["base"]
+        reps = (n + base.numel() - 1) // base.numel()
+        return (base.repeat(reps)[:n] if reps > 1 else base[:n].clone()).view(tuple(shape))
+    return fill
+
+
+def build_reference(dims, sd: dict | None, vsd: dict | None, device="cpu", fill=None):
     """The reference `Bagel` (+ AutoEncoder) exactly as interactive_image_generator.py:226-238 assembles it, at `dims`,
-    holding the tensors of `sd` / `vsd` (bf16, reference state-dict names) on `device`.  Returns (model, vae)."""
+    holding the tensors of `sd` / `vsd` (bf16, reference state-dict names) on `device` -- or, with `sd=None`, whatever
+    `fill(name, shape)` returns for every tensor of the model (random_fill above).  Returns (model, vae)."""
     R = load()
     device = torch.device(device)
     if device.type == "cpu":
@@ -108,15 +134,23 @@ def build_reference(dims, sd: dict, vsd: dict | None, device="cpu"):
                             latent_patch_size=dims.latent_patch_size, max_latent_size=dims.max_latent_size)
         model = R.Bagel(R.qn.Qwen2ForCausalLM(llm_cfg), R.sn.SiglipVisionModel(vit_cfg), cfg, vae_model=vae)
         model.vit_model.vision_model.embeddings.convert_conv2d_to_linear(vit_cfg, meta=True)
+    if sd is None:
+        assert fill is not None, "build_reference: give a state dict or a filler"
+        full = {k: fill(k, t.shape) for k, t in model.state_dict().items()}
+        model.load_state_dict(full, strict=True, assign=True)
+        full = None
     own = {k for k in model.state_dict() if not k.startswith("vae_model.")}
-    assert own == set(sd), (sorted(own - set(sd))[:5], sorted(set(sd) - own)[:5])
-    full = {k: t.to(device=device, dtype=torch.bfloat16) for k, t in sd.items()}     # S4: parameters only
-    if vsd is not None:
+    assert sd is None or own == set(sd), (sorted(own - set(sd))[:5], sorted(set(sd) - own)[:5])
+    full = {k: t.to(device=device, dtype=torch.bfloat16) for k, t in sd.items()} if sd is not None else {}     # S4: parameters only
+    if sd is None:
+        pass
+    elif vsd is not None:
         assert set(vae.state_dict()) == set(vsd)
         full.update({"vae_model." + k: t.to(device=device, dtype=torch.bfloat16) for k, t in vsd.items()})
     else:       # no VAE weights wanted: give the unused autoencoder zeros so nothing stays on the meta device
         full.update({"vae_model." + k: torch.zeros(t.shape, dtype=torch.bfloat16, device=device) for k, t in vae.state_dict().items()})
-    model.load_state_dict(full, strict=True, assign=True)
+    if sd is not None:
+        model.load_state_dict(full, strict=True, assign=True)
     rot = model.language_model.model.rotary_emb
     inv, _ = _default_rope(llm_cfg, device)
     rot.register_buffer("inv_freq", inv, persistent=False)                          # fp32, as under accelerate (S4)

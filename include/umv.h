@@ -268,6 +268,12 @@ int umv_op_attention_block(umv_engine* e, int32_t layer, const void* qkv, const 
                            const void* bias, int32_t n_seqs, const int32_t* seqs, const int32_t* q_lens, const int32_t* positions,
                            const uint8_t* row_is_gen, int32_t is_causal, int32_t update_kv, void* out, int32_t* path_out,
                            void* stream);
+/* ONE block of the autoencoder (autoencoder.py:38-119) on a caller-provided activation, for block-level parity: `path` is the reference's
+ * module path inside AutoEncoder -- "decoder.mid.block_1", "decoder.mid.attn_1", "decoder.up.3.block.0", "decoder.up.2.upsample" (nearest x2 +
+ * conv), "encoder.down.0.downsample", "decoder.conv_in", "decoder.norm_out" (GroupNorm + swish) ... x: bf16 [C, H, W] (one image); out: bf16
+ * [out_chw[0], out_chw[1], out_chw[2]] (the caller sizes it for 4x the input pixels and 512 channels at most). */
+int umv_op_vae_block(umv_engine* e, const char* path, const void* x, int32_t C, int32_t H, int32_t W, void* out, int32_t* out_chw,
+                     void* stream);
 int umv_op_argmax(const void* logits, int32_t rows, int32_t vocab, int64_t* out, void* stream);
 /* The sampling branch of generate_text (bagel.py:1297-1301: softmax(pred_logits / temperature) in fp32 + multinomial) as the
  * decode loop runs it: row r draws from softmax(bf16(logits[r] * (1/T))) by inverse CDF with u from the engine's counter-based

@@ -3,7 +3,8 @@ fixtures; image-conditioned context (VAE encode -> generation-expert prefill) vs
 
 About 30 convolutions with a GroupNorm between each: a 1-ulp flip anywhere is renormalised into every channel,
 so whole-image agreement between two correct bf16 implementations is a few 1e-2 relative (reference on CPU vs
-oracle: 1.8e-2, tests/test_oracle_golden.py); block-level agreement is much tighter and is what pins the math."""
+oracle: 1.8e-2, tests/test_oracle_golden.py; reference on CUDA vs engine / oracle: 2.0e-2, tests/test_reference_gpu.py); block-level
+agreement is much tighter and is what pins the math: test_decoder_block_by_block runs every block alone (umv_op_vae_block)."""
 import pytest
 import torch
 
@@ -85,3 +86,61 @@ def test_edit_context_matches_oracle(stack):
         assert ulp_stats(cache.key_cache[li], oc.key[li])["rel_l2"] < 6e-2
         assert ulp_stats(cache.value_cache[li], oc.value[li])["rel_l2"] < 6e-2
     assert cache._umv.lens() == [int(gi["packed_seqlens"][0])]
+
+
+# ------------------------------------------------------------------------------------------------ block level
+def _blocks(d):
+    """(reference module path, cin, cout, kind) of every decoder block, in execution order (autoencoder.py:240-257)."""
+    nres = len(d.ch_mult)
+    cin = d.ch * d.ch_mult[-1]
+    out = [("decoder.conv_in", d.z_channels, cin, "conv"), ("decoder.mid.block_1", cin, cin, "res"), ("decoder.mid.attn_1", cin, cin, "attn"),
+           ("decoder.mid.block_2", cin, cin, "res")]
+    for lvl in reversed(range(nres)):
+        cout = d.ch * d.ch_mult[lvl]
+        for bi in range(d.num_res_blocks + 1):
+            out.append((f"decoder.up.{lvl}.block.{bi}", cin, cout, "res"))
+            cin = cout
+        if lvl != 0:
+            out.append((f"decoder.up.{lvl}.upsample", cin, cin, "up"))
+    out += [("decoder.norm_out", cin, cin, "gn"), ("decoder.conv_out", cin, d.out_ch, "conv")]
+    return out
+
+
+def test_decoder_block_by_block(stack):
+    """Every block of the decoder ALONE (umv_op_vae_block) on the input the oracle's own forward hands it, against the oracle's block:
+    conv_in, the two mid ResnetBlocks, the mid attention, the 12 up ResnetBlocks (incl. the nin_shortcut ones), the 3 nearest-2x upsample
+    convolutions, norm_out + swish and conv_out.  One block is one or two GroupNorms and one to four contractions, so agreement is an
+    order of magnitude tighter than for the whole image -- this is what pins the VAE math (SURVEY.md R-points: GroupNorm / swish in fp32 under
+    CUDA autocast, bf16 conv outputs, residual adds in bf16)."""
+    import torch.nn.functional as F
+    from oracle import vae as ovae
+    eng, _, vae, o, dims = stack
+    d, sd, sem = o.dims.vae, o.vae_sd, Semantics.cuda
+    z = Golden("t2i").t("vae.decode_in")
+    x = (z / d.scale_factor + d.shift_factor)           # AutoEncoder.decode's affine, bf16 op by op
+    worst = {}
+    for path, cin, cout, kind in _blocks(d):
+        p = path[len("decoder."):] + "."
+        if kind == "conv":
+            want = ovae.conv(sd, path, x)
+        elif kind == "res":
+            want = ovae.resnet_block(sd, path + ".", x, cin, cout, d, sem)
+        elif kind == "attn":
+            want = ovae.attn_block(sd, path + ".", x, d, sem)
+        elif kind == "up":
+            want = ovae.conv(sd, path + ".conv", F.interpolate(x, scale_factor=2.0, mode="nearest"))
+        else:
+            want = ovae.gn_swish(sd, path, x, d, sem)
+        got = eng.vae_block(path, x.to(torch.bfloat16))
+        assert got.shape == want.shape, (path, got.shape, want.shape)
+        s = ulp_stats(got, want.to(torch.bfloat16))
+        worst[kind] = max(worst.get(kind, 0.0), s["rel_l2"])
+        bound = {"conv": 2e-3, "gn": 2e-3, "up": 2e-3, "res": 6e-3, "attn": 6e-3}[kind]
+        assert s["rel_l2"] < bound, (path, s)
+        x = want                                         # the next block sees the ORACLE's activation: errors do not accumulate
+    assert x.shape == (1, 3, 64, 64)
+    print("worst rel-L2 per block kind:", {k: round(v, 5) for k, v in worst.items()})
+    with pytest.raises(ValueError):
+        eng.vae_block("decoder.up.9.block.0", z)
+    with pytest.raises(ValueError):
+        eng.vae_block("decoder.mid.block_1", z)          # 16 channels into a 512-channel block

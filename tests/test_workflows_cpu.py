@@ -95,3 +95,38 @@ def test_vqa_reconstruction_workflows(inf, variant):
     for i, im in enumerate(images):
         mean, far = _diff(im, gold[f"recon.{variant}_image{i}"])
         assert np.asarray(im).shape == gold[f"recon.{variant}_image{i}"].shape and mean < 4.0 and far < 0.01, (variant, i, mean, far)
+
+
+def test_batched_inferencer_host_logic_on_cpu():
+    """unimedvl_b200.BatchedInferencer's host orchestration (a batch of ONE, over the oracle's forwards) reproduces the reference's
+    fixtures exactly like the single-request driver: interleaved I2T / T2I, think mode, and reconstruction ver0_1."""
+    import unimedvl_b200.batched as batched_mod
+    dims, _, _ = tiny_weights(vae=True)
+    o = make_oracle(Semantics.cpu, vae=True, exact=False)
+    mp = pytest.MonkeyPatch()
+    mp.setattr(batched_mod, "NaiveCache", OracleCache)
+    try:
+        bi = batched_mod.BatchedInferencer(OracleBagel(o, dims), OracleVAE(o), FakeTokenizer(), ImageTransform(1024, 32, 16),
+                                           ImageTransform(980, 28, 14), TOK)
+        gold = Golden("e2e").z
+        r = bi(images=[_img()], texts=["What is shown in this image?"], understanding_output=True, max_think_token_n=9, do_sample=False)
+        assert len(r) == 1 and r[0]["image"] is None and r[0]["text"] == str(gold["e2e.i2t_text"])
+        torch.manual_seed(42)
+        r = bi(texts=["a chest x-ray with cardiomegaly"], understanding_output=False, num_timesteps=5, image_shapes=(64, 64),
+               cfg_text_scale=4.0, cfg_img_scale=1.5)
+        mean, far = _diff(r[0]["image"], gold["e2e.t2i_image"])
+        assert r[0]["text"] is None and mean < 4.0 and far < 0.01, (mean, far)
+        g = Golden("recon").z
+        imgs = [Image.fromarray(synth.synthetic_image(30 + i, h, w)) for i, (h, w) in enumerate([(70, 98), (64, 64)])]
+        torch.manual_seed(52)
+        out = bi.vqa_reconstruction([imgs + ["Describe the findings."]], "ver0_1", reconstruct_image=True, max_think_token_n=7,
+                                    do_sample=False, num_timesteps=3, cfg_interval=[0.0, 1.0])[0]
+        assert out[0] == str(g["recon.ver0_1_text"]) and len(out) == 3
+        for i, im in enumerate(out[1:]):
+            mean, far = _diff(im, g[f"recon.ver0_1_image{i}"])
+            assert mean < 4.0 and far < 0.01, (i, mean, far)
+        with pytest.raises(ValueError):
+            bi.interleave_inference([[_img(), "a"], ["b"]], understanding_output=True)
+        assert bi() == []
+    finally:
+        mp.undo()

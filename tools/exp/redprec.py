@@ -1,7 +1,7 @@
 """Experiment: does torch.backends.cuda.matmul.allow_bf16_reduced_precision_reduction explain the reference-CUDA vs oracle gap?"""
 import os, sys, json
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests")); sys.path.insert(0, os.path.join(ROOT, "baseline"))
 import torch
 import refharness as rh
 from util import tiny_weights, Golden, make_oracle, Semantics, ulp_stats

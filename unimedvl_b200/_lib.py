@@ -90,6 +90,7 @@ SIGNATURES = {
     "umv_op_layernorm": (C.c_int, [_P, _P, _P, _P, _I, _I, _F, _P]),
     "umv_op_attention": (C.c_int, [_P, _P, _P, _P, _I, _IP, _IP, _I, _I, _I, _I, _P]),
     "umv_op_attention_block": (C.c_int, [_P, _I, _P, _P, _I, _P, _I, _IP, _IP, _IP, C.POINTER(C.c_uint8), _I, _I, _P, _IP, _P]),
+    "umv_op_vae_block": (C.c_int, [_P, C.c_char_p, _P, _I, _I, _I, _P, _IP, _P]),
     "umv_op_argmax": (C.c_int, [_P, _I, _I, _P, _P]),
     "umv_op_sample": (C.c_int, [_P, _I, _I, _F, _U64, _F, _P, _P]),
     "umv_bench_decode_linear": (C.c_int, [_P, _I, _I, _I, _LP, _P]),

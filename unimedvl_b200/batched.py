@@ -149,9 +149,11 @@ class BatchedInferencer(InterleaveInferencer):
     @torch.no_grad()
     def interleave_inference(self, requests, think=False, understanding_output=False, max_think_token_n=1000, do_sample=False,
                              text_temperature=0.3, cfg_text_scale=3.0, cfg_img_scale=1.5, cfg_interval=(0.4, 1.0), timestep_shift=3.0,
-                             num_timesteps=50, cfg_renorm_min=0.0, cfg_renorm_type="global", image_shapes=(1024, 1024)):
+                             num_timesteps=50, cfg_renorm_min=0.0, cfg_renorm_type="global", image_shapes=(1024, 1024),
+                             return_uint8: bool = False):
         """inferencer.py:551-638 for a batch: `requests` is a list of input lists (or one input list: the reference's call).
-        Returns one output list per request."""
+        Returns one output list per request.  `return_uint8`: generated images come back as DEVICE uint8 [H, W, 3] tensors (one
+        image size for the batch) instead of PIL images -- for a server's encoder or the data-parallel image gather."""
         single = bool(requests) and isinstance(requests[0], (str, Image.Image))
         reqs = [list(requests)] if single else [list(r) for r in requests]
         B = len(reqs)
@@ -192,9 +194,9 @@ class BatchedInferencer(InterleaveInferencer):
         imgs = self.gen_image(image_shapes, gen_context, cfg_text_precontext=cfg_text_context, cfg_img_precontext=cfg_img_context,
                               cfg_text_scale=cfg_text_scale, cfg_img_scale=cfg_img_scale, cfg_interval=cfg_interval,
                               timestep_shift=timestep_shift, num_timesteps=num_timesteps, cfg_renorm_min=cfg_renorm_min,
-                              cfg_renorm_type=cfg_renorm_type)
-        for b, im in enumerate(imgs):
-            outs[b].append(im)
+                              cfg_renorm_type=cfg_renorm_type, as_uint8=return_uint8)
+        for b in range(B):
+            outs[b].append(imgs[b])
         return outs[0] if single else outs
 
     # ------------------------------------------------------------------ VQA + reconstruction, batched

@@ -89,6 +89,22 @@ class NaiveCache:
         c._umv = None if self._umv is None else self._umv.fork()
         return c
 
+    @classmethod
+    def concat(cls, caches) -> "NaiveCache":
+        """One cache over the samples of several (batch order = argument order).  The sequences MOVE: the inputs are left empty.
+        Lets a large batch be prefilled in chunks that fit the workspace and decoded as one."""
+        caches = list(caches)
+        out = cls(caches[0]._num_layers)
+        seqs, engine = [], None
+        for c in caches:
+            if c._umv is not None:
+                engine = c._umv.engine
+                seqs += c._umv.seqs
+                c._umv.seqs = []
+        if engine is not None:
+            out._umv = PagedKV(engine, seqs=seqs)
+        return out
+
 
 def paged_handle(past_key_values, engine, n_seqs: int) -> PagedKV:
     """PagedKV attached to a cache object (ours or the reference's NaiveCache); created on first use."""

@@ -562,6 +562,70 @@ int umv_vae_decode(umv_engine* e, const void* z, int32_t n, int32_t h, int32_t w
     return UMV_OK;
 }
 
+// Parity hook: ONE block of the autoencoder on a caller-provided activation (block-level tests against the oracle / the reference's
+// own sub-modules).  path: the reference's module path inside AutoEncoder, e.g. "decoder.mid.block_1", "decoder.mid.attn_1",
+// "decoder.up.3.block.0", "decoder.up.2.upsample" (nearest x2 + conv), "encoder.down.0.downsample", "decoder.conv_in",
+// "decoder.norm_out" (GroupNorm + swish).  x / out: bf16 [C, H, W] (one image, NCHW as the reference); out_chw receives the output shape.
+int umv_op_vae_block(umv_engine* e, const char* path, const void* x, int32_t C, int32_t Hh, int32_t Ww, void* out, int32_t* out_chw,
+                     void* stream) {
+    UMV_REQUIRE(e && e->finalized, UMV_ERR_STATE, "engine not finalized");
+    UMV_REQUIRE(e->vae, UMV_ERR_STATE, "VAE weights were not enabled");
+    UMV_REQUIRE(path && x && out && out_chw && C > 0 && Hh > 0 && Ww > 0, UMV_ERR_INVALID, "umv_op_vae_block: null/empty argument");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    VaeState& V = *e->vae;
+    const std::string p(path);
+    const bool dec = p.rfind("decoder.", 0) == 0;
+    UMV_REQUIRE(dec || p.rfind("encoder.", 0) == 0, UMV_ERR_INVALID, "umv_op_vae_block: path must start with encoder. / decoder.");
+    const VaeHalf& Hf = dec ? V.dec : V.enc;
+    const std::string rest = p.substr(8);
+    const size_t px = (size_t)Hh * Ww;
+    UMV_TRY(vae_reserve(e, px * 4 * 512 + 64, px * 4 * 9 * 512 + 64, px <= 4096 ? px * px : 1));
+    launch_k(nchw_to_nhwc_kernel, dim3((unsigned)((C * px + 255) / 256)), dim3(256), 0, st, static_cast<const bf16*>(x), V.a0, C, (int)px, 1.f, 0.f, 0);
+    UMV_LAUNCH_CHECK("nchw_to_nhwc_kernel");
+    Img im{Hh, Ww};
+    const bf16* res = V.a0;
+    int Cout = C;
+    auto res_at = [&](const VaeRes& r) -> int {
+        UMV_REQUIRE(r.cin == C, UMV_ERR_INVALID, "umv_op_vae_block: '%s' takes %d channels, got %d", path, r.cin, C);
+        Cout = r.cout;
+        return res_block(e, r, im, st);
+    };
+    int lvl = -1, bi = -1;
+    if (rest == "mid.block_1") { UMV_TRY(res_at(Hf.mid1)); }
+    else if (rest == "mid.block_2") { UMV_TRY(res_at(Hf.mid2)); }
+    else if (rest == "mid.attn_1") {
+        UMV_REQUIRE(Hf.attn.c == C, UMV_ERR_INVALID, "umv_op_vae_block: attention takes %d channels", Hf.attn.c);
+        UMV_TRY(attn_block(e, Hf.attn, im, st));
+    } else if (sscanf(rest.c_str(), dec ? "up.%d.block.%d" : "down.%d.block.%d", &lvl, &bi) == 2) {
+        UMV_REQUIRE(lvl >= 0 && lvl < V.nlev && bi >= 0 && bi < (int)Hf.levels[lvl].blocks.size(), UMV_ERR_INVALID, "no block '%s'", path);
+        UMV_TRY(res_at(Hf.levels[lvl].blocks[bi]));
+    } else if (sscanf(rest.c_str(), dec ? "up.%d.upsample" : "down.%d.downsample", &lvl) == 1) {
+        UMV_REQUIRE(lvl >= 0 && lvl < V.nlev && Hf.levels[lvl].has_resample && Hf.levels[lvl].resample.cin == C, UMV_ERR_INVALID,
+                    "no resample '%s' for %d channels", path, C);
+        UMV_TRY(conv(e, Hf.levels[lvl].resample, V.a0, im, V.a1, &im, dec ? 1 : 0, dec ? 1 : 2, nullptr, st));
+        Cout = Hf.levels[lvl].resample.cout;
+        res = V.a1;
+    } else if (rest == "conv_in" || rest == "conv_out") {
+        const VaeConv& c = rest == "conv_in" ? Hf.conv_in : Hf.conv_out;
+        UMV_REQUIRE(c.cin == C, UMV_ERR_INVALID, "umv_op_vae_block: '%s' takes %d channels", path, c.cin);
+        UMV_TRY(conv(e, c, V.a0, im, V.a1, nullptr, 0, 1, nullptr, st));
+        Cout = c.cout;
+        res = V.a1;
+    } else if (rest == "norm_out") {
+        UMV_REQUIRE(Hf.norm_out.c == C, UMV_ERR_INVALID, "umv_op_vae_block: norm_out takes %d channels", Hf.norm_out.c);
+        UMV_TRY(gn(e, Hf.norm_out, V.a0, im, V.a1, 1, st));
+        res = V.a1;
+    } else {
+        set_error("umv_op_vae_block: unknown block '%s'", path);
+        return UMV_ERR_INVALID;
+    }
+    const int HW = im.H * im.W;
+    launch_k(nhwc_to_nchw_kernel, dim3((Cout * HW + 255) / 256), dim3(256), 0, st, res, static_cast<bf16*>(out), Cout, HW);
+    UMV_LAUNCH_CHECK("nhwc_to_nchw_kernel");
+    out_chw[0] = Cout; out_chw[1] = im.H; out_chw[2] = im.W;
+    return UMV_OK;
+}
+
 int umv_decode_image_u8(umv_engine* e, const float* latent_tokens, int32_t n, int32_t h, int32_t w, int32_t p, uint8_t* out,
                         void* stream) {
     UMV_REQUIRE(e && e->finalized, UMV_ERR_STATE, "engine not finalized");

@@ -399,6 +399,20 @@ class Engine:
         self._exit()
         return out
 
+    def vae_block(self, path: str, x: torch.Tensor) -> torch.Tensor:
+        """umv_op_vae_block: one autoencoder block (`path` = the reference's module path) on bf16 [1, C, H, W] or [C, H, W]."""
+        x4 = x if x.dim() == 4 else x[None]
+        assert x4.shape[0] == 1
+        x4 = x4.to(self.device, torch.bfloat16).contiguous()
+        _, c, h, w = x4.shape
+        out = torch.empty((512 * 4 * h * w,), dtype=torch.bfloat16, device=self.device)
+        chw = (C.c_int32 * 3)()
+        self._enter()
+        _lib.check(self.lib.umv_op_vae_block(self.h, path.encode(), _ptr(x4), c, h, w, _ptr(out), chw, _stream_ptr(self.stream)))
+        self._exit()
+        co, ho, wo = chw[0], chw[1], chw[2]
+        return out[:co * ho * wo].reshape(1, co, ho, wo).clone()
+
     def vae_decode(self, z: torch.Tensor) -> torch.Tensor:
         """AutoEncoder.decode: bf16 [n, 16, h, w] -> bf16 [n, 3, 8h, 8w]."""
         z = z.to(self.device, torch.bfloat16).contiguous()
