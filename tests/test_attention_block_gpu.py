@@ -119,11 +119,15 @@ def test_prefill_attention_tcgen05_vs_oracle(eng, name, past, q_lens, causal):
     _free(e, seqs)
 
 
+@pytest.mark.parametrize("early", ["0", "2"])
 @pytest.mark.parametrize("ctx,splits", [([1058] * 8, 3), ([1570, 1185, 1058, 777, 513, 512, 65, 64], 2), ([1569] * 16, 0), ([63, 1], 1)])
-def test_decode_attention_fused_vs_oracle(eng, ctx, splits):
+def test_decode_attention_fused_vs_oracle(eng, ctx, splits, early, monkeypatch):
     """One query token per sample on top of `ctx` cached keys -- config 2 (ctx 1058 -> 1185) and config 3 (16 per GPU,
     ctx -> 1569) geometries, ragged, page-boundary lengths -- with the projection outputs arriving as split-K partials + bias
     (what the decode step's weight-major linear produces) or as bf16 rows (splits == 0)."""
+    # early = "2": the step state is read and the K/V tiles are requested BEFORE griddepcontrol.wait (what layers >= 1 of the decode
+    # step do); "0": after it (layer 0)
+    monkeypatch.setenv("UMV_ATTN_EARLY", early)
     e, dims, w = eng
     B = len(ctx)
     seqs, pk, pv = _context(e, ctx, seed=B)

@@ -352,6 +352,7 @@ attn_decode_kernel(const __grid_constant__ CUtensorMap tmKV, DecodeAttnArgs a, f
     constexpr int HD = 128;
     pdl_launch_dependents();
     trace_start(a.trace);
+    trace_dbg_max(a.trace, 3);             // dbg3: the LAST CTA of the grid to start
     cluster_arrive();                      // phase 1: "this CTA runs" (its shared memory may be written by peers later)
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -397,19 +398,61 @@ attn_decode_kernel(const __grid_constant__ CUtensorMap tmKV, DecodeAttnArgs a, f
             if (is_kv) bv = *reinterpret_cast<const uint2*>(a.bias + col_v);
         }
     }
+    // Two groups of loads.  STATE (kv_len, the page-table row, the step's cos / sin) belongs to the decode step, not to the previous
+    // kernel: with `a.early` (every layer but the first, whose predecessors are the step's own state kernels) it is read -- and the
+    // K/V tiles requested from TMA -- BEFORE griddepcontrol.wait, while the q/k/v projection is still running: the cache rows of earlier
+    // tokens were written a whole forward ago.  The projection's split-K partials are the only loads that need the wait.
+    int kvlen = 0, blocks_total = 0, kb_begin = 0, kb_end = 0, last_block = 0, new_slot = 0;
+    bool owner = false;
+    float xa[4] = {0.f, 0.f, 0.f, 0.f}, xv[4] = {0.f, 0.f, 0.f, 0.f};
+    float4 rc = make_float4(0.f, 0.f, 0.f, 0.f), rs = rc;            // bf16-rounded cos / sin of this lane's 4 elements
+    // ---- round trip 2 (issue): one thread asks TMA for up to kDecStages blocks (the CTA's whole range at B = 8, ctx <= 1.5k): four
+    // 8 KB boxes per block (K / V x column halves) completing on the slot's mbarrier.  The block that receives the new
+    // token is loaded like the others; its new row is patched in shared memory from the registers of the K/V warp.
+    auto issue_kv = [&](int kb, int stage) {
+        const int page = s_pages[kb];
+        const int row_k = (int)(a.pool.tile_offset(page, a.layer, 0, kvh) / HD);
+        const int row_v = (int)(a.pool.tile_offset(page, a.layer, 1, kvh) / HD);
+        uint8_t* dk = sKV + stage * kDecStageBytes;
+        mbar_expect_tx(&kvbar[stage], kDecStageBytes);
+        tma_load_2d(dk, &tmKV, &kvbar[stage], 0, row_k, kEvictNormal);
+        tma_load_2d(dk + 8192, &tmKV, &kvbar[stage], 64, row_k, kEvictNormal);
+        tma_load_2d(dk + 16384, &tmKV, &kvbar[stage], 0, row_v, kEvictNormal);
+        tma_load_2d(dk + 24576, &tmKV, &kvbar[stage], 64, row_v, kEvictNormal);
+    };
+    auto load_state = [&]() {
+        kvlen = a.kv_len[b];
+        for (int i = tid; i < a.max_pages; i += kDecThreads) s_pages[i] = a.page_table[(size_t)b * a.max_pages + i];
+        if ((is_q || is_kv) && a.rope_cs) {
+            rc = *reinterpret_cast<const float4*>(a.rope_cs + (size_t)b * HD + (lane * 4) % (HD / 2));
+            rs = *reinterpret_cast<const float4*>(a.rope_cs + (size_t)b * HD + HD / 2 + (lane * 4) % (HD / 2));
+        }
+    };
+    auto request_tiles = [&]() {
+        // key-block range of this CTA (balanced: sizes differ by at most one)
+        blocks_total = (kvlen + kTileKeys - 1) / kTileKeys;
+        kb_begin = (int)(((long long)blocks_total * rank) / S);
+        kb_end = (int)(((long long)blocks_total * (rank + 1)) / S);
+        last_block = (kvlen - 1) / kTileKeys;
+        new_slot = (kvlen - 1) % kTileKeys;
+        owner = kb_begin <= last_block && last_block < kb_end;     // this CTA appends the new K/V row
+        __syncthreads();                                           // s_pages (and the Q padding, the mbarriers) visible
+        // one issuing lane per block (lane 0 of warp j takes ring slot j): the descriptor fetch + 4 requests of a block cost a
+        // few hundred cycles of a single thread, and every warp has to pass the barrier below before the key loop starts
+        static_assert(kDecStages <= kDecThreads / 32, "one warp per first-pass ring slot");
+        if (lane == 0 && warp < kDecStages && kb_begin + warp < kb_end) issue_kv(kb_begin + warp, warp);
+    };
+    if (a.early) {
+        load_state();
+        request_tiles();
+    }
     pdl_wait();
     trace_wait(a.trace);
 
     // ---- round trip 1: everything that needs no other load
-    const int kvlen = a.kv_len[b];
-    for (int i = tid; i < a.max_pages; i += kDecThreads) s_pages[i] = a.page_table[(size_t)b * a.max_pages + i];
-    float xa[4] = {0.f, 0.f, 0.f, 0.f}, xv[4] = {0.f, 0.f, 0.f, 0.f};
-    float4 rc = make_float4(0.f, 0.f, 0.f, 0.f), rs = rc;            // bf16-rounded cos / sin of this lane's 4 elements
+    if (!a.early) load_state();
     if (is_q || is_kv) {
-        if (a.rope_cs) {
-            rc = *reinterpret_cast<const float4*>(a.rope_cs + (size_t)b * HD + (lane * 4) % (HD / 2));
-            rs = *reinterpret_cast<const float4*>(a.rope_cs + (size_t)b * HD + HD / 2 + (lane * 4) % (HD / 2));
-        } else {
+        if (!a.rope_cs) {
             const float pos = (float)a.positions[b];
             const float4 fr = *reinterpret_cast<const float4*>(a.inv_freq + (lane * 4) % (HD / 2));
             const float f[4] = {fr.x, fr.y, fr.z, fr.w};
@@ -455,32 +498,8 @@ attn_decode_kernel(const __grid_constant__ CUtensorMap tmKV, DecodeAttnArgs a, f
         }
     }
 
-    // key-block range of this CTA (balanced: sizes differ by at most one)
-    const int blocks_total = (kvlen + kTileKeys - 1) / kTileKeys;
-    const int kb_begin = (int)(((long long)blocks_total * rank) / S), kb_end = (int)(((long long)blocks_total * (rank + 1)) / S);
-    const int last_block = (kvlen - 1) / kTileKeys, new_slot = (kvlen - 1) % kTileKeys;
-    const bool owner = kb_begin <= last_block && last_block < kb_end;     // this CTA appends the new K/V row
-    __syncthreads();                                                      // s_pages (and the Q padding) visible
+    if (!a.early) request_tiles();
     trace_dbg(a.trace, 0);
-
-    // ---- round trip 2: one thread asks TMA for up to kDecStages blocks (the CTA's whole range at B = 8, ctx <= 1.5k): four
-    // 8 KB boxes per block (K / V x column halves) completing on the slot's mbarrier.  The block that receives the new
-    // token is loaded like the others; its new row is patched in shared memory from the registers of the K/V warp.
-    auto issue_kv = [&](int kb, int stage) {
-        const int page = s_pages[kb];
-        const int row_k = (int)(a.pool.tile_offset(page, a.layer, 0, kvh) / HD);
-        const int row_v = (int)(a.pool.tile_offset(page, a.layer, 1, kvh) / HD);
-        uint8_t* dk = sKV + stage * kDecStageBytes;
-        mbar_expect_tx(&kvbar[stage], kDecStageBytes);
-        tma_load_2d(dk, &tmKV, &kvbar[stage], 0, row_k, kEvictNormal);
-        tma_load_2d(dk + 8192, &tmKV, &kvbar[stage], 64, row_k, kEvictNormal);
-        tma_load_2d(dk + 16384, &tmKV, &kvbar[stage], 0, row_v, kEvictNormal);
-        tma_load_2d(dk + 24576, &tmKV, &kvbar[stage], 64, row_v, kEvictNormal);
-    };
-    // one issuing lane per block (lane 0 of warp j takes ring slot j): the descriptor fetch + 4 requests of a block cost a
-    // few hundred cycles of a single thread, and every warp has to pass the barrier below before the key loop starts
-    static_assert(kDecStages <= kDecThreads / 32, "one warp per first-pass ring slot");
-    if (lane == 0 && warp < kDecStages && kb_begin + warp < kb_end) issue_kv(kb_begin + warp, warp);
 
     // ---- rows of this step: RMSNorm + RoPE of the query heads (-> sQ) and of the new K row, V row as is (-> page)
     uint2 k_new = make_uint2(0u, 0u), v_new = make_uint2(0u, 0u);
@@ -545,7 +564,7 @@ attn_decode_kernel(const __grid_constant__ CUtensorMap tmKV, DecodeAttnArgs a, f
             __syncthreads();
         }
         if (j < nblk) mbar_wait(&kvbar[stage], (j / kDecStages) & 1);
-        if (rd < 3) trace_dbg(a.trace, 2 + rd);
+        if (rd == 0) trace_dbg(a.trace, 2);
         const uint8_t* cK = sKV + stage * kDecStageBytes;
         const uint8_t* cV = cK + 16384;
         if (j < nblk) {
@@ -606,6 +625,7 @@ attn_decode_kernel(const __grid_constant__ CUtensorMap tmKV, DecodeAttnArgs a, f
     // ---- merge the 8 (key-quarter, block parity) partials of this CTA (buffers alias the dead stage ring)
     __syncthreads();
     trace_dbg(a.trace, 5);
+    trace_dbg_max(a.trace, 4);             // dbg4: the LAST CTA of the grid to finish its key loop
     if (t == 0) { red_m[warp * 8 + g] = m_a; red_l[warp * 8 + g] = l_a; }
 #pragma unroll
     for (int dt = 0; dt < 16; ++dt)

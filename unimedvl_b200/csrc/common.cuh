@@ -128,6 +128,9 @@ __device__ __forceinline__ bool trace_lead() { return threadIdx.x == 0 && blockI
 __device__ __forceinline__ void trace_start(TraceSlot* s) { if (s && trace_lead()) s->t_start = gtime(); }
 __device__ __forceinline__ void trace_dbg(TraceSlot* s, int i) { if (s && trace_lead()) s->dbg[i] = gtime(); }
 __device__ __forceinline__ void trace_wait(TraceSlot* s) { if (s && trace_lead()) s->t_wait = gtime(); }
+// latest time over ALL CTAs at which thread 0 passes this point (stamps grow monotonically, so after graph replays the slot holds the
+// last replay's value)
+__device__ __forceinline__ void trace_dbg_max(TraceSlot* s, int i) { if (s && threadIdx.x == 0) atomicMax(&s->dbg[i], gtime()); }
 // kSync = false for kernels whose threads may have returned early (thread 0's own end is stamped)
 template <bool kSync = true>
 __device__ __forceinline__ void trace_end(TraceSlot* s) {

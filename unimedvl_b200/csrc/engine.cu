@@ -210,6 +210,7 @@ static int build_runtime(umv_engine* e) {
     cudaMemcpy(e->inv_freq, inv.data(), inv.size() * sizeof(float), cudaMemcpyHostToDevice);
     // KV pool
     e->pool.layers = d.layers;
+    e->pool.pages = d.kv_pages;
     e->pool.kv_heads = d.kv_heads;
     e->pool.head_dim = e->dh;
     const size_t page_elems = (size_t)d.layers * 2 * d.kv_heads * kPageTokens * e->dh;
@@ -365,6 +366,10 @@ int lin(umv_engine* e, const bf16* x, int ldx, const bf16* w, const bf16* bias, 
     LinearCall c;
     c.stages = stages;
     c.x = x; c.ldx = ldx; c.w = w; c.bias = bias; c.residual = res; c.y = y; c.ldy = ldy;
+    if (M <= 64 && !e->tiled.empty()) {
+        auto it = e->tiled.find(w);
+        if (it != e->tiled.end()) c.w_tiled = it->second;
+    }
     c.M = M; c.N = N; c.K = K; c.epi = epi; c.ws = ws; c.splits = splits;
     c.impl = e->gemm_impl ? e->gemm_impl : impl;
     if (c.impl == GEMM_SIMPLE && epi == EPI_PARTIAL) c.impl = GEMM_WEIGHT_MAJOR;
@@ -440,6 +445,11 @@ static int llm_layers(umv_engine* e, const LlmRun& r, bf16* out, cudaStream_t st
             const int blocks = (r.max_kv_len + kPageTokens - 1) / kPageTokens;
             // key ranges per (sample, kv head): as many as fit one wave of 2 CTAs per SM, at most one per 64-key block
             da.cluster = std::max(1, std::min(std::min(attn_cluster_max, blocks), e->sm_count / std::max(1, M * Hkv)));
+            // K/V tiles requested before the dependency wait: from layer 1 on (layer 0 follows the step's own state kernels, whose
+            // kv_len / cos-sin writes the early reads must not overtake).  UMV_ATTN_EARLY=0 off, 2 = also layer 0 (op-level tests).
+            const char* early_env = getenv("UMV_ATTN_EARLY");         // read per call: tests switch inside one process
+            const int early_mode = early_env ? atoi(early_env) : 1;
+            da.early = early_mode == 2 ? 1 : (early_mode == 1 && li > 0 ? 1 : 0);
             if (path) *path = 3;
             return decode_attention(da, st);
         }
@@ -595,6 +605,7 @@ int umv_destroy(umv_engine* e) {
     if (!e) return UMV_OK;
     cudaDeviceSynchronize();
     for (void* p : e->allocs) cudaFree(p);
+    for (void* p : e->tiled_allocs) cudaFree(p);
     for (auto& g : e->dec_graphs) cudaGraphExecDestroy(g.exec);
     if (e->dec_out) cudaFree(e->dec_out);
     delete e->vae;
@@ -650,7 +661,7 @@ int umv_load_tensor(umv_engine* e, const char* name, const void* data, int dtype
             for (int c = 0; c < cin; ++c)
                 for (int t = 0; t < kk; ++t) dst[(o * kk + t) * cin + c] = src[(o * cin + c) * kk + t];
         int rc2 = slot_copy(e, s, dst.data(), true);
-        if (rc2 == UMV_OK) s.loaded = true;
+        if (rc2 == UMV_OK) { s.loaded = true; e->finalized = false; }
         return rc2;
     }
     const int64_t rows = ndim == 2 ? shape[0] : 1, cols = ndim == 2 ? shape[1] : shape[0];
@@ -670,7 +681,7 @@ int umv_load_tensor(umv_engine* e, const char* name, const void* data, int dtype
     } else {
         rc = slot_copy(e, s, const_cast<void*>(data), true);
     }
-    if (rc == UMV_OK) s.loaded = true;
+    if (rc == UMV_OK) { s.loaded = true; e->finalized = false; }      // umv_finalize re-derives the tile-major twins
     return rc;
 }
 
@@ -720,6 +731,34 @@ int umv_finalize(umv_engine* e) {
     for (auto& kv : e->slots)
         UMV_REQUIRE(kv.second.loaded, UMV_ERR_STATE, "umv_finalize: tensor '%s' was never loaded", kv.first.c_str());
     UMV_CUDA_OK(cudaDeviceSynchronize());
+    // tile-major twins of what a decode step streams: the understanding expert's four linears per layer and lm_head
+    for (void* p : e->tiled_allocs) cudaFree(p);
+    e->tiled_allocs.clear();
+    e->tiled.clear();
+    const char* tl = getenv("UMV_TILED");
+    if (!(tl && atoi(tl) == 0) && gemm_init() == UMV_OK) {
+        const int D = e->d.hidden, I = e->d.inter, QN = e->qkvn;
+        auto twin = [&](const bf16* w, int N, int K) -> int {
+            if (!w || N % 128 != 0 || K % 64 != 0) return UMV_OK;
+            void* p = nullptr;
+            if (cudaMalloc(&p, (size_t)N * K * sizeof(bf16)) != cudaSuccess) {
+                cudaGetLastError();
+                return UMV_OK;                    // no room for the second copy: the row-major weights serve
+            }
+            e->tiled_allocs.push_back(p);
+            UMV_TRY(tile_weights(w, static_cast<bf16*>(p), N, K, nullptr));
+            e->tiled[w] = static_cast<bf16*>(p);
+            return UMV_OK;
+        };
+        for (const LayerW& L : e->layers) {
+            UMV_TRY(twin(L.wqkv[0], QN, D));
+            UMV_TRY(twin(L.wo[0], D, D));
+            UMV_TRY(twin(L.wgu[0], 2 * I, D));
+            UMV_TRY(twin(L.wdown[0], D, I));
+        }
+        UMV_TRY(twin(e->lm_head, e->d.vocab, D));
+        UMV_CUDA_OK(cudaDeviceSynchronize());
+    }
     e->finalized = true;
     return UMV_OK;
 }

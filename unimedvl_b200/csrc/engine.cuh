@@ -108,6 +108,10 @@ struct umv_engine {
     int gemm_impl = 0;
 
     std::vector<void*> allocs;
+    // tile-major twins of the weights the decode step streams (LinearCall::w_tiled): row-major pointer -> twin.  Built by umv_finalize
+    // (UMV_TILED=0: none).  180 GB of HBM per GPU pays for the second copy (+14.1 GB at the 14B dims) of the understanding expert.
+    std::map<const umv::bf16*, umv::bf16*> tiled;
+    std::vector<void*> tiled_allocs;
     std::map<std::string, umv::Slot> slots;
 
     // LLM

@@ -84,6 +84,7 @@ struct GemmParams {
     TraceSlot* trace;
     int hd, hp;     // output head padding (LinearCall::out_head_dim / out_head_pad), 0 = off
     int stages;     // ring depth of this launch (<= TcCfg::kStages); a shallow ring leaves shared memory for a neighbour CTA
+    int a_tiled;    // weight-major: the A tensor map views a tile-major weight copy as [tiles * 128 rows, 64 columns]
 };
 
 template <int BN, bool SWAP>
@@ -188,7 +189,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     }
                     mbar_wait(&empty[stage], phase ^ 1u);
                     mbar_expect_tx(&full[stage], Cfg::kStageBytes);
-                    tma_load_2d(sA + stage * kATile, &tmA, &full[stage], kb * BK, a_tile * BM, hintA);
+                    if (SWAP && p.a_tiled) tma_load_2d(sA + stage * kATile, &tmA, &full[stage], 0, (a_tile * p.kb_total + kb) * BM, hintA);
+                    else tma_load_2d(sA + stage * kATile, &tmA, &full[stage], kb * BK, a_tile * BM, hintA);
                     if (waited) {
                         tma_load_2d(sB + stage * Cfg::kBTile, &tmB, &full[stage], kb * BK, b_tile * BN, hintB);
                     } else {
@@ -632,7 +634,13 @@ static int launch_tc(const LinearCall& c, cudaStream_t stream) {
     }
     p.stages = (c.stages > 0 && c.stages < TcCfg<BN, SWAP>::kStages) ? (c.stages < 2 ? 2 : c.stages) : TcCfg<BN, SWAP>::kStages;
     CUtensorMap tmA, tmB;
-    int rc = make_tmap(&tmA, A, p.a_rows, c.K, lda, BM);
+    int rc;
+    if (SWAP && c.w_tiled && c.N % BM == 0 && c.K % BK == 0) {
+        p.a_tiled = 1;
+        rc = make_tmap(&tmA, c.w_tiled, (uint64_t)p.a_tiles * p.kb_total * BM, BK, BK, BM);
+    } else {
+        rc = make_tmap(&tmA, A, p.a_rows, c.K, lda, BM);
+    }
     if (rc) return rc;
     rc = make_tmap(&tmB, B, p.b_rows, c.K, ldb, BN);
     if (rc) return rc;
@@ -643,6 +651,29 @@ static int launch_tc(const LinearCall& c, cudaStream_t stream) {
     if (e == cudaSuccess) e = cudaGetLastError();
     if (e != cudaSuccess) {
         set_error("gemm_tc_kernel<%d,%d,%d> launch failed: %s", BN, MODE, (int)SWAP, cudaGetErrorString(e));
+        return UMV_ERR_CUDA;
+    }
+    return UMV_OK;
+}
+
+// [N, K] row-major -> [N/128][K/64][128][64]: one thread per 16-byte chunk
+__global__ void tile_weights_kernel(const bf16* __restrict__ src, bf16* __restrict__ dst, int N, int K) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;          // destination chunk
+    const size_t total = (size_t)N * K / 8;
+    if (i >= total) return;
+    const int c8 = (int)(i % 8), r = (int)((i / 8) % BM);
+    const size_t tile = i / (8 * BM);
+    const int KT = K / BK;
+    const int kt = (int)(tile % KT), nt = (int)(tile / KT);
+    *reinterpret_cast<U4*>(dst + i * 8) = *reinterpret_cast<const U4*>(src + ((size_t)nt * BM + r) * K + (size_t)kt * BK + c8 * 8);
+}
+int tile_weights(const bf16* src, bf16* dst, int N, int K, cudaStream_t stream) {
+    UMV_REQUIRE(N % BM == 0 && K % BK == 0, UMV_ERR_INVALID, "tile_weights: N=%d K=%d", N, K);
+    const size_t total = (size_t)N * K / 8;
+    tile_weights_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(src, dst, N, K);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        set_error("tile_weights_kernel launch failed: %s", cudaGetErrorString(e));
         return UMV_ERR_CUDA;
     }
     return UMV_OK;

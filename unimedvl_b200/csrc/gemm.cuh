@@ -34,7 +34,14 @@ struct LinearCall {
                                     //   (heads of `dim` columns padded to `pad`; the pad columns are never written)
     int stages = 0;                 // 0: deepest TMA ring that fits; else ring depth (shared memory left for a co-resident kernel)
     bool w_static = true;           // false: `w` is produced by the preceding kernel (activation x activation product)
+    // Weight-major path only: a copy of `w` in TILE-major order -- [N / 128][K / 64] tiles of 128 rows x 64 columns, each tile 16 KB
+    // contiguous (N % 128 == 0, K % 64 == 0).  A CTA's K range is then one contiguous run in HBM instead of 128-byte pieces
+    // a row pitch (7-37 KB) apart: measured 7.3 TB/s for contiguous 16 KB reads against 6.6 TB/s for the strided boxes
+    // (tools/micro/read_bw.cu, profiles/r2_decode_experiments.md).
+    const bf16* w_tiled = nullptr;
 };
+// dst <- tile-major copy of the row-major [N, K] matrix src (see LinearCall::w_tiled)
+int tile_weights(const bf16* src, bf16* dst, int N, int K, cudaStream_t stream);
 
 // shared TMA helpers
 int make_tmap_2d(CUtensorMap* m, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows);

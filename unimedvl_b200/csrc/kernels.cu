@@ -1153,10 +1153,14 @@ int export_kv(KVPool pool, int layer, const int* pages, int len, bf16* k_out, bf
 __global__ void copy_page_kernel(KVPool pool, int src_page, int dst_page) {
     pdl_launch_dependents();
     pdl_wait();
-    const size_t n = (size_t)pool.layers * 2 * pool.kv_heads * pool.tile_elems() / 8;
-    const U4* s = reinterpret_cast<const U4*>(pool.base + pool.tile_offset(src_page, 0, 0, 0));
-    U4* d = reinterpret_cast<U4*>(pool.base + pool.tile_offset(dst_page, 0, 0, 0));
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) d[i] = s[i];
+    const size_t per = pool.page_layer_elems() / 8;            // 16-byte chunks of one (layer, page) block
+    const size_t n = (size_t)pool.layers * per;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const int layer = (int)(i / per);
+        const size_t off = (i % per) * 8;
+        *reinterpret_cast<U4*>(pool.base + pool.tile_offset(dst_page, layer, 0, 0) + off) =
+            *reinterpret_cast<const U4*>(pool.base + pool.tile_offset(src_page, layer, 0, 0) + off);
+    }
 }
 int copy_page(KVPool pool, int src_page, int dst_page, cudaStream_t s) {
     launch_k(copy_page_kernel, dim3(148), dim3(256), 0, s, pool, src_page, dst_page);

@@ -9,14 +9,18 @@ namespace umv {
 
 constexpr int kPageTokens = 64;
 
-// Paged KV pool geometry: pool[page][layer][k|v][kv_head][slot][head_dim] bf16.
+// Paged KV pool geometry: pool[layer][page][k|v][kv_head][slot][head_dim] bf16.  LAYER-major: the tiles one attention launch reads
+// (one layer, the pages of the running samples) lie within pages * 128 KB of each other instead of one 3.67 MB page-stride apart, so a
+// launch touches tens of 2 MB translations rather than one per KV page (the TLB reaches 256 MB; at the 1,000+ page pools of the serving configs the page-major layout put every tile of a launch on its own
+// translation).  Measured neutral at B = 8 / 208 pages (profiles/r2_decode_experiments.md).
 struct KVPool {
     bf16* base = nullptr;
-    int layers = 0, kv_heads = 0, head_dim = 0;
+    int layers = 0, kv_heads = 0, head_dim = 0, pages = 0;
     __host__ __device__ size_t tile_elems() const { return (size_t)kPageTokens * head_dim; }
     __host__ __device__ size_t tile_offset(int page, int layer, int kv, int head) const {
-        return ((((size_t)page * layers + layer) * 2 + kv) * kv_heads + head) * tile_elems();
+        return ((((size_t)layer * pages + page) * 2 + kv) * kv_heads + head) * tile_elems();
     }
+    __host__ __device__ size_t page_layer_elems() const { return (size_t)2 * kv_heads * tile_elems(); }   // one (layer, page): contiguous
 };
 
 // ---- residual add + RMSNorm (Qwen2RMSNorm, modeling_qwen2.py:89-94; residual adds qwen2_navit.py:883,901)
@@ -175,6 +179,7 @@ struct DecodeAttnArgs {
     int M = 0, H = 0, Hkv = 0;
     const CUtensorMap* kv_tmap = nullptr;   // host pointer: the pool as a 2-D tensor [slot rows, 128], 64 x 64 boxes, 128 B swizzle
     int cluster = 8;                  // CTAs (key ranges) per (sample, kv head)
+    int early = 0;                    // 1: read the step state and request the K/V tiles before griddepcontrol.wait (not for layer 0)
     float eps = 1e-6f;
     TraceSlot* trace = nullptr;
 };
