@@ -205,6 +205,29 @@ int umv_forward_cache_update_vit(umv_engine* e, int32_t n_seqs, const int32_t* s
                                  const int64_t* text_ids, const int32_t* text_rows, const float* pixels, const int64_t* vit_pos_ids,
                                  int32_t n_images, const int32_t* vit_seqlens, const int32_t* vit_rows, const int32_t* positions,
                                  void* stream);
+/* Mixed prefill + decode in ONE forward (the reference's loop to replace: inferencer.py:552-638, which runs
+ * a request's prefills and its decode strictly one after the other).  `riders` are running requests: rider i feeds token tokens[i] at
+ * rope position positions[i] as ONE extra query row of sequence seqs[i], appended after the prefill rows of the same packed forward; its K/V
+ * row is appended to its cache and next_tokens[i] (DEVICE i64 [n]) receives argmax (temperature <= 0) or a sample of its logits.  A single
+ * query row attends to its whole context under either mask, so riders join the causal text prefill and the full-attention image block
+ * alike.  riders == NULL or n == 0: exactly the plain driver.  n <= 64. */
+typedef struct umv_decode_riders {
+    int32_t n;
+    const int32_t* seqs;        /* host [n] */
+    const int64_t* tokens;      /* host [n] current input token of each rider */
+    const int32_t* positions;   /* host [n] rope position of that token */
+    float temperature;
+    uint64_t seed;
+    int64_t* next_tokens;       /* device [n] */
+} umv_decode_riders;
+int umv_forward_cache_update_text_riders(umv_engine* e, int32_t n_seqs, const int32_t* seqs, const int32_t* text_lens,
+                                         const int64_t* text_ids, const int32_t* positions, const umv_decode_riders* riders,
+                                         void* stream);
+int umv_forward_cache_update_vit_riders(umv_engine* e, int32_t n_seqs, const int32_t* seqs, const int32_t* seq_lens, int32_t n_text,
+                                        const int64_t* text_ids, const int32_t* text_rows, const float* pixels,
+                                        const int64_t* vit_pos_ids, int32_t n_images, const int32_t* vit_seqlens,
+                                        const int32_t* vit_rows, const int32_t* positions, const umv_decode_riders* riders,
+                                        void* stream);
 int umv_forward_cache_update_vae(umv_engine* e, int32_t n_seqs, const int32_t* seqs, const int32_t* seq_lens, int32_t n_text,
                                  const int64_t* text_ids, const int32_t* text_rows, const void* latent, int32_t n_images, int32_t Hl,
                                  int32_t Wl, const int32_t* latent_hw, int32_t patch, const int64_t* lat_pos_ids, const int32_t* lat_rows,

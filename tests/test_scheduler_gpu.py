@@ -82,20 +82,57 @@ def test_continuous_batching_matches_solo_runs(stack):
     gc.collect()
     assert eng.pages_free() == free0
 
-    cb = ContinuousBatcher(model, tok, TOK, vit_tf, max_batch=3, chunk=4, end_token_id=eos)
-    ids = [cb.submit(**r) for r in reqs]
-    got = cb.run()
-    assert sorted(got) == ids
-    for i, w in zip(ids, want):
-        assert torch.equal(got[i], w), (i, got[i].tolist(), w.tolist())
-    st = cb.stats
-    assert st["admitted"] == len(reqs) and st["prefill_calls"] > 2          # admitted in several waves, not one batch
-    assert st["slot_steps_used"] == sum(len(w) for w in want)
-    # a slot is held only until its request ends (at most chunk - 1 wasted steps in its last chunk), not until the batch ends
-    assert st["decode_steps"] <= st["slot_steps_used"] + len(reqs) * (4 - 1)
-    cb.close()
-    gc.collect()
-    assert eng.pages_free() == free0
+    for mixed in (False, True):
+        # mixed=True: the admission forwards (image block / prompt prefill of the NEW requests) carry one decode row per RUNNING request
+        # (umv_decode_riders) -- prefill and decode of different requests in one packed forward; same tokens either way
+        cb = ContinuousBatcher(model, tok, TOK, vit_tf, max_batch=3, chunk=4, end_token_id=eos, mixed=mixed)
+        ids = [cb.submit(**r) for r in reqs]
+        got = cb.run()
+        assert sorted(got) == ids
+        for i, w in zip(ids, want):
+            assert torch.equal(got[i], w), (mixed, i, got[i].tolist(), w.tolist())
+        st = cb.stats
+        assert st["admitted"] == len(reqs) and st["prefill_calls"] > 2          # admitted in several waves, not one batch
+        assert st["slot_steps_used"] == sum(len(w) for w in want)
+        # a slot is held only until its request ends (at most chunk - 1 wasted steps in its last chunk), not until the batch ends
+        assert st["decode_steps"] + st["rider_steps"] <= st["slot_steps_used"] + len(reqs) * (4 - 1)
+        assert (st["rider_steps"] > 0) == mixed, st
+        cb.close()
+        gc.collect()
+        assert eng.pages_free() == free0
+
+
+def test_decode_riders_match_a_plain_decode_step(stack):
+    """umv_forward_cache_update_{text,vit}_riders: a running request's next token computed inside another request's prefill forward is
+    the token a plain decode step gives, and its cache advances by exactly that row."""
+    from unimedvl_b200.cache import NaiveCache
+    eng, model, dims, vit_tf = stack
+    tok = FakeTokenizer()
+    L = dims.llm.layers
+
+    def context(prompt):
+        g, lens, rope = model.prepare_prompts([0], [0], [prompt], tok, TOK)
+        return model.forward_cache_update_text(NaiveCache(L), **g), lens, rope
+    ca, la, ra = context("a running request with some context")
+    cb_, lb, rb = context("another one, longer than the first request by a few tokens")
+    import copy
+    # plain decode: 2 steps from the start token
+    start = TOK["bos_token_id"]
+    fa, fb = copy.deepcopy(ca), copy.deepcopy(cb_)                        # forks: the originals stay at their prefill length
+    plain = eng.generate_text(fa._umv.seqs + fb._umv.seqs, [start, start], [ra[0], rb[0]], 2, return_next=True)
+    toks, nxt = plain[0].cpu(), plain[1].cpu()
+    # the same two steps as riders: step 1 on a text prefill of a third request, step 2 on an image-block prefill of a fourth
+    g, _, _ = model.prepare_prompts([0], [0], ["the newcomer's prompt"], tok, TOK)
+    riders = ([ca._umv.seqs[0], cb_._umv.seqs[0]], [start, start], [ra[0], rb[0]])
+    model.forward_cache_update_text(NaiveCache(L), **g, decode_riders=riders)
+    first = model.rider_tokens.cpu()
+    assert torch.equal(first, toks[1]), (first.tolist(), toks[1].tolist())
+    img = Image.fromarray(synth.synthetic_image(77, 70, 98))
+    g, _, _ = model.prepare_vit_images([0], [0], [img], vit_tf, TOK)
+    riders = (riders[0], first.tolist(), [ra[0] + 1, rb[0] + 1])
+    model.forward_cache_update_vit(NaiveCache(L), **g, decode_riders=riders)
+    assert torch.equal(model.rider_tokens.cpu(), nxt), (model.rider_tokens.tolist(), nxt.tolist())
+    assert ca._umv.lens() == [la[0] + 2] and cb_._umv.lens() == [lb[0] + 2]
 
 
 def test_admission_respects_the_page_pool(stack):

@@ -69,10 +69,15 @@ class FakeModel:
         n = [len(tokenizer.encode(p)) + 2 for p in prompts]
         return dict(n=n, prompts=prompts), [k + m for k, m in zip(curr_kvlens, n)], [r + m for r, m in zip(curr_rope, n)]
 
-    def forward_cache_update_text(self, cache, n, prompts):
+    def forward_cache_update_text(self, cache, n, prompts, decode_riders=None):
         seqs = cache._umv.seqs
         assert len(seqs) == len(n)
         self.prefill_batches.append(len(seqs))
+        if decode_riders is not None:           # mixed step: the running requests decode one token inside this prefill forward
+            rs, rt, rp = decode_riders
+            assert not set(rs) & set(seqs)
+            self.rider_tokens = self.engine.generate_text(rs, rt, rp, 1, return_next=True)[1]
+            self.rider_calls = getattr(self, "rider_calls", 0) + 1
         for s, m, p in zip(seqs, n, prompts):
             self.engine.seqs[s] += m
             if p.startswith("q"):
@@ -101,7 +106,13 @@ def test_every_request_gets_its_own_column_and_slots_are_reused():
         assert out[i].tolist() == _expected(i, n)
     assert max(len(c[0]) for c in eng.calls) == 3 and not eng.seqs          # never more than max_batch; everything freed
     assert cb.stats["admitted"] == 7 and cb.stats["slot_steps_used"] == sum(lens)
-    assert cb.stats["decode_steps"] <= sum(lens) + len(lens) * 3
+    assert cb.stats["decode_steps"] + cb.stats["rider_steps"] <= sum(lens) + len(lens) * 3
+    assert cb.stats["rider_steps"] > 0 and model.rider_calls > 0            # later admissions carried the running requests along
+    cb2, eng2, model2 = _batcher(max_batch=3, chunk=4, end_token_id=-1, mixed=False)
+    for i, n in enumerate(lens):
+        cb2.submit(prompt=f"q{i}", max_length=n)
+    out2 = cb2.run()
+    assert all(out2[i].tolist() == out[i].tolist() for i in out) and cb2.stats["rider_steps"] == 0
     assert len(model.prefill_batches) > 2 and model.prefill_batches[0] == 3   # first wave packed together, later waves refill
 
 

@@ -25,6 +25,11 @@ class Dims(C.Structure):
     ]
 
 
+class DecodeRiders(C.Structure):
+    _fields_ = [("n", C.c_int32), ("seqs", C.POINTER(C.c_int32)), ("tokens", C.POINTER(C.c_int64)), ("positions", C.POINTER(C.c_int32)),
+                ("temperature", C.c_float), ("seed", C.c_uint64), ("next_tokens", C.c_void_p)]
+
+
 class FlowArgs(C.Structure):
     _fields_ = [
         ("n_seqs", C.c_int32),
@@ -76,6 +81,8 @@ SIGNATURES = {
     "umv_vae_encode_moments": (C.c_int, [_P, _P, _I, _I, _I, _P, _P]),
     "umv_forward_cache_update_text": (C.c_int, [_P, _I, _IP, _IP, _LP, _IP, _P]),
     "umv_forward_cache_update_vit": (C.c_int, [_P, _I, _IP, _IP, _I, _LP, _IP, _P, _P, _I, _IP, _IP, _IP, _P]),
+    "umv_forward_cache_update_text_riders": (C.c_int, [_P, _I, _IP, _IP, _LP, _IP, C.POINTER(DecodeRiders), _P]),
+    "umv_forward_cache_update_vit_riders": (C.c_int, [_P, _I, _IP, _IP, _I, _LP, _IP, _P, _P, _I, _IP, _IP, _IP, C.POINTER(DecodeRiders), _P]),
     "umv_forward_cache_update_vae": (C.c_int, [_P, _I, _IP, _IP, _I, _LP, _IP, _P, _I, _I, _I, _IP, _I, _P, _IP, _F, _IP, _P]),
     "umv_vit_model": (C.c_int, [_P, _P, _P, _IP, _I, _P, _P]),
     "umv_connector": (C.c_int, [_P, _P, _I, _P, _P]),

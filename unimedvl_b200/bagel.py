@@ -192,25 +192,29 @@ class Bagel:
     # latent embeddings written at their packed rows) -- no torch index_put / permute / cat on the path.
     @torch.no_grad()
     def forward_cache_update_text(self, past_key_values, packed_text_ids, packed_text_position_ids, text_token_lens,
-                                  packed_text_indexes, packed_key_value_indexes, key_values_lens):
-        """bagel.py:412-458: embed -> LLM forward (mode und, causal) -> cache update."""
+                                  packed_text_indexes, packed_key_value_indexes, key_values_lens, decode_riders=None):
+        """bagel.py:412-458: embed -> LLM forward (mode und, causal) -> cache update.
+        `decode_riders` (extension): (seqs, tokens, positions) of running requests that decode one token
+        inside this same forward; their next tokens are left in ``self.rider_tokens`` (device i64)."""
         lens = self._ints(text_token_lens)
         h = paged_handle(past_key_values, self.engine, len(lens))
         self._check_kv(h, key_values_lens, packed_key_value_indexes, lens, packed_text_indexes, "forward_cache_update_text")
-        self.engine.forward_cache_update_text(h.seqs, lens, self._ints(packed_text_ids), self._ints(packed_text_position_ids))
+        self.rider_tokens = self.engine.forward_cache_update_text(h.seqs, lens, self._ints(packed_text_ids),
+                                                                  self._ints(packed_text_position_ids), riders=decode_riders)
         return past_key_values
 
     @torch.no_grad()
     def forward_cache_update_vit(self, past_key_values, packed_text_ids, packed_text_indexes, packed_vit_tokens,
                                  packed_vit_token_indexes, packed_vit_position_ids, vit_token_seqlens, packed_position_ids,
-                                 packed_seqlens, packed_indexes, packed_key_value_indexes, key_values_lens):
-        """bagel.py:523-615: markers + ViT/connector embeddings -> LLM forward (mode und, full attention)."""
+                                 packed_seqlens, packed_indexes, packed_key_value_indexes, key_values_lens, decode_riders=None):
+        """bagel.py:523-615: markers + ViT/connector embeddings -> LLM forward (mode und, full attention).  `decode_riders`: as in
+        forward_cache_update_text."""
         lens = self._ints(packed_seqlens)
         h = paged_handle(past_key_values, self.engine, len(lens))
         self._check_kv(h, key_values_lens, packed_key_value_indexes, lens, packed_indexes, "forward_cache_update_vit")
-        self.engine.forward_cache_update_vit(h.seqs, lens, self._ints(packed_text_ids), self._ints(packed_text_indexes),
-                                             packed_vit_tokens, packed_vit_position_ids, self._ints(vit_token_seqlens),
-                                             self._ints(packed_vit_token_indexes), self._ints(packed_position_ids))
+        self.rider_tokens = self.engine.forward_cache_update_vit(
+            h.seqs, lens, self._ints(packed_text_ids), self._ints(packed_text_indexes), packed_vit_tokens, packed_vit_position_ids,
+            self._ints(vit_token_seqlens), self._ints(packed_vit_token_indexes), self._ints(packed_position_ids), riders=decode_riders)
         return past_key_values
 
     @torch.no_grad()

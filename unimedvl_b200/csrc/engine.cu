@@ -1384,8 +1384,47 @@ int umv_time_embedder(umv_engine* e, const float* timesteps, int32_t n, void* ou
 }
 
 // ---- prefill drivers: one call per reference method, the packed query sequence is composed inside the engine
-int umv_forward_cache_update_text(umv_engine* e, int32_t n_seqs, const int32_t* seqs, const int32_t* text_lens,
-                                  const int64_t* text_ids, const int32_t* positions, void* stream) {
+}  // extern "C"
+
+// Decode riders (umv_decode_riders): running requests whose next token is computed by the SAME forward that prefills other requests'
+// blocks.  Their rows (one per rider: the embedding of its current token) are appended after the M prefill rows already composed in
+// e->h; after the forward their final hidden states go through lm_head and argmax / sampling.  A single query row sees its whole
+// context under either mask, so riders join causal (text) and full-attention (image block) prefills alike.
+static int run_with_riders(umv_engine* e, int M, int n_seqs, const int32_t* seqs, const int32_t* q_lens, const int32_t* positions,
+                           const uint8_t* row_is_gen, int is_causal, const umv_decode_riders* rd, cudaStream_t st) {
+    const int n = rd ? rd->n : 0;
+    if (n <= 0) return umv::llm_run(e, nullptr, n_seqs, seqs, q_lens, positions, row_is_gen, is_causal, 1, nullptr, st);
+    UMV_REQUIRE(rd->seqs && rd->tokens && rd->positions && rd->next_tokens && n <= 64, UMV_ERR_INVALID, "decode riders: bad argument (n <= 64)");
+    UMV_REQUIRE(M + n <= e->d.max_tokens, UMV_ERR_NOMEM, "prefill rows + decode riders (%d) > max_tokens %d", M + n, e->d.max_tokens);
+    const int D = e->d.hidden, V = e->d.vocab;
+    for (int i = 0; i < n; ++i) UMV_REQUIRE(rd->tokens[i] >= 0 && rd->tokens[i] < V, UMV_ERR_INVALID, "rider token id out of range");
+    MetaBuilder mb;
+    UMV_TRY(meta_begin(e, &mb, (size_t)n * 8 + 64));
+    int64_t* d_ids;
+    mb.put<int64_t>(rd->tokens, n, &d_ids);
+    UMV_TRY(meta_commit(e, &mb, st));
+    UMV_TRY(embed_rows(e->embed, d_ids, n, D, V, e->h + (size_t)M * D, st));
+    std::vector<int32_t> sq(seqs, seqs + n_seqs), ql(q_lens, q_lens + n_seqs), pos(positions, positions + M);
+    std::vector<uint8_t> gen;
+    if (row_is_gen) gen.assign(row_is_gen, row_is_gen + M);
+    for (int i = 0; i < n; ++i) {
+        sq.push_back(rd->seqs[i]);
+        ql.push_back(1);
+        pos.push_back(rd->positions[i]);
+        if (row_is_gen) gen.push_back(0);                    // a decode row is a text row: understanding expert
+    }
+    UMV_TRY(umv::llm_run(e, nullptr, n_seqs + n, sq.data(), ql.data(), pos.data(), row_is_gen ? gen.data() : nullptr, is_causal, 1, nullptr, st));
+    // final-normed hidden states of all rows are in e->xn; the riders' are the last n
+    UMV_TRY(lin(e, e->xn + (size_t)M * D, D, e->lm_head, nullptr, nullptr, e->logits, V, n, V, D, EPI_BF16, st));
+    if (rd->temperature > 0.f) return sample_rows(e->logits, n, V, rd->temperature, rd->seed, nullptr, rd->next_tokens, st);
+    return argmax_rows(e->logits, n, V, rd->next_tokens, st);
+}
+
+extern "C" {
+
+int umv_forward_cache_update_text_riders(umv_engine* e, int32_t n_seqs, const int32_t* seqs, const int32_t* text_lens,
+                                         const int64_t* text_ids, const int32_t* positions, const umv_decode_riders* riders,
+                                         void* stream) {
     UMV_REQUIRE(e && e->finalized, UMV_ERR_STATE, "engine not finalized");
     UMV_REQUIRE(seqs && text_lens && text_ids && positions && n_seqs > 0, UMV_ERR_INVALID, "umv_forward_cache_update_text: null/empty argument");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -1400,13 +1439,25 @@ int umv_forward_cache_update_text(umv_engine* e, int32_t n_seqs, const int32_t* 
     mb.put<int64_t>(text_ids, M, &d_ids);
     UMV_TRY(meta_commit(e, &mb, st));
     UMV_TRY(embed_rows(e->embed, d_ids, M, e->d.hidden, e->d.vocab, e->h, st));
-    return umv::llm_run(e, nullptr, n_seqs, seqs, text_lens, positions, nullptr, 1, 1, nullptr, st);
+    return run_with_riders(e, M, n_seqs, seqs, text_lens, positions, nullptr, 1, riders, st);
+}
+int umv_forward_cache_update_text(umv_engine* e, int32_t n_seqs, const int32_t* seqs, const int32_t* text_lens,
+                                  const int64_t* text_ids, const int32_t* positions, void* stream) {
+    return umv_forward_cache_update_text_riders(e, n_seqs, seqs, text_lens, text_ids, positions, nullptr, stream);
 }
 
 int umv_forward_cache_update_vit(umv_engine* e, int32_t n_seqs, const int32_t* seqs, const int32_t* seq_lens, int32_t n_text,
                                  const int64_t* text_ids, const int32_t* text_rows, const float* pixels, const int64_t* vit_pos_ids,
                                  int32_t n_images, const int32_t* vit_seqlens, const int32_t* vit_rows, const int32_t* positions,
                                  void* stream) {
+    return umv_forward_cache_update_vit_riders(e, n_seqs, seqs, seq_lens, n_text, text_ids, text_rows, pixels, vit_pos_ids, n_images,
+                                               vit_seqlens, vit_rows, positions, nullptr, stream);
+}
+int umv_forward_cache_update_vit_riders(umv_engine* e, int32_t n_seqs, const int32_t* seqs, const int32_t* seq_lens, int32_t n_text,
+                                        const int64_t* text_ids, const int32_t* text_rows, const float* pixels,
+                                        const int64_t* vit_pos_ids, int32_t n_images, const int32_t* vit_seqlens,
+                                        const int32_t* vit_rows, const int32_t* positions, const umv_decode_riders* riders,
+                                        void* stream) {
     UMV_REQUIRE(e && e->finalized, UMV_ERR_STATE, "engine not finalized");
     UMV_REQUIRE(seqs && seq_lens && text_ids && text_rows && vit_rows && positions && n_seqs > 0 && n_text >= 0, UMV_ERR_INVALID,
                 "umv_forward_cache_update_vit: null/empty argument");
@@ -1431,7 +1482,7 @@ int umv_forward_cache_update_vit(umv_engine* e, int32_t n_seqs, const int32_t* s
     UMV_TRY(meta_commit(e, &mb, st));
     UMV_TRY(scatter_add_rows(e->attn, e->vit_pos_embed, vit_pos_ids, d_vrows, e->h, N, D, st));      // + vit_pos_embed, to its rows
     UMV_TRY(embed_rows_scatter(e->embed, d_ids, d_trows, n_text, D, e->d.vocab, e->h, st));          // marker embeddings
-    return umv::llm_run(e, nullptr, n_seqs, seqs, seq_lens, positions, nullptr, 0, 1, nullptr, st);
+    return run_with_riders(e, M, n_seqs, seqs, seq_lens, positions, nullptr, 0, riders, st);
 }
 
 int umv_forward_cache_update_vae(umv_engine* e, int32_t n_seqs, const int32_t* seqs, const int32_t* seq_lens, int32_t n_text,

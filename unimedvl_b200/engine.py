@@ -302,22 +302,42 @@ class Engine:
         return out
 
     # ------------------------------------------------------------------ prefill drivers (one C call per reference method)
-    def forward_cache_update_text(self, seqs, text_lens, text_ids, positions) -> None:
-        """umv_forward_cache_update_text: host index lists in, KV pages updated."""
-        self._enter()
-        _lib.check(self.lib.umv_forward_cache_update_text(self.h, len(seqs), _lib.i32_array(seqs), _lib.i32_array(text_lens),
-                                                          _lib.i64_array(text_ids), _lib.i32_array(positions), _stream_ptr(self.stream)))
-        self._exit()
+    def _riders(self, riders, temperature: float, seed: int):
+        """riders = (seqs, tokens, positions) of running requests that decode ONE token inside this prefill forward
+        (umv_decode_riders).  Returns (struct or None, keep-alive list, device next-token tensor or None)."""
+        if not riders or not riders[0]:
+            return None, [], None
+        seqs, tokens, positions = riders
+        nxt = torch.empty((len(seqs),), dtype=torch.int64, device=self.device)
+        keep = [_lib.i32_array(seqs), _lib.i64_array(tokens), _lib.i32_array(positions)]
+        r = _lib.DecodeRiders()
+        r.n, r.seqs, r.tokens, r.positions = len(seqs), keep[0], keep[1], keep[2]
+        r.temperature, r.seed, r.next_tokens = float(temperature), int(seed), nxt.data_ptr()
+        return C.byref(r), keep + [r], nxt
 
-    def forward_cache_update_vit(self, seqs, seq_lens, text_ids, text_rows, pixels, vit_pos_ids, vit_seqlens, vit_rows, positions) -> None:
+    def forward_cache_update_text(self, seqs, text_lens, text_ids, positions, riders=None, temperature: float = 0.0, seed: int = 0):
+        """umv_forward_cache_update_text[_riders]: host index lists in, KV pages updated.  With `riders` returns their next tokens
+        (device i64 [n]): running requests decode one token inside the same packed forward."""
+        rd, keep, nxt = self._riders(riders, temperature, seed)
+        self._enter()
+        _lib.check(self.lib.umv_forward_cache_update_text_riders(self.h, len(seqs), _lib.i32_array(seqs), _lib.i32_array(text_lens),
+                                                                 _lib.i64_array(text_ids), _lib.i32_array(positions), rd,
+                                                                 _stream_ptr(self.stream)))
+        self._exit()
+        return nxt
+
+    def forward_cache_update_vit(self, seqs, seq_lens, text_ids, text_rows, pixels, vit_pos_ids, vit_seqlens, vit_rows, positions,
+                                 riders=None, temperature: float = 0.0, seed: int = 0):
         pixels = pixels.to(self.device, torch.float32, non_blocking=True).contiguous()
         vit_pos_ids = vit_pos_ids.to(self.device, torch.int64, non_blocking=True).contiguous()
+        rd, keep, nxt = self._riders(riders, temperature, seed)
         self._enter()
-        _lib.check(self.lib.umv_forward_cache_update_vit(
+        _lib.check(self.lib.umv_forward_cache_update_vit_riders(
             self.h, len(seqs), _lib.i32_array(seqs), _lib.i32_array(seq_lens), len(text_ids), _lib.i64_array(text_ids),
             _lib.i32_array(text_rows), _ptr(pixels), _ptr(vit_pos_ids), len(vit_seqlens), _lib.i32_array(vit_seqlens),
-            _lib.i32_array(vit_rows), _lib.i32_array(positions), _stream_ptr(self.stream)))
+            _lib.i32_array(vit_rows), _lib.i32_array(positions), rd, _stream_ptr(self.stream)))
         self._exit()
+        return nxt
 
     def forward_cache_update_vae(self, seqs, seq_lens, text_ids, text_rows, latent, latent_hw, patch, lat_pos_ids, lat_rows, timestep,
                                  positions) -> None:

@@ -12,7 +12,10 @@ between calls:
   * retirement -- a request ends at ITS OWN end token or length budget; its pages return to the pool and its slot is
     re-used by the next admission;
   * shared prefixes -- requests naming the same ``prefix`` (e.g. the think-mode system prompt, inferencer.py:574-577)
-    fork one prefilled sequence (ref-counted pages, copy-on-write tail) instead of prefilling it again.
+    fork one prefilled sequence (ref-counted pages, copy-on-write tail) instead of prefilling it again;
+  * mixed steps -- the admission forwards (image block, prompt) carry the running requests along as DECODE RIDERS
+    (``umv_decode_riders``): one query row per running request rides in the same packed forward, so decoding does not stop while
+    new requests are prefilled (``mixed=True``, the default).
 
 Samples are independent (SURVEY.md section 8a "Batching semantics verified"), so every request returns exactly the
 tokens ``Bagel.chat`` / ``generate_text`` would return for it alone (tests/test_scheduler_gpu.py).
@@ -65,11 +68,13 @@ class _Borrowed:
 
 class ContinuousBatcher:
     def __init__(self, model, tokenizer, new_token_ids: Dict[str, int], vit_transform, max_batch: int = 8, chunk: int = 16,
-                 end_token_id: Optional[int] = None, max_prefill_tokens: Optional[int] = None):
+                 end_token_id: Optional[int] = None, max_prefill_tokens: Optional[int] = None, mixed: bool = True):
         self.model, self.engine = model, model.engine
         self.tokenizer, self.tok, self.vit_transform = tokenizer, new_token_ids, vit_transform
         self.max_batch = min(max_batch, self.engine.max_seqs, 64)
         self.chunk = chunk
+        self.mixed = mixed
+        self._riding: List[Request] = []
         self.eos = new_token_ids["eos_token_id"] if end_token_id is None else end_token_id
         self.max_prefill_tokens = max_prefill_tokens or self.engine.max_tokens
         self.layers = model.config.llm_config.num_hidden_layers
@@ -79,7 +84,7 @@ class ContinuousBatcher:
         self._prefixes: Dict[str, tuple] = {}           # text -> (seq, kv_len, rope)
         self._next_id = 0
         self.capacity = self.engine.pages_free()
-        self.stats = {"prefill_calls": 0, "decode_calls": 0, "decode_steps": 0, "slot_steps_used": 0, "admitted": 0}
+        self.stats = {"prefill_calls": 0, "decode_calls": 0, "decode_steps": 0, "slot_steps_used": 0, "admitted": 0, "rider_steps": 0}
 
     # ------------------------------------------------------------------ public
     def submit(self, prompt: str, image=None, max_length: int = 128, prefix: Optional[str] = None) -> int:
@@ -169,15 +174,19 @@ class ContinuousBatcher:
         if with_img:
             g, lens, ropes = m.prepare_vit_images([r.kv_len for r in with_img], [r.rope for r in with_img],
                                                   [r.image for r in with_img], self.vit_transform, self.tok)
+            riders = self._riders(sum(lens) - sum(r.kv_len for r in with_img))
             with _Borrowed(self.engine, self.layers, [r.seq for r in with_img]) as c:
-                m.forward_cache_update_vit(c, **g)
+                m.forward_cache_update_vit(c, **g, decode_riders=riders)
+            self._riders_done(riders)
             for r, l, p in zip(with_img, lens, ropes):
                 r.kv_len, r.rope = l, p
             self.stats["prefill_calls"] += 1
         g, lens, ropes = m.prepare_prompts([r.kv_len for r in group], [r.rope for r in group], [r.prompt for r in group],
                                            self.tokenizer, self.tok)
+        riders = self._riders(sum(lens) - sum(r.kv_len for r in group))
         with _Borrowed(self.engine, self.layers, [r.seq for r in group]) as c:
-            m.forward_cache_update_text(c, **g)
+            m.forward_cache_update_text(c, **g, decode_riders=riders)
+        self._riders_done(riders)
         self.stats["prefill_calls"] += 1
         for r, l, p in zip(group, lens, ropes):
             r.kv_len, r.rope = l, p
@@ -186,6 +195,27 @@ class ContinuousBatcher:
         self.running.extend(group)
         self.stats["admitted"] += len(group)
 
+    # ------------------------------------------------------------------ mixed steps: running requests ride the admission forwards
+    def _riders(self, prefill_rows: int):
+        """(seqs, tokens, positions) of the running requests for ONE rider step, or None.  A request whose budget is exhausted does not
+        ride; the packed forward (prefill rows + riders) must fit the engine's workspace."""
+        if not self.mixed:
+            return None
+        run = [r for r in self.running if len(r.inputs) < r.max_length][:64]
+        if not run or prefill_rows + len(run) > self.engine.max_tokens:
+            return None
+        self._riding = run
+        return [r.seq for r in run], [r.next_token for r in run], [r.rope for r in run]
+
+    def _riders_done(self, riders) -> None:
+        if riders is None:
+            return
+        run, self._riding = self._riding, []
+        nxt = self.model.rider_tokens.cpu()
+        toks = torch.tensor([riders[1]], dtype=torch.int64)          # the tokens that were fed: one executed step per rider
+        self.stats["rider_steps"] += len(run)
+        self._advance(run, toks, nxt, 1)
+
     def _decode_chunk(self) -> List[int]:
         if not self.running:
             return []
@@ -193,10 +223,14 @@ class ContinuousBatcher:
         n = min(self.chunk, max(r.max_length - len(r.inputs) for r in run))
         toks, nxt = self.engine.generate_text([r.seq for r in run], [r.next_token for r in run], [r.rope for r in run], n,
                                               return_next=True)
-        toks, nxt = toks.cpu(), nxt.cpu()
-        computed = torch.cat([toks[1:], nxt[None]], dim=0)          # token computed by each executed step, per sample
         self.stats["decode_calls"] += 1
         self.stats["decode_steps"] += n * len(run)
+        return self._advance(run, toks.cpu(), nxt.cpu(), n)
+
+    def _advance(self, run: List[Request], toks: torch.Tensor, nxt: torch.Tensor, n: int) -> List[int]:
+        """Book-keeping after `n` executed decode steps of the requests `run`: toks [n, len(run)] the tokens fed, nxt the token the
+        last step computed.  Retires requests at their own end token / budget, returns the retired ids."""
+        computed = torch.cat([toks[1:], nxt[None]], dim=0)          # token computed by each executed step, per sample
         done: List[int] = []
         still: List[Request] = []
         for b, r in enumerate(run):
@@ -214,5 +248,6 @@ class ContinuousBatcher:
                 r.kv_len += n
                 r.rope += n
                 still.append(r)
-        self.running = still
+        gone = {id(r) for r in run} - {id(r) for r in still}
+        self.running = [r for r in self.running if id(r) not in gone]
         return done
