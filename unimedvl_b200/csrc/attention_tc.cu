@@ -292,7 +292,8 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         tc_fence_after();
         const float inv = lt > 0.f ? 1.f / lt : 0.f;
         const int odh = a.out_dh ? a.out_dh : HD;             // real head width of the output (padded-head callers: < 128)
-        bf16* dst = a.out + (size_t)(qs + t0 + (valid ? tok_l : 0)) * a.ldo + (kvh * G + (valid ? head_l : 0)) * odh + part * kKeys;
+        const int orow = qs + t0 + (valid ? tok_l : 0);
+        bf16* dst = a.out + (size_t)(a.out_row_map ? a.out_row_map[orow] : orow) * a.ldo + (kvh * G + (valid ? head_l : 0)) * odh + part * kKeys;
 #pragma unroll
         for (int c = 0; c < kKeys / 32; ++c) tmem_ld32(lane_base + kColO + part * kKeys + c * 32, *reinterpret_cast<uint32_t(*)[32]>(&r[c * 32]));
         tmem_ld_wait();

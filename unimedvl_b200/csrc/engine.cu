@@ -354,6 +354,8 @@ static int meta_commit(umv_engine* e, MetaBuilder* mb, cudaStream_t st) {
 struct LlmRun {
     int M = 0, n_seqs = 0, max_q_len = 0, max_kv_len = 0;
     bool causal = true, gen = false, weight_major = false;
+    bool seg = false;           // gen mode, segregated rows: [0, Mg) generation expert, [Mg, M) understanding expert (llm_run)
+    int Mg = 0;
     CallMeta m;
     AttnProbe* probe = nullptr;
 };
@@ -402,6 +404,11 @@ static int llm_layers(umv_engine* e, const LlmRun& r, bf16* out, cudaStream_t st
     const int E = r.gen ? 1 : 0;
     const bool partial = r.weight_major && !r.gen && e->use_splitk && e->gemm_impl != GEMM_SIMPLE;
     const int T = r.gen ? r.m.n_text : 0;
+    // segregated gen-mode rows (llm_run): each expert's linears run on its own contiguous slice -- the generation expert never touches
+    // the marker rows (256-row tiles stay full: 12 x 256 latent rows instead of 13 tiles for 3,096 packed rows) and the understanding
+    // expert's few rows need no gather / scatter
+    const bool seg = r.seg;
+    const int Mg = seg ? r.Mg : M;
     int pending_splits = 0;     // >0: e->ws holds split-K partials of the last residual-branch linear
 
     static const int attn_cluster_max = getenv("UMV_ATTN_CLUSTER") ? atoi(getenv("UMV_ATTN_CLUSTER")) : 8;
@@ -411,7 +418,7 @@ static int llm_layers(umv_engine* e, const LlmRun& r, bf16* out, cudaStream_t st
         a.h = e->h; a.M = M; a.D = D; a.eps = d.rms_eps; a.w0 = w0; a.w1 = w1 ? w1 : w0;
         a.row_sel = r.gen ? r.m.row_sel : nullptr;
         a.y = y;
-        if (T > 0 && y == e->xn) { a.y2 = e->xt; a.row_slot = r.m.text_slot; }     // text rows also land gathered in xt
+        if (T > 0 && y == e->xn && !seg) { a.y2 = e->xt; a.row_slot = r.m.text_slot; }     // text rows also land gathered in xt
         if (pending_splits > 0) { a.partial = e->ws; a.splits = pending_splits; }
         pending_splits = 0;
         return add_rmsnorm(a, st);
@@ -454,6 +461,7 @@ static int llm_layers(umv_engine* e, const LlmRun& r, bf16* out, cudaStream_t st
             return decode_attention(da, st);
         }
         ra.q_out = e->qkv; ra.ldq = QN;
+        if (seg) { ra.q_out = e->act; ra.ldq = H * dh; ra.q_row_map = r.m.seg_to_packed; }    // queries to their packed rows (e->act is idle here)
         ra.positions = r.m.positions; ra.row_seq = r.m.row_seq; ra.row_kvpos = r.m.row_kvpos;
         ra.page_table = r.m.page_table; ra.max_pages = r.m.max_pages; ra.inv_freq = e->inv_freq; ra.rope_cs = r.m.rope_cs;
         ra.qn0 = L.qn[0]; ra.kn0 = L.kn[0]; ra.qn1 = L.qn[E]; ra.kn1 = L.kn[E];
@@ -461,7 +469,8 @@ static int llm_layers(umv_engine* e, const LlmRun& r, bf16* out, cudaStream_t st
         ra.pool = e->pool; ra.layer = li; ra.M = M; ra.H = H; ra.Hkv = Hkv; ra.dh = dh; ra.eps = d.rms_eps;
         UMV_TRY(rope_append(ra, st));
         AttnArgs aa;
-        aa.q = e->qkv; aa.ldq = QN; aa.out = e->attn; aa.ldo = D;
+        aa.q = ra.q_out; aa.ldq = ra.ldq; aa.out = e->attn; aa.ldo = D;
+        aa.out_row_map = seg ? r.m.packed_to_seg : nullptr;
         aa.paged = 1; aa.pool = e->pool; aa.layer = li; aa.page_table = r.m.page_table; aa.max_pages = r.m.max_pages;
         aa.q_start = r.m.q_start; aa.q_len = r.m.q_len; aa.kv_len = r.m.kv_len;
         aa.n = r.n_seqs; aa.H = H; aa.Hkv = Hkv; aa.dh = dh; aa.causal = r.causal ? 1 : 0;
@@ -498,8 +507,10 @@ static int llm_layers(umv_engine* e, const LlmRun& r, bf16* out, cudaStream_t st
             UMV_TRY(lin(e, e->xn, D, L.wqkv[0], nullptr, nullptr, nullptr, 0, M, QN, D, EPI_PARTIAL, st, GEMM_WEIGHT_MAJOR, e->ws, s));
             ra.partial = e->ws; ra.splits = s; ra.bias = L.bqkv[0];
         } else {
-            UMV_TRY(lin(e, e->xn, D, L.wqkv[E], L.bqkv[E], nullptr, e->qkv, QN, M, QN, D, EPI_BF16, st));
-            if (T > 0) {      // xt = text rows of xn (written by the norm kernel)
+            UMV_TRY(lin(e, e->xn, D, L.wqkv[E], L.bqkv[E], nullptr, e->qkv, QN, Mg, QN, D, EPI_BF16, st));
+            if (T > 0 && seg) {
+                UMV_TRY(lin(e, e->xn + (size_t)Mg * D, D, L.wqkv[0], L.bqkv[0], nullptr, e->qkv + (size_t)Mg * QN, QN, T, QN, D, EPI_BF16, st));
+            } else if (T > 0) {      // xt = text rows of xn (written by the norm kernel)
                 UMV_TRY(lin(e, e->xt, D, L.wqkv[0], L.bqkv[0], nullptr, e->yt, QN, T, QN, D, EPI_BF16, st));
                 UMV_TRY(copy_rows(e->yt, QN, r.m.text_rows, e->qkv, QN, T, QN, 1, st));
             }
@@ -512,27 +523,34 @@ static int llm_layers(umv_engine* e, const LlmRun& r, bf16* out, cudaStream_t st
             UMV_TRY(lin(e, e->attn, D, L.wo[0], nullptr, nullptr, nullptr, 0, M, D, D, EPI_PARTIAL, st, GEMM_WEIGHT_MAJOR, e->ws, s));
             pending_splits = s;
         } else {
-            if (T > 0) {
+            bf16* ht = e->h + (size_t)Mg * D;       // segregated: the understanding-expert rows of the residual stream
+            if (T > 0 && seg) {
+                UMV_TRY(lin(e, e->attn + (size_t)Mg * D, D, L.wo[0], nullptr, ht, ht, D, T, D, D, EPI_RESID, st));
+            } else if (T > 0) {
                 UMV_TRY(copy_rows(e->attn, D, r.m.text_rows, e->xt, D, T, D, 0, st));
                 UMV_TRY(lin(e, e->xt, D, L.wo[0], nullptr, e->h, e->yt, D, T, D, D, EPI_RESID, st, 0, nullptr, 1, 0, r.m.text_rows, e->ht));
             }
-            UMV_TRY(lin(e, e->attn, D, L.wo[E], nullptr, e->h, e->h, D, M, D, D, EPI_RESID, st));
-            if (T > 0) UMV_TRY(copy_rows(e->yt, D, r.m.text_rows, e->h, D, T, D, 1, st));
+            UMV_TRY(lin(e, e->attn, D, L.wo[E], nullptr, e->h, e->h, D, Mg, D, D, EPI_RESID, st));
+            if (T > 0 && !seg) UMV_TRY(copy_rows(e->yt, D, r.m.text_rows, e->h, D, T, D, 1, st));
         }
         UMV_TRY(norm(L.ln2[0], L.ln2[1], e->xn));
         // ---- SwiGLU MLP + residual
-        if (T > 0) {
+        if (T > 0 && seg) {
+            bf16* ht = e->h + (size_t)Mg * D;
+            UMV_TRY(lin(e, e->xn + (size_t)Mg * D, D, L.wgu[0], nullptr, nullptr, e->act + (size_t)Mg * I, I, T, 2 * I, D, EPI_SWIGLU, st));
+            UMV_TRY(lin(e, e->act + (size_t)Mg * I, I, L.wdown[0], nullptr, ht, ht, D, T, D, I, EPI_RESID, st));
+        } else if (T > 0) {
             UMV_TRY(lin(e, e->xt, D, L.wgu[0], nullptr, nullptr, e->actt, I, T, 2 * I, D, EPI_SWIGLU, st));
             UMV_TRY(lin(e, e->actt, I, L.wdown[0], nullptr, e->h, e->yt, D, T, D, I, EPI_RESID, st, 0, nullptr, 1, 0, r.m.text_rows, e->ht));
         }
-        UMV_TRY(lin(e, e->xn, D, L.wgu[E], nullptr, nullptr, e->act, I, M, 2 * I, D, EPI_SWIGLU, st));
+        UMV_TRY(lin(e, e->xn, D, L.wgu[E], nullptr, nullptr, e->act, I, Mg, 2 * I, D, EPI_SWIGLU, st));
         if (partial) {
             const int s = pick_splits(D, I, e->sm_count);
             UMV_TRY(lin(e, e->act, I, L.wdown[0], nullptr, nullptr, nullptr, 0, M, D, I, EPI_PARTIAL, st, GEMM_WEIGHT_MAJOR, e->ws, s));
             pending_splits = s;
         } else {
-            UMV_TRY(lin(e, e->act, I, L.wdown[E], nullptr, e->h, e->h, D, M, D, I, EPI_RESID, st));
-            if (T > 0) UMV_TRY(copy_rows(e->yt, D, r.m.text_rows, e->h, D, T, D, 1, st));
+            UMV_TRY(lin(e, e->act, I, L.wdown[E], nullptr, e->h, e->h, D, Mg, D, I, EPI_RESID, st));
+            if (T > 0 && !seg) UMV_TRY(copy_rows(e->yt, D, r.m.text_rows, e->h, D, T, D, 1, st));
         }
     }
     // final norm (norm / norm_moe_gen, qwen2_navit.py:1162-1169); also folds the last down-proj partials
@@ -884,16 +902,29 @@ int umv_llm_forward(umv_engine* e, const void* x, int32_t n_seqs, const int32_t*
 }  // extern "C"
 
 namespace umv {
-// Packed forward over n_seqs sequences; x == nullptr means the packed query sequence is already in e->h.
+bool gen_rows_segregate(int n_seqs, const int32_t* q_lens, const uint8_t* row_is_gen, int is_causal, int* n_gen) {
+    if (n_gen) *n_gen = 0;
+    if (!row_is_gen || is_causal) return false;
+    const char* env = getenv("UMV_GEN_SEG");              // read per call: tests switch layouts inside one process
+    if (env && atoi(env) == 0) return false;
+    int M = 0, ng = 0;
+    for (int b = 0; b < n_seqs; ++b) M += q_lens[b];
+    for (int i = 0; i < M; ++i) ng += row_is_gen[i] ? 1 : 0;
+    const int nt = M - ng;
+    if (n_gen) *n_gen = ng;
+    return ng > 0 && nt > 0;
+}
+
+// Packed forward over n_seqs sequences; x == nullptr means the packed query sequence is already in e->h (presegregated: in the
+// segregated row order of gen_rows_segregate, and `out` is wanted in that order too -- the flow step composes and consumes it so).
 int llm_run(umv_engine* e, const bf16* x, int n_seqs, const int32_t* seqs, const int32_t* q_lens, const int32_t* positions,
-            const uint8_t* row_is_gen, int is_causal, int update_kv, bf16* out, cudaStream_t st, AttnProbe* probe) {
+            const uint8_t* row_is_gen, int is_causal, int update_kv, bf16* out, cudaStream_t st, AttnProbe* probe, int presegregated) {
     UMV_REQUIRE(seqs && q_lens && positions && n_seqs > 0, UMV_ERR_INVALID, "umv_llm_forward: null/empty argument");
     UMV_REQUIRE(n_seqs <= 3 * e->d.max_seqs, UMV_ERR_INVALID, "umv_llm_forward: %d sequences > 3*max_seqs", n_seqs);
     UMV_REQUIRE(!row_is_gen || e->d.enable_gen, UMV_ERR_STATE, "generation expert weights were not enabled");
     const int D = e->d.hidden;
     LlmRun r;
     r.probe = probe;
-    r.n_seqs = n_seqs;
     r.causal = is_causal != 0;
     r.gen = row_is_gen != nullptr;
     int M = 0;
@@ -903,6 +934,8 @@ int llm_run(umv_engine* e, const bf16* x, int n_seqs, const int32_t* seqs, const
     }
     UMV_REQUIRE(M <= e->d.max_tokens, UMV_ERR_NOMEM, "umv_llm_forward: %d tokens > max_tokens %d", M, e->d.max_tokens);
     r.M = M;
+    r.seg = !probe && e->d.heads * e->dh <= e->w_act && gen_rows_segregate(n_seqs, q_lens, row_is_gen, is_causal, &r.Mg);
+    UMV_REQUIRE(!presegregated || r.seg, UMV_ERR_STATE, "llm_run: rows were laid out segregated but the forward is not");
     // reserve pages, gather geometry
     int max_pages = 0;
     std::vector<Seq*> sq(n_seqs);
@@ -912,33 +945,58 @@ int llm_run(umv_engine* e, const bf16* x, int n_seqs, const int32_t* seqs, const
         for (int c = 0; c < b; ++c) UMV_REQUIRE(seqs[c] != seqs[b], UMV_ERR_INVALID, "sequence %d appears twice in one call", seqs[b]);
         UMV_TRY(seq_reserve(e, sq[b], sq[b]->len + q_lens[b], st));
         max_pages = std::max(max_pages, (int)sq[b]->pages.size());
-        r.max_q_len = std::max(r.max_q_len, q_lens[b]);
         r.max_kv_len = std::max(r.max_kv_len, sq[b]->len + q_lens[b]);
     }
+    // Segregated rows: the LINEARS and norms see [generation rows of every sample | marker rows]; ATTENTION keeps the packed order
+    // (one contiguous query range per sample, so the 128-row query tiles stay as full as the reference's packing makes them): the
+    // q/k-norm + RoPE kernel writes the rotated queries to their packed rows of a separate buffer, the attention kernels store each
+    // row's output to its segregated row.  The cache keeps the packed order either way.
+    std::vector<int> order, inverse;             // segregated: new row -> packed row, packed row -> new row
+    if (r.seg) {
+        order.reserve(M);
+        for (int pass = 1; pass >= 0; --pass)    // generation rows first
+            for (int i = 0; i < M; ++i)
+                if ((row_is_gen[i] != 0) == (pass == 1)) order.push_back(i);
+        inverse.resize(M);
+        for (int i = 0; i < M; ++i) inverse[order[i]] = i;
+    }
+    r.n_seqs = n_seqs;
+    for (int b = 0; b < n_seqs; ++b) r.max_q_len = std::max(r.max_q_len, q_lens[b]);
     MetaBuilder mb;
-    UMV_TRY(meta_begin(e, &mb, (size_t)(n_seqs * 16 + 64) + (size_t)M * 24 + (size_t)n_seqs * max_pages * 4));
+    UMV_TRY(meta_begin(e, &mb, (size_t)(n_seqs * 16 + 64) + (size_t)M * 32 + (size_t)n_seqs * max_pages * 4));
     CallMeta& m = r.m;
     m.max_pages = max_pages;
     int* hq = mb.put<int>(nullptr, n_seqs + 1, &m.q_start);
     int* hql = mb.put<int>(nullptr, n_seqs, &m.q_len);
     int* hkl = mb.put<int>(nullptr, n_seqs, &m.kv_len);
-    mb.put<int>(positions, M, &m.positions);
+    int* hpos = mb.put<int>(r.seg ? nullptr : positions, M, &m.positions);
     int* hrs = mb.put<int>(nullptr, M, &m.row_seq);
     int* hrp = mb.put<int>(nullptr, M, &m.row_kvpos);
     int* hpt = mb.put<int>(nullptr, (size_t)n_seqs * max_pages, &m.page_table);
+    if (r.seg) {
+        mb.put<int>(order.data(), M, &m.seg_to_packed);
+        mb.put<int>(inverse.data(), M, &m.packed_to_seg);
+    }
     int row = 0;
     hq[0] = 0;
     for (int b = 0; b < n_seqs; ++b) {
         hql[b] = q_lens[b];
         hkl[b] = sq[b]->len + q_lens[b];
         for (int j = 0; j < q_lens[b]; ++j, ++row) {
-            hrs[row] = b;
-            hrp[row] = sq[b]->len + j;
+            const int at = r.seg ? inverse[row] : row;     // where the per-row metadata of packed row `row` lives
+            hrs[at] = b;
+            hrp[at] = sq[b]->len + j;
+            if (r.seg) hpos[at] = positions[row];
         }
         hq[b + 1] = row;
         for (int p = 0; p < max_pages; ++p) hpt[(size_t)b * max_pages + p] = p < (int)sq[b]->pages.size() ? sq[b]->pages[p] : 0;
     }
-    if (r.gen) {
+    if (r.gen && r.seg) {
+        std::vector<uint8_t> sel(M, 0);
+        std::fill(sel.begin(), sel.begin() + r.Mg, 1);
+        mb.put<uint8_t>(sel.data(), M, &m.row_sel);
+        m.n_text = M - r.Mg;
+    } else if (r.gen) {
         std::vector<int> text;
         for (int i = 0; i < M; ++i)
             if (!row_is_gen[i]) text.push_back(i);
@@ -952,11 +1010,25 @@ int llm_run(umv_engine* e, const bf16* x, int n_seqs, const int32_t* seqs, const
         mb.put<int>(slot.data(), M, &m.text_slot);
     }
     UMV_TRY(meta_commit(e, &mb, st));
-    if (x) UMV_CUDA_OK(cudaMemcpy2DAsync(e->h, (size_t)D * 2, x, (size_t)D * 2, (size_t)D * 2, M, cudaMemcpyDeviceToDevice, st));
+    if (r.seg && !presegregated) {               // packed rows -> segregated rows, once per forward
+        if (x) {
+            UMV_TRY(copy_rows(x, D, m.seg_to_packed, e->h, D, M, D, 0, st));
+        } else {
+            UMV_TRY(copy_rows(e->h, D, m.seg_to_packed, e->act, D, M, D, 0, st));
+            UMV_CUDA_OK(cudaMemcpyAsync(e->h, e->act, (size_t)M * D * 2, cudaMemcpyDeviceToDevice, st));
+        }
+    } else if (x) {
+        UMV_CUDA_OK(cudaMemcpy2DAsync(e->h, (size_t)D * 2, x, (size_t)D * 2, (size_t)D * 2, M, cudaMemcpyDeviceToDevice, st));
+    }
     r.weight_major = M <= 64;
     UMV_TRY(rope_table(m.positions, e->inv_freq, M, e->dh, e->rope_tab, st));
     r.m.rope_cs = e->rope_tab;
-    UMV_TRY(llm_layers(e, r, out, st));
+    if (r.seg && !presegregated && out) {        // final norm into a dead workspace, then back to the caller's packed order
+        UMV_TRY(llm_layers(e, r, e->act, st));
+        UMV_TRY(copy_rows(e->act, D, m.seg_to_packed, out, D, M, D, 1, st));
+    } else {
+        UMV_TRY(llm_layers(e, r, out, st));
+    }
     if (update_kv)
         for (int b = 0; b < n_seqs; ++b) sq[b]->len += q_lens[b];
     return UMV_OK;
@@ -1290,9 +1362,28 @@ int umv_flow_velocity(umv_engine* e, const umv_flow_args* a, const float* x_t, f
     const int nb = 1 + (has_text ? 1 : 0) + (has_img ? 1 : 0);
     UMV_REQUIRE(nb * Mb <= d.max_tokens, UMV_ERR_NOMEM, "flow step needs %d rows > max_tokens %d", nb * Mb, d.max_tokens);
     // the reference evaluates cfg_img only inside the cfg_text branch (bagel.py:1173-1207): img without text is ignored
-    // per-image geometry
+    // branch / sample / row geometry of the one packed gen-mode forward over all branches (rows are independent; contexts and rope
+    // positions differ per branch)
+    std::vector<int32_t> seqs, qlens, pos;
+    std::vector<uint8_t> is_gen;
+    const int32_t* bseq[3] = {a->seqs, nullptr, nullptr};
+    const int32_t* bpos[3] = {a->positions, nullptr, nullptr};
+    if (has_text) { bseq[text_branch] = a->cfg_text_seqs; bpos[text_branch] = a->cfg_text_positions; }
+    if (has_img) { bseq[img_branch] = a->cfg_img_seqs; bpos[img_branch] = a->cfg_img_positions; }
+    for (int br = 0; br < nb; ++br)
+        for (int b = 0; b < B; ++b) {
+            seqs.push_back(bseq[br][b]);
+            qlens.push_back(a->lat_lens[b] + 2);
+            for (int j = 0; j < a->lat_lens[b] + 2; ++j) {
+                pos.push_back(bpos[br][b]);
+                is_gen.push_back(j > 0 && j < a->lat_lens[b] + 1 ? 1 : 0);
+            }
+        }
+    // the forward's segregated row order (llm_run): latent rows of every branch first, then the marker rows; flow_compose writes it directly
+    int n_gen_rows = 0;
+    const bool seg = gen_rows_segregate(nb * B, qlens.data(), is_gen.data(), 0, &n_gen_rows);
     MetaBuilder mb;
-    UMV_TRY(meta_begin(e, &mb, (size_t)Mb * 4 + (size_t)B * 16 + 64));
+    UMV_TRY(meta_begin(e, &mb, (size_t)Mb * 4 + (size_t)B * 16 + 64 + (seg ? (size_t)nb * Mb * 4 : 0)));
     int *d_row_src, *d_row0, *d_lat0, *d_n;
     int* h_src = mb.put<int>(nullptr, Mb, &d_row_src);
     int* h_row0 = mb.put<int>(nullptr, B, &d_row0);
@@ -1305,6 +1396,12 @@ int umv_flow_velocity(umv_engine* e, const umv_flow_args* a, const float* x_t, f
         h_lat0[b] = l;
         for (int j = 0; j < a->lat_lens[b]; ++j) h_src[r++] = l++;
         h_src[r++] = -2;
+    }
+    int* d_row_dst = nullptr;
+    if (seg) {
+        int* h_dst = mb.put<int>(nullptr, (size_t)nb * Mb, &d_row_dst);
+        int ig = 0, it = n_gen_rows;
+        for (int i = 0; i < nb * Mb; ++i) h_dst[i] = is_gen[i] ? ig++ : it++;
     }
     UMV_TRY(meta_commit(e, &mb, st));
     // 1. vae2llm(x_t): fp32 latents enter the autocast Linear as bf16
@@ -1324,31 +1421,17 @@ int umv_flow_velocity(umv_engine* e, const umv_flow_args* a, const float* x_t, f
     UMV_REQUIRE(a->marker_ids[0] >= 0 && a->marker_ids[0] < d.vocab && a->marker_ids[1] >= 0 && a->marker_ids[1] < d.vocab,
                 UMV_ERR_INVALID, "marker token id out of range");
     UMV_TRY(flow_compose(lat, temb, e->latent_pos, a->lat_pos_ids, e->embed, a->marker_ids[0], a->marker_ids[1], d_row_src, Mb, nb,
-                         D, e->h, st));
-    // 4. one packed gen-mode forward over all branches (rows are independent; contexts / rope positions differ)
-    std::vector<int32_t> seqs, qlens, pos;
-    std::vector<uint8_t> is_gen;
-    const int32_t* bseq[3] = {a->seqs, nullptr, nullptr};
-    const int32_t* bpos[3] = {a->positions, nullptr, nullptr};
-    if (has_text) { bseq[text_branch] = a->cfg_text_seqs; bpos[text_branch] = a->cfg_text_positions; }
-    if (has_img) { bseq[img_branch] = a->cfg_img_seqs; bpos[img_branch] = a->cfg_img_positions; }
-    for (int br = 0; br < nb; ++br)
-        for (int b = 0; b < B; ++b) {
-            seqs.push_back(bseq[br][b]);
-            qlens.push_back(a->lat_lens[b] + 2);
-            for (int j = 0; j < a->lat_lens[b] + 2; ++j) {
-                pos.push_back(bpos[br][b]);
-                is_gen.push_back(j > 0 && j < a->lat_lens[b] + 1 ? 1 : 0);
-            }
-        }
-    UMV_TRY(llm_run(e, nullptr, nb * B, seqs.data(), qlens.data(), pos.data(), is_gen.data(), 0, 0, e->xn, st));
-    // 5. llm2vae on every row, then CFG on the latent rows
+                         D, e->h, st, d_row_dst));
+    // 4. one packed gen-mode forward over all branches
+    UMV_TRY(llm_run(e, nullptr, nb * B, seqs.data(), qlens.data(), pos.data(), is_gen.data(), 0, 0, e->xn, st, nullptr, seg ? 1 : 0));
+    // 5. llm2vae (segregated: on the latent rows only; else on every row), then CFG on the latent rows
     bf16* vall = e->qkv;
-    UMV_TRY(lin(e, e->xn, D, e->llm2vae_w, e->llm2vae_b, nullptr, vall, C, nb * Mb, C, D, EPI_BF16, st));
+    const int rows_per_branch = seg ? n_lat : Mb;
+    UMV_TRY(lin(e, e->xn, D, e->llm2vae_w, e->llm2vae_b, nullptr, vall, C, nb * rows_per_branch, C, D, EPI_BF16, st));
     CfgArgs c;
-    c.v = vall; c.rows_per_branch = Mb; c.C = C; c.text_branch = text_branch; c.img_branch = has_text ? img_branch : -1;
+    c.v = vall; c.rows_per_branch = rows_per_branch; c.C = C; c.text_branch = text_branch; c.img_branch = has_text ? img_branch : -1;
     c.text_scale = a->cfg_text_scale; c.img_scale = a->cfg_img_scale; c.renorm_min = a->cfg_renorm_min;
-    c.renorm_type = a->renorm_type; c.img_row0 = d_row0; c.img_lat0 = d_lat0; c.img_n = d_n; c.out = v_out;
+    c.renorm_type = a->renorm_type; c.img_row0 = seg ? d_lat0 : d_row0; c.img_lat0 = d_lat0; c.img_n = d_n; c.out = v_out;
     return cfg_combine(c, B, st);
 }
 

@@ -52,6 +52,8 @@ struct CallMeta {
     int* text_rows = nullptr;   // [T] rows routed to the understanding expert (gen mode)
     int* text_slot = nullptr;   // [M] inverse map: index into text_rows, or -1
     uint8_t* row_sel = nullptr; // [M]
+    int* seg_to_packed = nullptr;     // [M] segregated gen-mode rows (llm_run): packed row of segregated row i ...
+    int* packed_to_seg = nullptr;     // [M] ... and the inverse
     const float* rope_cs = nullptr;   // decode loop: per-step cos | sin table [n][dh]
     int max_pages = 0, n_text = 0;
 };
@@ -97,7 +99,12 @@ struct AttnProbe {
     int path = 0;                     // out: 1 mma.sync, 2 tcgen05, 3 fused decode cluster kernel
 };
 int llm_run(umv_engine* e, const bf16* x, int n_seqs, const int32_t* seqs, const int32_t* q_lens, const int32_t* positions,
-            const uint8_t* row_is_gen, int is_causal, int update_kv, bf16* out, cudaStream_t st, AttnProbe* probe = nullptr);
+            const uint8_t* row_is_gen, int is_causal, int update_kv, bf16* out, cudaStream_t st, AttnProbe* probe = nullptr,
+            int presegregated = 0);
+// A non-causal gen-mode forward runs on SEGREGATED rows: the generation-expert rows of all samples first (packed order), then the
+// understanding-expert (marker) rows.  True when llm_run will use that layout for these arguments (a full-mask forward with rows of both
+// kinds; UMV_GEN_SEG=0 switches it off); *n_gen = generation rows.
+bool gen_rows_segregate(int n_seqs, const int32_t* q_lens, const uint8_t* row_is_gen, int is_causal, int* n_gen);
 }  // namespace umv
 
 struct umv_engine {

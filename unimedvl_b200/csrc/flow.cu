@@ -54,13 +54,13 @@ int silu_inplace(bf16* x, int n, cudaStream_t s) {
 // row_src[r] >= 0: latent token -> bf16(bf16(lat + t_emb) + pos_table[pos_id]);  -1 / -2: start / end marker embedding.
 __global__ void flow_compose_kernel(const bf16* __restrict__ lat, const bf16* __restrict__ temb, const bf16* __restrict__ pos_table,
                                     const int64_t* __restrict__ pos_ids, const bf16* __restrict__ embed, int64_t id_start,
-                                    int64_t id_end, const int* __restrict__ row_src, int rows_per_branch, int D,
-                                    bf16* __restrict__ out) {
+                                    int64_t id_end, const int* __restrict__ row_src, const int* __restrict__ row_dst,
+                                    int rows_per_branch, int D, bf16* __restrict__ out) {
     pdl_launch_dependents();
     pdl_wait();
     const int r = blockIdx.x;
     const int src = row_src[r % rows_per_branch];
-    bf16* dst = out + (size_t)r * D;
+    bf16* dst = out + (size_t)(row_dst ? row_dst[r] : r) * D;      // row_dst: the forward's segregated row order (llm_run)
     if (src < 0) {
         const bf16* e = embed + (size_t)(src == -1 ? id_start : id_end) * D;
         for (int c = threadIdx.x; c < D / 8; c += blockDim.x) stg16(dst + c * 8, ldg16(e + c * 8));
@@ -82,9 +82,9 @@ __global__ void flow_compose_kernel(const bf16* __restrict__ lat, const bf16* __
 }
 int flow_compose(const bf16* lat, const bf16* temb, const bf16* pos_table, const int64_t* pos_ids, const bf16* embed,
                  int64_t id_start, int64_t id_end, const int* row_src, int rows_per_branch, int branches, int D, bf16* out,
-                 cudaStream_t s) {
+                 cudaStream_t s, const int* row_dst) {
     launch_k(flow_compose_kernel, dim3(rows_per_branch * branches), dim3(128), 0, s, lat, temb, pos_table, pos_ids, embed,
-             id_start, id_end, row_src, rows_per_branch, D, out);
+             id_start, id_end, row_src, row_dst, rows_per_branch, D, out);
     UMV_LAUNCH_CHECK("flow_compose_kernel");
     return UMV_OK;
 }

@@ -588,7 +588,7 @@ __global__ void __launch_bounds__(kRopeWarps * 32, 8) rope_append_kernel(RopeApp
         }
         const uint2 packed = make_uint2(pack2(o[0], o[1]), pack2(o[2], o[3]));
         if (is_q) {
-            *reinterpret_cast<uint2*>(a.q_out + (size_t)row * a.ldq + col) = packed;
+            *reinterpret_cast<uint2*>(a.q_out + (size_t)(a.q_row_map ? a.q_row_map[row] : row) * a.ldq + col) = packed;
         } else {
             const int kv = is_v ? 1 : 0;
             const int head = slot - a.H - (is_v ? a.Hkv : 0);
@@ -734,7 +734,7 @@ __global__ void __launch_bounds__(kRopeWarps * 32, 8) rope_append_rows_kernel(Ro
             if (!valid) continue;
             const U4 outv = is_v ? raw[i] : U4{o2[0], o2[1], o2[2], o2[3]};
             if (is_q) {
-                stg16(a.q_out + (size_t)row * a.ldq + slot * 128 + sub * 8, outv);
+                stg16(a.q_out + (size_t)(a.q_row_map ? a.q_row_map[row] : row) * a.ldq + slot * 128 + sub * 8, outv);
             } else {
                 const int kv = is_v ? 1 : 0;
                 const int head = slot - a.H - (is_v ? a.Hkv : 0);

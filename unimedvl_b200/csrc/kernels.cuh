@@ -52,6 +52,7 @@ struct RopeAppendArgs {
     const bf16* bias = nullptr;      // used with `partial`
     bf16* q_out = nullptr;           // [M, ldq] rotated queries (may alias qkv)
     int ldq = 0;
+    const int* q_row_map = nullptr;  // optional: the queries of row m land in row q_row_map[m] of q_out (which must then NOT alias qkv)
     const int* positions = nullptr;  // [M] rope position per row
     const int* row_seq = nullptr;    // [M] index into the page table rows
     const int* row_kvpos = nullptr;  // [M] absolute KV slot of the row within its sequence
@@ -77,6 +78,7 @@ int rope_table(const int* positions, const float* inv_freq, int M, int dh, float
 struct AttnArgs {
     const bf16* q = nullptr; int ldq = 0;     // row (token) stride in elements; head h at column h*dh
     bf16* out = nullptr; int ldo = 0;
+    const int* out_row_map = nullptr;         // optional: the output of query row m lands in row out_row_map[m] of out
     // un-paged K/V (ViT, op-level): [Tk, Hkv, dh] with row strides
     const bf16* k = nullptr; const bf16* v = nullptr; int ldk = 0, ldv = 0;
     // paged K/V (LLM)
@@ -154,7 +156,7 @@ int timestep_freq(float t, const float* freqs, int half, bf16* out, cudaStream_t
 int silu_inplace(bf16* x, int n, cudaStream_t s);
 int flow_compose(const bf16* lat, const bf16* temb, const bf16* pos_table, const int64_t* pos_ids, const bf16* embed,
                  int64_t id_start, int64_t id_end, const int* row_src, int rows_per_branch, int branches, int D, bf16* out,
-                 cudaStream_t s);
+                 cudaStream_t s, const int* row_dst = nullptr);
 int cfg_combine(const CfgArgs& a, int n_images, cudaStream_t s);
 int euler_step(float* x, const float* v, int64_t n, float dt, int v_is_bf16, cudaStream_t s);
 
