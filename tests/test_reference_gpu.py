@@ -270,7 +270,7 @@ def test_wide_oracle_cuda_semantics_pinned(wide):
             s = ulp_stats((oc.key if w == 0 else oc.value)[li], v["kv_all"][li][w])
             _note(f"pin.wide.kv.{name}{li}", **s)
             assert s["rel_l2"] < 1.5e-2, (li, name, s)
-    gs, T = v["gs"], v["rtoks"].shape[0]
+    gs, T = _to(v["gs"], "cpu"), v["rtoks"].shape[0]
     lg = []
     o.generate_text(oc, gs["packed_key_value_indexes"], gs["key_values_lens"], gs["packed_start_tokens"], gs["packed_query_position_ids"], T,
                     forced_tokens=v["rtoks"], logits_out=lg)
