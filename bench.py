@@ -117,6 +117,26 @@ def synthetic_requests(first: int, n: int, size: int = IMG):
     return pinned, [Image.fromarray(r) for r in raws], ids, [" ".join(str(t) for t in p) for p in ids]
 
 
+def synthetic_job(rank: int):
+    """Host-preprocessed inputs of one configs[1] batch (tools/prefill_trace.py, e2e_phases.py, decode_after_prefill.py): the images of
+    synthetic_requests through the reference's transform + patchify on the host, pinned; 30 prompt ids per sample."""
+    import torch
+    from PIL import Image
+    from unimedvl_b200 import packing, synth
+    tf = packing.ImageTransform(980, 378, 14, max_pixels=2_007_040)
+    toks, pos, lens, prompts, images = [], [], [], [], []
+    for i in range(B_PER_GPU):
+        gid = rank * B_PER_GPU + i
+        raw = synth.synthetic_image(gid, IMG, IMG)
+        images.append(torch.from_numpy(raw.copy()).pin_memory())     # 448x448 passes the reference's resize rule unchanged
+        t = tf(Image.fromarray(raw))
+        toks.append(packing.patchify(t, 14))
+        pos.append(packing.flattened_position_ids(t.size(1), t.size(2), 14, 70))
+        lens.append(toks[-1].shape[0])
+        prompts.append(synth.synthetic_prompt_ids(gid, PROMPT_TOKENS))
+    return torch.cat(toks, 0).pin_memory(), torch.cat(pos, 0).pin_memory(), lens, prompts, images
+
+
 # ================================================================================================ reference (CPU / GPU) helpers
 def _refharness():
     sys.path.insert(0, os.path.join(ROOT, "baseline"))

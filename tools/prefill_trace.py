@@ -67,6 +67,12 @@ if ig:
     for i in range(i0 - 6, i0 + 4):
         out.append(f"| {i} | `{nm[i]}` | {(t[i, 0] - t[i0 - 6, 0]) / 1e3:.1f} | {(t[i, 1] - t[i0 - 6, 0]) / 1e3:.1f} | "
                    f"{(t[i, 3] - t[i0 - 6, 0]) / 1e3:.1f} | {(t[i, 3] - t[i - 1, 3]) / 1e3:.1f} |\n")
+    i0 = ig[(3 * len(ig)) // 4]         # a gate/up launch of the prompt prefill (8 x 34 rows on the image context)
+    out.append("\n## around one prompt-prefill layer (272 rows; us)\n\n"
+               "| # | kernel | first CTA start | wait passed | last CTA end | share |\n|---|---|---:|---:|---:|---:|\n")
+    for i in range(i0 - 6, i0 + 4):
+        out.append(f"| {i} | `{nm[i]}` | {(t[i, 0] - t[i0 - 6, 0]) / 1e3:.1f} | {(t[i, 1] - t[i0 - 6, 0]) / 1e3:.1f} | "
+                   f"{(t[i, 3] - t[i0 - 6, 0]) / 1e3:.1f} | {(t[i, 3] - t[i - 1, 3]) / 1e3:.1f} |\n")
 iv = [i for i in range(n) if "K4304" in nm[i]]
 if iv:
     i0 = iv[len(iv) // 2]               # an fc2 launch in the middle of the ViT
