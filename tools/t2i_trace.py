@@ -54,10 +54,14 @@ torch.cuda.synchronize()
 CAP, NL = 4096, 32
 _lib.check(eng.lib.umv_trace_begin(CAP))
 ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+if os.environ.get("UMV_NCU"):           # ncu --profile-from-start off: only these two steps are profiled
+    torch.cuda.profiler.start()
 ev0.record()
 run(3)                      # two Euler steps, both inside the CFG interval
 ev1.record()
 torch.cuda.synchronize()
+if os.environ.get("UMV_NCU"):
+    torch.cuda.profiler.stop()
 stamps = np.zeros((CAP, 12), dtype=np.uint64)
 names = C.create_string_buffer(CAP * NL)
 n = C.c_int32()
