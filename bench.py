@@ -40,9 +40,9 @@ IMG = 448
 B_REPORT, REPORT_STEPS = 16, 512      # configs[2]: 32 samples over 2 GPUs
 B_T2I, T2I_SIZE, T2I_STEPS = 4, 256, 50   # configs[3]: 16 images over 4 GPUs
 B_INTER, INTER_TOKENS = 8, 64         # configs[4]: 64 requests over 8 GPUs
-# DRAM traffic of one weight-major gate/up + SwiGLU launch at M=8 (ncu --set full, profiles/r1_decode_kernels_full.md):
-# 271,748,096 B read + 3,301,632 B written; the algorithmic figure is 271,941,632 B.
-NCU_TRAFFIC_GATE_UP = 275_049_728
+# DRAM traffic of one weight-major gate/up + SwiGLU launch at M=8 (ncu --set full, profiles/r2_decode_kernels_full.md, second layer):
+# 271,748,864 B read + 3,923,712 B written (round 1: 271,748,096 + 3,301,632); the algorithmic figure is 271,941,632 B.
+NCU_TRAFFIC_GATE_UP = 275_672_576
 
 METRIC = "VQA decode tok/s @14B (B=8/GPU, 448x448, 128-token greedy)"
 WORKLOAD = ("VQA batch=8 per GPU, 448x448 (1024 ViT tokens + 2 markers), 32-token prompt, 14B MoT bf16 "
@@ -504,7 +504,7 @@ def run_engine(args, rank: int, local_rank: int, world: int):
         roof = {"bound": "hbm", "kernel": "gemm_tc_kernel<16,2,true> (weight-major gate/up + SwiGLU, M=8)",
                 "achieved": round(alg_bytes / (k_ms / 1e3) / 1e9, 1), "peak": hbm_peak, "peak_source": peak_src, "unit": "GB/s",
                 "frac": round(alg_bytes / (k_ms / 1e3) / 1e9 / hbm_peak, 4), "traffic": NCU_TRAFFIC_GATE_UP,
-                "traffic_source": "profiles/r1_decode_kernels_full.md (ncu --set full: dram__bytes_read.sum + dram__bytes_write.sum of this kernel, per launch)",
+                "traffic_source": "profiles/r2_decode_kernels_full.md (ncu --set full: dram__bytes_read.sum + dram__bytes_write.sum of this kernel, per launch)",
                 "algorithmic_bytes_per_launch": int(alg_bytes), "us_per_launch": round(k_ms * 1e3, 2),
                 "us_per_launch_source": "CUDA events over 8 x 28 back-to-back launches on 28 distinct layers' weights", "in_graph": in_graph}
         if in_graph and "us_per_launch" in in_graph:
