@@ -9,7 +9,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)
 sys.path.insert(0, ROOT)
 from unimedvl_b200.engine import op_linear  # noqa: E402
 
-shapes = [("prefill gate|up", 8208, 37888, 3584, 2), ("prefill down", 8208, 3584, 18944, 3), ("prefill o_proj", 8208, 3584, 3584, 3),
+shapes = [("prefill q|k|v", 8208, 4608, 3584, 0), ("prefill gate|up", 8208, 37888, 3584, 2), ("prefill down", 8208, 3584, 18944, 3), ("prefill o_proj", 8208, 3584, 3584, 3),
           ("flow gate|up", 3072, 37888, 3584, 2), ("flow down", 3072, 3584, 18944, 3), ("flow o_proj", 3072, 3584, 3584, 3),
           ("flow q|k|v", 3072, 4608, 3584, 0)]
 only = os.environ.get("ONLY")

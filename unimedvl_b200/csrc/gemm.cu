@@ -85,6 +85,7 @@ struct GemmParams {
     int hd, hp;     // output head padding (LinearCall::out_head_dim / out_head_pad), 0 = off
     int stages;     // ring depth of this launch (<= TcCfg::kStages); a shallow ring leaves shared memory for a neighbour CTA
     int a_tiled;    // weight-major: the A tensor map views a tile-major weight copy as [tiles * 128 rows, 64 columns]
+    int group_a;    // token-major tile order: column tiles are swept inside groups of group_a row tiles (see gemm_2cta.cu: tile_coords)
 };
 
 template <int BN, bool SWAP>
@@ -112,6 +113,24 @@ __device__ __forceinline__ float epi_value(int epi, float acc, float bias) {
 // so that short-K tiles (ViT K = 1152, VAE) are not paced by the epilogue.
 template <bool SWAP>
 constexpr int gemm_threads() { return SWAP ? 192 : 320; }
+
+// (row tile, column tile) of tile index t2.  Weight-major: weight tiles fastest.  Token-major: row tiles fastest inside groups of
+// p.group_a row tiles, column tiles next, groups last -- the grouped order of gemm_2cta.cu (tile_coords); results do not depend on it.
+template <bool SWAP>
+__device__ __forceinline__ void tile_ab(int t2, const GemmParams& p, int& a_tile, int& b_tile) {
+    if (SWAP || p.group_a >= p.a_tiles) {
+        a_tile = t2 % p.a_tiles;
+        b_tile = t2 / p.a_tiles;
+        return;
+    }
+    const int per_group = p.group_a * p.b_tiles;
+    const int g = t2 / per_group;
+    const int first = g * p.group_a;
+    const int gsz = min(p.group_a, p.a_tiles - first);
+    const int r = t2 - g * per_group;
+    a_tile = first + r % gsz;
+    b_tile = r / gsz;
+}
 
 template <int BN, int MODE, bool SWAP>
 __global__ void __launch_bounds__(gemm_threads<SWAP>(), 1)
@@ -177,7 +196,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
                 const int split = tile % p.splits;
                 const int t2 = tile / p.splits;
-                const int a_tile = t2 % p.a_tiles, b_tile = t2 / p.a_tiles;
+                int a_tile, b_tile;
+                tile_ab<SWAP>(t2, p, a_tile, b_tile);
                 const int kb0 = split * p.kb_per_split;
                 const int kb1 = min(p.kb_total, kb0 + p.kb_per_split);
                 for (int kb = kb0; kb < kb1; ++kb) {
@@ -249,7 +269,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
             const int split = tile % p.splits;
             const int t2 = tile / p.splits;
-            const int a_tile = t2 % p.a_tiles, b_tile = t2 / p.a_tiles;
+            int a_tile, b_tile;
+            tile_ab<SWAP>(t2, p, a_tile, b_tile);
             mbar_wait(&tfull[acc], acc_phase);
             tc_fence_after();
             const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN;
@@ -594,6 +615,35 @@ int pick_splits(int N, int K, int sm_count) {
     return (kb_total + per - 1) / per;        // effective count: no empty split
 }
 
+// Row tiles per tile-order group of a token-major linear: the candidate with the least estimated DRAM traffic.  Per group the weights
+// are read once (every column tile is visited) and the group's activation rows once per wave of the group, unless they are small
+// enough to stay in L2 next to the streaming weights and outputs (a quarter of the 126 MB; measured: the prefill's 59 MB of gate/up
+// activations are already re-read by a third per wave).  The estimate is crude (the 8,208-row down_proj went from 2.5 to 1.9 GB of DRAM
+// reads where it predicts 1.2), so the plain all-rows order stays unless a quarter of the traffic is at stake (at 3,072 rows the
+// candidates are within +-1 % of each other in time, profiles/r2_tile_order.md).  UMV_RASTER_G forces a value (>= tiles: plain order).
+int pick_tile_group(int a_tiles, int b_tiles, int rows_a, int rows_b, int K, int slots) {
+    const char* env = getenv("UMV_RASTER_G");               // read per call: experiments switch inside one process
+    if (env && atoi(env) > 0) return std::min(atoi(env), a_tiles);
+    const double act_tile = (double)rows_a * K * 2, w_all = (double)b_tiles * rows_b * K * 2, l2_keep = 32e6;
+    auto estimate = [&](int g) {
+        double traffic = 0;
+        for (int first = 0; first < a_tiles; first += g) {
+            const int gsz = std::min(g, a_tiles - first);
+            const double act = gsz * act_tile;
+            const int waves = (gsz * b_tiles + slots - 1) / slots;
+            traffic += w_all + act * (act <= l2_keep ? 1 : waves);
+        }
+        return traffic;
+    };
+    double best = 1e300;
+    int best_g = a_tiles;
+    for (int g = 1; g <= a_tiles; ++g) {
+        const double t = estimate(g);
+        if (t <= best) { best = t; best_g = g; }                 // ties: the larger group (fewer weight passes)
+    }
+    return best < 0.75 * estimate(a_tiles) ? best_g : a_tiles;
+}
+
 template <int BN, int MODE, bool SWAP>
 static int launch_tc(const LinearCall& c, cudaStream_t stream) {
     GemmParams p{};
@@ -622,6 +672,7 @@ static int launch_tc(const LinearCall& c, cudaStream_t stream) {
     p.ws = c.ws;
     p.epi = c.epi;
     p.early_a = c.w_static ? 1 : 0;
+    p.group_a = SWAP ? p.a_tiles : pick_tile_group(p.a_tiles, p.b_tiles, BM, BN, c.K, g_sm_count);
     p.hd = c.out_head_dim; p.hp = c.out_head_pad;
     if (p.hd && (SWAP || MODE != 0 || c.epi != EPI_BF16 || p.hd % 8 != 0 || p.hp % 8 != 0)) {
         set_error("linear: output head padding exists only on the token-major bf16 epilogue with 8-column aligned heads");

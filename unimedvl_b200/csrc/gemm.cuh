@@ -61,6 +61,8 @@ int splitk_finish(const float* ws, int splits, int M, int N, const bf16* bias, c
                   cudaStream_t stream, const int* res_rows = nullptr);
 // Heuristic split count for a weight-major (decode) GEMM: fills the 148 SMs without starving a split.
 int pick_splits(int N, int K, int sm_count);
+// tile-order group (row tiles of rows_a rows; column tiles of rows_b weight rows; `slots` concurrent tiles) -- gemm.cu
+int pick_tile_group(int a_tiles, int b_tiles, int rows_a, int rows_b, int K, int slots);
 // Must be called once before the first tcgen05 launch (resolves cuTensorMapEncodeTiled, sets smem attrs).
 int gemm_init();
 

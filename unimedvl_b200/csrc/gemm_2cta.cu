@@ -46,7 +46,7 @@ struct Gemm2Params {
 // needs it is in flight together, and again for every later wave that needs it.  Row pairs fastest over ALL rows (group_m = m_pairs)
 // makes each wave touch every activation row: at K = 18944 the 8,208-row prefill re-read its 311 MB of activations in each of 7 waves
 // (ncu: 2.5 GB of DRAM reads for 0.5 GB of operands).  Sweeping the column tiles inside groups of group_m row pairs keeps a wave's
-// operand set near-square; the host picks group_m from the operand sizes (launch_2cta).  The order changes no result bit.
+// operand set near-square; the host picks group_m from the operand sizes (pick_tile_group, gemm.cu).  The order changes no result bit.
 __device__ __forceinline__ void tile_coords(int tile, const Gemm2Params& p, int& mp, int& b_tile) {
     const int per_group = p.group_m * p.n_tiles;
     const int g = tile / per_group;
@@ -310,35 +310,6 @@ gemm_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     trace_end(p.trace);
 }
 
-// Row pairs per tile-order group (tile_coords): the candidate with the least estimated DRAM traffic.  Per group the weights are read
-// once (every column tile is visited) and the group's activation rows once per wave of the group, unless they are small enough to stay
-// in L2 next to the streaming weights and outputs (a quarter of the 126 MB, measured: the prefill's 59 MB of gate/up activations are
-// already re-read by a third per wave).  UMV_RASTER_G forces a value (0 / unset: automatic; >= m_pairs: the old all-rows order).
-static int pick_group_m(int m_pairs, int n_tiles, int bn, int K, int clusters) {
-    const char* env = getenv("UMV_RASTER_G");               // read per call: experiments switch inside one process
-    if (env && atoi(env) > 0) return std::min(atoi(env), m_pairs);
-    const double act_pair = 256.0 * K * 2, w_all = (double)n_tiles * bn * K * 2, l2_keep = 32e6;
-    auto estimate = [&](int g) {
-        double traffic = 0;
-        for (int first = 0; first < m_pairs; first += g) {
-            const int gsz = std::min(g, m_pairs - first);
-            const double act = gsz * act_pair;
-            const int waves = (gsz * n_tiles + clusters - 1) / clusters;
-            traffic += w_all + act * (act <= l2_keep ? 1 : waves);
-        }
-        return traffic;
-    };
-    double best = 1e300;
-    int best_g = m_pairs;
-    for (int g = 1; g <= m_pairs; ++g) {
-        const double t = estimate(g);
-        if (t <= best) { best = t; best_g = g; }                 // ties: the larger group (fewer weight passes)
-    }
-    // the estimate is crude (measured: the 8,208-row down_proj went from 2.5 to 1.9 GB where it predicts 1.2): leave the plain order
-    // unless a quarter of the traffic is at stake -- at 3,072 rows the candidates are within +-1 % of each other in time
-    return best < 0.75 * estimate(m_pairs) ? best_g : m_pairs;
-}
-
 template <int BN, int MODE>
 int launch_2cta(const LinearCall& c, cudaStream_t stream) {
     using C2 = Cfg2<BN>;
@@ -353,7 +324,7 @@ int launch_2cta(const LinearCall& c, cudaStream_t stream) {
     UMV_REQUIRE(!p.hd || (MODE == 0 && c.epi == EPI_BF16 && p.hd % 8 == 0 && p.hp % 8 == 0), UMV_ERR_UNSUPPORTED,
                 "linear: output head padding exists only on the bf16 epilogue with 8-column aligned heads");
     p.stages = C2::kStages;
-    p.group_m = pick_group_m(p.m_pairs, p.n_tiles, BN, c.K, gemm_sm_count() / 2);
+    p.group_m = pick_tile_group(p.m_pairs, p.n_tiles, 2 * BM, BN, c.K, gemm_sm_count() / 2);
     static bool attr_set = false;
     if (!attr_set) {
         cudaError_t ae = cudaFuncSetAttribute(gemm_2cta_kernel<BN, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, C2::kSmemBytes);
