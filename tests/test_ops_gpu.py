@@ -55,6 +55,32 @@ def test_linear_all_paths(ops, M, N, K):
             assert s["rel_l2"] < 1e-3 and s["frac_gt1"] < (1e-2 if epi == 2 else 2e-3), (M, N, K, epi, impl, s)
 
 
+@pytest.mark.parametrize("M,N,K,epi", [(2100, 3584, 2048, 3), (2100, 4096, 1024, 2), (1500, 1152, 4304, 0), (700, 2048, 896, 1)])
+def test_linear_tile_order_never_changes_a_bit(ops, M, N, K, epi, monkeypatch):
+    """The token-major linears sweep the column tiles inside groups of row tiles (csrc/gemm.cu: pick_tile_group / tile_ab,
+    csrc/gemm_2cta.cu: tile_coords).  The order only decides WHEN a tile is computed: every forced group size, the automatic choice and
+    the plain all-rows order give the same bytes, on the pair kernel and on the single-CTA kernel, with ragged last tiles."""
+    torch.manual_seed(M + N)
+    x = torch.randn(M, K, device="cuda").bfloat16()
+    w = (torch.randn(N, K, device="cuda") / K ** 0.5).bfloat16()
+    b = None if epi == 2 else (torch.randn(N, device="cuda") * 0.1).bfloat16()
+    res = torch.randn(M, N, device="cuda").bfloat16() if epi == 3 else None
+    outs = {}
+    for pair in ("1", "0"):
+        monkeypatch.setenv("UMV_2CTA", pair)
+        for g in ("100000", "1", "2", "3", "5", None):
+            if g is None:
+                monkeypatch.delenv("UMV_RASTER_G", raising=False)
+            else:
+                monkeypatch.setenv("UMV_RASTER_G", g)
+            outs[pair, g] = ops.op_linear(x, w, b, res, epi=epi, impl=1).clone()
+    ref = outs["1", "100000"]
+    assert torch.isfinite(ref.float()).all()
+    assert ulp_stats(ref, _ref_linear(x, w, b if b is not None else None, res, epi))["rel_l2"] < 1e-3
+    for key, y in outs.items():
+        assert torch.equal(y, ref), key
+
+
 def test_linear_rejects_unaligned_rows(ops):
     x = torch.randn(4, 588, device="cuda").bfloat16()
     w = torch.randn(64, 588, device="cuda").bfloat16()
