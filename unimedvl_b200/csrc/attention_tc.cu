@@ -30,11 +30,31 @@ namespace {
 
 constexpr int HD = 128;
 constexpr int TQ = 128;                 // query rows per CTA (UMMA M)
-constexpr int TK = 128;                 // keys per block (UMMA N of the score product, K extent of P V)
-constexpr int kHalf = 128 * 64 * 2;     // a [128 x 64] bf16 half tile
+constexpr int kHalf = 128 * 64 * 2;     // a [128 x 64] bf16 half tile (Q, P)
 constexpr int kTile = 2 * kHalf;        // [128 x 128]
-constexpr int kSmemBytes = 1024 + kTile /*Q*/ + 2 * kTile /*K*/ + 2 * kTile /*V*/ + kTile /*P*/ + 256;
-constexpr int kColS = 0, kColO = 256;   // TMEM columns: S0 [0,128), S1 [128,256), O [256,384)
+constexpr int kSplit = 2;               // softmax threads per query row (4: measured slower, 290 vs 239 us per 14B prefill layer)
+constexpr int kOCols = HD / kSplit;     // O columns per softmax thread
+constexpr int kTcThreads = 64 + kSplit * 128;      // TMA warp, MMA warp, 4 * kSplit softmax warps
+constexpr int kPairedMaxKeys = 512;     // key ranges up to this may use the 64-key, two-CTAs-per-SM build (attention_tc_forward)
+
+// Two builds of the kernel.  TK = 128 keys per block: one CTA per SM (193 KB of shared memory, 512 TMEM columns), the fewest
+// per-key overheads -- long key ranges.  TK = 64: half-size K / V / P stages, a single V stage and 256 TMEM columns, so TWO CTAs
+// share an SM (100 KB each, <= 96 registers): a tile over a short key range is a chain of dependent latencies (Q / K load, first
+// S, softmax, P V, store: ~13 us for 3 blocks at the flow step, 4 of them arithmetic), and the second CTA fills the other's bubbles.
+template <int TK_>
+struct TcAttn {
+    static constexpr int TK = TK_;                       // keys per block (UMMA N of the score product, K extent of P V)
+    static constexpr int kKeys = TK / kSplit;            // keys per softmax thread and block
+    static constexpr int kKVHalf = TK * 64 * 2;          // [TK keys x 64 columns]
+    static constexpr int kKVTile = 2 * kKVHalf;          // [TK x 128]
+    static constexpr int kPTile = (TK / 64) * kHalf;     // [128 rows x TK keys]
+    static constexpr int kVStages = TK == 128 ? 2 : 1;
+    static constexpr int kSmemBytes = 1024 + kTile /*Q*/ + 2 * kKVTile /*K*/ + kVStages * kKVTile /*V*/ + kPTile + 256;
+    static constexpr int kColS = 0, kColO = 2 * TK;      // TMEM columns: S0 [0, TK), S1 [TK, 2 TK), O [2 TK, 2 TK + 128)
+    static constexpr int kTmemCols = TK == 128 ? 512 : 256;
+    static constexpr int kCtasPerSm = TK == 128 ? 1 : 2;
+    static_assert(kKeys % 32 == 0, "whole 32-column TMEM loads per thread");
+};
 
 __device__ __forceinline__ float ex2_approx(float x) {
     float y;
@@ -42,23 +62,21 @@ __device__ __forceinline__ float ex2_approx(float x) {
     return y;
 }
 
-constexpr int kSplit = 2;                // softmax threads per query row (4: measured slower, 290 vs 239 us per 14B prefill layer)
-constexpr int kKeys = TK / kSplit;       // keys (and O columns) per softmax thread
-static_assert(kKeys % 32 == 0, "whole 32-column TMEM loads per thread");
-constexpr int kTcThreads = 64 + kSplit * 128;      // TMA warp, MMA warp, 4 * kSplit softmax warps
-
-__global__ void __launch_bounds__(kTcThreads, 1)
+template <int TK>
+__global__ void __launch_bounds__(kTcThreads, TcAttn<TK>::kCtasPerSm)
 attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                const __grid_constant__ CUtensorMap tmV, AttnArgs a, int G, int TOK, float scale_log2) {
+    using C = TcAttn<TK>;
+    constexpr int kKeys = C::kKeys, kKVHalf = C::kKVHalf, kKVTile = C::kKVTile, kVStages = C::kVStages, kColS = C::kColS, kColO = C::kColO;
     pdl_launch_dependents();
     trace_start(a.trace);
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     uint8_t* sQ = smem;
     uint8_t* sK = sQ + kTile;
-    uint8_t* sV = sK + 2 * kTile;
-    uint8_t* sP = sV + 2 * kTile;
-    uint64_t* q_full = reinterpret_cast<uint64_t*>(sP + kTile);
+    uint8_t* sV = sK + 2 * kKVTile;
+    uint8_t* sP = sV + kVStages * kKVTile;
+    uint64_t* q_full = reinterpret_cast<uint64_t*>(sP + C::kPTile);
     uint64_t* k_full = q_full + 1;       // [2]  K and V have separate rings: a K stage is free as soon as its score
     uint64_t* k_empty = k_full + 2;      // [2]  product has completed, one whole block before P V releases the V stage --
     uint64_t* v_full = k_empty + 2;      // [2]  so the next K block is requested a block period ahead of its use
@@ -101,7 +119,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
             fence_mbar_init();
         }
         __syncwarp();
-        tmem_alloc<512>(tmem_slot);
+        tmem_alloc<C::kTmemCols>(tmem_slot);
     }
     if (warp >= 2) {
         // rows of the Q tile the TMA box does not cover (TOK * G .. 127): keep them finite
@@ -123,13 +141,14 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
             mbar_expect_tx(q_full, (uint32_t)(2 * 64 * G * TOK * 2));
             tma_load_3d(sQ, &tmQ, q_full, 0, kvh * G, qs + t0);
             tma_load_3d(sQ + kHalf, &tmQ, q_full, 64, kvh * G, qs + t0);
+            constexpr int kPages = TK / 64;                  // 64-slot KV pages per key block
             for (int j = 0; j < nkb; ++j) {
-                const int stage = j & 1;
-                int row_k[2], row_v[2];
+                const int stage = j & 1, vstage = j % kVStages;
+                int row_k[kPages], row_v[kPages];
                 int col0 = 0;                      // column of the kv head's first element in the K / V matrices
 #pragma unroll
-                for (int pg = 0; pg < 2; ++pg) {
-                    const int kb64 = 2 * j + pg;
+                for (int pg = 0; pg < kPages; ++pg) {
+                    const int kb64 = kPages * j + pg;
                     if (a.paged) {
                         const int page = kb64 < a.max_pages ? a.page_table[(size_t)b * a.max_pages + kb64] : 0;
                         row_k[pg] = (int)(a.pool.tile_offset(page, a.layer, 0, kvh) / HD);
@@ -140,25 +159,25 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
                     }
                 }
                 mbar_wait(&k_empty[stage], ((j >> 1) & 1) ^ 1u);
-                mbar_expect_tx(&k_full[stage], kTile);
+                mbar_expect_tx(&k_full[stage], kKVTile);
 #pragma unroll
-                for (int pg = 0; pg < 2; ++pg)
-#pragma unroll
-                    for (int half = 0; half < 2; ++half)
-                        tma_load_2d(sK + stage * kTile + half * kHalf + pg * 8192, &tmK, &k_full[stage], col0 + half * 64, row_k[pg], kEvictNormal);
-                mbar_wait(&v_empty[stage], ((j >> 1) & 1) ^ 1u);
-                mbar_expect_tx(&v_full[stage], kTile);
-#pragma unroll
-                for (int pg = 0; pg < 2; ++pg)
+                for (int pg = 0; pg < kPages; ++pg)
 #pragma unroll
                     for (int half = 0; half < 2; ++half)
-                        tma_load_2d(sV + stage * kTile + half * kHalf + pg * 8192, &tmV, &v_full[stage], col0 + half * 64, row_v[pg], kEvictNormal);
+                        tma_load_2d(sK + stage * kKVTile + half * kKVHalf + pg * 8192, &tmK, &k_full[stage], col0 + half * 64, row_k[pg], kEvictNormal);
+                mbar_wait(&v_empty[vstage], ((j / kVStages) & 1) ^ 1u);
+                mbar_expect_tx(&v_full[vstage], kKVTile);
+#pragma unroll
+                for (int pg = 0; pg < kPages; ++pg)
+#pragma unroll
+                    for (int half = 0; half < 2; ++half)
+                        tma_load_2d(sV + vstage * kKVTile + half * kKVHalf + pg * 8192, &tmV, &v_full[vstage], col0 + half * 64, row_v[pg], kEvictNormal);
             }
         }
     } else if (warp == 1) {
         // ------------------------------------------------------------ MMA issuer
         if (elect_one()) {
-            constexpr uint32_t idesc_s = umma_idesc_bf16(TK);
+            constexpr uint32_t idesc_s = umma_idesc_bf16(TK);       // M 128, N = TK
             constexpr uint32_t idesc_pv = umma_idesc_bf16(HD) | (1u << 16);      // B (= V) is MN-major
             mbar_wait(q_full, 0);
             auto issue_s = [&](int j) {
@@ -166,10 +185,10 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
                 mbar_wait(&k_full[stage], (j >> 1) & 1);
                 tc_fence_after();
                 const uint32_t d = tmem_base + kColS + (j & 1) * TK;
-                const uint32_t qa = smem_u32(sQ), ka = smem_u32(sK + stage * kTile);
+                const uint32_t qa = smem_u32(sQ), ka = smem_u32(sK + stage * kKVTile);
 #pragma unroll
                 for (int k = 0; k < HD / 16; ++k)
-                    umma_bf16(d, umma_desc_sw128(qa + (k >> 2) * kHalf + (k & 3) * 32), umma_desc_sw128(ka + (k >> 2) * kHalf + (k & 3) * 32),
+                    umma_bf16(d, umma_desc_sw128(qa + (k >> 2) * kHalf + (k & 3) * 32), umma_desc_sw128(ka + (k >> 2) * kKVHalf + (k & 3) * 32),
                               idesc_s, k > 0 ? 1u : 0u);
                 umma_commit(&s_full[j & 1]);
                 umma_commit(&k_empty[stage]);
@@ -177,18 +196,18 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
             issue_s(0);
             for (int j = 0; j < nkb; ++j) {
                 if (j + 1 < nkb) issue_s(j + 1);             // next scores while the softmax warps work on block j
-                const int stage = j & 1;
-                mbar_wait(&v_full[stage], (j >> 1) & 1);
+                const int vstage = j % kVStages;
+                mbar_wait(&v_full[vstage], (j / kVStages) & 1);
                 mbar_wait(p_ready, j & 1);
                 tc_fence_after();
                 const uint32_t d = tmem_base + kColO;
-                const uint32_t pa = smem_u32(sP), va = smem_u32(sV + stage * kTile);
+                const uint32_t pa = smem_u32(sP), va = smem_u32(sV + vstage * kKVTile);
 #pragma unroll
                 for (int k = 0; k < TK / 16; ++k)
-                    umma_bf16(d, umma_desc_sw128(pa + (k >> 2) * kHalf + (k & 3) * 32), umma_desc_sw128_mn(va + k * 2048, kHalf), idesc_pv,
+                    umma_bf16(d, umma_desc_sw128(pa + (k >> 2) * kHalf + (k & 3) * 32), umma_desc_sw128_mn(va + k * 2048, kKVHalf), idesc_pv,
                               (j > 0 || k > 0) ? 1u : 0u);
                 umma_commit(pv_done);
-                umma_commit(&v_empty[stage]);
+                umma_commit(&v_empty[vstage]);
             }
         }
     } else {
@@ -204,7 +223,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         const int lim = (a.causal && valid) ? (kvlen - qlen + t0 + tok_l) : (kvlen - 1);     // last visible key of the row
         const uint32_t lane_base = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
         float m = -INFINITY, l = 0.f;          // l: this thread's part of the row sum (all parts share the maxima)
-        uint32_t r[kKeys];
+        uint32_t r[kKeys > kOCols ? kKeys : kOCols];
         for (int j = 0; j < nkb; ++j) {
             mbar_wait(&s_full[j & 1], (j >> 1) & 1);
             tc_fence_after();
@@ -260,13 +279,13 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
                 tc_fence_after();
                 if (__any_sync(0xffffffffu, alpha != 1.f)) {
 #pragma unroll 1
-                    for (int c = 0; c < kKeys / 32; ++c) {
+                    for (int c = 0; c < kOCols / 32; ++c) {
                         uint32_t o[32];
-                        tmem_ld32(lane_base + kColO + part * kKeys + c * 32, o);
+                        tmem_ld32(lane_base + kColO + part * kOCols + c * 32, o);
                         tmem_ld_wait();
 #pragma unroll
                         for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-                        tmem_st32(lane_base + kColO + part * kKeys + c * 32, o);
+                        tmem_st32(lane_base + kColO + part * kOCols + c * 32, o);
                     }
                     tmem_st_wait();
                 }
@@ -293,24 +312,24 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         const float inv = lt > 0.f ? 1.f / lt : 0.f;
         const int odh = a.out_dh ? a.out_dh : HD;             // real head width of the output (padded-head callers: < 128)
         const int orow = qs + t0 + (valid ? tok_l : 0);
-        bf16* dst = a.out + (size_t)(a.out_row_map ? a.out_row_map[orow] : orow) * a.ldo + (kvh * G + (valid ? head_l : 0)) * odh + part * kKeys;
+        bf16* dst = a.out + (size_t)(a.out_row_map ? a.out_row_map[orow] : orow) * a.ldo + (kvh * G + (valid ? head_l : 0)) * odh + part * kOCols;
 #pragma unroll
-        for (int c = 0; c < kKeys / 32; ++c) tmem_ld32(lane_base + kColO + part * kKeys + c * 32, *reinterpret_cast<uint32_t(*)[32]>(&r[c * 32]));
+        for (int c = 0; c < kOCols / 32; ++c) tmem_ld32(lane_base + kColO + part * kOCols + c * 32, *reinterpret_cast<uint32_t(*)[32]>(&r[c * 32]));
         tmem_ld_wait();
         if (valid) {
 #pragma unroll
-            for (int q = 0; q < kKeys / 8; ++q) {
+            for (int q = 0; q < kOCols / 8; ++q) {
                 uint32_t o[4];
 #pragma unroll
                 for (int i = 0; i < 4; ++i)
                     o[i] = pack2(__uint_as_float(r[8 * q + 2 * i]) * inv, __uint_as_float(r[8 * q + 2 * i + 1]) * inv);
-                if (part * kKeys + q * 8 < odh) stg16(dst + q * 8, U4{o[0], o[1], o[2], o[3]});
+                if (part * kOCols + q * 8 < odh) stg16(dst + q * 8, U4{o[0], o[1], o[2], o[3]});
             }
         }
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 1) tmem_dealloc<512>(tmem_base);
+    if (warp == 1) tmem_dealloc<C::kTmemCols>(tmem_base);
     trace_end(a.trace);
 }
 
@@ -332,20 +351,35 @@ bool attention_tc_supported(const AttnArgs& a) {
            ((reinterpret_cast<uintptr_t>(a.out) & 15) == 0);
 }
 
+template <int TK>
+static int launch_attn_tc(const AttnArgs& a, const CUtensorMap& tmQ, const CUtensorMap& tmK, const CUtensorMap& tmV, int G, int TOK,
+                          float scale_log2, cudaStream_t s) {
+    using C = TcAttn<TK>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t ae = cudaFuncSetAttribute(attn_tc_kernel<TK>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes);
+        if (ae != cudaSuccess) {
+            set_error("attn_tc_kernel<%d>: cudaFuncSetAttribute(max dynamic smem) failed: %s", TK, cudaGetErrorString(ae));
+            return UMV_ERR_CUDA;
+        }
+        attr_set = true;
+    }
+    dim3 grid((a.max_q_len + TOK - 1) / TOK, a.n * a.Hkv);
+    cudaError_t e = launch_k(attn_tc_kernel<TK>, grid, dim3(kTcThreads), C::kSmemBytes, s, tmQ, tmK, tmV, a, G, TOK, scale_log2);
+    ++g_launches;
+    if (e == cudaSuccess) e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        set_error("attn_tc_kernel<%d> launch failed: %s", TK, cudaGetErrorString(e));
+        return UMV_ERR_CUDA;
+    }
+    return UMV_OK;
+}
+
 int attention_tc_forward(const AttnArgs& a0, cudaStream_t s) {
     AttnArgs a = a0;
     const int G = a.H / a.Hkv, TOK = TQ / G;
     int rc = gemm_init();
     if (rc) return rc;
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaError_t ae = cudaFuncSetAttribute(attn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
-        if (ae != cudaSuccess) {
-            set_error("attn_tc_kernel: cudaFuncSetAttribute(max dynamic smem) failed: %s", cudaGetErrorString(ae));
-            return UMV_ERR_CUDA;
-        }
-        attr_set = true;
-    }
     CUtensorMap tmQ, tmK, tmV;
     // q rows viewed as [tokens][heads][128]: a box of 64 columns x G heads x TOK tokens is the tile's [row][128 B] image
     rc = make_tmap_3d(&tmQ, a.q, HD, a.H, a.total_q, (uint64_t)HD * 2, (uint64_t)a.ldq * 2, G, TOK);
@@ -356,18 +390,21 @@ int attention_tc_forward(const AttnArgs& a0, cudaStream_t s) {
         if ((rc = make_tmap_2d(&tmK, a.k, a.total_k, (uint64_t)a.Hkv * HD, a.ldk, 64))) return rc;
         if ((rc = make_tmap_2d(&tmV, a.v, a.total_k, (uint64_t)a.Hkv * HD, a.ldv, 64))) return rc;
     }
-    a.trace = trace_next("attn_tc");
     a.kv_tmap = nullptr;
     const float scale_log2 = (a.scale > 0.f ? a.scale : 1.0f / sqrtf((float)HD)) * 1.4426950408889634f;
-    dim3 grid((a.max_q_len + TOK - 1) / TOK, a.n * a.Hkv);
-    cudaError_t e = launch_k(attn_tc_kernel, grid, dim3(kTcThreads), kSmemBytes, s, tmQ, tmK, tmV, a, G, TOK, scale_log2);
-    ++g_launches;
-    if (e == cudaSuccess) e = cudaGetLastError();
-    if (e != cudaSuccess) {
-        set_error("attn_tc_kernel launch failed: %s", cudaGetErrorString(e));
-        return UMV_ERR_CUDA;
-    }
-    return UMV_OK;
+    // Key-block size.  Two co-resident CTAs with 64-key blocks when there are tiles enough to double up on every SM and the key
+    // range is short -- the flow step: 12 x 258 rows on 292 keys, 49.0 -> 39.6 us for the kernel alone, 65.6 -> 51.5 us per layer inside
+    // the step.  One CTA with 128-key blocks otherwise: few tiles (8 x 34 prompt rows on 1,060 keys: 15.9 vs 23.5 us), long ranges
+    // (4,096 causal: 191 vs 216 us), and the ~1k-key image / ViT prefill, where the paired build wins alone (227 -> 216 us) but loses
+    // inside the job (ViT + image prefill 97.8 -> 102.4 ms: two half-size CTAs per SM delay the next linear's early-launched CTAs,
+    // which need the whole SM's shared memory and all 512 TMEM columns).
+    // UMV_ATTN_TK = 64 | 128 forces one (read per call: tests switch inside one process).
+    const char* tk_env = getenv("UMV_ATTN_TK");
+    const long tiles = (long)((a.max_q_len + TOK - 1) / TOK) * a.n * a.Hkv;
+    const int tk = tk_env && (atoi(tk_env) == 64 || atoi(tk_env) == 128) ? atoi(tk_env)
+                   : (tiles >= 2L * gemm_sm_count() && a.max_kv_len <= kPairedMaxKeys ? 64 : 128);
+    a.trace = trace_next(tk == 64 ? "attn_tc64" : "attn_tc");
+    return tk == 64 ? launch_attn_tc<64>(a, tmQ, tmK, tmV, G, TOK, scale_log2, s) : launch_attn_tc<128>(a, tmQ, tmK, tmV, G, TOK, scale_log2, s);
 }
 
 }  // namespace umv
