@@ -2,7 +2,9 @@
 """Workload for compute-sanitizer (tools/sanitize.sh): the tiny-dims hot path end to end -- ViT + connector, image and prompt
 prefill (tcgen05 linears + attention), 6 greedy decode steps (weight-major split-K linears, fused cluster decode attention;
 eager launches, UMV_GRAPH=0, so every launch is visible to the tool), one guided flow step with three CFG branches (gen-mode
-routing) and one VAE decode + encode.  Exits non-zero if any output is non-finite."""
+routing) and one VAE decode + encode; "r2": the round-2 paths -- a gen-mode full-mask forward of 2 x (marker + 256 latents + marker)
+rows on segregated rows (row maps in the RoPE and attention kernels) through BOTH tcgen05 attention builds (UMV_ATTN_TK = 64 / 128), and
+the token-major linears with forced tile-order groups (pair and single-CTA kernels).  Exits non-zero if any output is non-finite."""
 import os
 import sys
 
@@ -59,6 +61,38 @@ def main():
         fin = bool(torch.isfinite(img.float()).all() and torch.isfinite(mom.float()).all())
         ok &= fin
         print("vae finite:", fin)
+    if "r2" in which:
+        from unimedvl_b200.engine import op_linear
+        D = dims.llm.hidden
+        gsd = torch.Generator().manual_seed(0)
+        outs = []
+        for tk in ("64", "128"):
+            os.environ["UMV_ATTN_TK"] = tk
+            seqs = [eng.seq_new() for _ in range(2)]
+            ctx = (torch.randn(40, D, generator=torch.Generator().manual_seed(1)) * 0.5).bfloat16()
+            eng.llm_forward(ctx, seqs, [30, 10], list(range(30)) + list(range(10)), want_hidden=False)
+            x = (torch.randn(2 * 258, D, generator=torch.Generator().manual_seed(2)) * 0.5).bfloat16()
+            is_gen = ([0] + [1] * 256 + [0]) * 2
+            h = eng.llm_forward(x, seqs, [258, 258], [30] * 258 + [10] * 258, row_is_gen=is_gen, is_causal=False, update_kv=True)
+            outs.append(h.float().cpu())
+            for s_ in seqs:
+                eng.seq_free(s_)
+        os.environ.pop("UMV_ATTN_TK", None)
+        rel = ((outs[0] - outs[1]).norm() / outs[1].norm()).item()
+        fin = bool(torch.isfinite(outs[0]).all()) and rel < 2e-2
+        xs = torch.randn(700, 512, generator=gsd).bfloat16().cuda()
+        ws = (torch.randn(1024, 512, generator=gsd) * 0.05).bfloat16().cuda()
+        ys = []
+        for pair in ("1", "0"):
+            os.environ["UMV_2CTA"] = pair
+            for g_ in ("1", "2", "100000"):
+                os.environ["UMV_RASTER_G"] = g_
+                ys.append(op_linear(xs, ws, None, None, epi=0, impl=1).clone())
+        os.environ.pop("UMV_2CTA", None)
+        os.environ.pop("UMV_RASTER_G", None)
+        same = all(bool(torch.equal(y, ys[0])) for y in ys)
+        ok &= fin and same
+        print("r2: segregated gen forward, attention builds agree to", f"{rel:.2e}", "; tile orders bit-identical:", same)
     torch.cuda.synchronize()
     print("launches", eng.launch_count())
     sys.exit(0 if ok else 1)
