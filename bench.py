@@ -373,7 +373,7 @@ def run_engine(args, rank: int, local_rank: int, world: int):
     B = B_PER_GPU
     ntok_img = (IMG // 14) ** 2 + 2
     ctx0 = ntok_img + PROMPT_TOKENS + 2
-    eng = Engine(dims, max_tokens=B * ntok_img, max_seqs=max(B_REPORT, B), kv_pages=1152, enable_vit=True, enable_gen=True, enable_vae=True)
+    eng = Engine(dims, max_tokens=B * (ntok_img + PROMPT_TOKENS + 2), max_seqs=max(B_REPORT, B), kv_pages=1152, enable_vit=True, enable_gen=True, enable_vae=True)
     eng.fill_synthetic(seed=0)          # random-init weights of the reference architecture: both experts, ViT, VAE resident
     eng.finalize()
     model = Bagel(eng, dims)

@@ -228,6 +228,17 @@ int umv_forward_cache_update_vit_riders(umv_engine* e, int32_t n_seqs, const int
                                         const int64_t* vit_pos_ids, int32_t n_images, const int32_t* vit_seqlens,
                                         const int32_t* vit_rows, const int32_t* positions, const umv_decode_riders* riders,
                                         void* stream);
+/* Image block AND prompt of every sample in ONE forward -- what the reference does as forward_cache_update_vit (bagel.py:522-615, full
+ * mask) followed by forward_cache_update_text (bagel.py:411-458, causal) in the VQA drivers (inferencer.py:640-680,
+ * interactive_vqa_inferencer.py:312-321), with one pass over the weights instead of two.  seq_lens[b] counts ALL packed rows of
+ * sample b, the last prompt_lens[b] of which are the prompt (text rows: their ids are part of text_ids / text_rows, their rope positions
+ * part of positions); those rows attend causally -- to the whole block and to the prompt rows before them -- while the block's rows see
+ * the block only.  K / V and hidden states are bit-identical to the two separate calls.  prompt_lens == NULL: umv_forward_cache_update_vit. */
+int umv_forward_cache_update_vit_prompt(umv_engine* e, int32_t n_seqs, const int32_t* seqs, const int32_t* seq_lens,
+                                        const int32_t* prompt_lens, int32_t n_text, const int64_t* text_ids, const int32_t* text_rows,
+                                        const float* pixels, const int64_t* vit_pos_ids, int32_t n_images, const int32_t* vit_seqlens,
+                                        const int32_t* vit_rows, const int32_t* positions, const umv_decode_riders* riders,
+                                        void* stream);
 int umv_forward_cache_update_vae(umv_engine* e, int32_t n_seqs, const int32_t* seqs, const int32_t* seq_lens, int32_t n_text,
                                  const int64_t* text_ids, const int32_t* text_rows, const void* latent, int32_t n_images, int32_t Hl,
                                  int32_t Wl, const int32_t* latent_hw, int32_t patch, const int64_t* lat_pos_ids, const int32_t* lat_rows,

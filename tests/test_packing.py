@@ -103,3 +103,30 @@ def test_reconstruction_target_size_matches_reference():
     inf = InterleaveInferencer(None, None, None, ImageTransform(1024, 32, 16), ImageTransform(980, 28, 14), {})
     got = [inf._calculate_target_size_with_aspect_ratio(int(w), int(h)) for w, h in z["recon.sizes_in"]]
     assert got == [tuple(int(v) for v in r) for r in z["recon.sizes_out"]]
+
+
+def test_image_prompt_layout_matches_the_two_packers():
+    """packing.image_prompt_layout (one fused prefill) lays out exactly the rows prepare_vit_images' block layout followed by
+    prepare_prompts would (bagel.py:460-520, 377-409): same ids, same rope positions, same cache state afterwards."""
+    n_img, prompts = [6, 20, 1], [[11, 12, 13], [], [7] * 9]
+
+    class _Ids:
+        def encode(self, i): return list(prompts[i])
+    L = packing.image_prompt_layout(n_img, prompts, TOK)
+    blk = packing._image_block_layout([0] * 3, [0] * 3, n_img, TOK)
+    gp, lens, rope = packing.prepare_prompts(blk["seqlens"], [1] * 3, [0, 1, 2], _Ids(), TOK)
+    assert L["kv_lens"] == lens and L["rope"] == rope
+    assert L["seq_lens"] == [a + b for a, b in zip(blk["seqlens"], gp["text_token_lens"].tolist())]
+    assert L["prompt_lens"] == gp["text_token_lens"].tolist()
+    row, ids, pos, k = 0, [], [], 0
+    text = dict(zip(L["text_rows"], L["text_ids"]))
+    for b, n in enumerate(n_img):
+        pl = L["prompt_lens"][b]
+        assert [text[row], text[row + n + 1]] == [TOK["start_of_image"], TOK["end_of_image"]]
+        assert L["positions"][row:row + n + 2] == [0] * (n + 2)
+        assert [text[r] for r in range(row + n + 2, row + n + 2 + pl)] == gp["packed_text_ids"][k:k + pl].tolist()
+        assert L["positions"][row + n + 2:row + n + 2 + pl] == gp["packed_text_position_ids"][k:k + pl].tolist()
+        assert L["vit_rows"][sum(n_img[:b]):sum(n_img[:b + 1])] == list(range(row + 1, row + 1 + n))
+        row += n + 2 + pl
+        k += pl
+    assert sorted(L["text_rows"] + L["vit_rows"]) == list(range(row))

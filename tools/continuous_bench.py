@@ -24,7 +24,7 @@ from unimedvl_b200.scheduler import ContinuousBatcher  # noqa: E402
 B, N = bench.B_PER_GPU, 32
 dims = ucfg.bagel_7b_mot()
 ntok_img = (bench.IMG // 14) ** 2 + 2
-eng = Engine(dims, max_tokens=B * ntok_img, max_seqs=2 * B, kv_pages=B * 64, enable_vit=True, enable_gen=False)
+eng = Engine(dims, max_tokens=B * (ntok_img + 34), max_seqs=2 * B, kv_pages=B * 64, enable_vit=True, enable_gen=False)
 eng.fill_synthetic(0)
 eng.finalize()
 model = Bagel(eng, dims)

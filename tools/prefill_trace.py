@@ -20,7 +20,7 @@ from unimedvl_b200.engine import Engine  # noqa: E402
 B = bench.B_PER_GPU
 dims = ucfg.bagel_7b_mot()
 ntok_img = (bench.IMG // 14) ** 2 + 2
-eng = Engine(dims, max_tokens=B * ntok_img, max_seqs=B, kv_pages=B * 24, enable_vit=True, enable_gen=False)
+eng = Engine(dims, max_tokens=B * (ntok_img + 34), max_seqs=B, kv_pages=B * 24, enable_vit=True, enable_gen=False)
 eng.fill_synthetic(0)
 eng.finalize()
 model = Bagel(eng, dims)

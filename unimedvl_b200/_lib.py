@@ -83,6 +83,7 @@ SIGNATURES = {
     "umv_forward_cache_update_vit": (C.c_int, [_P, _I, _IP, _IP, _I, _LP, _IP, _P, _P, _I, _IP, _IP, _IP, _P]),
     "umv_forward_cache_update_text_riders": (C.c_int, [_P, _I, _IP, _IP, _LP, _IP, C.POINTER(DecodeRiders), _P]),
     "umv_forward_cache_update_vit_riders": (C.c_int, [_P, _I, _IP, _IP, _I, _LP, _IP, _P, _P, _I, _IP, _IP, _IP, C.POINTER(DecodeRiders), _P]),
+    "umv_forward_cache_update_vit_prompt": (C.c_int, [_P, _I, _IP, _IP, _IP, _I, _LP, _IP, _P, _P, _I, _IP, _IP, _IP, C.POINTER(DecodeRiders), _P]),
     "umv_forward_cache_update_vae": (C.c_int, [_P, _I, _IP, _IP, _I, _LP, _IP, _P, _I, _I, _I, _IP, _I, _P, _IP, _F, _IP, _P]),
     "umv_vit_model": (C.c_int, [_P, _P, _P, _IP, _I, _P, _P]),
     "umv_connector": (C.c_int, [_P, _P, _I, _P, _P]),

@@ -395,7 +395,7 @@ class Bagel:
     # ------------------------------------------------------------------ batched VQA job (bench / serving)
     @torch.no_grad()
     def vqa_generate_images(self, images: Sequence[torch.Tensor], prompt_ids: Sequence[Sequence[int]], new_token_ids: dict,
-                            max_length: int, resize_transform=None) -> torch.Tensor:
+                            max_length: int, resize_transform=None, fused_prefill: bool = True) -> torch.Tensor:
         """vqa_generate from uint8 [H, W, 3] images in pinned host memory: the images go up as uint8 and are normalised /
         patchified on the device (Engine.patchify_u8).  Without `resize_transform` they must already be at their ViT size
         (sides multiples of the patch); with it (``vit_transform.resize_transform``, data/transforms.py:15-87) each image is
@@ -407,17 +407,23 @@ class Bagel:
                 sized.append(im if (h, w) == tuple(im.shape[:2]) else self.engine.resize_u8(im, h, w))
             images = sized
         pixels, pos, lens = self.engine.patchify_u8(images)
-        return self.vqa_generate(pixels, pos, lens, prompt_ids, new_token_ids, max_length)
+        return self.vqa_generate(pixels, pos, lens, prompt_ids, new_token_ids, max_length, fused_prefill)
 
     @torch.no_grad()
-    def vqa_generate(self, pixels: torch.Tensor, vit_pos_ids: torch.Tensor, vit_seqlens: Sequence[int],
-                     prompt_ids: Sequence[Sequence[int]], new_token_ids: dict, max_length: int) -> torch.Tensor:
-        """One packed VQA job for B samples (one image each): host (pinned) tensors in, host tokens out.
-        The same sequence of calls the reference's chat() makes, batched over samples as
-        InterleaveInferencer's packed API allows: ViT prefill -> prompt prefill -> greedy decode."""
+    def vqa_prefill(self, pixels: torch.Tensor, vit_pos_ids: torch.Tensor, vit_seqlens: Sequence[int],
+                    prompt_ids: Sequence[Sequence[int]], new_token_ids: dict, fused_prefill: bool = True):
+        """Context of a fresh VQA job for B samples (one image each): image block + prompt.  Returns (cache, kv_lens, rope)."""
         B = len(vit_seqlens)
         dev = self.device
         cache = NaiveCache(self.config.llm_config.num_hidden_layers)
+        if fused_prefill:
+            # image block and prompt of every sample in one pass over the weights (umv_forward_cache_update_vit_prompt): the prompt rows
+            # attend causally behind the full-mask block; K / V are bit-identical to the two calls below
+            L = packing.image_prompt_layout([int(n) for n in vit_seqlens], prompt_ids, new_token_ids)
+            h = paged_handle(cache, self.engine, B)
+            self.engine.forward_cache_update_vit(h.seqs, L["seq_lens"], L["text_ids"], L["text_rows"], pixels, vit_pos_ids,
+                                                 [int(n) for n in vit_seqlens], L["vit_rows"], L["positions"], prompt_lens=L["prompt_lens"])
+            return cache, L["kv_lens"], L["rope"]
         zeros = [0] * B
         # image block: [<vision_start>, patches, <vision_end>] per sample, one rope position
         L = packing._image_block_layout(zeros, zeros, [int(n) for n in vit_seqlens], new_token_ids)
@@ -435,6 +441,16 @@ class Bagel:
             def encode(self, i): return list(self.t[i])
         g, lens, rope = packing.prepare_prompts(lens, rope, list(range(B)), _Ids(prompt_ids), new_token_ids)
         cache = self.forward_cache_update_text(cache, **g)
+        return cache, lens, rope
+
+    @torch.no_grad()
+    def vqa_generate(self, pixels: torch.Tensor, vit_pos_ids: torch.Tensor, vit_seqlens: Sequence[int],
+                     prompt_ids: Sequence[Sequence[int]], new_token_ids: dict, max_length: int, fused_prefill: bool = True) -> torch.Tensor:
+        """One packed VQA job for B samples (one image each): host (pinned) tensors in, host tokens out.
+        The same sequence of calls the reference's chat() makes, batched over samples as
+        InterleaveInferencer's packed API allows: ViT prefill -> prompt prefill -> greedy decode (fused_prefill: the two prefills in
+        one forward)."""
+        cache, lens, rope = self.vqa_prefill(pixels, vit_pos_ids, vit_seqlens, prompt_ids, new_token_ids, fused_prefill)
         g = packing.prepare_start_tokens(lens, rope, new_token_ids)
         toks = self.generate_text(past_key_values=cache, max_length=max_length, end_token_id=None, **g)
         out = torch.empty(toks.shape, dtype=toks.dtype, pin_memory=True)

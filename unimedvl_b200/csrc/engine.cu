@@ -463,7 +463,7 @@ static int llm_layers(umv_engine* e, const LlmRun& r, bf16* out, cudaStream_t st
         ra.q_out = e->qkv; ra.ldq = QN;
         if (seg) { ra.q_out = e->act; ra.ldq = H * dh; ra.q_row_map = r.m.seg_to_packed; }    // queries to their packed rows (e->act is idle here)
         ra.positions = r.m.positions; ra.row_seq = r.m.row_seq; ra.row_kvpos = r.m.row_kvpos;
-        ra.page_table = r.m.page_table; ra.max_pages = r.m.max_pages; ra.inv_freq = e->inv_freq; ra.rope_cs = r.m.rope_cs;
+        ra.page_table = r.m.rope_page_table; ra.max_pages = r.m.max_pages; ra.inv_freq = e->inv_freq; ra.rope_cs = r.m.rope_cs;
         ra.qn0 = L.qn[0]; ra.kn0 = L.kn[0]; ra.qn1 = L.qn[E]; ra.kn1 = L.kn[E];
         ra.row_sel = r.gen ? r.m.row_sel : nullptr; ra.gen_mode = r.gen ? 1 : 0;
         ra.pool = e->pool; ra.layer = li; ra.M = M; ra.H = H; ra.Hkv = Hkv; ra.dh = dh; ra.eps = d.rms_eps;
@@ -479,6 +479,11 @@ static int llm_layers(umv_engine* e, const LlmRun& r, bf16* out, cudaStream_t st
         if (path) {
             const char* tc_env = getenv("UMV_ATTN_TC");
             *path = (!(tc_env && atoi(tc_env) == 0) && attention_tc_supported(aa)) ? 2 : 1;
+        }
+        if (r.m.n_tail > 0) {        // causal tails (llm_run): the block groups under the call's mask, then the tail groups causally
+            if (aa.n > 0) UMV_TRY(attention_forward(aa, st));
+            aa.q_start = r.m.tail_q_start; aa.q_len = r.m.tail_q_len; aa.kv_len = r.m.tail_kv_len; aa.page_table = r.m.tail_page_table;
+            aa.n = r.m.n_tail; aa.max_q_len = r.m.tail_max_q; aa.causal = 1;
         }
         return attention_forward(aa, st);
     };
@@ -918,7 +923,8 @@ bool gen_rows_segregate(int n_seqs, const int32_t* q_lens, const uint8_t* row_is
 // Packed forward over n_seqs sequences; x == nullptr means the packed query sequence is already in e->h (presegregated: in the
 // segregated row order of gen_rows_segregate, and `out` is wanted in that order too -- the flow step composes and consumes it so).
 int llm_run(umv_engine* e, const bf16* x, int n_seqs, const int32_t* seqs, const int32_t* q_lens, const int32_t* positions,
-            const uint8_t* row_is_gen, int is_causal, int update_kv, bf16* out, cudaStream_t st, AttnProbe* probe, int presegregated) {
+            const uint8_t* row_is_gen, int is_causal, int update_kv, bf16* out, cudaStream_t st, AttnProbe* probe, int presegregated,
+            const int32_t* causal_tail) {
     UMV_REQUIRE(seqs && q_lens && positions && n_seqs > 0, UMV_ERR_INVALID, "umv_llm_forward: null/empty argument");
     UMV_REQUIRE(n_seqs <= 3 * e->d.max_seqs, UMV_ERR_INVALID, "umv_llm_forward: %d sequences > 3*max_seqs", n_seqs);
     UMV_REQUIRE(!row_is_gen || e->d.enable_gen, UMV_ERR_STATE, "generation expert weights were not enabled");
@@ -936,6 +942,16 @@ int llm_run(umv_engine* e, const bf16* x, int n_seqs, const int32_t* seqs, const
     r.M = M;
     r.seg = !probe && e->d.heads * e->dh <= e->w_act && gen_rows_segregate(n_seqs, q_lens, row_is_gen, is_causal, &r.Mg);
     UMV_REQUIRE(!presegregated || r.seg, UMV_ERR_STATE, "llm_run: rows were laid out segregated but the forward is not");
+    // causal_tail[b] > 0: the last causal_tail[b] rows of sample b are a causal continuation (a prompt) behind a block that runs under
+    // the call's mask (an image block, full mask) -- two prefills of the reference (forward_cache_update_vit, then _text) in ONE pass
+    // over the weights.  The block's rows do not see the tail; every tail row sees the block and the tail rows before it.
+    bool tails = false;
+    if (causal_tail)
+        for (int b = 0; b < n_seqs; ++b) {
+            UMV_REQUIRE(causal_tail[b] >= 0 && causal_tail[b] <= q_lens[b], UMV_ERR_INVALID, "llm_run: causal tail of sample %d out of range", b);
+            tails = tails || causal_tail[b] > 0;
+        }
+    UMV_REQUIRE(!tails || (!r.gen && !probe && !is_causal), UMV_ERR_UNSUPPORTED, "llm_run: causal tails exist for understanding-mode full-mask prefills");
     // reserve pages, gather geometry
     int max_pages = 0;
     std::vector<Seq*> sq(n_seqs);
@@ -963,33 +979,54 @@ int llm_run(umv_engine* e, const bf16* x, int n_seqs, const int32_t* seqs, const
     r.n_seqs = n_seqs;
     for (int b = 0; b < n_seqs; ++b) r.max_q_len = std::max(r.max_q_len, q_lens[b]);
     MetaBuilder mb;
-    UMV_TRY(meta_begin(e, &mb, (size_t)(n_seqs * 16 + 64) + (size_t)M * 32 + (size_t)n_seqs * max_pages * 4));
+    UMV_TRY(meta_begin(e, &mb, (size_t)(n_seqs * 48 + 256) + (size_t)M * 32 + (size_t)n_seqs * max_pages * (tails ? 12 : 4)));
     CallMeta& m = r.m;
     m.max_pages = max_pages;
-    int* hq = mb.put<int>(nullptr, n_seqs + 1, &m.q_start);
-    int* hql = mb.put<int>(nullptr, n_seqs, &m.q_len);
-    int* hkl = mb.put<int>(nullptr, n_seqs, &m.kv_len);
     int* hpos = mb.put<int>(r.seg ? nullptr : positions, M, &m.positions);
     int* hrs = mb.put<int>(nullptr, M, &m.row_seq);
     int* hrp = mb.put<int>(nullptr, M, &m.row_kvpos);
-    int* hpt = mb.put<int>(nullptr, (size_t)n_seqs * max_pages, &m.page_table);
+    int* hpt = mb.put<int>(nullptr, (size_t)n_seqs * max_pages, &m.rope_page_table);
     if (r.seg) {
         mb.put<int>(order.data(), M, &m.seg_to_packed);
         mb.put<int>(inverse.data(), M, &m.packed_to_seg);
     }
+    // attention groups: (sample, first row, rows, keys).  One per sample -- or, with causal tails, the block groups and the tail groups
+    struct Group { int b, row0, n, kv; };
+    std::vector<Group> main_groups, tail_groups;
     int row = 0;
-    hq[0] = 0;
     for (int b = 0; b < n_seqs; ++b) {
-        hql[b] = q_lens[b];
-        hkl[b] = sq[b]->len + q_lens[b];
+        const int tail = tails ? causal_tail[b] : 0, head = q_lens[b] - tail;
+        if (head > 0 || !tails) main_groups.push_back({b, row, head, sq[b]->len + head});
+        if (tail > 0) tail_groups.push_back({b, row + head, tail, sq[b]->len + q_lens[b]});
         for (int j = 0; j < q_lens[b]; ++j, ++row) {
             const int at = r.seg ? inverse[row] : row;     // where the per-row metadata of packed row `row` lives
             hrs[at] = b;
             hrp[at] = sq[b]->len + j;
             if (r.seg) hpos[at] = positions[row];
         }
-        hq[b + 1] = row;
         for (int p = 0; p < max_pages; ++p) hpt[(size_t)b * max_pages + p] = p < (int)sq[b]->pages.size() ? sq[b]->pages[p] : 0;
+    }
+    auto put_groups = [&](const std::vector<Group>& gs, int** q_start, int** q_len, int** kv_len, int** page_table, int* max_q) {
+        const int ng = (int)gs.size();
+        int* hq = mb.put<int>(nullptr, ng + 1, q_start);
+        int* hql = mb.put<int>(nullptr, ng, q_len);
+        int* hkl = mb.put<int>(nullptr, ng, kv_len);
+        int* pt = mb.put<int>(nullptr, (size_t)ng * max_pages, page_table);
+        *max_q = 0;
+        for (int gi = 0; gi < ng; ++gi) {
+            hq[gi] = gs[gi].row0;
+            hql[gi] = gs[gi].n;
+            hkl[gi] = gs[gi].kv;
+            *max_q = std::max(*max_q, gs[gi].n);
+            memcpy(pt + (size_t)gi * max_pages, hpt + (size_t)gs[gi].b * max_pages, (size_t)max_pages * sizeof(int));
+        }
+        hq[ng] = ng ? gs[ng - 1].row0 + gs[ng - 1].n : 0;
+    };
+    put_groups(main_groups, &m.q_start, &m.q_len, &m.kv_len, &m.page_table, &r.max_q_len);
+    r.n_seqs = (int)main_groups.size();
+    if (tails) {
+        put_groups(tail_groups, &m.tail_q_start, &m.tail_q_len, &m.tail_kv_len, &m.tail_page_table, &m.tail_max_q);
+        m.n_tail = (int)tail_groups.size();
     }
     if (r.gen && r.seg) {
         std::vector<uint8_t> sel(M, 0);
@@ -1229,6 +1266,7 @@ int umv_generate_text(umv_engine* e, int32_t n_seqs, const int32_t* seqs, const 
     UMV_CUDA_OK(cudaStreamSynchronize(st));     // host vectors above go out of scope; also a clean capture start
     r.m.q_start = e->dec_qstart; r.m.q_len = e->dec_qlen; r.m.kv_len = e->dec_kvlen; r.m.positions = e->dec_pos;
     r.m.row_seq = e->dec_rowseq; r.m.row_kvpos = e->dec_kvpos; r.m.page_table = e->dec_pages; r.m.max_pages = max_pages;
+    r.m.rope_page_table = e->dec_pages;
     DecodeState ds{e->dec_tokens, e->dec_pos, e->dec_kvlen, e->dec_kvpos, e->dec_step, e->dec_rope, e->inv_freq, e->dh};
     r.m.rope_cs = e->dec_rope;
 
@@ -1474,9 +1512,10 @@ int umv_time_embedder(umv_engine* e, const float* timesteps, int32_t n, void* ou
 // e->h; after the forward their final hidden states go through lm_head and argmax / sampling.  A single query row sees its whole
 // context under either mask, so riders join causal (text) and full-attention (image block) prefills alike.
 static int run_with_riders(umv_engine* e, int M, int n_seqs, const int32_t* seqs, const int32_t* q_lens, const int32_t* positions,
-                           const uint8_t* row_is_gen, int is_causal, const umv_decode_riders* rd, cudaStream_t st) {
+                           const uint8_t* row_is_gen, int is_causal, const umv_decode_riders* rd, cudaStream_t st,
+                           const int32_t* causal_tail = nullptr) {
     const int n = rd ? rd->n : 0;
-    if (n <= 0) return umv::llm_run(e, nullptr, n_seqs, seqs, q_lens, positions, row_is_gen, is_causal, 1, nullptr, st);
+    if (n <= 0) return umv::llm_run(e, nullptr, n_seqs, seqs, q_lens, positions, row_is_gen, is_causal, 1, nullptr, st, nullptr, 0, causal_tail);
     UMV_REQUIRE(rd->seqs && rd->tokens && rd->positions && rd->next_tokens && n <= 64, UMV_ERR_INVALID, "decode riders: bad argument (n <= 64)");
     UMV_REQUIRE(M + n <= e->d.max_tokens, UMV_ERR_NOMEM, "prefill rows + decode riders (%d) > max_tokens %d", M + n, e->d.max_tokens);
     const int D = e->d.hidden, V = e->d.vocab;
@@ -1496,7 +1535,13 @@ static int run_with_riders(umv_engine* e, int M, int n_seqs, const int32_t* seqs
         pos.push_back(rd->positions[i]);
         if (row_is_gen) gen.push_back(0);                    // a decode row is a text row: understanding expert
     }
-    UMV_TRY(umv::llm_run(e, nullptr, n_seqs + n, sq.data(), ql.data(), pos.data(), row_is_gen ? gen.data() : nullptr, is_causal, 1, nullptr, st));
+    std::vector<int32_t> ct;
+    if (causal_tail) {
+        ct.assign(causal_tail, causal_tail + n_seqs);
+        ct.resize(n_seqs + n, 0);                            // a rider is one row: no tail
+    }
+    UMV_TRY(umv::llm_run(e, nullptr, n_seqs + n, sq.data(), ql.data(), pos.data(), row_is_gen ? gen.data() : nullptr, is_causal, 1, nullptr, st,
+                         nullptr, 0, causal_tail ? ct.data() : nullptr));
     // final-normed hidden states of all rows are in e->xn; the riders' are the last n
     UMV_TRY(lin(e, e->xn + (size_t)M * D, D, e->lm_head, nullptr, nullptr, e->logits, V, n, V, D, EPI_BF16, st));
     if (rd->temperature > 0.f) return sample_rows(e->logits, n, V, rd->temperature, rd->seed, nullptr, rd->next_tokens, st);
@@ -1541,6 +1586,14 @@ int umv_forward_cache_update_vit_riders(umv_engine* e, int32_t n_seqs, const int
                                         const int64_t* vit_pos_ids, int32_t n_images, const int32_t* vit_seqlens,
                                         const int32_t* vit_rows, const int32_t* positions, const umv_decode_riders* riders,
                                         void* stream) {
+    return umv_forward_cache_update_vit_prompt(e, n_seqs, seqs, seq_lens, nullptr, n_text, text_ids, text_rows, pixels, vit_pos_ids, n_images,
+                                               vit_seqlens, vit_rows, positions, riders, stream);
+}
+int umv_forward_cache_update_vit_prompt(umv_engine* e, int32_t n_seqs, const int32_t* seqs, const int32_t* seq_lens,
+                                        const int32_t* prompt_lens, int32_t n_text, const int64_t* text_ids, const int32_t* text_rows,
+                                        const float* pixels, const int64_t* vit_pos_ids, int32_t n_images, const int32_t* vit_seqlens,
+                                        const int32_t* vit_rows, const int32_t* positions, const umv_decode_riders* riders,
+                                        void* stream) {
     UMV_REQUIRE(e && e->finalized, UMV_ERR_STATE, "engine not finalized");
     UMV_REQUIRE(seqs && seq_lens && text_ids && text_rows && vit_rows && positions && n_seqs > 0 && n_text >= 0, UMV_ERR_INVALID,
                 "umv_forward_cache_update_vit: null/empty argument");
@@ -1564,8 +1617,8 @@ int umv_forward_cache_update_vit_riders(umv_engine* e, int32_t n_seqs, const int
     mb.put<int>(vit_rows, N, &d_vrows);
     UMV_TRY(meta_commit(e, &mb, st));
     UMV_TRY(scatter_add_rows(e->attn, e->vit_pos_embed, vit_pos_ids, d_vrows, e->h, N, D, st));      // + vit_pos_embed, to its rows
-    UMV_TRY(embed_rows_scatter(e->embed, d_ids, d_trows, n_text, D, e->d.vocab, e->h, st));          // marker embeddings
-    return run_with_riders(e, M, n_seqs, seqs, seq_lens, positions, nullptr, 0, riders, st);
+    UMV_TRY(embed_rows_scatter(e->embed, d_ids, d_trows, n_text, D, e->d.vocab, e->h, st));          // marker (and prompt) embeddings
+    return run_with_riders(e, M, n_seqs, seqs, seq_lens, positions, nullptr, 0, riders, st, prompt_lens);
 }
 
 int umv_forward_cache_update_vae(umv_engine* e, int32_t n_seqs, const int32_t* seqs, const int32_t* seq_lens, int32_t n_text,

@@ -52,6 +52,11 @@ struct CallMeta {
     int* text_rows = nullptr;   // [T] rows routed to the understanding expert (gen mode)
     int* text_slot = nullptr;   // [M] inverse map: index into text_rows, or -1
     uint8_t* row_sel = nullptr; // [M]
+    // a prefill whose samples end in a CAUSAL tail behind a full-mask block (image block + prompt in one forward, llm_run's causal_tail):
+    // attention runs twice per layer -- the block groups above with the call's mask, the tail groups below causally
+    int* tail_q_start = nullptr; int* tail_q_len = nullptr; int* tail_kv_len = nullptr; int* tail_page_table = nullptr;
+    int* rope_page_table = nullptr;   // [samples][max_pages]: the K/V append indexes pages by SAMPLE (row_seq), the attention launches by group
+    int n_tail = 0, tail_max_q = 0;
     int* seg_to_packed = nullptr;     // [M] segregated gen-mode rows (llm_run): packed row of segregated row i ...
     int* packed_to_seg = nullptr;     // [M] ... and the inverse
     const float* rope_cs = nullptr;   // decode loop: per-step cos | sin table [n][dh]
@@ -100,7 +105,7 @@ struct AttnProbe {
 };
 int llm_run(umv_engine* e, const bf16* x, int n_seqs, const int32_t* seqs, const int32_t* q_lens, const int32_t* positions,
             const uint8_t* row_is_gen, int is_causal, int update_kv, bf16* out, cudaStream_t st, AttnProbe* probe = nullptr,
-            int presegregated = 0);
+            int presegregated = 0, const int32_t* causal_tail = nullptr);
 // A non-causal gen-mode forward runs on SEGREGATED rows: the generation-expert rows of all samples first (packed order), then the
 // understanding-expert (marker) rows.  True when llm_run will use that layout for these arguments (a full-mask forward with rows of both
 // kinds; UMV_GEN_SEG=0 switches it off); *n_gen = generation rows.

@@ -327,13 +327,16 @@ class Engine:
         return nxt
 
     def forward_cache_update_vit(self, seqs, seq_lens, text_ids, text_rows, pixels, vit_pos_ids, vit_seqlens, vit_rows, positions,
-                                 riders=None, temperature: float = 0.0, seed: int = 0):
+                                 riders=None, temperature: float = 0.0, seed: int = 0, prompt_lens=None):
+        """prompt_lens (umv_forward_cache_update_vit_prompt): the last prompt_lens[b] packed rows of sample b are its prompt, prefilled
+        causally behind the image block in the same forward."""
         pixels = pixels.to(self.device, torch.float32, non_blocking=True).contiguous()
         vit_pos_ids = vit_pos_ids.to(self.device, torch.int64, non_blocking=True).contiguous()
         rd, keep, nxt = self._riders(riders, temperature, seed)
         self._enter()
-        _lib.check(self.lib.umv_forward_cache_update_vit_riders(
-            self.h, len(seqs), _lib.i32_array(seqs), _lib.i32_array(seq_lens), len(text_ids), _lib.i64_array(text_ids),
+        _lib.check(self.lib.umv_forward_cache_update_vit_prompt(
+            self.h, len(seqs), _lib.i32_array(seqs), _lib.i32_array(seq_lens),
+            _lib.i32_array(prompt_lens) if prompt_lens is not None else None, len(text_ids), _lib.i64_array(text_ids),
             _lib.i32_array(text_rows), _ptr(pixels), _ptr(vit_pos_ids), len(vit_seqlens), _lib.i32_array(vit_seqlens),
             _lib.i32_array(vit_rows), _lib.i32_array(positions), rd, _stream_ptr(self.stream)))
         self._exit()

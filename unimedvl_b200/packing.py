@@ -148,6 +148,27 @@ def _image_block_layout(curr_kvlens, curr_rope, n_img_tokens, new_token_ids):
                 packed_idx=cat(packed_idx), pos=cat(pos))
 
 
+def image_prompt_layout(n_img_tokens, prompt_ids, new_token_ids):
+    """Packed rows of a fresh VQA job prefilled in ONE forward (Engine.forward_cache_update_vit(prompt_lens=...)): per sample
+    [start_of_image, n image tokens, end_of_image] at rope position 0 -- the block prepare_vit_images lays out (bagel.py:460-520) -- followed
+    by [bos, prompt ids, eos] at rope positions 1, 2, ... -- the rows prepare_prompts lays out on top of it (bagel.py:377-409).  Returns the
+    row lists the engine call takes and the (kv_lens, rope) state after both prefills."""
+    seq_lens, prompt_lens, text_ids, text_rows, vit_rows, pos = [], [], [], [], [], []
+    row = 0
+    for n, ids in zip(n_img_tokens, prompt_ids):
+        n = int(n)
+        p = [new_token_ids["bos_token_id"]] + [int(t) for t in ids] + [new_token_ids["eos_token_id"]]
+        text_ids += [new_token_ids["start_of_image"], new_token_ids["end_of_image"]] + p
+        text_rows += [row, row + n + 1] + list(range(row + n + 2, row + n + 2 + len(p)))
+        vit_rows += list(range(row + 1, row + 1 + n))
+        pos += [0] * (n + 2) + list(range(1, 1 + len(p)))
+        seq_lens.append(n + 2 + len(p))
+        prompt_lens.append(len(p))
+        row += n + 2 + len(p)
+    return dict(seq_lens=seq_lens, prompt_lens=prompt_lens, text_ids=text_ids, text_rows=text_rows, vit_rows=vit_rows, positions=pos,
+                kv_lens=list(seq_lens), rope=[1 + p for p in prompt_lens])
+
+
 def prepare_vit_images(curr_kvlens, curr_rope, images, transforms, new_token_ids, vit_patch_size=14,
                        vit_max_num_patch_per_side=70):
     tensors = [transforms(im) for im in images]
