@@ -82,17 +82,19 @@ def test_continuous_batching_matches_solo_runs(stack):
     gc.collect()
     assert eng.pages_free() == free0
 
-    for mixed in (False, True):
+    for mixed, fused in ((False, False), (True, False), (False, True), (True, True)):
         # mixed=True: the admission forwards (image block / prompt prefill of the NEW requests) carry one decode row per RUNNING request
         # (umv_decode_riders) -- prefill and decode of different requests in one packed forward; same tokens either way
-        cb = ContinuousBatcher(model, tok, TOK, vit_tf, max_batch=3, chunk=4, end_token_id=eos, mixed=mixed)
+        # fused=True: image block + prompt of an admission group in ONE forward (umv_forward_cache_update_vit_prompt) when every request
+        # of the group has an image
+        cb = ContinuousBatcher(model, tok, TOK, vit_tf, max_batch=3, chunk=4, end_token_id=eos, mixed=mixed, fused_prefill=fused)
         ids = [cb.submit(**r) for r in reqs]
         got = cb.run()
         assert sorted(got) == ids
         for i, w in zip(ids, want):
-            assert torch.equal(got[i], w), (mixed, i, got[i].tolist(), w.tolist())
+            assert torch.equal(got[i], w), (mixed, fused, i, got[i].tolist(), w.tolist())
         st = cb.stats
-        assert st["admitted"] == len(reqs) and st["prefill_calls"] > 2          # admitted in several waves, not one batch
+        assert st["admitted"] == len(reqs) and st["prefill_calls"] > (1 if fused else 2)      # admitted in several waves, not one batch
         assert st["slot_steps_used"] == sum(len(w) for w in want)
         # a slot is held only until its request ends (at most chunk - 1 wasted steps in its last chunk), not until the batch ends
         assert st["decode_steps"] + st["rider_steps"] <= st["slot_steps_used"] + len(reqs) * (4 - 1)

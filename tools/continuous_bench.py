@@ -42,8 +42,8 @@ lengths = rng.integers(16, 129, N).tolist()
 images = [Image.fromarray(synth.synthetic_image(i, bench.IMG, bench.IMG)) for i in range(N)]
 
 
-def run(continuous: bool, chunk: int):
-    cb = ContinuousBatcher(model, Ids(), tok, vit_tf, max_batch=B, chunk=chunk, end_token_id=-1)
+def run(continuous: bool, chunk: int, fused: bool = True):
+    cb = ContinuousBatcher(model, Ids(), tok, vit_tf, max_batch=B, chunk=chunk, end_token_id=-1, fused_prefill=fused)
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     out = {}
@@ -64,9 +64,13 @@ def run(continuous: bool, chunk: int):
 
 rows = []
 ref = None
-for name, cont, chunk in (("static, batches of 8", False, 128), ("continuous, chunk 16", True, 16), ("continuous, chunk 8", True, 8)):
-    run(cont, chunk)                                  # warm-up (graphs of every block count, allocator)
-    dt, st, out = run(cont, chunk)
+for name, cont, chunk, fused in (("static, batches of 8, two prefill forwards", False, 128, False),
+                                 ("static, batches of 8, fused image + prompt prefill", False, 128, True),
+                                 ("continuous, chunk 16, two prefill forwards per admission", True, 16, False),
+                                 ("continuous, chunk 16, fused admission prefill", True, 16, True),
+                                 ("continuous, chunk 8, fused admission prefill", True, 8, True)):
+    run(cont, chunk, fused)                           # warm-up (graphs of every block count, allocator)
+    dt, st, out = run(cont, chunk, fused)
     toks = [out[k] for k in sorted(out)]
     if ref is None:
         ref = toks

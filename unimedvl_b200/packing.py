@@ -148,25 +148,29 @@ def _image_block_layout(curr_kvlens, curr_rope, n_img_tokens, new_token_ids):
                 packed_idx=cat(packed_idx), pos=cat(pos))
 
 
-def image_prompt_layout(n_img_tokens, prompt_ids, new_token_ids):
-    """Packed rows of a fresh VQA job prefilled in ONE forward (Engine.forward_cache_update_vit(prompt_lens=...)): per sample
-    [start_of_image, n image tokens, end_of_image] at rope position 0 -- the block prepare_vit_images lays out (bagel.py:460-520) -- followed
-    by [bos, prompt ids, eos] at rope positions 1, 2, ... -- the rows prepare_prompts lays out on top of it (bagel.py:377-409).  Returns the
-    row lists the engine call takes and the (kv_lens, rope) state after both prefills."""
+def image_prompt_layout(n_img_tokens, prompt_ids, new_token_ids, curr_kvlens=None, curr_rope=None):
+    """Packed rows of VQA requests prefilled in ONE forward (Engine.forward_cache_update_vit(prompt_lens=...)): per sample
+    [start_of_image, n image tokens, end_of_image] at the sample's rope position r -- the block prepare_vit_images lays out
+    (bagel.py:460-520) -- followed by [bos, prompt ids, eos] at rope positions r + 1, r + 2, ... -- the rows prepare_prompts lays out on top
+    of it (bagel.py:377-409).  curr_kvlens / curr_rope: cache length and rope position each sample starts from (a shared prefix; default
+    0).  Returns the row lists the engine call takes and the (kv_lens, rope) state after both prefills."""
+    B = len(n_img_tokens)
+    curr_kvlens = [0] * B if curr_kvlens is None else [int(k) for k in curr_kvlens]
+    curr_rope = [0] * B if curr_rope is None else [int(r) for r in curr_rope]
     seq_lens, prompt_lens, text_ids, text_rows, vit_rows, pos = [], [], [], [], [], []
     row = 0
-    for n, ids in zip(n_img_tokens, prompt_ids):
+    for n, ids, r in zip(n_img_tokens, prompt_ids, curr_rope):
         n = int(n)
         p = [new_token_ids["bos_token_id"]] + [int(t) for t in ids] + [new_token_ids["eos_token_id"]]
         text_ids += [new_token_ids["start_of_image"], new_token_ids["end_of_image"]] + p
         text_rows += [row, row + n + 1] + list(range(row + n + 2, row + n + 2 + len(p)))
         vit_rows += list(range(row + 1, row + 1 + n))
-        pos += [0] * (n + 2) + list(range(1, 1 + len(p)))
+        pos += [r] * (n + 2) + list(range(r + 1, r + 1 + len(p)))
         seq_lens.append(n + 2 + len(p))
         prompt_lens.append(len(p))
         row += n + 2 + len(p)
     return dict(seq_lens=seq_lens, prompt_lens=prompt_lens, text_ids=text_ids, text_rows=text_rows, vit_rows=vit_rows, positions=pos,
-                kv_lens=list(seq_lens), rope=[1 + p for p in prompt_lens])
+                kv_lens=[k + s_ for k, s_ in zip(curr_kvlens, seq_lens)], rope=[r + 1 + p for r, p in zip(curr_rope, prompt_lens)])
 
 
 def prepare_vit_images(curr_kvlens, curr_rope, images, transforms, new_token_ids, vit_patch_size=14,

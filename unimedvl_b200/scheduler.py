@@ -13,6 +13,8 @@ between calls:
     re-used by the next admission;
   * shared prefixes -- requests naming the same ``prefix`` (e.g. the think-mode system prompt, inferencer.py:574-577)
     fork one prefilled sequence (ref-counted pages, copy-on-write tail) instead of prefilling it again;
+  * fused admission -- when every admitted request carries an image, its image block (full mask) and its prompt (causal) are
+    prefilled in ONE forward (``umv_forward_cache_update_vit_prompt``): one pass over the weights instead of two;
   * mixed steps -- the admission forwards (image block, prompt) carry the running requests along as DECODE RIDERS
     (``umv_decode_riders``): one query row per running request rides in the same packed forward, so decoding does not stop while
     new requests are prefilled (``mixed=True``, the default).
@@ -68,12 +70,14 @@ class _Borrowed:
 
 class ContinuousBatcher:
     def __init__(self, model, tokenizer, new_token_ids: Dict[str, int], vit_transform, max_batch: int = 8, chunk: int = 16,
-                 end_token_id: Optional[int] = None, max_prefill_tokens: Optional[int] = None, mixed: bool = True):
+                 end_token_id: Optional[int] = None, max_prefill_tokens: Optional[int] = None, mixed: bool = True,
+                 fused_prefill: bool = True):
         self.model, self.engine = model, model.engine
         self.tokenizer, self.tok, self.vit_transform = tokenizer, new_token_ids, vit_transform
         self.max_batch = min(max_batch, self.engine.max_seqs, 64)
         self.chunk = chunk
         self.mixed = mixed
+        self.fused_prefill = fused_prefill         # image block + prompt of an admission group in one forward (when every request has an image)
         self._riding: List[Request] = []
         self.eos = new_token_ids["eos_token_id"] if end_token_id is None else end_token_id
         self.max_prefill_tokens = max_prefill_tokens or self.engine.max_tokens
@@ -126,7 +130,8 @@ class ContinuousBatcher:
         # a chunk runs min(chunk, longest remaining budget) steps for EVERY running sequence, so a request may grow up to
         # chunk - 1 tokens past its own budget before it is retired; +1: copy-on-write tail of a forked prefix
         total = prefix_len + n_img + n_txt + r.max_length + self.chunk
-        return max(n_img, n_txt), (total + _PAGE - 1) // _PAGE + 1
+        rows = n_img + n_txt if self.fused_prefill else max(n_img, n_txt)      # one fused forward, or the larger of the two
+        return rows, (total + _PAGE - 1) // _PAGE + 1
 
     def _prefix(self, text: str):
         if text not in self._prefixes:
@@ -171,23 +176,40 @@ class ContinuousBatcher:
             else:
                 r.seq, r.kv_len, r.rope = self.engine.seq_new(), 0, 0
         with_img = [r for r in group if r.image is not None]
-        if with_img:
-            g, lens, ropes = m.prepare_vit_images([r.kv_len for r in with_img], [r.rope for r in with_img],
-                                                  [r.image for r in with_img], self.vit_transform, self.tok)
-            riders = self._riders(sum(lens) - sum(r.kv_len for r in with_img))
-            with _Borrowed(self.engine, self.layers, [r.seq for r in with_img]) as c:
-                m.forward_cache_update_vit(c, **g, decode_riders=riders)
+        if self.fused_prefill and len(with_img) == len(group):
+            # image block + prompt of every admitted request in ONE forward (umv_forward_cache_update_vit_prompt): one pass over the
+            # weights and one rider step instead of two
+            from . import packing
+            gv, _, _ = m.prepare_vit_images([r.kv_len for r in group], [r.rope for r in group], [r.image for r in group],
+                                            self.vit_transform, self.tok)
+            n_img = [int(n) for n in gv["vit_token_seqlens"]]
+            L = packing.image_prompt_layout(n_img, [self.tokenizer.encode(r.prompt) for r in group], self.tok,
+                                            [r.kv_len for r in group], [r.rope for r in group])
+            riders = self._riders(sum(L["seq_lens"]))
+            self.model.rider_tokens = self.engine.forward_cache_update_vit(
+                [r.seq for r in group], L["seq_lens"], L["text_ids"], L["text_rows"], gv["packed_vit_tokens"], gv["packed_vit_position_ids"],
+                n_img, L["vit_rows"], L["positions"], riders=riders, prompt_lens=L["prompt_lens"])
             self._riders_done(riders)
-            for r, l, p in zip(with_img, lens, ropes):
-                r.kv_len, r.rope = l, p
             self.stats["prefill_calls"] += 1
-        g, lens, ropes = m.prepare_prompts([r.kv_len for r in group], [r.rope for r in group], [r.prompt for r in group],
-                                           self.tokenizer, self.tok)
-        riders = self._riders(sum(lens) - sum(r.kv_len for r in group))
-        with _Borrowed(self.engine, self.layers, [r.seq for r in group]) as c:
-            m.forward_cache_update_text(c, **g, decode_riders=riders)
-        self._riders_done(riders)
-        self.stats["prefill_calls"] += 1
+            lens, ropes = L["kv_lens"], L["rope"]
+        else:
+            if with_img:
+                g, lens, ropes = m.prepare_vit_images([r.kv_len for r in with_img], [r.rope for r in with_img],
+                                                      [r.image for r in with_img], self.vit_transform, self.tok)
+                riders = self._riders(sum(lens) - sum(r.kv_len for r in with_img))
+                with _Borrowed(self.engine, self.layers, [r.seq for r in with_img]) as c:
+                    m.forward_cache_update_vit(c, **g, decode_riders=riders)
+                self._riders_done(riders)
+                for r, l, p in zip(with_img, lens, ropes):
+                    r.kv_len, r.rope = l, p
+                self.stats["prefill_calls"] += 1
+            g, lens, ropes = m.prepare_prompts([r.kv_len for r in group], [r.rope for r in group], [r.prompt for r in group],
+                                               self.tokenizer, self.tok)
+            riders = self._riders(sum(lens) - sum(r.kv_len for r in group))
+            with _Borrowed(self.engine, self.layers, [r.seq for r in group]) as c:
+                m.forward_cache_update_text(c, **g, decode_riders=riders)
+            self._riders_done(riders)
+            self.stats["prefill_calls"] += 1
         for r, l, p in zip(group, lens, ropes):
             r.kv_len, r.rope = l, p
             r.next_token = self.tok["bos_token_id"]             # prepare_start_tokens (bagel.py:1213-1233)
