@@ -547,7 +547,7 @@ def run_engine(args, rank: int, local_rank: int, world: int):
         """prompts -> uint8 images on the host: what interleave_inference does for [text] (inferencer.py:552-638), packed over n."""
         ps = [prompt_strs[i % len(prompt_strs)] for i in range(n)]
         ctx = bi.update_context_text(ps, bi.init_gen_context(n))
-        cfg_img = bi.update_context_text(ps, bi.init_gen_context(n))
+        cfg_img = deepcopy(ctx)        # text only: the image-free context holds the same tokens -- a page fork, not a second prefill
         torch.manual_seed(42)
         u8 = bi.gen_image((T2I_SIZE, T2I_SIZE), ctx, cfg_text_precontext=bi.init_gen_context(n), cfg_img_precontext=cfg_img, as_uint8=True,
                           **t2i_kw)
@@ -563,8 +563,8 @@ def run_engine(args, rank: int, local_rank: int, world: int):
         img = t2i_job(B_T2I)
         tf = t2i_flops_img * B_T2I / (ms_t / 1e3) / 1e12
         extra["t2i"] = {
-            "config": f"BASELINE configs[3] per-GPU share, the whole job: {B_T2I} prompts per GPU -> {T2I_SIZE}x{T2I_SIZE}: prompt prefill (main + cfg_img "
-                      "contexts), 50 timesteps (41 x 3 CFG branches + 8 x 1), shift 3.0, CFG 4.0 / 1.5 on (0.4, 1], per-image global renorm, VAE decode, "
+            "config": f"BASELINE configs[3] per-GPU share, the whole job: {B_T2I} prompts per GPU -> {T2I_SIZE}x{T2I_SIZE}: prompt prefill (the cfg_img "
+                      "context is a page fork of it), 50 timesteps (41 x 3 CFG branches + 8 x 1), shift 3.0, CFG 4.0 / 1.5 on (0.4, 1], per-image global renorm, VAE decode, "
                       "uint8 conversion on the device, NCCL all_gather of the images, D2H; device-timed, max over ranks, 2 runs after 1 warm-up",
             "value": round(world * B_T2I / (ms_t / 1e3), 4), "unit": "img/s", "ms_per_batch": round(ms_t, 1), "images_per_gpu": B_T2I,
             "algorithmic_tflop_per_image": round(t2i_flops_img / 1e12, 1), "d2h_bytes_per_step": int(img.numel()),

@@ -163,21 +163,25 @@ class BatchedInferencer(InterleaveInferencer):
         need_cfg = not understanding_output
         cfg_img_context = deepcopy(gen_context) if need_cfg else None
         cfg_text_context = None
+        # The image-free context (cfg_img) receives every text the main context receives (inferencer.py:578-600).  Until the first image
+        # the two hold the same tokens, hence the same K / V: cfg_img is then a page fork of the main context, not a second prefill.
+        same_so_far = True
         if think:
             system_prompt = VLM_THINK_SYSTEM_PROMPT if understanding_output else GEN_THINK_SYSTEM_PROMPT
             gen_context = self.update_context_text([system_prompt] * B, gen_context)
             if need_cfg:
-                cfg_img_context = self.update_context_text([system_prompt] * B, cfg_img_context)
+                cfg_img_context = deepcopy(gen_context)
         for kind, col in zip(kinds, cols):
             if kind == "text":
                 if need_cfg:
                     cfg_text_context = deepcopy(gen_context)
                 gen_context = self.update_context_text(col, gen_context)
                 if need_cfg:
-                    cfg_img_context = self.update_context_text(col, cfg_img_context)
+                    cfg_img_context = deepcopy(gen_context) if same_so_far else self.update_context_text(col, cfg_img_context)
             else:
                 col = [self.vae_transform.resize_transform(pil_img2rgb(im)) for im in col]
                 gen_context = self.update_context_image(col, gen_context, vae=not understanding_output)
+                same_so_far = False
                 if need_cfg:
                     cfg_text_context = deepcopy(gen_context)
         if understanding_output:
