@@ -170,6 +170,10 @@ typedef struct umv_flow_args {
     float cfg_text_scale, cfg_img_scale, cfg_renorm_min;
     int32_t renorm_type;
 } umv_flow_args;
+/* Number of CFG branches the last umv_flow_velocity call evaluated: 1 + (cfg_text) + (cfg_img), minus the cfg_img branch when its context
+ * is known to hold the main context's tokens (a fork of it: pure text-to-image, inferencer.py:578-600) -- that velocity is the main
+ * branch's, bit for bit, and is computed once.  Measurement / test hook. */
+int umv_flow_branches_last(umv_engine* e, int32_t* n);
 int umv_flow_velocity(umv_engine* e, const umv_flow_args* a, const float* x_t, float* v_out, void* stream);
 /* x_t <- x_t - bf16(v * dt) (bagel.py:983; v*dt rounds to bf16 when v is bf16-valued). */
 int umv_flow_euler(umv_engine* e, float* x_t, const float* v, int64_t n, float dt, int32_t v_is_bf16, void* stream);

@@ -126,3 +126,41 @@ def test_flow_velocity_segregated_is_bit_identical_to_packed(eng, renorm):
     assert [e.seq_len(s) for s in main] == ctx_lens                     # update_past_key_values=False: caches untouched
     for s in main + cfg_text + cfg_img:
         e.seq_free(s)
+
+
+def test_cfg_branch_over_the_same_context_is_evaluated_once(eng, monkeypatch):
+    """Pure text-to-image: the image-free CFG context holds the main context's tokens (inferencer.py:578-600), so the cfg_img velocity IS
+    the main one.  umv_flow_velocity recognises a fork of the main context (same content id, length, rope position) and runs two branches
+    instead of three; the guided velocity is bit-identical to the three-branch evaluation (UMV_CFG_DEDUP=0), the third branch's rows are not computed.  A context that received its own (identical) prefill, or differs in length, is NOT deduplicated."""
+    e, dims = eng
+    g = torch.Generator().manual_seed(5)
+    D, C = dims.llm.hidden, dims.patch_latent_dim
+    ctx_lens = [30, 18]
+    ctx = (torch.randn(sum(ctx_lens), D, generator=g) * 0.5).bfloat16()
+    pos0 = [j for n in ctx_lens for j in range(n)]
+    main = [e.seq_new() for _ in ctx_lens]
+    e.llm_forward(ctx, main, ctx_lens, pos0, want_hidden=False)
+    fork = [e.seq_fork(s) for s in main]
+    own = [e.seq_new() for _ in ctx_lens]                     # same tokens, prefilled separately: equal K / V, but not known to be
+    e.llm_forward(ctx, own, ctx_lens, pos0, want_hidden=False)
+    empty = [e.seq_new() for _ in ctx_lens]
+    lat_lens = [256, 256]
+    x_t = torch.randn(sum(lat_lens), C, generator=g).cuda().contiguous()
+    lat_pos = torch.cat([torch.arange(n) for n in lat_lens])
+
+    def run(img, dedup):
+        monkeypatch.setenv("UMV_CFG_DEDUP", dedup)
+        v = e.flow_velocity(x_t, lat_pos, lat_lens, main, ctx_lens, [5, 6], 0.7, cfg_text=(empty, [0, 0]), cfg_img=(img, ctx_lens),
+                            cfg_text_scale=4.0, cfg_img_scale=1.5, renorm_type=0).cpu().clone()
+        return v, e.flow_branches_last()
+    v3, n3 = run(fork, "0")
+    v2, n2 = run(fork, "1")
+    assert (n3, n2) == (3, 2) and torch.equal(v2, v3)
+    vo, no = run(own, "1")
+    assert no == 3 and torch.equal(vo, v3)                     # not deduplicated; equal all the same (deterministic kernels)
+    vs, ns = run(main, "1")                                     # the main context itself as the image-free context
+    assert ns == 2 and torch.equal(vs, v3)
+    e.llm_forward(ctx[:1], [fork[0]], [1], [ctx_lens[0]], want_hidden=False)      # the fork moves on: no longer the main context
+    assert run(fork, "1")[1] == 3
+    for s in main + fork + own + empty:
+        e.seq_free(s)

@@ -75,6 +75,7 @@ SIGNATURES = {
     "umv_lm_head": (C.c_int, [_P, _P, _I, _P, _P]),
     "umv_generate_text": (C.c_int, [_P, _I, _IP, _LP, _IP, _I, _F, _U64, _P, _P, _P, _P, _P]),
     "umv_flow_velocity": (C.c_int, [_P, C.POINTER(FlowArgs), _P, _P, _P]),
+    "umv_flow_branches_last": (C.c_int, [_P, _IP]),
     "umv_flow_euler": (C.c_int, [_P, _P, _P, C.c_int64, _F, _I, _P]),
     "umv_latent_embed": (C.c_int, [_P, _P, _P, _I, _F, _P, _P]),
     "umv_vae_decode": (C.c_int, [_P, _P, _I, _I, _I, _P, _P]),

@@ -820,6 +820,7 @@ int umv_seq_fork(umv_engine* e, int32_t src, int32_t* dst) {
     Seq& n = e->seqs[*dst];
     n.pages = pages;
     n.len = len;
+    n.content = e->seqs[src].content;          // same committed tokens, same K / V
     for (int p : n.pages) ++e->page_ref[p];
     return UMV_OK;
 }
@@ -843,6 +844,7 @@ int umv_seq_truncate(umv_engine* e, int32_t seq, int32_t len) {
     Seq* s = get_seq(e, seq);
     if (!s) return UMV_ERR_INVALID;
     UMV_REQUIRE(len >= 0 && len <= s->len, UMV_ERR_INVALID, "umv_seq_truncate: %d not in [0,%d]", len, s->len);
+    if (len != s->len) s->content = len ? ++e->content_counter : 0;
     s->len = len;
     const int keep = (len + kPageTokens - 1) / kPageTokens;
     while ((int)s->pages.size() > keep) {
@@ -1067,7 +1069,10 @@ int llm_run(umv_engine* e, const bf16* x, int n_seqs, const int32_t* seqs, const
         UMV_TRY(llm_layers(e, r, out, st));
     }
     if (update_kv)
-        for (int b = 0; b < n_seqs; ++b) sq[b]->len += q_lens[b];
+        for (int b = 0; b < n_seqs; ++b) {
+            sq[b]->len += q_lens[b];
+            sq[b]->content = ++e->content_counter;
+        }
     return UMV_OK;
 }
 }  // namespace umv
@@ -1372,12 +1377,20 @@ int umv_generate_text(umv_engine* e, int32_t n_seqs, const int32_t* seqs, const 
     }
     if (next_tokens_out)
         UMV_CUDA_OK(cudaMemcpyAsync(next_tokens_out, e->dec_tokens, B * sizeof(int64_t), cudaMemcpyDeviceToDevice, st));
-    for (int b = 0; b < B; ++b) sq[b]->len += n_steps;
+    for (int b = 0; b < B; ++b) {
+        sq[b]->len += n_steps;
+        sq[b]->content = ++e->content_counter;
+    }
     return UMV_OK;
 }
 
 
 // ------------------------------------------------------------------------------ rectified flow
+int umv_flow_branches_last(umv_engine* e, int32_t* n) {
+    UMV_REQUIRE(e && n, UMV_ERR_INVALID, "null argument");
+    *n = e->last_flow_branches;
+    return UMV_OK;
+}
 int umv_flow_velocity(umv_engine* e, const umv_flow_args* a, const float* x_t, float* v_out, void* stream) {
     UMV_REQUIRE(e && e->finalized, UMV_ERR_STATE, "engine not finalized");
     UMV_REQUIRE(e->d.enable_gen, UMV_ERR_STATE, "generation expert weights were not enabled");
@@ -1396,8 +1409,27 @@ int umv_flow_velocity(umv_engine* e, const umv_flow_args* a, const float* x_t, f
         n_lat += a->lat_lens[b];
     }
     const int Mb = n_lat + 2 * B;
-    const int text_branch = has_text ? 1 : -1, img_branch = has_img ? (has_text ? 2 : 1) : -1;
-    const int nb = 1 + (has_text ? 1 : 0) + (has_img ? 1 : 0);
+    // Two branches over the SAME context are one forward: in a pure text-to-image request the image-free context (cfg_img) holds
+    // exactly the main context's tokens (inferencer.py:578-600 feeds both the same text), so its velocity IS the main branch's, bit for
+    // bit (same rows, same keys, batch-invariant kernels) -- evaluate it once and let the CFG mix read it twice.  Detected from the
+    // sequences' content ids (a fork of the main context, or the main context itself), same lengths and rope positions; the reference
+    // runs the third forward anyway.  UMV_CFG_DEDUP=0 switches it off (read per call).
+    bool img_is_main = false;
+    if (has_img && has_text) {
+        const char* dd = getenv("UMV_CFG_DEDUP");
+        img_is_main = !(dd && atoi(dd) == 0);
+        for (int b = 0; b < B && img_is_main; ++b) {
+            const Seq* sm = get_seq(e, a->seqs[b]);
+            const Seq* si = get_seq(e, a->cfg_img_seqs[b]);
+            if (!sm || !si) return UMV_ERR_INVALID;
+            img_is_main = sm->content == si->content && sm->len == si->len && a->positions[b] == a->cfg_img_positions[b];
+        }
+    }
+    // the reference evaluates cfg_img only inside the cfg_text branch (bagel.py:1173-1207): without cfg_text it is not run at all
+    const bool run_img = has_img && has_text && !img_is_main;
+    const int text_branch = has_text ? 1 : -1, img_branch = (has_img && has_text) ? (img_is_main ? 0 : 2) : -1;
+    const int nb = 1 + (has_text ? 1 : 0) + (run_img ? 1 : 0);
+    e->last_flow_branches = nb;
     UMV_REQUIRE(nb * Mb <= d.max_tokens, UMV_ERR_NOMEM, "flow step needs %d rows > max_tokens %d", nb * Mb, d.max_tokens);
     // the reference evaluates cfg_img only inside the cfg_text branch (bagel.py:1173-1207): img without text is ignored
     // branch / sample / row geometry of the one packed gen-mode forward over all branches (rows are independent; contexts and rope
@@ -1407,7 +1439,7 @@ int umv_flow_velocity(umv_engine* e, const umv_flow_args* a, const float* x_t, f
     const int32_t* bseq[3] = {a->seqs, nullptr, nullptr};
     const int32_t* bpos[3] = {a->positions, nullptr, nullptr};
     if (has_text) { bseq[text_branch] = a->cfg_text_seqs; bpos[text_branch] = a->cfg_text_positions; }
-    if (has_img) { bseq[img_branch] = a->cfg_img_seqs; bpos[img_branch] = a->cfg_img_positions; }
+    if (run_img) { bseq[img_branch] = a->cfg_img_seqs; bpos[img_branch] = a->cfg_img_positions; }
     for (int br = 0; br < nb; ++br)
         for (int b = 0; b < B; ++b) {
             seqs.push_back(bseq[br][b]);
@@ -1467,7 +1499,7 @@ int umv_flow_velocity(umv_engine* e, const umv_flow_args* a, const float* x_t, f
     const int rows_per_branch = seg ? n_lat : Mb;
     UMV_TRY(lin(e, e->xn, D, e->llm2vae_w, e->llm2vae_b, nullptr, vall, C, nb * rows_per_branch, C, D, EPI_BF16, st));
     CfgArgs c;
-    c.v = vall; c.rows_per_branch = rows_per_branch; c.C = C; c.text_branch = text_branch; c.img_branch = has_text ? img_branch : -1;
+    c.v = vall; c.rows_per_branch = rows_per_branch; c.C = C; c.text_branch = text_branch; c.img_branch = img_branch;
     c.text_scale = a->cfg_text_scale; c.img_scale = a->cfg_img_scale; c.renorm_min = a->cfg_renorm_min;
     c.renorm_type = a->renorm_type; c.img_row0 = seg ? d_lat0 : d_row0; c.img_lat0 = d_lat0; c.img_n = d_n; c.out = v_out;
     return cfg_combine(c, B, st);

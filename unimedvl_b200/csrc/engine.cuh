@@ -37,6 +37,10 @@ struct Seq {
     std::vector<int> pages;
     int len = 0;
     bool alive = false;
+    // Identity of the committed token history: 0 = empty, a fork inherits its parent's, every committed append / truncation draws a
+    // fresh one.  Equal ids (and lengths) mean bit-identical K / V -- what lets a flow step evaluate two CFG branches over the same
+    // context once (umv_flow_velocity).
+    uint64_t content = 0;
 };
 
 // Device-side metadata of one packed forward call (one H2D copy).
@@ -144,6 +148,8 @@ struct umv_engine {
     bool kv_tmap_ok = false;
     std::vector<int> page_ref, free_pages;
     std::vector<umv::Seq> seqs;
+    uint64_t content_counter = 0;   // source of Seq::content ids
+    int last_flow_branches = 0;     // CFG branches the last umv_flow_velocity ran (umv_flow_branches_last)
 
     // workspaces
     umv::bf16 *h = nullptr, *xn = nullptr, *qkv = nullptr, *attn = nullptr, *act = nullptr, *logits = nullptr;

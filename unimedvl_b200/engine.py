@@ -291,6 +291,12 @@ class Engine:
         self._exit()
         return v
 
+    def flow_branches_last(self) -> int:
+        """CFG branches the last flow_velocity call evaluated (umv_flow_branches_last)."""
+        n = C.c_int32()
+        _lib.check(self.lib.umv_flow_branches_last(self.h, C.byref(n)))
+        return n.value
+
     def latent_embed(self, x: torch.Tensor, pos_ids: torch.Tensor, timestep: float) -> torch.Tensor:
         x = x.to(self.device, torch.float32).contiguous()
         pos_ids = pos_ids.to(self.device, torch.int64).contiguous()
