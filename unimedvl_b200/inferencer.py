@@ -141,21 +141,26 @@ class InterleaveInferencer:
         need_cfg = not understanding_output
         cfg_img_context = deepcopy(gen_context) if need_cfg else None
         cfg_text_context = None
+        # Until the first image the image-free context receives exactly the main context's text (inferencer.py:578-600): it is then a
+        # page fork of the main context instead of a second prefill -- same K / V, and the flow step evaluates the two CFG branches
+        # over it once (umv_flow_velocity).
+        same_so_far = True
         if think:
             system_prompt = VLM_THINK_SYSTEM_PROMPT if understanding_output else GEN_THINK_SYSTEM_PROMPT
             gen_context = self.update_context_text(system_prompt, gen_context)
             if need_cfg:
-                cfg_img_context = self.update_context_text(system_prompt, cfg_img_context)
+                cfg_img_context = deepcopy(gen_context)
         for term in input_lists:
             if isinstance(term, str):
                 if need_cfg:
                     cfg_text_context = deepcopy(gen_context)           # the context WITHOUT this text
                 gen_context = self.update_context_text(term, gen_context)
                 if need_cfg:
-                    cfg_img_context = self.update_context_text(term, cfg_img_context)
+                    cfg_img_context = deepcopy(gen_context) if same_so_far else self.update_context_text(term, cfg_img_context)
             elif isinstance(term, Image.Image):
                 term = self.vae_transform.resize_transform(pil_img2rgb(term))
                 gen_context = self.update_context_image(term, gen_context, vae=not understanding_output)
+                same_so_far = False
                 if need_cfg:
                     cfg_text_context = deepcopy(gen_context)
             else:
