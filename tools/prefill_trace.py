@@ -49,13 +49,19 @@ n = n.value
 nm = [names.raw[i * NL:(i + 1) * NL].split(b"\0")[0].decode() for i in range(n)]
 t = stamps[:n].astype(np.int64)
 out = [f"# VQA prefill timeline: {B} samples x (1024 ViT tokens + 2 markers + 32 prompt tokens), + 2 decode steps; {n} traced "
-       f"launches; wall {ev0.elapsed_time(ev1):.2f} ms\n\ncritical-path share = this kernel's last-CTA end minus the previous traced "
-       "kernel's last-CTA end\n\n| kernel | launches | mean us | total ms | share |\n|---|---:|---:|---:|---:|\n"]
+       f"launches; wall {ev0.elapsed_time(ev1):.2f} ms\n\ncritical-path share = this kernel's last-CTA end minus the later of (the previous "
+       "traced kernel's last-CTA end, this kernel's first-CTA start); the GPU-idle time before a kernel starts (host work between the prefill "
+       "and the decode loop -- with tracing on, the decode graph is re-captured there, ~7 ms -- and untraced kernels) is the row `(idle before "
+       "a kernel starts)`, not charged to the kernel that follows it\n\n| kernel | launches | mean us | total ms | share |\n|---|---:|---:|---:|---:|\n"]
 agg = {}
+idle = 0.0
 for i in range(1, n):
     a = agg.setdefault(nm[i], [0, 0.0])
     a[0] += 1
-    a[1] += (t[i, 3] - t[i - 1, 3]) / 1e3
+    gap = max(0, t[i, 0] - t[i - 1, 3])
+    idle += gap / 1e3
+    a[1] += (t[i, 3] - t[i - 1, 3] - gap) / 1e3
+agg["(idle before a kernel starts)"] = [n - 1, idle]
 tot = sum(a[1] for a in agg.values())
 for k, (c, s) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:24]:
     out.append(f"| `{k}` | {c} | {s / c:.1f} | {s / 1e3:.3f} | {100 * s / tot:.1f}% |\n")
