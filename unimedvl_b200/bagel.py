@@ -416,10 +416,10 @@ class Bagel:
         B = len(vit_seqlens)
         dev = self.device
         cache = NaiveCache(self.config.llm_config.num_hidden_layers)
-        if fused_prefill:
+        L = packing.image_prompt_layout([int(n) for n in vit_seqlens], prompt_ids, new_token_ids) if fused_prefill else None
+        if L is not None and sum(L["seq_lens"]) <= self.engine.max_tokens:      # else: the engine's workspace only holds the two calls
             # image block and prompt of every sample in one pass over the weights (umv_forward_cache_update_vit_prompt): the prompt rows
             # attend causally behind the full-mask block; K / V are bit-identical to the two calls below
-            L = packing.image_prompt_layout([int(n) for n in vit_seqlens], prompt_ids, new_token_ids)
             h = paged_handle(cache, self.engine, B)
             self.engine.forward_cache_update_vit(h.seqs, L["seq_lens"], L["text_ids"], L["text_rows"], pixels, vit_pos_ids,
                                                  [int(n) for n in vit_seqlens], L["vit_rows"], L["positions"], prompt_lens=L["prompt_lens"])

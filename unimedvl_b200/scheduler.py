@@ -176,15 +176,19 @@ class ContinuousBatcher:
             else:
                 r.seq, r.kv_len, r.rope = self.engine.seq_new(), 0, 0
         with_img = [r for r in group if r.image is not None]
+        L = None
         if self.fused_prefill and len(with_img) == len(group):
-            # image block + prompt of every admitted request in ONE forward (umv_forward_cache_update_vit_prompt): one pass over the
-            # weights and one rider step instead of two
             from . import packing
             gv, _, _ = m.prepare_vit_images([r.kv_len for r in group], [r.rope for r in group], [r.image for r in group],
                                             self.vit_transform, self.tok)
             n_img = [int(n) for n in gv["vit_token_seqlens"]]
             L = packing.image_prompt_layout(n_img, [self.tokenizer.encode(r.prompt) for r in group], self.tok,
                                             [r.kv_len for r in group], [r.rope for r in group])
+            if sum(L["seq_lens"]) > self.engine.max_tokens:       # the workspace only holds the two forwards one after the other
+                L = None
+        if L is not None:
+            # image block + prompt of every admitted request in ONE forward (umv_forward_cache_update_vit_prompt): one pass over the
+            # weights and one rider step instead of two
             riders = self._riders(sum(L["seq_lens"]))
             self.model.rider_tokens = self.engine.forward_cache_update_vit(
                 [r.seq for r in group], L["seq_lens"], L["text_ids"], L["text_rows"], gv["packed_vit_tokens"], gv["packed_vit_position_ids"],
